@@ -1,0 +1,203 @@
+/* tm_b200.h — C-ABI of the B200-native triplet_match search path.
+ *
+ * The reference (richard-vock/triplet_match) has no FFI: its boundary is the C++
+ * class API in include/model, include/scene, include/feature, include/discretize
+ * and the *_traits headers.  This header is what the new model::impl /
+ * scene::impl (include/triplet_match/, triplet_match_b200/host/) bind instead of
+ * the reference's CPU loops; every entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers unless a
+ * parameter is documented as resident; opaque handles; every function returns
+ * a tm_status (0 = ok) and never throws; tm_last_error() gives the message of
+ * the calling thread's last failure.  A context owns one device and one
+ * stream; a handle is used by one host thread at a time.  Transforms are
+ * column-major float[16] (Eigen mat4f_t).  Clouds are passed as strided views
+ * so that both packed xyz arrays (stride 3) and pcl::PointSurfel AoS records
+ * (stride 12 floats; tangent = data_c[1..3], include/common:62-70) bind
+ * without a copy on the host.  There is no CPU fallback: without a CUDA device
+ * tm_ctx_create fails with TM_ERR_CUDA.
+ */
+#ifndef TM_B200_H
+#define TM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tm_status {
+    TM_OK = 0,
+    TM_ERR_INVALID = 1,     /* bad argument (null, size, unsupported matrix) */
+    TM_ERR_CUDA = 2,        /* CUDA runtime failure (message has the cudaError) */
+    TM_ERR_CAPACITY = 3,    /* caller buffer / configured capacity too small  */
+    TM_ERR_UNINITIALIZED = 4, /* model not initialised (include/impl/model.hpp:171-173) */
+    TM_ERR_NCCL = 5
+} tm_status;
+
+typedef struct tm_ctx tm_ctx;
+typedef struct tm_model tm_model;
+typedef struct tm_scene tm_scene;
+typedef struct tm_query tm_query;
+typedef struct tm_comm tm_comm;
+
+/* strided cloud view: point i has pos[i*stride + 0..2] etc. */
+typedef struct tm_cloud_view {
+    const float* pos;
+    const float* nrm;
+    const float* tgt;
+    uint32_t stride; /* in floats; 3 = packed, 12 = pcl::PointSurfel */
+    uint32_t n;
+} tm_cloud_view;
+
+/* What model::init (include/impl/model.hpp:16-167) produced on the host. */
+typedef struct tm_model_desc {
+    const uint32_t* voxel; /* voxel_data_, lin = k*ex*ey + j*ex + i (model.hpp:85) */
+    int32_t extents[3];    /* extents_ (model.hpp:50) */
+    float to_voxel[16];    /* to_voxel_ column-major (model.hpp:56-61); must be diag+translation */
+    float resolution;      /* cloud()->resolution() (pointcloud.hpp:66-82) */
+    float diameter;        /* diameter_ (model.hpp:39) */
+    /* hash_map_t (include/model:25-26) flattened: unique keys, CSR offsets, (i,j)
+     * values in equal_range order, at most query_limit kept per key */
+    const uint32_t* keys;    /* n_keys x 4 */
+    const uint32_t* offsets; /* n_keys + 1 */
+    const uint32_t* pairs;   /* offsets[n_keys] x 2 */
+    uint32_t n_keys;
+    float feat_min[4], feat_max[4]; /* feat_bounds_ (model.hpp:122) */
+    float distance_step_count;      /* discretization_params (include/discretize:8-12) */
+    float angle_step;
+} tm_model_desc;
+
+/* ---- context ------------------------------------------------------------ */
+const char* tm_last_error(void);
+const char* tm_version(void);
+int tm_ctx_create(int device, tm_ctx** out);
+void tm_ctx_destroy(tm_ctx* ctx);
+int tm_ctx_sync(tm_ctx* ctx);
+void* tm_ctx_stream(tm_ctx* ctx);              /* cudaStream_t */
+int tm_ctx_sm_count(tm_ctx* ctx);
+int tm_timer_start(tm_ctx* ctx);               /* CUDA event on the context stream */
+int tm_timer_stop(tm_ctx* ctx, float* ms);     /* records, synchronises, elapsed ms */
+int tm_ctx_flush_l2(tm_ctx* ctx);              /* overwrites a 256 MiB scratch buffer */
+uint64_t tm_ctx_kernel_launches(tm_ctx* ctx);  /* kernels launched so far on this context */
+
+/* ---- resident model / scene -------------------------------------------- */
+/* replaces the CPU-resident state probed by model::query / model::voxel_query
+ * (include/impl/model.hpp:169-192) */
+int tm_model_upload(tm_ctx* ctx, const tm_cloud_view* cloud, const tm_model_desc* desc,
+                    tm_model** out);
+void tm_model_destroy(tm_model* m);
+/* GPU grid fill: exact 1-NN of every voxel centre (include/impl/model.hpp:81-94).
+ * voxel_out: ex*ey*ez u32. */
+int tm_voxel_fill(tm_ctx* ctx, const tm_cloud_view* cloud, const int32_t extents[3],
+                  const float to_voxel[16], uint32_t* voxel_out);
+
+/* scene cloud + tangent_mask_ (include/impl/scene.hpp:46-58); mask_ starts 0 */
+int tm_scene_upload(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
+                    tm_scene** out);
+int tm_scene_set_mask(tm_scene* s, const uint8_t* mask); /* mask_ (scene.hpp:87-90); NULL clears */
+void tm_scene_destroy(tm_scene* s);
+
+/* ---- stage calls, host buffers in / out -------------------------------- */
+/* pair filter + feature + valid + discretize_feature for scene pairs (i,j):
+ * include/impl/scene.hpp:290-302, include/impl/feature.hpp:15-88, src/discretize.cpp:19-30.
+ * feats may be NULL. */
+int tm_features(tm_scene* s, tm_model* m, const uint32_t* pair_i, const uint32_t* pair_j,
+                uint64_t n, float min_diameter_factor, float max_diameter_factor, float* feats,
+                uint32_t* keys, uint8_t* valid);
+/* model::query + query_limit (include/impl/model.hpp:169-178, scene.hpp:304-311).
+ * offsets: n+1 (CSR over pairs); hits: 2 x offsets[n] (m_i, m_j), may be NULL to size. */
+int tm_probe(tm_model* m, const uint32_t* keys, const uint8_t* valid, uint64_t n, uint32_t limit,
+             uint64_t* offsets, uint32_t* hits, uint64_t hits_capacity);
+/* base_transform_ + force_up filter (include/impl/scene.hpp:312-319, 538-567) for
+ * every hit of every pair.  T16s: 16 x offsets[n]; hyp_valid: offsets[n]. */
+int tm_hypotheses(tm_scene* s, tm_model* m, const uint32_t* pair_i, const uint32_t* pair_j,
+                  uint64_t n, const uint64_t* offsets, const uint32_t* hits, int force_up,
+                  float* T16s, uint8_t* hyp_valid);
+/* radius subset around scene points (scene.hpp:273): ascending indices with
+ * ||p - c||^2 < radius^2.  indices may be NULL to size. */
+int tm_ball_subsets(tm_scene* s, const uint32_t* centres, uint32_t n_centres, float radius,
+                    uint64_t* offsets, int32_t* indices, uint64_t capacity);
+/* project_ per hypothesis (include/impl/scene.hpp:411-510): inlier count
+ * (= scene_corrs.size()), score, and (early_out != 0) the reference's early-drop
+ * outcome.  hyp_sub[h] selects subset CSR row; hyp_sub == NULL scores against all
+ * scene points (finish_find, scene.hpp:100-106).  scores/dropped may be NULL. */
+int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const uint32_t* hyp_sub,
+             const uint64_t* sub_offsets, const int32_t* sub_indices, uint32_t n_sub,
+             float dist_thres, float accept_prob, int early_out, uint32_t* counts, double* scores,
+             uint8_t* dropped);
+/* correspondences of one transform over the whole scene (finish_find's
+ * scene_corrs / model_corrs, ascending scene index).  Buffers sized scene n. */
+int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
+                       uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,
+                       double* score);
+/* icp_ (include/impl/scene.hpp:369-404; replaces opencl/icp.cl icp_projection +
+ * icp_correlation + the absent host reduction) for n start transforms. */
+int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
+           float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters);
+/* traits project closed forms (a14; replaces opencl/cylinder.cl uv_project).
+ * kind: 0 cylinder, 1 plane, 2 plane2, 3 identity.  xyz/uvw packed n x 3; ok: n. */
+int tm_traits_project(tm_ctx* ctx, int kind, const float g2l[16], float radius, float threshold,
+                      const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
+
+/* ---- resident query: the whole recorded-list search in one call --------- */
+typedef struct tm_query_params {
+    float min_diameter_factor; /* sample_parameters (include/common:72-82) */
+    float max_diameter_factor;
+    int32_t force_up;
+    uint32_t query_limit;      /* detail::query_limit = 200 (scene.hpp:19) */
+    float dist_thres;
+    float accept_prob;         /* model_match_factor */
+    int32_t early_out;         /* 0 = finish_find semantics, 1 = reference early-drop */
+    uint32_t icp_top_k;        /* 0 = no ICP stage */
+    uint32_t max_icp_iterations;
+    uint64_t max_hypotheses;   /* capacity; 0 = n_pairs * query_limit */
+    uint64_t hyp_limit;        /* score only the first hyp_limit hypotheses (0 = all) */
+} tm_query_params;
+
+typedef struct tm_query_result {
+    uint64_t n_pairs_valid;
+    uint64_t n_hypotheses;      /* global, before sharding */
+    uint64_t n_scored;          /* hypotheses scored by this shard */
+    uint64_t n_tests;           /* hypothesis-point tests of this shard */
+    uint64_t best_key;          /* (inliers << 32) | (0xFFFFFFFF - global hypothesis id); 0 = none */
+    uint32_t best_hypothesis;
+    uint32_t best_inliers;
+    double best_score;
+    float best_T[16];
+} tm_query_result;
+
+int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query** out);
+void tm_query_destroy(tm_query* q);
+/* recorded sample list: outer[o] = scene index of p1; pair k = (outer[pair_outer[k]], pair_j[k]),
+ * pairs sorted by pair_outer.  Copies host -> device. */
+int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
+                       const uint32_t* pair_outer, const uint32_t* pair_j, uint64_t n_pairs);
+/* this rank scores hypotheses [rank*ceil(H/world), ...) of the global list */
+int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world);
+/* enqueue subsets -> features -> probe -> hypotheses -> score -> argmax (-> ICP) on the
+ * context stream; inputs and outputs stay resident */
+int tm_query_run(tm_query* q);
+int tm_query_result_get(tm_query* q, tm_query_result* out); /* synchronises, small D2H */
+void* tm_query_best_key_device(tm_query* q); /* resident u64 for the NCCL max-reduce */
+int tm_query_set_global_best(tm_query* q, uint64_t key); /* after the all-reduce */
+/* full per-hypothesis arrays of this shard (parity tests); any pointer may be NULL */
+int tm_query_download(tm_query* q, uint64_t capacity, uint32_t* counts, double* scores,
+                      float* T16s, uint8_t* valid, uint32_t* hyp_pair, uint8_t* dropped);
+/* top-k ICP results (k = icp_top_k): hypothesis ids, refined transforms, counts */
+int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* counts,
+                         double* scores, uint32_t* iters);
+
+/* ---- the one collective: best-pose argmax over ranks ------- */
+int tm_nccl_unique_id(uint8_t out[128]);
+int tm_comm_create(tm_ctx* ctx, const uint8_t id[128], int rank, int world, tm_comm** out);
+void tm_comm_destroy(tm_comm* c);
+/* ncclAllReduce(max) of the packed best key, then broadcast of the winner's pose */
+int tm_query_allreduce_best(tm_query* q, tm_comm* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TM_B200_H */

@@ -1,0 +1,93 @@
+"""In-tree build of the CUDA library (sm_100a) and of the CPU oracle.
+
+`build_native()` compiles triplet_match_b200/csrc/*.cu with nvcc into
+triplet_match_b200/libtriplet_match_b200.so (git-ignored, travels with gpurun).
+Flags: -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 and -fmad=false:
+the kernels must round every FP32 multiply and add separately to stay
+bit-exact with the reference's SSE2 (no-FMA) build.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(ROOT)
+CSRC = os.path.join(ROOT, "csrc")
+OBJ = os.path.join(ROOT, "_obj")
+LIB = os.path.join(ROOT, "libtriplet_match_b200.so")
+HOSTLIB = os.path.join(ROOT, "libtriplet_match_host.so")
+ORACLE_DIR = os.path.join(REPO, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    "-Xptxas", "-v",
+]
+SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_icp.cu", "k_query.cu", "capi.cu"]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _headers() -> list[str]:
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(REPO, "include", "tm_b200.h"))
+    return hs
+
+
+def _run(cmd: list[str], log: str | None = None) -> None:
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if log:
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout + p.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    objs, jobs = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or not _newer(o, [s] + hdrs):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        _run([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
+        if verbose:
+            print("compiled", os.path.basename(s))
+
+    with ThreadPoolExecutor(max_workers=max(1, min(6, os.cpu_count() or 1))) as ex:
+        list(ex.map(compile_one, jobs))
+    if force or jobs or not _newer(LIB, objs):
+        _run([NVCC, "-shared", "-o", LIB] + objs + ["-ldl", "-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+def build_oracle(force: bool = False) -> str:
+    deps = [os.path.join(ORACLE_DIR, f) for f in ("oracle.hpp", "oracle_capi.cpp", "Makefile")]
+    if force or not _newer(ORACLE_LIB, deps):
+        _run(["make", "-C", ORACLE_DIR, "-s", "all"])
+    elif os.path.isdir("/root/reference"):
+        _run(["make", "-C", ORACLE_DIR, "-s", "ref"])
+    return ORACLE_LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_oracle(force="--force" in sys.argv))

@@ -1,0 +1,1391 @@
+// capi.cu — implementation of include/tm_b200.h: resident model/scene state,
+// the stage calls with host buffers, and the resident query pipeline.  Host
+// logic only; every data-parallel step is one of the kernels in k_*.cu.
+#include "../../include/tm_b200.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tm_kernels.cuh"
+
+namespace tmk {
+unsigned long long g_launch_count = 0;
+}
+using namespace tmk;
+
+// ------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(TM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+#define REQUIRE(cond, msg)                          \
+    do {                                            \
+        if (!(cond)) return fail(TM_ERR_INVALID, msg); \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return TM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess)
+            return fail(TM_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) +
+                                         "): " + cudaGetErrorString(e));
+        cap = want;
+        return TM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+struct tm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    DevBuf flush;
+    DevBuf scratch[12];  // stage-call scratch, grow-only
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+struct tm_model {
+    tm_ctx* ctx;
+    DevBuf pos, nrm, tgt, voxel, vcell, slots, hits;
+    ModelDev dev;
+    float centre[3];
+    float half_diag;
+    bool fused;
+};
+
+struct tm_scene {
+    tm_ctx* ctx;
+    DevBuf pos, nrm, tgt, mask_tmp;
+    CloudDev dev;
+};
+
+static int bind(tm_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return TM_OK;
+}
+static int pinned_ensure(tm_ctx* c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return TM_OK;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->pinned_cap = 0;
+    CU(cudaMallocHost(&c->pinned, bytes));
+    c->pinned_cap = bytes;
+    return TM_OK;
+}
+
+// `dist > thres` with dist = sqrtf(sq) (scene.hpp:464-465) <=> sq > S, where S is the
+// largest float whose correctly rounded square root is <= thres.
+static float sq_threshold(float thres) {
+    if (!(thres >= 0.f)) return -1.f;
+    float c = thres * thres;
+    while (sqrtf(c) > thres) c = nextafterf(c, 0.f);
+    for (;;) {
+        float n = nextafterf(c, INFINITY);
+        if (std::isinf(n) || sqrtf(n) > thres) break;
+        c = n;
+    }
+    return c;
+}
+
+extern "C" {
+
+const char* tm_last_error(void) { return g_err.c_str(); }
+const char* tm_version(void) { return "triplet_match_b200 0.1 (sm_100a)"; }
+
+int tm_ctx_create(int device, tm_ctx** out) {
+    REQUIRE(out, "tm_ctx_create: out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(TM_ERR_CUDA, std::string("no CUDA device: ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                     " (this library has no CPU fallback)");
+    REQUIRE(device >= 0 && device < n, "tm_ctx_create: device out of range");
+    tm_ctx* c = new tm_ctx();
+    c->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = c;
+    return TM_OK;
+}
+void tm_ctx_destroy(tm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->flush.release();
+    for (auto& s : c->scratch) s.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+int tm_ctx_sync(tm_ctx* c) {
+    REQUIRE(c, "null ctx");
+    TRY(bind(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+void* tm_ctx_stream(tm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int tm_ctx_sm_count(tm_ctx* c) { return c ? c->sm_count : 0; }
+int tm_timer_start(tm_ctx* c) {
+    REQUIRE(c, "null ctx");
+    TRY(bind(c));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    return TM_OK;
+}
+int tm_timer_stop(tm_ctx* c, float* ms) {
+    REQUIRE(c && ms, "null arg");
+    TRY(bind(c));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return TM_OK;
+}
+int tm_ctx_flush_l2(tm_ctx* c) {
+    REQUIRE(c, "null ctx");
+    TRY(bind(c));
+    const size_t bytes = 256ull << 20;
+    TRY(c->flush.ensure(bytes));
+    launch_flush(c->stream, c->flush.as<float4>(), bytes / sizeof(float4), 1.f);
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+uint64_t tm_ctx_kernel_launches(tm_ctx*) { return g_launch_count; }
+
+// ------------------------------------------------------------- cloud upload
+static int upload_cloud(tm_ctx* c, const tm_cloud_view* v, const uint8_t* flags, int model_mode,
+                        DevBuf& pos, DevBuf& nrm, DevBuf& tgt) {
+    REQUIRE(v && v->pos && v->nrm && v->tgt, "cloud view has null arrays");
+    REQUIRE(v->stride >= 3, "cloud stride must be >= 3 floats");
+    const uint32_t n = v->n;
+    TRY(pos.ensure(sizeof(float4) * (size_t)std::max(n, 1u)));
+    TRY(nrm.ensure(sizeof(float4) * (size_t)std::max(n, 1u)));
+    TRY(tgt.ensure(sizeof(float4) * (size_t)std::max(n, 1u)));
+    if (!n) return TM_OK;
+    // The three arrays may alias one AoS buffer (PointSurfel) or be separate packed
+    // arrays; copy the covering byte range of each verbatim, then pack on the device.
+    const size_t span = ((size_t)(n - 1) * v->stride + 3) * sizeof(float);
+    DevBuf &rp = c->scratch[0], &rn = c->scratch[1], &rt = c->scratch[2], &rf = c->scratch[3];
+    const float *dp, *dn, *dt;
+    const float* lo = std::min(v->pos, std::min(v->nrm, v->tgt));
+    const float* hi = std::max(v->pos, std::max(v->nrm, v->tgt));
+    if (v->stride > 3 && (size_t)(hi - lo) < v->stride) {
+        // interleaved: one copy
+        size_t bytes = span + (size_t)(hi - lo) * sizeof(float);
+        TRY(rp.ensure(bytes));
+        CU(cudaMemcpyAsync(rp.p, lo, bytes, cudaMemcpyHostToDevice, c->stream));
+        dp = rp.as<float>() + (v->pos - lo);
+        dn = rp.as<float>() + (v->nrm - lo);
+        dt = rp.as<float>() + (v->tgt - lo);
+    } else {
+        TRY(rp.ensure(span));
+        TRY(rn.ensure(span));
+        TRY(rt.ensure(span));
+        CU(cudaMemcpyAsync(rp.p, v->pos, span, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(rn.p, v->nrm, span, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(rt.p, v->tgt, span, cudaMemcpyHostToDevice, c->stream));
+        dp = rp.as<float>();
+        dn = rn.as<float>();
+        dt = rt.as<float>();
+    }
+    const uint8_t* dflags = nullptr;
+    if (flags) {
+        TRY(rf.ensure(n));
+        CU(cudaMemcpyAsync(rf.p, flags, n, cudaMemcpyHostToDevice, c->stream));
+        dflags = rf.as<uint8_t>();
+    }
+    launch_pack_cloud(c->stream, dp, dn, dt, v->stride, n, dflags, model_mode, pos.as<float4>(),
+                      nrm.as<float4>(), tgt.as<float4>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));  // host buffers may be reused by the caller
+    return TM_OK;
+}
+
+static int check_to_voxel(const float* t, float s[3], float tr[3]) {
+    // column-major; must be diag(s) + translation with last row (0,0,0,1)
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 4; ++row) {
+            float v = t[col * 4 + row];
+            bool diag = row == col, transl = col == 3 && row < 3;
+            if (!diag && !transl && v != 0.f)
+                return fail(TM_ERR_INVALID, "to_voxel must be diagonal + translation");
+        }
+    if (t[15] != 1.f) return fail(TM_ERR_INVALID, "to_voxel[3][3] must be 1");
+    for (int k = 0; k < 3; ++k) {
+        s[k] = t[k * 4 + k];
+        tr[k] = t[12 + k];
+    }
+    return TM_OK;
+}
+
+int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* d, tm_model** out) {
+    REQUIRE(c && cloud && d && out, "tm_model_upload: null argument");
+    TRY(bind(c));
+    REQUIRE(cloud->n > 0, "model cloud is empty");
+    REQUIRE(d->voxel, "model not initialised: voxel grid missing");
+    REQUIRE(d->extents[0] > 0 && d->extents[1] > 0 && d->extents[2] > 0, "bad extents");
+    const size_t cells = (size_t)d->extents[0] * d->extents[1] * d->extents[2];
+    REQUIRE(cells < (1ull << 31), "voxel grid too large for 32-bit linear index");
+    float s[3], tr[3];
+    TRY(check_to_voxel(d->to_voxel, s, tr));
+    tm_model* m = new tm_model();
+    m->ctx = c;
+    int rc = upload_cloud(c, cloud, nullptr, 1, m->pos, m->nrm, m->tgt);
+    if (rc) {
+        tm_model_destroy(m);
+        return rc;
+    }
+    auto bail = [&](int code) {
+        tm_model_destroy(m);
+        return code;
+    };
+    if ((rc = m->voxel.ensure(cells * sizeof(uint32_t)))) return bail(rc);
+    for (size_t i = 0; i < cells; ++i)
+        if (d->voxel[i] >= cloud->n) return bail(fail(TM_ERR_INVALID, "voxel entry out of range"));
+    CU(cudaMemcpyAsync(m->voxel.p, d->voxel, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       c->stream));
+    // hash table: open addressing over the unique keys
+    uint32_t cap = 16;
+    while (cap < 2u * std::max(d->n_keys, 1u)) cap <<= 1;
+    std::vector<HashSlot> slots(cap);
+    memset(slots.data(), 0, sizeof(HashSlot) * cap);
+    uint32_t n_hits = d->n_keys ? d->offsets[d->n_keys] : 0;
+    for (uint32_t k = 0; k < d->n_keys; ++k) {
+        const uint32_t* key = d->keys + 4 * (size_t)k;
+        uint32_t cnt = d->offsets[k + 1] - d->offsets[k];
+        if (!cnt) continue;
+        uint32_t h = murmur4(key[0], key[1], key[2], key[3]) & (cap - 1);
+        while (slots[h].count) h = (h + 1) & (cap - 1);
+        for (int a = 0; a < 4; ++a) slots[h].k[a] = key[a];
+        slots[h].begin = d->offsets[k];
+        slots[h].count = cnt;
+    }
+    for (uint32_t i = 0; i < 2 * (size_t)n_hits; ++i)
+        if (d->pairs[i] >= cloud->n) return bail(fail(TM_ERR_INVALID, "hash pair out of range"));
+    if ((rc = m->slots.ensure(sizeof(HashSlot) * cap))) return bail(rc);
+    if ((rc = m->hits.ensure(sizeof(uint2) * (size_t)std::max(n_hits, 1u)))) return bail(rc);
+    CU(cudaMemcpyAsync(m->slots.p, slots.data(), sizeof(HashSlot) * cap, cudaMemcpyHostToDevice,
+                       c->stream));
+    if (n_hits)
+        CU(cudaMemcpyAsync(m->hits.p, d->pairs, sizeof(uint2) * (size_t)n_hits,
+                           cudaMemcpyHostToDevice, c->stream));
+    // fused grid (cell -> model point) when it stays L2-sized
+    m->fused = cells * sizeof(float4) <= (96ull << 20);
+    if (const char* e = getenv("TM_FUSED_GRID")) m->fused = atoi(e) != 0;
+    if (m->fused) {
+        if ((rc = m->vcell.ensure(cells * sizeof(float4)))) return bail(rc);
+        launch_fuse_grid(c->stream, m->voxel.as<uint32_t>(), cells, m->pos.as<float4>(),
+                         m->vcell.as<float4>());
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    ModelDev& dv = m->dev;
+    dv.cloud = CloudDev{m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n};
+    dv.voxel = m->voxel.as<uint32_t>();
+    dv.vcell = m->fused ? m->vcell.as<float4>() : nullptr;
+    dv.vcell_idx = nullptr;
+    dv.ex = d->extents[0];
+    dv.ey = d->extents[1];
+    dv.ez = d->extents[2];
+    dv.exf = (float)dv.ex;
+    dv.eyf = (float)dv.ey;
+    dv.ezf = (float)dv.ez;
+    dv.sx = s[0]; dv.sy = s[1]; dv.sz = s[2];
+    dv.tx = tr[0]; dv.ty = tr[1]; dv.tz = tr[2];
+    dv.slots = m->slots.as<HashSlot>();
+    dv.slot_mask = cap - 1;
+    dv.hits = m->hits.as<uint2>();
+    dv.n_hits = n_hits;
+    dv.fb_min0 = d->feat_min[0];
+    dv.fb_max0 = d->feat_max[0];
+    dv.dist_steps = (uint32_t)d->distance_step_count;  // float -> uint32 (feature.hpp:41)
+    dv.angle_step = d->angle_step;
+    dv.resolution = d->resolution;
+    dv.diameter = d->diameter;
+    // bbox centre / radius for the ICP fixed-point sums
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < cloud->n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float v = cloud->pos[(size_t)i * cloud->stride + k];
+            if (std::isfinite(v)) {
+                lo[k] = std::min(lo[k], v);
+                hi[k] = std::max(hi[k], v);
+            }
+        }
+    double dd = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (!(lo[k] <= hi[k])) lo[k] = hi[k] = 0.f;
+        m->centre[k] = 0.5f * (lo[k] + hi[k]);
+        dd += 0.25 * (double)(hi[k] - lo[k]) * (double)(hi[k] - lo[k]);
+    }
+    m->half_diag = (float)std::sqrt(dd);
+    *out = m;
+    return TM_OK;
+}
+void tm_model_destroy(tm_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    for (DevBuf* b : {&m->pos, &m->nrm, &m->tgt, &m->voxel, &m->vcell, &m->slots, &m->hits})
+        b->release();
+    delete m;
+}
+
+int tm_voxel_fill(tm_ctx* c, const tm_cloud_view* cloud, const int32_t extents[3],
+                  const float to_voxel[16], uint32_t* voxel_out) {
+    REQUIRE(c && cloud && extents && to_voxel && voxel_out, "tm_voxel_fill: null argument");
+    TRY(bind(c));
+    REQUIRE(cloud->n > 0, "cloud is empty");
+    float s[3], tr[3];
+    TRY(check_to_voxel(to_voxel, s, tr));
+    const size_t cells = (size_t)extents[0] * extents[1] * extents[2];
+    REQUIRE(cells > 0 && cells < (1ull << 31), "bad extents");
+    DevBuf pos, nrm, tgt, vox;
+    int rc = upload_cloud(c, cloud, nullptr, 1, pos, nrm, tgt);
+    if (!rc) rc = vox.ensure(cells * sizeof(uint32_t));
+    if (!rc) {
+        launch_voxel_fill(c->stream, pos.as<float4>(), cloud->n, extents[0], extents[1], extents[2],
+                          s[0], s[1], s[2], tr[0], tr[1], tr[2], vox.as<uint32_t>());
+        cudaError_t e = cudaMemcpyAsync(voxel_out, vox.p, cells * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(TM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    pos.release(); nrm.release(); tgt.release(); vox.release();
+    return rc;
+}
+
+int tm_scene_upload(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
+                    tm_scene** out) {
+    REQUIRE(c && cloud && out, "tm_scene_upload: null argument");
+    TRY(bind(c));
+    tm_scene* s = new tm_scene();
+    s->ctx = c;
+    int rc = upload_cloud(c, cloud, tangent_mask, 0, s->pos, s->nrm, s->tgt);
+    if (rc) {
+        tm_scene_destroy(s);
+        return rc;
+    }
+    s->dev = CloudDev{s->pos.as<float4>(), s->nrm.as<float4>(), s->tgt.as<float4>(), cloud->n};
+    *out = s;
+    return TM_OK;
+}
+int tm_scene_set_mask(tm_scene* s, const uint8_t* mask) {
+    REQUIRE(s, "null scene");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    const uint8_t* d = nullptr;
+    if (mask && s->dev.n) {
+        TRY(s->mask_tmp.ensure(s->dev.n));
+        CU(cudaMemcpyAsync(s->mask_tmp.p, mask, s->dev.n, cudaMemcpyHostToDevice, c->stream));
+        d = s->mask_tmp.as<uint8_t>();
+    }
+    launch_set_mask(c->stream, s->pos.as<float4>(), s->dev.n, d);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+void tm_scene_destroy(tm_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    for (DevBuf* b : {&s->pos, &s->nrm, &s->tgt, &s->mask_tmp}) b->release();
+    delete s;
+}
+
+// ------------------------------------------------------------- stage calls
+static void pair_window(const tm_model* m, float min_df, float max_df, float& lower, float& upper) {
+    lower = m->dev.diameter * min_df;  // scene.hpp:117-120
+    upper = m->dev.diameter * max_df;
+    lower *= lower;
+    upper *= upper;
+}
+
+int tm_features(tm_scene* s, tm_model* m, const uint32_t* pi, const uint32_t* pj, uint64_t n,
+                float min_df, float max_df, float* feats, uint32_t* keys, uint8_t* valid) {
+    REQUIRE(s && m, "null handle");
+    REQUIRE(n == 0 || (pi && pj && keys && valid), "tm_features: null buffer");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n) return TM_OK;
+    DevBuf &di = c->scratch[0], &dj = c->scratch[1], &df = c->scratch[2], &dk = c->scratch[3],
+           &dv = c->scratch[4];
+    TRY(di.ensure(n * 4)); TRY(dj.ensure(n * 4)); TRY(df.ensure(n * 16)); TRY(dk.ensure(n * 16));
+    TRY(dv.ensure(n));
+    CU(cudaMemcpyAsync(di.p, pi, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dj.p, pj, n * 4, cudaMemcpyHostToDevice, c->stream));
+    float lower, upper;
+    pair_window(m, min_df, max_df, lower, upper);
+    launch_pair_features_probe(c->stream, s->dev, m->dev, nullptr, di.as<uint32_t>(),
+                               dj.as<uint32_t>(), n, lower, upper, 0, df.as<float>(),
+                               dk.as<uint4>(), dv.as<uint8_t>(), nullptr, nullptr, nullptr);
+    CU(cudaGetLastError());
+    if (feats) CU(cudaMemcpyAsync(feats, df.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(keys, dk.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(valid, dv.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_probe(tm_model* m, const uint32_t* keys, const uint8_t* valid, uint64_t n, uint32_t limit,
+             uint64_t* offsets, uint32_t* hits, uint64_t hits_capacity) {
+    REQUIRE(m && offsets, "tm_probe: null argument");
+    REQUIRE(n == 0 || keys, "tm_probe: null keys");
+    tm_ctx* c = m->ctx;
+    TRY(bind(c));
+    offsets[0] = 0;
+    if (!n) return TM_OK;
+    DevBuf &dk = c->scratch[0], &dv = c->scratch[1], &hb = c->scratch[2], &hc = c->scratch[3],
+           &off = c->scratch[4], &out = c->scratch[5];
+    TRY(dk.ensure(n * 16)); TRY(dv.ensure(n)); TRY(hb.ensure(n * 4)); TRY(hc.ensure(n * 4));
+    TRY(off.ensure((n + 1) * 8));
+    CU(cudaMemcpyAsync(dk.p, keys, n * 16, cudaMemcpyHostToDevice, c->stream));
+    if (valid) CU(cudaMemcpyAsync(dv.p, valid, n, cudaMemcpyHostToDevice, c->stream));
+    launch_probe(c->stream, m->dev, dk.as<uint4>(), valid ? dv.as<uint8_t>() : nullptr, n, limit,
+                 hb.as<uint32_t>(), hc.as<uint32_t>());
+    launch_exclusive_scan_u64(c->stream, hc.as<uint32_t>(), off.as<unsigned long long>(), n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(offsets, off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!hits) return TM_OK;
+    uint64_t total = offsets[n];
+    if (total > hits_capacity) return fail(TM_ERR_CAPACITY, "tm_probe: hits buffer too small");
+    if (!total) return TM_OK;
+    TRY(out.ensure(total * 8));
+    launch_gather_hits(c->stream, m->dev, hb.as<uint32_t>(), off.as<unsigned long long>(), n,
+                       out.as<uint2>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hits, out.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_hypotheses(tm_scene* s, tm_model* m, const uint32_t* pi, const uint32_t* pj, uint64_t n,
+                  const uint64_t* offsets, const uint32_t* hits, int force_up, float* T16s,
+                  uint8_t* hyp_valid) {
+    REQUIRE(s && m, "null handle");
+    REQUIRE(n == 0 || (pi && pj && offsets), "tm_hypotheses: null buffer");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n) return TM_OK;
+    uint64_t total = offsets[n];
+    if (!total) return TM_OK;
+    REQUIRE(hits && T16s && hyp_valid, "tm_hypotheses: null output");
+    for (uint64_t i = 0; i < 2 * total; ++i)
+        REQUIRE(hits[i] < m->dev.cloud.n, "tm_hypotheses: model index out of range");
+    for (uint64_t i = 0; i < n; ++i)
+        REQUIRE(pi[i] < s->dev.n && pj[i] < s->dev.n, "tm_hypotheses: scene index out of range");
+    DevBuf &di = c->scratch[0], &dj = c->scratch[1], &off = c->scratch[2], &dh = c->scratch[3],
+           &dT = c->scratch[4], &dv = c->scratch[5], &d16 = c->scratch[6], &sh = c->scratch[7];
+    TRY(di.ensure(n * 4)); TRY(dj.ensure(n * 4)); TRY(off.ensure((n + 1) * 8));
+    TRY(dh.ensure(total * 8)); TRY(dT.ensure(total * 48)); TRY(dv.ensure(total));
+    TRY(d16.ensure(total * 64)); TRY(sh.ensure(24));
+    unsigned long long shard[3] = {0ull, total, total};
+    CU(cudaMemcpyAsync(di.p, pi, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dj.p, pj, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dh.p, hits, total * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(sh.p, shard, 24, cudaMemcpyHostToDevice, c->stream));
+    launch_hypotheses(c->stream, s->dev, m->dev, nullptr, di.as<uint32_t>(), dj.as<uint32_t>(), n,
+                      off.as<unsigned long long>(), nullptr, dh.as<uint2>(), force_up,
+                      sh.as<unsigned long long>(), dT.as<float4>(), dv.as<uint8_t>(), nullptr);
+    launch_colmajor_from_rows(c->stream, dT.as<float4>(), total, d16.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(T16s, d16.p, total * 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hyp_valid, dv.p, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+// device-side ball subsets into (row offsets u64, indices); returns total via host sync
+static int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t* d_centres,
+                            uint32_t n_centres, float radius, DevBuf& counts, DevBuf& seg_off,
+                            DevBuf& row_off, DevBuf* indices, uint64_t* total_out) {
+    const uint32_t n_seg = (scene.n + BALL_SEG - 1) / BALL_SEG;
+    const size_t nc = (size_t)n_centres * n_seg;
+    TRY(counts.ensure(std::max<size_t>(nc, 1) * 4));
+    TRY(seg_off.ensure((nc + 1) * 8));
+    TRY(row_off.ensure(((size_t)n_centres + 1) * 8));
+    float r2 = radius * radius;
+    launch_ball_count(c->stream, scene.pos, scene.n, d_centres, n_centres, r2, n_seg,
+                      counts.as<uint32_t>());
+    launch_exclusive_scan_u64(c->stream, counts.as<uint32_t>(), seg_off.as<unsigned long long>(),
+                              nc);
+    launch_ball_row_offsets(c->stream, seg_off.as<unsigned long long>(), n_centres, n_seg,
+                            row_off.as<unsigned long long>());
+    CU(cudaGetLastError());
+    if (total_out) {
+        unsigned long long t = 0;
+        CU(cudaMemcpyAsync(&t, seg_off.as<unsigned long long>() + nc, 8, cudaMemcpyDeviceToHost,
+                           c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *total_out = t;
+        if (indices) TRY(indices->ensure(std::max<uint64_t>(t, 1) * 4));
+    }
+    if (indices && indices->p) {
+        launch_ball_fill(c->stream, scene.pos, scene.n, d_centres, n_centres, r2, n_seg,
+                         seg_off.as<unsigned long long>(), indices->as<int32_t>());
+        CU(cudaGetLastError());
+    }
+    return TM_OK;
+}
+
+int tm_ball_subsets(tm_scene* s, const uint32_t* centres, uint32_t n_centres, float radius,
+                    uint64_t* offsets, int32_t* indices, uint64_t capacity) {
+    REQUIRE(s && offsets, "tm_ball_subsets: null argument");
+    REQUIRE(n_centres == 0 || centres, "tm_ball_subsets: null centres");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    offsets[0] = 0;
+    if (!n_centres) return TM_OK;
+    for (uint32_t i = 0; i < n_centres; ++i)
+        REQUIRE(centres[i] < s->dev.n, "tm_ball_subsets: centre out of range");
+    DevBuf &dc = c->scratch[0], &cnt = c->scratch[1], &so = c->scratch[2], &ro = c->scratch[3],
+           &idx = c->scratch[4];
+    TRY(dc.ensure((size_t)n_centres * 4));
+    CU(cudaMemcpyAsync(dc.p, centres, (size_t)n_centres * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t total = 0;
+    TRY(ball_subsets_dev(c, s->dev, dc.as<uint32_t>(), n_centres, radius, cnt, so, ro,
+                         indices ? &idx : nullptr, &total));
+    CU(cudaMemcpyAsync(offsets, ro.p, ((size_t)n_centres + 1) * 8, cudaMemcpyDeviceToHost,
+                       c->stream));
+    if (indices) {
+        if (total > capacity) {
+            cudaStreamSynchronize(c->stream);
+            return fail(TM_ERR_CAPACITY, "tm_ball_subsets: indices buffer too small");
+        }
+        if (total)
+            CU(cudaMemcpyAsync(indices, idx.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+// score hypotheses whose rows are resident in d_T; groups = subset rows.
+// Full mode: work list + persistent register-tiled kernel.
+static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, const float4* d_T,
+                          const int32_t* d_sub_idx, const unsigned long long* d_sub_off,
+                          const uint32_t* d_g_hyp, uint32_t n_groups, uint32_t items_capacity,
+                          DevBuf& n_items_g, DevBuf& item_off, DevBuf& items, DevBuf& ctrl,
+                          float sq_thres, uint32_t* d_counts, unsigned long long* d_scores,
+                          bool with_score) {
+    // ctrl: [0] work counter (u32) [1] pad, [2..3] n_tests (u64)
+    TRY(n_items_g.ensure(std::max<size_t>(n_groups, 1) * 4));
+    TRY(item_off.ensure(((size_t)n_groups + 1) * 4));
+    TRY(items.ensure(std::max<size_t>(items_capacity, 1) * sizeof(WorkItem)));
+    CU(cudaMemsetAsync(ctrl.p, 0, 16, c->stream));
+    launch_work_count(c->stream, d_sub_off, d_g_hyp, n_groups, n_items_g.as<uint32_t>(),
+                      (unsigned long long*)(ctrl.as<uint32_t>() + 2));
+    launch_exclusive_scan_u32(c->stream, n_items_g.as<uint32_t>(), item_off.as<uint32_t>(), n_groups);
+    launch_work_fill(c->stream, d_sub_off, d_g_hyp, n_groups, item_off.as<uint32_t>(),
+                     items.as<WorkItem>());
+    ScoreArgs a;
+    a.scene = scene;
+    a.model = m->dev;
+    a.sub_idx = d_sub_idx;
+    a.items = items.as<WorkItem>();
+    a.n_items = item_off.as<uint32_t>() + n_groups;
+    a.work_counter = ctrl.as<uint32_t>();
+    a.T = d_T;
+    a.counts = d_counts;
+    a.scores = d_scores;
+    a.sq_thres = sq_thres;
+    static int bps[2][2] = {{0, 0}, {0, 0}};
+    int& b = bps[m->fused ? 1 : 0][with_score ? 1 : 0];
+    if (!b) b = score_full_max_blocks_per_sm(m->fused, with_score);
+    int grid = c->sm_count * b;
+    if (const char* e = getenv("TM_SCORE_GRID")) grid = std::max(1, atoi(e));
+    launch_score_full(c->stream, a, grid, m->fused, with_score);
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const uint32_t* hyp_sub,
+             const uint64_t* sub_offsets, const int32_t* sub_indices, uint32_t n_sub,
+             float dist_thres, float accept_prob, int early_out, uint32_t* counts, double* scores,
+             uint8_t* dropped) {
+    REQUIRE(s && m, "null handle");
+    REQUIRE(n_hyp == 0 || (T16s && counts), "tm_score: null buffer");
+    REQUIRE(n_hyp < (1ull << 31), "tm_score: too many hypotheses for one call");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n_hyp) return TM_OK;
+    const bool all_scene = hyp_sub == nullptr;
+    if (!all_scene) REQUIRE(sub_offsets && (sub_indices || sub_offsets[n_sub] == 0) && n_sub > 0,
+                            "tm_score: subset CSR missing");
+    // group hypotheses by subset row (stable counting sort on the host)
+    const uint32_t n_groups = all_scene ? 1u : n_sub;
+    std::vector<uint32_t> g_hyp(n_groups + 1, 0), perm(n_hyp);
+    if (all_scene) {
+        g_hyp[1] = (uint32_t)n_hyp;
+        for (uint64_t h = 0; h < n_hyp; ++h) perm[h] = (uint32_t)h;
+    } else {
+        for (uint64_t h = 0; h < n_hyp; ++h) {
+            REQUIRE(hyp_sub[h] < n_sub, "tm_score: hyp_sub out of range");
+            ++g_hyp[hyp_sub[h] + 1];
+        }
+        for (uint32_t g = 0; g < n_groups; ++g) g_hyp[g + 1] += g_hyp[g];
+        std::vector<uint32_t> cur(g_hyp.begin(), g_hyp.end() - 1);
+        for (uint64_t h = 0; h < n_hyp; ++h) perm[cur[hyp_sub[h]]++] = (uint32_t)h;
+        uint64_t tot = sub_offsets[n_sub];
+        for (uint64_t i = 0; i < tot; ++i)
+            REQUIRE(sub_indices[i] >= 0 && (uint32_t)sub_indices[i] < s->dev.n,
+                    "tm_score: subset index out of range");
+    }
+    std::vector<float> Tp(16 * n_hyp);
+    for (uint64_t l = 0; l < n_hyp; ++l) memcpy(&Tp[16 * l], T16s + 16 * (size_t)perm[l], 64);
+    std::vector<unsigned long long> soff(n_groups + 1);
+    uint64_t items_cap = 0;
+    if (all_scene) {
+        soff[0] = 0;
+        soff[1] = s->dev.n;
+    } else {
+        for (uint32_t g = 0; g <= n_groups; ++g) soff[g] = sub_offsets[g];
+    }
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        uint64_t np = soff[g + 1] - soff[g], nh = g_hyp[g + 1] - g_hyp[g];
+        items_cap += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK);
+    }
+    REQUIRE(items_cap < (1ull << 31), "tm_score: too many work items");
+    DevBuf &d16 = c->scratch[0], &dT = c->scratch[1], &dso = c->scratch[2], &dsi = c->scratch[3],
+           &dgh = c->scratch[4], &dcnt = c->scratch[5], &dsc = c->scratch[6], &w0 = c->scratch[7],
+           &w1 = c->scratch[8], &w2 = c->scratch[9], &ctrl = c->scratch[10], &ddrop = c->scratch[11];
+    TRY(d16.ensure(n_hyp * 64)); TRY(dT.ensure(n_hyp * 48));
+    TRY(dso.ensure((n_groups + 1) * 8)); TRY(dgh.ensure((n_groups + 1) * 4));
+    TRY(dcnt.ensure(n_hyp * 4)); TRY(dsc.ensure(n_hyp * 8)); TRY(ctrl.ensure(64));
+    CU(cudaMemcpyAsync(d16.p, Tp.data(), n_hyp * 64, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dso.p, soff.data(), (n_groups + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dgh.p, g_hyp.data(), (n_groups + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    const int32_t* d_idx = nullptr;
+    if (!all_scene && sub_offsets[n_sub]) {
+        TRY(dsi.ensure(sub_offsets[n_sub] * 4));
+        CU(cudaMemcpyAsync(dsi.p, sub_indices, sub_offsets[n_sub] * 4, cudaMemcpyHostToDevice,
+                           c->stream));
+        d_idx = dsi.as<int32_t>();
+    }
+    launch_rows_from_colmajor(c->stream, d16.as<float>(), n_hyp, dT.as<float4>());
+    CU(cudaMemsetAsync(dcnt.p, 0, n_hyp * 4, c->stream));
+    CU(cudaMemsetAsync(dsc.p, 0, n_hyp * 8, c->stream));
+    const float thres = dist_thres * m->dev.resolution;  // scene.hpp:413
+    const float sqt = sq_threshold(thres);
+    std::vector<uint8_t> drop_l(n_hyp, 0);
+    if (!early_out) {
+        TRY(score_full_dev(c, s->dev, m, dT.as<float4>(), d_idx, dso.as<unsigned long long>(),
+                           dgh.as<uint32_t>(), n_groups, (uint32_t)items_cap, w0, w1, w2, ctrl, sqt,
+                           dcnt.as<uint32_t>(), dsc.as<unsigned long long>(), scores != nullptr));
+    } else {
+        TRY(w0.ensure(n_hyp * 4)); TRY(ddrop.ensure(n_hyp));
+        launch_group_of_hyp(c->stream, dgh.as<uint32_t>(), n_groups, w0.as<uint32_t>());
+        EarlyArgs a;
+        a.scene = s->dev;
+        a.model = m->dev;
+        a.sub_idx = d_idx;
+        a.sub_off = dso.as<unsigned long long>();
+        a.g_of_hyp = w0.as<uint32_t>();
+        a.T = dT.as<float4>();
+        a.n_hyp = (uint32_t)n_hyp;
+        a.n_hyp_dev = nullptr;
+        a.n_tests = nullptr;
+        a.sq_thres = sqt;
+        a.accept_prob = accept_prob;
+        a.early_out = 1;
+        a.counts = dcnt.as<uint32_t>();
+        a.scores = dsc.as<unsigned long long>();
+        a.dropped = ddrop.as<uint8_t>();
+        a.tested = nullptr;
+        launch_score_early_drop(c->stream, a, m->fused);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(drop_l.data(), ddrop.p, n_hyp, cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<uint32_t> cnt_l(n_hyp);
+    std::vector<unsigned long long> sc_l(n_hyp);
+    CU(cudaMemcpyAsync(cnt_l.data(), dcnt.p, n_hyp * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(sc_l.data(), dsc.p, n_hyp * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double mn = (double)m->dev.cloud.n;
+    for (uint64_t l = 0; l < n_hyp; ++l) {
+        uint32_t h = perm[l];
+        counts[h] = cnt_l[l];
+        if (scores) {
+            double v = (double)sc_l[l] / SCORE_SCALE;
+            scores[h] = drop_l[l] ? v : v / mn;  // un-normalised on drop (scene.hpp:502 vs 509)
+        }
+        if (dropped) dropped[h] = drop_l[l];
+    }
+    return TM_OK;
+}
+
+int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
+                       uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,
+                       double* score) {
+    REQUIRE(s && m && T16 && n_corr, "tm_correspondences: null argument");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    *n_corr = 0;
+    if (score) *score = 0.0;
+    if (!s->dev.n) return TM_OK;
+    Rows R;
+    R.r0 = make_float4(T16[0], T16[4], T16[8], T16[12]);
+    R.r1 = make_float4(T16[1], T16[5], T16[9], T16[13]);
+    R.r2 = make_float4(T16[2], T16[6], T16[10], T16[14]);
+    const uint32_t n_seg = (s->dev.n + CORR_SEG - 1) / CORR_SEG;
+    DevBuf &cnt = c->scratch[0], &off = c->scratch[1], &sc = c->scratch[2], &mc = c->scratch[3],
+           &acc = c->scratch[4];
+    TRY(cnt.ensure(n_seg * 4)); TRY(off.ensure((n_seg + 1) * 4)); TRY(acc.ensure(8));
+    TRY(sc.ensure((size_t)s->dev.n * 4)); TRY(mc.ensure((size_t)s->dev.n * 4));
+    const float sqt = sq_threshold(dist_thres * m->dev.resolution);
+    CU(cudaMemsetAsync(acc.p, 0, 8, c->stream));
+    launch_corr_count(c->stream, s->dev, m->dev, R, sqt, n_seg, cnt.as<uint32_t>(),
+                      acc.as<unsigned long long>(), m->fused);
+    launch_exclusive_scan_u32(c->stream, cnt.as<uint32_t>(), off.as<uint32_t>(), n_seg);
+    launch_corr_fill(c->stream, s->dev, m->dev, R, sqt, n_seg, off.as<uint32_t>(),
+                     sc.as<uint32_t>(), mc.as<uint32_t>(), m->fused);
+    CU(cudaGetLastError());
+    uint32_t total = 0;
+    unsigned long long fx = 0;
+    CU(cudaMemcpyAsync(&total, off.as<uint32_t>() + n_seg, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&fx, acc.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (total && scene_corrs)
+        CU(cudaMemcpyAsync(scene_corrs, sc.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (total && model_corrs)
+        CU(cudaMemcpyAsync(model_corrs, mc.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n_corr = total;
+    if (score) *score = (double)fx / SCORE_SCALE / (double)m->dev.cloud.n;
+    return TM_OK;
+}
+
+// --------------------------------------------------------------------- ICP
+struct IcpBufs {
+    DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
+    void release() {
+        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
+    }
+    int ensure(uint32_t k) {
+        size_t kk = std::max(k, 1u);
+        TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
+        TRY(sums_cur.ensure(kk * ICP_NSUM * 8)); TRY(sums_best.ensure(kk * ICP_NSUM * 8));
+        TRY(iters.ensure(kk * 4)); TRY(active.ensure(kk * 4));
+        return TM_OK;
+    }
+    IcpState state() {
+        return IcpState{Tcur.as<float4>(), Tbest.as<float4>(), sums_cur.as<long long>(),
+                        sums_best.as<long long>(), iters.as<uint32_t>(), active.as<uint32_t>()};
+    }
+};
+static double icp_fix_scale(const tm_model* m, uint32_t n_scene, float thres) {
+    // |s'|,|m'| <= r = half bbox diagonal + thres; n * r^2 * 2^bits < 2^62
+    double r = (double)m->half_diag + (double)thres + 1e-6;
+    double bound = std::max(1.0, (double)std::max(n_scene, 1u) * std::max(r * r, r));
+    int bits = (int)std::floor(62.0 - std::log2(bound));
+    bits = std::max(8, std::min(40, bits));
+    return std::ldexp(1.0, bits);
+}
+// enqueue the ICP loop for k transforms already in b.Tcur with b.active set
+static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpBufs& b, uint32_t k,
+                       uint32_t max_iterations, float dist_thres) {
+    const float thres = (2 * dist_thres) * m->dev.resolution;  // scene.hpp:373 + :413
+    const float sqt = sq_threshold(thres);
+    const double fs = icp_fix_scale(m, scene.n, thres);
+    CU(cudaMemsetAsync(b.sums_cur.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
+    CU(cudaMemsetAsync(b.sums_best.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
+    CU(cudaMemsetAsync(b.iters.p, 0, (size_t)k * 4, c->stream));
+    const int grid = c->sm_count * 4;
+    IcpState st = b.state();
+    for (uint32_t it = 0; it <= max_iterations; ++it) {
+        launch_icp_accumulate(c->stream, scene, m->dev, st.Tcur, st.active, k, 0, scene.n, sqt,
+                              m->centre[0], m->centre[1], m->centre[2], fs, st.sums_cur, grid,
+                              m->fused);
+        launch_icp_step(c->stream, st, k, it == 0 ? 1 : 0, max_iterations, 1.0 / fs, m->centre[0],
+                        m->centre[1], m->centre[2]);
+    }
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
+           float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters) {
+    REQUIRE(s && m, "null handle");
+    REQUIRE(n == 0 || (T16s && T16s_out && counts), "tm_icp: null buffer");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n) return TM_OK;
+    if (max_iterations == 0) {  // scene.hpp:371: the match is returned unchanged
+        memcpy(T16s_out, T16s, (size_t)n * 64);
+        if (iters) memset(iters, 0, (size_t)n * 4);
+        return tm_score(s, m, T16s, n, nullptr, nullptr, nullptr, 0, dist_thres, 0.f, 0, counts,
+                        scores, nullptr);
+    }
+    IcpBufs b;
+    int rc = b.ensure(n);
+    DevBuf d16;
+    if (!rc) rc = d16.ensure((size_t)n * 64);
+    auto done = [&](int code) {
+        b.release();
+        d16.release();
+        return code;
+    };
+    if (rc) return done(rc);
+    std::vector<uint32_t> ones(n, 1u);
+    cudaError_t e = cudaMemcpyAsync(d16.p, T16s, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(b.active.p, ones.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return done(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
+    launch_rows_from_colmajor(c->stream, d16.as<float>(), n, b.Tcur.as<float4>());
+    if ((rc = icp_enqueue(c, s->dev, m, b, n, max_iterations, dist_thres))) return done(rc);
+    launch_colmajor_from_rows(c->stream, b.Tbest.as<float4>(), n, d16.as<float>());
+    std::vector<long long> sums((size_t)n * ICP_NSUM);
+    e = cudaMemcpyAsync(T16s_out, d16.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(sums.data(), b.sums_best.p, sums.size() * 8, cudaMemcpyDeviceToHost,
+                            c->stream);
+    if (e == cudaSuccess && iters)
+        e = cudaMemcpyAsync(iters, b.iters.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
+    for (uint32_t h = 0; h < n; ++h) {
+        counts[h] = (uint32_t)sums[(size_t)h * ICP_NSUM];
+        if (scores)
+            scores[h] = (double)sums[(size_t)h * ICP_NSUM + 16] / SCORE_SCALE / (double)m->dev.cloud.n;
+    }
+    return done(TM_OK);
+}
+
+int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, float threshold,
+                      const float* xyz, uint64_t n, float* uvw, uint8_t* ok) {
+    REQUIRE(c && g2l, "tm_traits_project: null argument");
+    REQUIRE(kind >= 0 && kind <= 3, "tm_traits_project: unknown kind");
+    REQUIRE(n == 0 || (xyz && uvw && ok), "tm_traits_project: null buffer");
+    TRY(bind(c));
+    if (!n) return TM_OK;
+    DevBuf &in = c->scratch[0], &out = c->scratch[1], &dok = c->scratch[2];
+    TRY(in.ensure(n * 12)); TRY(out.ensure(n * 12)); TRY(dok.ensure(n));
+    CU(cudaMemcpyAsync(in.p, xyz, n * 12, cudaMemcpyHostToDevice, c->stream));
+    float4 r0 = make_float4(g2l[0], g2l[4], g2l[8], g2l[12]);
+    float4 r1 = make_float4(g2l[1], g2l[5], g2l[9], g2l[13]);
+    float4 r2 = make_float4(g2l[2], g2l[6], g2l[10], g2l[14]);
+    launch_traits_project(c->stream, kind, r0, r1, r2, radius, threshold, in.as<float>(), n,
+                          out.as<float>(), dok.as<uint8_t>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(uvw, out.p, n * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+// ------------------------------------------------------------ resident query
+struct QueryOut {  // one contiguous device block, read back in one copy
+    unsigned long long shard[3];  // h_begin, h_end, H
+    unsigned long long best;
+    unsigned long long n_tests;
+    unsigned long long n_valid;
+    double best_score;
+    float best_T16[16];
+    uint32_t n_local;
+    uint32_t err;
+    uint32_t work_counter;
+    uint32_t pad;
+};
+
+struct tm_query {
+    tm_scene* s;
+    tm_model* m;
+    tm_query_params p;
+    uint32_t rank = 0, world = 1;
+    uint32_t n_outer = 0;
+    uint64_t n_pairs = 0;
+    uint64_t cap_hyp = 0;
+    uint32_t items_cap = 0;
+    uint64_t sub_total = 0;
+    DevBuf outer, pair_outer, pair_j, outer_pair_off;
+    DevBuf ball_counts, ball_seg_off, sub_off, sub_idx;
+    DevBuf valid, hit_begin, hit_count, hyp_off;
+    DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
+    DevBuf n_items_g, item_off, items, ctrl;
+    DevBuf out;  // QueryOut
+    DevBuf topk_ids, icp_T16;
+    IcpBufs icp;
+    QueryOut host_out;
+    bool ran = false;
+};
+
+static int count_valid_pairs_dev(tm_query* q);
+
+int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query** out) {
+    REQUIRE(s && m && p && out, "tm_query_create: null argument");
+    REQUIRE(s->ctx == m->ctx, "scene and model live in different contexts");
+    REQUIRE(p->icp_top_k <= 4096, "icp_top_k too large");
+    tm_query* q = new tm_query();
+    q->s = s;
+    q->m = m;
+    q->p = *p;
+    memset(&q->host_out, 0, sizeof(QueryOut));
+    *out = q;
+    return TM_OK;
+}
+void tm_query_destroy(tm_query* q) {
+    if (!q) return;
+    cudaSetDevice(q->s->ctx->device);
+    for (DevBuf* b :
+         {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
+          &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
+          &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
+          &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
+          &q->topk_ids, &q->icp_T16})
+        b->release();
+    q->icp.release();
+    delete q;
+}
+
+int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world) {
+    REQUIRE(q && world > 0 && rank < world, "tm_query_set_shard: bad rank/world");
+    q->rank = rank;
+    q->world = world;
+    return TM_OK;
+}
+
+int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
+                       const uint32_t* pair_outer, const uint32_t* pair_j, uint64_t n_pairs) {
+    REQUIRE(q, "null query");
+    REQUIRE(n_outer == 0 || outer, "null outer");
+    REQUIRE(n_pairs == 0 || (pair_outer && pair_j), "null pairs");
+    REQUIRE(n_pairs < (1ull << 31), "too many pairs");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    const uint32_t ns = q->s->dev.n;
+    for (uint32_t o = 0; o < n_outer; ++o) REQUIRE(outer[o] < ns, "outer index out of range");
+    std::vector<uint32_t> opo(n_outer + 1, 0);
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        REQUIRE(pair_outer[k] < n_outer && pair_j[k] < ns, "pair index out of range");
+        REQUIRE(k == 0 || pair_outer[k] >= pair_outer[k - 1], "pairs must be sorted by outer");
+        ++opo[pair_outer[k] + 1];
+    }
+    for (uint32_t o = 0; o < n_outer; ++o) opo[o + 1] += opo[o];
+    q->n_outer = n_outer;
+    q->n_pairs = n_pairs;
+    TRY(q->outer.ensure(std::max(n_outer, 1u) * 4ull));
+    TRY(q->pair_outer.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->pair_j.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->outer_pair_off.ensure((n_outer + 1) * 4ull));
+    if (n_outer) CU(cudaMemcpyAsync(q->outer.p, outer, n_outer * 4ull, cudaMemcpyHostToDevice, c->stream));
+    if (n_pairs) {
+        CU(cudaMemcpyAsync(q->pair_outer.p, pair_outer, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(q->pair_j.p, pair_j, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(q->outer_pair_off.p, opo.data(), (n_outer + 1) * 4ull, cudaMemcpyHostToDevice,
+                       c->stream));
+    // capacities: hypotheses, subset indices (one sizing pass), work items
+    uint64_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    uint64_t cap = q->p.max_hypotheses ? q->p.max_hypotheses
+                                       : std::min<uint64_t>(n_pairs * limit, 1ull << 24);
+    if (q->p.hyp_limit) cap = std::min<uint64_t>(cap, q->p.hyp_limit);
+    cap = std::max<uint64_t>(cap, 1);
+    q->cap_hyp = cap;
+    TRY(q->T.ensure(cap * 48)); TRY(q->hyp_valid.ensure(cap)); TRY(q->hyp_pair.ensure(cap * 4));
+    TRY(q->counts.ensure(cap * 4)); TRY(q->scores.ensure(cap * 8)); TRY(q->dropped.ensure(cap));
+    TRY(q->g_of_hyp.ensure(cap * 4));
+    TRY(q->valid.ensure(std::max<uint64_t>(n_pairs, 1))); TRY(q->hit_begin.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->hit_count.ensure(std::max<uint64_t>(n_pairs, 1) * 4)); TRY(q->hyp_off.ensure((n_pairs + 1) * 8));
+    TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
+    TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
+    uint64_t total = 0;
+    std::vector<unsigned long long> so(n_outer + 1, 0);
+    if (n_outer) {
+        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, q->m->dev.diameter,
+                             q->ball_counts, q->ball_seg_off, q->sub_off, &q->sub_idx, &total));
+        CU(cudaMemcpyAsync(so.data(), q->sub_off.p, (n_outer + 1) * 8ull, cudaMemcpyDeviceToHost,
+                           c->stream));
+    } else {
+        TRY(q->sub_off.ensure(8));
+        CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    q->sub_total = total;
+    uint64_t items = 0;
+    for (uint32_t o = 0; o < n_outer; ++o) {
+        uint64_t np = so[o + 1] - so[o];
+        uint64_t nh = std::min<uint64_t>((uint64_t)(opo[o + 1] - opo[o]) * limit, cap);
+        items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
+    }
+    REQUIRE(items < (1ull << 31), "too many work items");
+    q->items_cap = (uint32_t)std::max<uint64_t>(items, 1);
+    TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
+    TRY(q->item_off.ensure((n_outer + 1) * 4ull));
+    TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
+    if (q->p.icp_top_k) {
+        TRY(q->icp.ensure(q->p.icp_top_k));
+        TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
+        TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
+    }
+    q->ran = false;
+    return TM_OK;
+}
+
+int tm_query_run(tm_query* q) {
+    REQUIRE(q, "null query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    const tm_model* m = q->m;
+    const CloudDev& sc = q->s->dev;
+    QueryOut* out = q->out.as<QueryOut>();
+    CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
+    CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
+    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
+    const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
+    // (a8) radius subsets of the outer samples
+    if (q->n_outer) {
+        const float r2 = m->dev.diameter * m->dev.diameter;
+        const size_t nc = (size_t)q->n_outer * n_seg;
+        launch_ball_count(c->stream, sc.pos, sc.n, q->outer.as<uint32_t>(), q->n_outer, r2, n_seg,
+                          q->ball_counts.as<uint32_t>());
+        launch_exclusive_scan_u64(c->stream, q->ball_counts.as<uint32_t>(),
+                                  q->ball_seg_off.as<unsigned long long>(), nc);
+        launch_ball_row_offsets(c->stream, q->ball_seg_off.as<unsigned long long>(), q->n_outer,
+                                n_seg, q->sub_off.as<unsigned long long>());
+        launch_ball_fill(c->stream, sc.pos, sc.n, q->outer.as<uint32_t>(), q->n_outer, r2, n_seg,
+                         q->ball_seg_off.as<unsigned long long>(), q->sub_idx.as<int32_t>());
+    }
+    // (a1-a5) pair filter, feature, key, probe
+    float lower, upper;
+    pair_window(m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
+    const uint32_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    launch_pair_features_probe(c->stream, sc, m->dev, q->outer.as<uint32_t>(),
+                               q->pair_outer.as<uint32_t>(), q->pair_j.as<uint32_t>(), q->n_pairs,
+                               lower, upper, limit, nullptr, nullptr, q->valid.as<uint8_t>(),
+                               q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(),
+                               &out->n_valid);
+    if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
+    else
+        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(),
+                                  q->hyp_off.as<unsigned long long>(), q->n_pairs);
+    launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
+                       q->rank, q->world, q->cap_hyp, out->shard, &out->n_local, &out->err);
+    launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
+                            q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
+                            q->g_hyp.as<uint32_t>());
+    // (a6, a7) hypotheses
+    launch_hypotheses(c->stream, sc, m->dev, q->outer.as<uint32_t>(), q->pair_outer.as<uint32_t>(),
+                      q->pair_j.as<uint32_t>(), q->n_pairs, q->hyp_off.as<unsigned long long>(),
+                      q->hit_begin.as<uint32_t>(), m->dev.hits, q->p.force_up, out->shard,
+                      q->T.as<float4>(), q->hyp_valid.as<uint8_t>(), q->hyp_pair.as<uint32_t>());
+    // (a10) scoring
+    const float thres = q->p.dist_thres * m->dev.resolution;
+    const float sqt = sq_threshold(thres);
+    if (q->n_outer) {
+        if (!q->p.early_out) {
+            launch_work_count(c->stream, q->sub_off.as<unsigned long long>(),
+                              q->g_hyp.as<uint32_t>(), q->n_outer, q->n_items_g.as<uint32_t>(),
+                              &out->n_tests);
+            launch_exclusive_scan_u32(c->stream, q->n_items_g.as<uint32_t>(),
+                                      q->item_off.as<uint32_t>(), q->n_outer);
+            launch_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(),
+                             q->n_outer, q->item_off.as<uint32_t>(), q->items.as<WorkItem>());
+            ScoreArgs a;
+            a.scene = sc;
+            a.model = m->dev;
+            a.sub_idx = q->sub_idx.as<int32_t>();
+            a.items = q->items.as<WorkItem>();
+            a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
+            a.work_counter = &out->work_counter;
+            a.T = q->T.as<float4>();
+            a.counts = q->counts.as<uint32_t>();
+            a.scores = q->scores.as<unsigned long long>();
+            a.sq_thres = sqt;
+            static int bps[2] = {0, 0};
+            int& b = bps[m->fused ? 1 : 0];
+            if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
+            int grid = c->sm_count * b;
+            if (const char* e = getenv("TM_SCORE_GRID")) grid = std::max(1, atoi(e));
+            launch_score_full(c->stream, a, grid, m->fused, true);
+        } else {
+            launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
+                                q->g_of_hyp.as<uint32_t>());
+            EarlyArgs a;
+            a.scene = sc;
+            a.model = m->dev;
+            a.sub_idx = q->sub_idx.as<int32_t>();
+            a.sub_off = q->sub_off.as<unsigned long long>();
+            a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
+            a.T = q->T.as<float4>();
+            a.n_hyp = (uint32_t)q->cap_hyp;  // grid bound; the kernel clips to n_local
+            a.n_hyp_dev = &out->n_local;
+            a.n_tests = &out->n_tests;
+            a.sq_thres = sqt;
+            a.accept_prob = q->p.accept_prob;
+            a.early_out = 1;
+            a.counts = q->counts.as<uint32_t>();
+            a.scores = q->scores.as<unsigned long long>();
+            a.dropped = q->dropped.as<uint8_t>();
+            a.tested = nullptr;
+            launch_score_early_drop(c->stream, a, m->fused);
+        }
+    }
+    launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(), &out->n_local,
+                  out->shard, &out->best, c->sm_count * 2);
+    // (a12) ICP of the local top-k
+    if (q->p.icp_top_k && q->p.max_icp_iterations) {
+        launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
+                           &out->n_local, q->p.icp_top_k, q->topk_ids.as<uint32_t>(), nullptr);
+        launch_gather_rows(c->stream, q->T.as<float4>(), q->topk_ids.as<uint32_t>(), q->p.icp_top_k,
+                           q->icp.Tcur.as<float4>(), q->icp.active.as<uint32_t>());
+        TRY(icp_enqueue(c, sc, m, q->icp, q->p.icp_top_k, q->p.max_icp_iterations, q->p.dist_thres));
+    }
+    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
+                         q->scores.as<unsigned long long>(), m->dev.cloud.n, out->best_T16,
+                         &out->best_score);
+    CU(cudaGetLastError());
+    q->ran = true;
+    return TM_OK;
+}
+
+int tm_query_result_get(tm_query* q, tm_query_result* r) {
+    REQUIRE(q && r, "null argument");
+    REQUIRE(q->ran, "tm_query_result_get before tm_query_run");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    TRY(pinned_ensure(c, sizeof(QueryOut) + 16));
+    CU(cudaMemcpyAsync(c->pinned, q->out.p, sizeof(QueryOut), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
+    const QueryOut& o = q->host_out;
+    if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
+    memset(r, 0, sizeof(*r));
+    r->n_pairs_valid = o.n_valid;
+    r->n_hypotheses = o.shard[2];
+    r->n_scored = o.n_local;
+    r->n_tests = o.n_tests;
+    r->best_key = o.best;
+    if (o.best) {
+        r->best_inliers = (uint32_t)(o.best >> 32);
+        r->best_hypothesis = 0xFFFFFFFFu - (uint32_t)(o.best & 0xFFFFFFFFull);
+        r->best_score = o.best_score;
+        memcpy(r->best_T, o.best_T16, 64);
+    }
+    return TM_OK;
+}
+void* tm_query_best_key_device(tm_query* q) {
+    return q ? (void*)&q->out.as<QueryOut>()->best : nullptr;
+}
+int tm_query_set_global_best(tm_query* q, uint64_t key) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    QueryOut* out = q->out.as<QueryOut>();
+    CU(cudaMemcpyAsync(&out->best, &key, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
+    CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
+    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
+                         q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
+                         &out->best_score);
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_query_download(tm_query* q, uint64_t capacity, uint32_t* counts, double* scores,
+                      float* T16s, uint8_t* valid, uint32_t* hyp_pair, uint8_t* dropped) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    tm_query_result r;
+    TRY(tm_query_result_get(q, &r));
+    const uint64_t n = r.n_scored;
+    if (n > capacity) return fail(TM_ERR_CAPACITY, "tm_query_download: capacity too small");
+    if (!n) return TM_OK;
+    if (counts) CU(cudaMemcpyAsync(counts, q->counts.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (valid) CU(cudaMemcpyAsync(valid, q->hyp_valid.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (hyp_pair) CU(cudaMemcpyAsync(hyp_pair, q->hyp_pair.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (dropped) {
+        if (q->p.early_out) CU(cudaMemcpyAsync(dropped, q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
+        else memset(dropped, 0, n);
+    }
+    std::vector<unsigned long long> fx;
+    std::vector<uint8_t> dr;
+    if (scores && q->p.early_out) {
+        dr.resize(n);
+        CU(cudaMemcpyAsync(dr.data(), q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (scores) {
+        fx.resize(n);
+        CU(cudaMemcpyAsync(fx.data(), q->scores.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (T16s) {
+        DevBuf& d16 = c->scratch[0];
+        TRY(d16.ensure(n * 64));
+        launch_colmajor_from_rows(c->stream, q->T.as<float4>(), n, d16.as<float>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(T16s, d16.p, n * 64, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (scores)
+        for (uint64_t i = 0; i < n; ++i) {
+            double v = (double)fx[i] / SCORE_SCALE;
+            scores[i] = (!dr.empty() && dr[i]) ? v : v / (double)q->m->dev.cloud.n;
+        }
+    return TM_OK;
+}
+
+int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* counts,
+                         double* scores, uint32_t* iters) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    const uint32_t k = q->p.icp_top_k;
+    REQUIRE(k && q->p.max_icp_iterations, "query has no ICP stage");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    std::vector<long long> sums((size_t)k * ICP_NSUM);
+    std::vector<uint32_t> ids(k);
+    launch_colmajor_from_rows(c->stream, q->icp.Tbest.as<float4>(), k, q->icp_T16.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sums.data(), q->icp.sums_best.p, sums.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ids.data(), q->topk_ids.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    if (T16s) CU(cudaMemcpyAsync(T16s, q->icp_T16.p, k * 64ull, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, q->icp.iters.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t r = 0; r < k; ++r) {
+        if (hyp_ids) hyp_ids[r] = ids[r];
+        if (counts) counts[r] = (uint32_t)sums[(size_t)r * ICP_NSUM];
+        if (scores)
+            scores[r] = (double)sums[(size_t)r * ICP_NSUM + 16] / SCORE_SCALE / (double)q->m->dev.cloud.n;
+    }
+    return TM_OK;
+}
+
+// ------------------------------------------------------------------- NCCL
+// The one collective of the path.  NCCL is resolved at run time
+// with dlopen so the library loads in processes that never go multi-GPU.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclUint8_ = 1, ncclUint64_ = 5 };  // ncclDataType_t
+enum { ncclSum_ = 0, ncclMax_ = 2 };       // ncclRedOp_t
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return TM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names)
+        if ((lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) return fail(TM_ERR_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
+        lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(TM_ERR_NCCL, "libnccl is missing required symbols");
+    g_nccl.lib = lib;
+    return TM_OK;
+}
+#define NC(call)                                                                             \
+    do {                                                                                     \
+        int r_ = (call);                                                                     \
+        if (r_ != 0)                                                                         \
+            return fail(TM_ERR_NCCL, std::string(#call) + ": " +                            \
+                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
+    } while (0)
+
+struct tm_comm {
+    tm_ctx* ctx;
+    ncclComm_t comm;
+    int rank, world;
+};
+
+int tm_nccl_unique_id(uint8_t out[128]) {
+    REQUIRE(out, "null out");
+    TRY(nccl_load());
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return TM_OK;
+}
+int tm_comm_create(tm_ctx* c, const uint8_t idb[128], int rank, int world, tm_comm** out) {
+    REQUIRE(c && idb && out && world > 0 && rank >= 0 && rank < world, "tm_comm_create: bad argument");
+    TRY(nccl_load());
+    TRY(bind(c));
+    ncclUniqueId id;
+    memcpy(id.internal, idb, 128);
+    tm_comm* cm = new tm_comm{c, nullptr, rank, world};
+    int r = g_nccl.CommInitRank(&cm->comm, world, id, rank);
+    if (r != 0) {
+        delete cm;
+        return fail(TM_ERR_NCCL, std::string("ncclCommInitRank: ") +
+                                     (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    }
+    *out = cm;
+    return TM_OK;
+}
+void tm_comm_destroy(tm_comm* cm) {
+    if (!cm) return;
+    cudaSetDevice(cm->ctx->device);
+    if (cm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm->comm);
+    delete cm;
+}
+int tm_query_allreduce_best(tm_query* q, tm_comm* cm) {
+    REQUIRE(q && cm && q->ran, "tm_query_allreduce_best: bad argument");
+    tm_ctx* c = q->s->ctx;
+    REQUIRE(c == cm->ctx, "communicator belongs to another context");
+    TRY(bind(c));
+    QueryOut* out = q->out.as<QueryOut>();
+    // max over ranks of (inliers << 32 | ~global id): 8 bytes, latency-bound
+    NC(g_nccl.AllReduce(&out->best, &out->best, 1, ncclUint64_, ncclMax_, cm->comm, c->stream));
+    // the owner re-exports the winning pose; everybody else contributes zeros
+    CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
+    CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
+    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
+                         q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
+                         &out->best_score);
+    CU(cudaGetLastError());
+    // best_score (8 B) and best_T16 (64 B) are adjacent in QueryOut
+    NC(g_nccl.AllReduce(&out->best_score, &out->best_score, 72, ncclUint8_, ncclSum_, cm->comm,
+                        c->stream));
+    return TM_OK;
+}
+
+}  // extern "C"

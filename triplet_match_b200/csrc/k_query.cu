@@ -1,0 +1,178 @@
+// k_query.cu — device-side glue of the resident query (tm_query_run): shard
+// range, per-outer hypothesis ranges, top-k selection for the ICP stage and the
+// best-pose read-out.  Everything stays on the device so the whole pipeline is
+// one stream-ordered sequence with no host round trip.
+#include "tm_kernels.cuh"
+
+namespace tmk {
+
+// shard = [h_begin, h_end) of the global hypothesis list owned by this rank
+__global__ void shard_range_kernel(const unsigned long long* __restrict__ hyp_off, uint64_t n_pairs,
+                                   unsigned long long hyp_limit, uint32_t rank, uint32_t world,
+                                   unsigned long long capacity, unsigned long long* shard,
+                                   uint32_t* n_local, uint32_t* err) {
+    unsigned long long H = hyp_off[n_pairs];
+    if (hyp_limit && H > hyp_limit) H = hyp_limit;
+    unsigned long long per = (H + world - 1) / world;
+    unsigned long long hb = min((unsigned long long)rank * per, H);
+    unsigned long long he = min(hb + per, H);
+    if (he - hb > capacity) {
+        *err = 1u;
+        he = hb + capacity;
+    }
+    shard[0] = hb;
+    shard[1] = he;
+    shard[2] = H;
+    *n_local = (uint32_t)(he - hb);
+}
+void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
+                        unsigned long long hyp_limit, uint32_t rank, uint32_t world,
+                        unsigned long long capacity, unsigned long long* shard, uint32_t* n_local,
+                        uint32_t* err) {
+    ++g_launch_count;
+    shard_range_kernel<<<1, 1, 0, st>>>(hyp_off, n_pairs, hyp_limit, rank, world, capacity, shard,
+                                        n_local, err);
+}
+
+// g_hyp[g] = local index of the first hypothesis of outer sample g (n_outer+1 entries)
+__global__ void group_hyp_ranges_kernel(const unsigned long long* __restrict__ hyp_off,
+                                        const uint32_t* __restrict__ outer_pair_off,
+                                        uint32_t n_outer,
+                                        const unsigned long long* __restrict__ shard,
+                                        uint32_t* __restrict__ g_hyp) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_outer) return;
+    unsigned long long h = hyp_off[outer_pair_off[g]];
+    unsigned long long hb = shard[0], he = shard[1];
+    h = h < hb ? hb : (h > he ? he : h);
+    g_hyp[g] = (uint32_t)(h - hb);
+}
+void launch_group_hyp_ranges(cudaStream_t st, const unsigned long long* hyp_off,
+                             const uint32_t* outer_pair_off, uint32_t n_outer,
+                             const unsigned long long* shard, uint32_t* g_hyp) {
+    ++g_launch_count;
+    group_hyp_ranges_kernel<<<(n_outer + 1 + 127) / 128, 128, 0, st>>>(hyp_off, outer_pair_off,
+                                                                       n_outer, shard, g_hyp);
+}
+
+__global__ void group_of_hyp_kernel(const uint32_t* __restrict__ g_hyp, uint32_t n_groups,
+                                    uint32_t* __restrict__ g_of_hyp) {
+    uint32_t g = blockIdx.x;
+    if (g >= n_groups) return;
+    for (uint32_t h = g_hyp[g] + threadIdx.x; h < g_hyp[g + 1]; h += blockDim.x) g_of_hyp[h] = g;
+}
+void launch_group_of_hyp(cudaStream_t st, const uint32_t* g_hyp, uint32_t n_groups,
+                         uint32_t* g_of_hyp) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    group_of_hyp_kernel<<<n_groups, 128, 0, st>>>(g_hyp, n_groups, g_of_hyp);
+}
+
+// top-k by (inliers desc, id asc): k rounds of a strictly-decreasing key search
+// in a single CTA (keys are unique because the id is embedded).
+__global__ void __launch_bounds__(1024)
+    select_topk_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
+                       const uint32_t* __restrict__ n_local, uint32_t k,
+                       uint32_t* __restrict__ topk_ids) {
+    __shared__ unsigned long long wbest[32];
+    __shared__ unsigned long long last_s;
+    const uint32_t n = *n_local;
+    if (threadIdx.x == 0) last_s = ~0ull;
+    __syncthreads();
+    for (uint32_t r = 0; r < k; ++r) {
+        const unsigned long long last = last_s;
+        unsigned long long best = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            if (valid && !valid[i]) continue;
+            if (!counts[i]) continue;
+            unsigned long long key =
+                ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+            if (key < last && key > best) best = key;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+            best = o > best ? o : best;
+        }
+        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 32; ++w) best = wbest[w] > best ? wbest[w] : best;
+            // best == 0 only when no candidate is left (a real key always has ~id bits set
+            // unless id == 0xFFFFFFFF, which never occurs for n < 2^32 - 1)
+            topk_ids[r] = best ? (0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) : 0xFFFFFFFFu;
+            last_s = best;
+        }
+        __syncthreads();
+        if (last_s == 0ull) {
+            for (uint32_t rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x)
+                topk_ids[rr] = 0xFFFFFFFFu;
+            break;
+        }
+    }
+}
+void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+                        const uint32_t* n_local, uint32_t k, uint32_t* topk_ids,
+                        unsigned long long*) {
+    if (!k) return;
+    ++g_launch_count;
+    select_topk_kernel<<<1, 1024, 0, st>>>(counts, valid, n_local, k, topk_ids);
+}
+
+__global__ void gather_rows_kernel(const float4* __restrict__ T, const uint32_t* __restrict__ ids,
+                                   uint32_t k, float4* __restrict__ out,
+                                   uint32_t* __restrict__ active) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= k) return;
+    uint32_t id = ids[r];
+    if (id == 0xFFFFFFFFu) {
+        const float nanv = __int_as_float(0x7fc00000);
+        out[3 * r] = out[3 * r + 1] = out[3 * r + 2] = make_float4(nanv, nanv, nanv, nanv);
+        active[r] = 0;
+    } else {
+        out[3 * r] = T[3 * (size_t)id];
+        out[3 * r + 1] = T[3 * (size_t)id + 1];
+        out[3 * r + 2] = T[3 * (size_t)id + 2];
+        active[r] = 1;
+    }
+}
+void launch_gather_rows(cudaStream_t st, const float4* T, const uint32_t* ids, uint32_t k,
+                        float4* out, uint32_t* active) {
+    if (!k) return;
+    ++g_launch_count;
+    gather_rows_kernel<<<(k + 63) / 64, 64, 0, st>>>(T, ids, k, out, active);
+}
+
+// after the (all-)reduce: if the winning hypothesis lives in this shard, export
+// its pose (column-major) and normalised score
+__global__ void finalize_best_kernel(const unsigned long long* __restrict__ best,
+                                     const unsigned long long* __restrict__ shard,
+                                     const float4* __restrict__ T,
+                                     const unsigned long long* __restrict__ scores,
+                                     uint32_t model_n, float* __restrict__ best_T16,
+                                     double* __restrict__ best_score) {
+    unsigned long long key = *best;
+    if (!key) return;
+    unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
+    if (gid < shard[0] || gid >= shard[1]) return;
+    size_t l = (size_t)(gid - shard[0]);
+    for (int r = 0; r < 3; ++r) {
+        float4 v = T[3 * l + r];
+        best_T16[r] = v.x;
+        best_T16[4 + r] = v.y;
+        best_T16[8 + r] = v.z;
+        best_T16[12 + r] = v.w;
+    }
+    best_T16[3] = best_T16[7] = best_T16[11] = 0.f;
+    best_T16[15] = 1.f;
+    if (scores) *best_score = (double)scores[l] / SCORE_SCALE / (double)model_n;
+}
+void launch_finalize_best(cudaStream_t st, const unsigned long long* best,
+                          const unsigned long long* shard, const float4* T,
+                          const unsigned long long* scores, uint32_t model_n, float* best_T16,
+                          double* best_score) {
+    ++g_launch_count;
+    finalize_best_kernel<<<1, 1, 0, st>>>(best, shard, T, scores, model_n, best_T16, best_score);
+}
+
+}  // namespace tmk

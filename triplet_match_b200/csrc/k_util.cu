@@ -1,0 +1,313 @@
+// k_util.cu — layout / utility kernels of the search path:
+//   pack_cloud      strided host layout (packed xyz or pcl::PointSurfel AoS) -> SoA float4 + flags
+//   set_mask        mask_ updates (include/impl/scene.hpp:87-90)
+//   exclusive scan  CSR offsets (hit counts, subset counts)
+//   ball subsets    radius subset of find_in_subset (include/impl/scene.hpp:273)
+//   voxel_fill      exact 1-NN grid fill (include/impl/model.hpp:81-94)
+//   traits_project  per-point closed forms (cylinder/plane/plane2/identity _traits::project)
+#include "tm_kernels.cuh"
+
+namespace tmk {
+
+// ------------------------------------------------------------------ pack_cloud
+// raw: the three strided arrays were copied verbatim into one device buffer
+// (n*stride floats each, or one shared AoS buffer).  flags: per-point byte
+// (scene: tangent_mask_) or null (model: computed ||tangent|| > 0.7,
+// include/impl/scene.hpp:470).
+__global__ void pack_cloud_kernel(const float* __restrict__ pos, const float* __restrict__ nrm,
+                                  const float* __restrict__ tgt, uint32_t stride, uint32_t n,
+                                  const uint8_t* __restrict__ flags, int model_mode,
+                                  float4* __restrict__ opos, float4* __restrict__ onrm,
+                                  float4* __restrict__ otgt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t b = (size_t)i * stride;
+    f3 p = {pos[b], pos[b + 1], pos[b + 2]};
+    f3 nn = {nrm[b], nrm[b + 1], nrm[b + 2]};
+    f3 t = {tgt[b], tgt[b + 1], tgt[b + 2]};
+    uint32_t fl = 0;
+    if (model_mode) {
+        if (norm3(t) > 0.7f) fl |= FLAG_TANGENT;
+    } else if (flags && flags[i]) {
+        fl |= FLAG_TANGENT;
+    }
+    opos[i] = make_float4(p.x, p.y, p.z, __uint_as_float(fl));
+    onrm[i] = make_float4(nn.x, nn.y, nn.z, 0.f);
+    otgt[i] = make_float4(t.x, t.y, t.z, 0.f);
+}
+
+void launch_pack_cloud(cudaStream_t st, const float* pos, const float* nrm, const float* tgt,
+                       uint32_t stride, uint32_t n, const uint8_t* flags, int model_mode,
+                       float4* opos, float4* onrm, float4* otgt) {
+    if (!n) return;
+    ++g_launch_count;
+    pack_cloud_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, nrm, tgt, stride, n, flags, model_mode,
+                                                       opos, onrm, otgt);
+}
+
+__global__ void set_mask_kernel(float4* __restrict__ pos, uint32_t n,
+                                const uint8_t* __restrict__ mask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t fl = __float_as_uint(pos[i].w) & ~FLAG_MASKED;
+    if (mask && mask[i]) fl |= FLAG_MASKED;
+    pos[i].w = __uint_as_float(fl);
+}
+void launch_set_mask(cudaStream_t st, float4* pos, uint32_t n, const uint8_t* mask) {
+    if (!n) return;
+    ++g_launch_count;
+    set_mask_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, n, mask);
+}
+
+// ------------------------------------------------------------ exclusive scan
+// Single-CTA tiled scan with carry (inputs here are at most a few million
+// counters; the launch is latency-, not bandwidth-critical).  out has n+1
+// entries; out[n] = total.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+template <typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    exclusive_scan_kernel(const uint32_t* __restrict__ in, TOut* __restrict__ out, uint64_t n) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0ull;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += (uint64_t)SCAN_THREADS * SCAN_ITEMS) {
+        uint64_t i0 = base + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        unsigned long long v[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+            tsum += v[k];
+        }
+        unsigned long long incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sums[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        unsigned long long carry = carry_s;
+        unsigned long long excl = carry + warp_sums[warp] + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = (TOut)excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl;  // total so far
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = (TOut)carry_s;
+}
+void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n) {
+    ++g_launch_count;
+    exclusive_scan_kernel<uint32_t><<<1, SCAN_THREADS, 0, st>>>(in, out, n);
+}
+void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned long long* out,
+                               uint64_t n) {
+    ++g_launch_count;
+    exclusive_scan_kernel<unsigned long long><<<1, SCAN_THREADS, 0, st>>>(in, out, n);
+}
+
+// -------------------------------------------------------------- ball subsets
+// One warp owns a segment of BALL_SEG consecutive scene points and walks all
+// centres; lane l visits points seg*BALL_SEG + k*32 + l, so ballot order is
+// ascending index order and the compaction is deterministic.  Predicate
+// (FLANN L2_Simple order): (dx*dx + dy*dy) + dz*dz < r^2.
+// counts layout: [centre][segment].
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+    ball_kernel(const float4* __restrict__ pos, uint32_t n, const uint32_t* __restrict__ centres,
+                uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* __restrict__ counts,
+                const unsigned long long* __restrict__ seg_offsets, int32_t* __restrict__ indices) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= n_seg) return;
+    const uint32_t base = seg * BALL_SEG;
+    for (uint32_t c = 0; c < n_centres; ++c) {
+        float4 cp = pos[centres[c]];
+        unsigned long long off = FILL ? seg_offsets[(size_t)c * n_seg + seg] : 0ull;
+        uint32_t cnt = 0;
+#pragma unroll 4
+        for (uint32_t k = 0; k < BALL_SEG / 32; ++k) {
+            uint32_t i = base + k * 32 + lane;
+            bool in = false;
+            if (i < n) {
+                float4 p = pos[i];
+                float dx = p.x - cp.x, dy = p.y - cp.y, dz = p.z - cp.z;
+                in = ((dx * dx + dy * dy) + dz * dz) < r2;
+            }
+            uint32_t b = __ballot_sync(0xffffffffu, in);
+            if (FILL) {
+                if (in) indices[off + cnt + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
+            }
+            cnt += __popc(b);
+        }
+        if (!FILL && lane == 0) counts[(size_t)c * n_seg + seg] = cnt;
+    }
+}
+void launch_ball_count(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
+                       uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* counts) {
+    if (!n_seg || !n_centres) return;
+    ++g_launch_count;
+    ball_kernel<false><<<(n_seg + 7) / 8, 256, 0, st>>>(pos, n, centres, n_centres, r2, n_seg,
+                                                       counts, nullptr, nullptr);
+}
+void launch_ball_fill(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
+                      uint32_t n_centres, float r2, uint32_t n_seg,
+                      const unsigned long long* seg_offsets, int32_t* indices) {
+    if (!n_seg || !n_centres) return;
+    ++g_launch_count;
+    ball_kernel<true><<<(n_seg + 7) / 8, 256, 0, st>>>(pos, n, centres, n_centres, r2, n_seg,
+                                                      nullptr, seg_offsets, indices);
+}
+// per-centre CSR offsets = flattened scan sampled at segment 0 of each centre
+__global__ void ball_row_offsets_kernel(const unsigned long long* __restrict__ seg_offsets,
+                                        uint32_t n_centres, uint32_t n_seg,
+                                        unsigned long long* __restrict__ row_offsets) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n_centres) row_offsets[c] = seg_offsets[(size_t)c * n_seg];
+}
+void launch_ball_row_offsets(cudaStream_t st, const unsigned long long* seg_offsets,
+                             uint32_t n_centres, uint32_t n_seg, unsigned long long* row_offsets) {
+    ++g_launch_count;
+    ball_row_offsets_kernel<<<(n_centres + 1 + 255) / 256, 256, 0, st>>>(seg_offsets, n_centres,
+                                                                         n_seg, row_offsets);
+}
+
+// ---------------------------------------------------------------- voxel_fill
+// One thread per voxel; model points streamed through shared memory in tiles.
+// centre = (index - t) / s; squared distance (dx*dx + dy*dy) + dz*dz; the
+// lowest point index wins ties (strict '<' while scanning ascending).
+constexpr int VF_TILE = 1024;
+__global__ void __launch_bounds__(256)
+    voxel_fill_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, float sx,
+                      float sy, float sz, float tx, float ty, float tz,
+                      uint32_t* __restrict__ voxel) {
+    __shared__ float4 tile[VF_TILE];
+    const size_t total = (size_t)ex * ey * ez;
+    size_t lin = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = lin < total;
+    int i = 0, j = 0, k = 0;
+    if (live) {
+        i = (int)(lin % ex);
+        j = (int)((lin / ex) % ey);
+        k = (int)(lin / ((size_t)ex * ey));
+    }
+    float qx = ((float)i - tx) / sx, qy = ((float)j - ty) / sy, qz = ((float)k - tz) / sz;
+    float best = 3.402823466e+38f;
+    uint32_t bi = 0;
+    for (uint32_t base = 0; base < n; base += VF_TILE) {
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < VF_TILE; t += blockDim.x)
+            if (base + t < n) tile[t] = mpos[base + t];
+        __syncthreads();
+        uint32_t m = min((uint32_t)VF_TILE, n - base);
+        for (uint32_t t = 0; t < m; ++t) {
+            float4 p = tile[t];
+            float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            float d = (dx * dx + dy * dy) + dz * dz;
+            if (d < best) {
+                best = d;
+                bi = base + t;
+            }
+        }
+    }
+    if (live) voxel[lin] = bi;
+}
+void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
+                       float sx, float sy, float sz, float tx, float ty, float tz,
+                       uint32_t* voxel) {
+    ++g_launch_count;
+    size_t total = (size_t)ex * ey * ez;
+    if (!total) return;
+    voxel_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy,
+                                                                      sz, tx, ty, tz, voxel);
+}
+
+// fused grid: cell -> (model pos.xyz, flags) so scoring needs one gather, not two
+__global__ void fuse_grid_kernel(const uint32_t* __restrict__ voxel, size_t total,
+                                 const float4* __restrict__ mpos, float4* __restrict__ vcell) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) vcell[i] = mpos[voxel[i]];
+}
+void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
+                      float4* vcell) {
+    if (!total) return;
+    ++g_launch_count;
+    fuse_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(voxel, total, mpos, vcell);
+}
+
+// ------------------------------------------------------------ traits project
+// g2l rows r0..r3 (row 3 unused).  kind: 0 cylinder (impl/cylinder_traits.hpp:102-114),
+// 1 plane (impl/plane_traits.hpp:66-72), 2 plane2 (impl/plane2_traits.hpp:86-89),
+// 3 identity (impl/identity_traits.hpp:33-36).
+__global__ void traits_project_kernel(int kind, float4 r0, float4 r1, float4 r2, float radius,
+                                      float threshold, const float* __restrict__ xyz, uint64_t n,
+                                      float* __restrict__ uvw, uint8_t* __restrict__ ok) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    float u = x, v = y, w = z;
+    bool good = true;
+    if (kind != 3) {
+        float lx = row_apply(r0, x, y, z), ly = row_apply(r1, x, y, z), lz = row_apply(r2, x, y, z);
+        if (kind == 0) {
+            float height = sqrtf(lx * lx + ly * ly) - radius;
+            if (fabsf(height) > threshold) {
+                good = false;
+                u = v = w = 0.f;
+            } else {
+                float ang = atan2f_full(ly, lx);
+                if (ang < 0.f) ang = (float)((double)ang + 2.0 * 3.14159265358979323846);
+                u = ang * radius;
+                v = lz;
+                w = height / radius;
+            }
+        } else {
+            u = lx; v = ly; w = lz;
+            if (kind == 1 && fabsf(lz) > threshold) {
+                good = false;
+                u = v = w = 0.f;
+            }
+        }
+    }
+    uvw[3 * i] = u;
+    uvw[3 * i + 1] = v;
+    uvw[3 * i + 2] = w;
+    ok[i] = good ? 1 : 0;
+}
+void launch_traits_project(cudaStream_t st, int kind, float4 r0, float4 r1, float4 r2, float radius,
+                           float threshold, const float* xyz, uint64_t n, float* uvw, uint8_t* ok) {
+    if (!n) return;
+    ++g_launch_count;
+    traits_project_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kind, r0, r1, r2, radius,
+                                                                      threshold, xyz, n, uvw, ok);
+}
+
+// ------------------------------------------------------------------ L2 flush
+__global__ void flush_kernel(float4* buf, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_float4(v, v, v, v);
+}
+void launch_flush(cudaStream_t st, float4* buf, size_t n, float v) {
+    ++g_launch_count;
+    flush_kernel<<<148 * 8, 256, 0, st>>>(buf, n, v);
+}
+
+}  // namespace tmk

@@ -1,0 +1,199 @@
+// tm_device.cuh — device layouts and the bit-exact FP32 helpers shared by all
+// kernels.  Every translation unit that includes this file is compiled with
+// -fmad=false (no FFMA/DFMA contraction) and nvcc's default -prec-div=true
+// -prec-sqrt=true, so +,-,*,/ and sqrt round exactly like the reference's SSE2
+// build (CMakeLists.txt:28-40: -O3, no -march, no fast-math).  The evaluation
+// orders are the Eigen 3.3 fixed-size orders (see DESIGN.md "Float contract"):
+//   Matrix4f*Vector4f : ((c0*x + c1*y) + c2*z) + c3*w
+//   3-redux (dot, squaredNorm, Matrix3f row*vec) : a0 + (a1 + a2)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmk {
+
+// ---- resident layouts ----------------------------------------------------
+// Clouds are SoA float4: pos.xyz + flag bits in pos.w, nrm.xyz, tgt.xyz.
+constexpr uint32_t FLAG_TANGENT = 1u;  // scene: tangent_mask_ ; model: ||tangent|| > 0.7
+constexpr uint32_t FLAG_MASKED = 2u;   // scene: mask_
+
+struct CloudDev {
+    const float4* pos;
+    const float4* nrm;
+    const float4* tgt;
+    uint32_t n;
+};
+
+struct HashSlot {  // open addressing, linear probing, home = murmur4(key) & mask
+    uint32_t k[4];
+    uint32_t begin;  // into hits[]
+    uint32_t count;  // 0 = empty slot
+    uint32_t pad[2];
+};
+
+struct ModelDev {
+    CloudDev cloud;
+    const uint32_t* voxel;  // lin = k*ex*ey + j*ex + i
+    const float4* vcell;    // optional fused grid: model pos + flag per cell (or null)
+    const uint32_t* vcell_idx;
+    int ex, ey, ez;
+    float exf, eyf, ezf;
+    float sx, sy, sz, tx, ty, tz;  // to_voxel_ = diag(s) + t
+    const HashSlot* slots;
+    uint32_t slot_mask;
+    const uint2* hits;
+    uint32_t n_hits;
+    float fb_min0, fb_max0;  // feat_bounds_ distance range
+    uint32_t dist_steps;
+    float angle_step;
+    float resolution, diameter;
+};
+
+// hypothesis transform: rows 0..2 of the 4x4 (row 3 is 0,0,0,1)
+struct Rows {
+    float4 r0, r1, r2;
+};
+
+// ---- no-FMA float helpers -------------------------------------------------
+__host__ __device__ __forceinline__ float sum3(float a0, float a1, float a2) {
+    return a0 + (a1 + a2);
+}
+struct f3 {
+    float x, y, z;
+};
+__host__ __device__ __forceinline__ f3 mk3(float4 v) { return {v.x, v.y, v.z}; }
+__host__ __device__ __forceinline__ f3 sub3(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ __forceinline__ float dot3(f3 a, f3 b) {
+    return sum3(a.x * b.x, a.y * b.y, a.z * b.z);
+}
+__host__ __device__ __forceinline__ float sqnorm3(f3 a) { return dot3(a, a); }
+__device__ __forceinline__ float norm3(f3 a) { return sqrtf(sqnorm3(a)); }
+__host__ __device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ f3 normalized3(f3 a) {
+    float z = sqnorm3(a);
+    if (z > 0.f) {
+        float s = sqrtf(z);
+        return {a.x / s, a.y / s, a.z / s};
+    }
+    return a;
+}
+// row of Matrix4f * (x,y,z,1): ((r.x*x + r.y*y) + r.z*z) + r.w
+__host__ __device__ __forceinline__ float row_apply(float4 r, float x, float y, float z) {
+    return ((r.x * x + r.y * y) + r.z * z) + r.w;
+}
+// row of Matrix3f * v
+__host__ __device__ __forceinline__ float row_rot(float4 r, f3 v) {
+    return sum3(r.x * v.x, r.y * v.y, r.z * v.z);
+}
+
+// ---- shared software atan (first quadrant), see DESIGN.md "atan2f" --------
+// Same algorithm, constants and operation order as the oracle's restatement:
+// IEEE double +,*,/ only, rounded once to float.
+__host__ __device__ inline double atan_pos(double x) {
+    const double hi0 = 4.63647609000806093515e-01, hi1 = 7.85398163397448278999e-01,
+                 hi2 = 9.82793723247329054082e-01, hi3 = 1.57079632679489655800e+00;
+    const double lo0 = 2.26987774529616870924e-17, lo1 = 3.06161699786838301793e-17,
+                 lo2 = 1.39033110312309984516e-17, lo3 = 6.12323399573676603587e-17;
+    const double a0 = 3.33333333333329318027e-01, a1 = -1.99999999998764832476e-01,
+                 a2 = 1.42857142725034663711e-01, a3 = -1.11111104054623557880e-01,
+                 a4 = 9.09088713343650656196e-02, a5 = -7.69187620504482999495e-02,
+                 a6 = 6.66107313738753120669e-02, a7 = -5.83357013379057348645e-02,
+                 a8 = 4.97687799461593236017e-02, a9 = -3.65315727442169155270e-02,
+                 a10 = 1.62858201153657823623e-02;
+    double hi, lo;
+    int id;
+    if (x >= 1.8446744073709552e19) return hi3 + lo3;
+    if (x < 0.4375) {
+        if (x < 1.862645149230957e-09) return x;
+        id = -1;
+        hi = 0.0;
+        lo = 0.0;
+    } else if (x < 1.1875) {
+        if (x < 0.6875) {
+            id = 0; hi = hi0; lo = lo0;
+            x = (2.0 * x - 1.0) / (2.0 + x);
+        } else {
+            id = 1; hi = hi1; lo = lo1;
+            x = (x - 1.0) / (x + 1.0);
+        }
+    } else if (x < 2.4375) {
+        id = 2; hi = hi2; lo = lo2;
+        x = (x - 1.5) / (1.0 + 1.5 * x);
+    } else {
+        id = 3; hi = hi3; lo = lo3;
+        x = -1.0 / x;
+    }
+    double z = x * x;
+    double w = z * z;
+    double s1 = z * (a0 + w * (a2 + w * (a4 + w * (a6 + w * (a8 + w * a10)))));
+    double s2 = w * (a1 + w * (a3 + w * (a5 + w * (a7 + w * a9))));
+    if (id < 0) return x - x * (s1 + s2);
+    return hi - ((x * (s1 + s2) - lo) - x);
+}
+__host__ __device__ inline float atan2f_q1(float y, float x) {  // y >= 0, x >= 0
+    if (y == 0.f) return 0.f;
+    if (x == 0.f) return (float)(1.57079632679489655800e+00 + 6.12323399573676603587e-17);
+    double q = (double)y / (double)x;
+    return (float)atan_pos(q);
+}
+__host__ __device__ inline float atan2f_full(float y, float x) {
+    const double pi_d = 3.14159265358979311600e+00;
+    double ay = y < 0.f ? -(double)y : (double)y, ax = x < 0.f ? -(double)x : (double)x;
+    double q;
+    if (ay == 0.0) q = 0.0;
+    else if (ax == 0.0) q = 1.57079632679489655800e+00 + 6.12323399573676603587e-17;
+    else q = atan_pos(ay / ax);
+    bool sx = signbit(x), sy = signbit(y);
+    double a = sx ? pi_d - q : q;
+    return (float)(sy ? -a : a);
+}
+
+// ---- discretise + murmur (src/discretize.cpp:19-30, impl/discretize.hpp:10-45)
+__host__ __device__ __forceinline__ uint32_t discretize_range(float value, float min_value,
+                                                              float range_value, uint32_t steps) {
+    float nval = (value - min_value) / range_value;
+    if (nval < 0.f) return 0u;
+    if (nval >= 1.f) return steps - 1u;
+    return (uint32_t)(nval * (float)steps);
+}
+__host__ __device__ __forceinline__ uint32_t discretize_step(float value, float step) {
+    return (uint32_t)(value / step);
+}
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) {
+    return (x << r) | (x >> (32 - r));
+}
+__host__ __device__ __forceinline__ uint32_t murmur4(uint32_t k0, uint32_t k1, uint32_t k2,
+                                                     uint32_t k3) {
+    uint32_t h1 = 42u;
+    const uint32_t c1 = 0xcc9e2d51u, c2 = 0x1b873593u;
+    uint32_t ks[4] = {k0, k1, k2, k3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t k = ks[i];
+        k *= c1;
+        k = rotl32(k, 15);
+        k *= c2;
+        h1 ^= k;
+        h1 = rotl32(h1, 13);
+        h1 = h1 * 5u + 0xe6546b64u;
+    }
+    h1 ^= 16u;
+    h1 ^= h1 >> 16;
+    h1 *= 0x85ebca6bu;
+    h1 ^= h1 >> 13;
+    h1 *= 0xc2b2ae35u;
+    h1 ^= h1 >> 16;
+    return h1;
+}
+
+// fixed-point score accumulation: |ref.ref_n| in [0, ~1] -> 2^-36 quanta in u64.
+// Integer sums are order-independent, so counts AND scores are reproducible for
+// any tiling, launch order or multi-GPU sharding.
+constexpr double SCORE_SCALE = 68719476736.0;  // 2^36
+__device__ __forceinline__ unsigned long long score_fixed(float term) {
+    return (unsigned long long)((double)term * SCORE_SCALE);
+}
+
+}  // namespace tmk

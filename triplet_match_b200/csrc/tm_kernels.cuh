@@ -1,0 +1,158 @@
+// tm_kernels.cuh — launch wrappers shared between the kernel files and capi.cu.
+#pragma once
+#include "tm_device.cuh"
+
+namespace tmk {
+
+// kernels launched by this process (every launch_* wrapper launches exactly one)
+extern unsigned long long g_launch_count;
+
+// ---- tuning constants ------------------------------------------------------
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_P = 4;                              // scene points per thread
+constexpr int SCORE_TILE = SCORE_THREADS * SCORE_P;     // points per work item
+constexpr int SCORE_HSTAGE = 128;                       // hypotheses staged in smem at a time
+constexpr int SCORE_HCHUNK = 2048;                      // hypotheses per work item
+constexpr uint32_t BALL_SEG = 1024;                     // scene points per warp segment
+constexpr uint32_t CORR_SEG = 1024;
+constexpr int ICP_P = 4;
+constexpr int ICP_NSUM = 17;
+
+struct WorkItem {
+    unsigned long long sub_begin;  // first subset position (or scene index if no index list)
+    uint32_t npts;
+    uint32_t hyp_begin, hyp_end;   // local hypothesis range
+    uint32_t pad;
+};
+
+struct ScoreArgs {
+    CloudDev scene;
+    ModelDev model;
+    const int32_t* sub_idx;  // null => identity
+    const WorkItem* items;
+    const uint32_t* n_items;
+    uint32_t* work_counter;
+    const float4* T;
+    uint32_t* counts;
+    unsigned long long* scores;
+    float sq_thres;
+};
+
+struct EarlyArgs {
+    CloudDev scene;
+    ModelDev model;
+    const int32_t* sub_idx;
+    const unsigned long long* sub_off;
+    const uint32_t* g_of_hyp;
+    const float4* T;
+    uint32_t n_hyp;              // upper bound (grid size)
+    const uint32_t* n_hyp_dev;   // optional device-side count (<= n_hyp)
+    unsigned long long* n_tests; // optional: sum of positions actually tried
+    float sq_thres;
+    float accept_prob;
+    int early_out;
+    uint32_t* counts;
+    unsigned long long* scores;
+    uint8_t* dropped;
+    uint32_t* tested;
+};
+
+struct IcpState {
+    float4* Tcur;
+    float4* Tbest;
+    long long* sums_cur;
+    long long* sums_best;
+    uint32_t* iters;
+    uint32_t* active;
+};
+
+// k_util.cu
+void launch_pack_cloud(cudaStream_t st, const float* pos, const float* nrm, const float* tgt,
+                       uint32_t stride, uint32_t n, const uint8_t* flags, int model_mode,
+                       float4* opos, float4* onrm, float4* otgt);
+void launch_set_mask(cudaStream_t st, float4* pos, uint32_t n, const uint8_t* mask);
+void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n);
+void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned long long* out,
+                               uint64_t n);
+void launch_ball_count(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
+                       uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* counts);
+void launch_ball_fill(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
+                      uint32_t n_centres, float r2, uint32_t n_seg,
+                      const unsigned long long* seg_offsets, int32_t* indices);
+void launch_ball_row_offsets(cudaStream_t st, const unsigned long long* seg_offsets,
+                             uint32_t n_centres, uint32_t n_seg, unsigned long long* row_offsets);
+void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
+                       float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel);
+void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
+                      float4* vcell);
+void launch_traits_project(cudaStream_t st, int kind, float4 r0, float4 r1, float4 r2, float radius,
+                           float threshold, const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
+void launch_flush(cudaStream_t st, float4* buf, size_t n, float v);
+
+// k_pairs.cu
+void launch_pair_features_probe(cudaStream_t st, const CloudDev& scene, const ModelDev& model,
+                                const uint32_t* outer, const uint32_t* pair_i,
+                                const uint32_t* pair_j, uint64_t n, float lower, float upper,
+                                uint32_t limit, float* feats, uint4* keys, uint8_t* valid,
+                                uint32_t* hit_begin, uint32_t* hit_count,
+                                unsigned long long* n_valid);
+void launch_probe(cudaStream_t st, const ModelDev& model, const uint4* keys, const uint8_t* valid,
+                  uint64_t n, uint32_t limit, uint32_t* hit_begin, uint32_t* hit_count);
+void launch_gather_hits(cudaStream_t st, const ModelDev& model, const uint32_t* hit_begin,
+                        const unsigned long long* offsets, uint64_t n, uint2* out);
+void launch_hypotheses(cudaStream_t st, const CloudDev& scene, const ModelDev& model,
+                       const uint32_t* outer, const uint32_t* pair_i, const uint32_t* pair_j,
+                       uint64_t n_pairs, const unsigned long long* hyp_off,
+                       const uint32_t* hit_begin, const uint2* hits, int force_up,
+                       const unsigned long long* shard, float4* T, uint8_t* hyp_valid,
+                       uint32_t* hyp_pair);
+void launch_rows_from_colmajor(cudaStream_t st, const float* T16, uint64_t n, float4* rows);
+void launch_colmajor_from_rows(cudaStream_t st, const float4* rows, uint64_t n, float* T16);
+
+// k_score.cu
+void launch_score_full(cudaStream_t st, const ScoreArgs& a, int grid, bool fused, bool with_score);
+int score_full_max_blocks_per_sm(bool fused, bool with_score);
+void launch_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
+                       uint32_t n_groups, uint32_t* n_items_g, unsigned long long* n_tests);
+void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
+                      uint32_t n_groups, const uint32_t* item_off, WorkItem* items);
+void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
+void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+                   const uint32_t* n_local, const unsigned long long* h_begin,
+                   unsigned long long* best, int grid);
+
+// k_icp.cu
+void launch_icp_accumulate(cudaStream_t st, const CloudDev& scene, const ModelDev& model,
+                           const float4* T, const uint32_t* active, uint32_t n_hyp,
+                           uint32_t pt_begin, uint32_t pt_end, float sq_thres, float cx, float cy,
+                           float cz, double fix_scale, long long* sums, int grid, bool fused);
+void launch_icp_step(cudaStream_t stream, const IcpState& st, uint32_t n_hyp, int first,
+                     uint32_t max_iterations, double inv_scale, float cx, float cy, float cz);
+void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
+                       float sq_thres, uint32_t n_seg, uint32_t* counts,
+                       unsigned long long* score, bool fused);
+void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
+                      float sq_thres, uint32_t n_seg, const uint32_t* seg_off,
+                      uint32_t* scene_corrs, uint32_t* model_corrs, bool fused);
+
+// k_query.cu (device-side glue of the resident query)
+void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
+                        unsigned long long hyp_limit, uint32_t rank, uint32_t world,
+                        unsigned long long capacity, unsigned long long* shard, uint32_t* n_local,
+                        uint32_t* err);
+void launch_group_hyp_ranges(cudaStream_t st, const unsigned long long* hyp_off,
+                             const uint32_t* outer_pair_off, uint32_t n_outer,
+                             const unsigned long long* shard, uint32_t* g_hyp);
+void launch_group_of_hyp(cudaStream_t st, const uint32_t* g_hyp, uint32_t n_groups,
+                         uint32_t* g_of_hyp);
+void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+                        const uint32_t* n_local, uint32_t k, uint32_t* topk_ids,
+                        unsigned long long* scratch_keys);
+void launch_gather_rows(cudaStream_t st, const float4* T, const uint32_t* ids, uint32_t k,
+                        float4* out, uint32_t* active);
+void launch_finalize_best(cudaStream_t st, const unsigned long long* best,
+                          const unsigned long long* shard, const float4* T,
+                          const unsigned long long* scores, uint32_t model_n, float* best_T16,
+                          double* best_score);
+
+}  // namespace tmk
