@@ -350,7 +350,11 @@ uint32_t orc_icp(void* sp, void* mp, const float* T16_in, uint32_t max_iteration
     const scene& s = static_cast<scene_h*>(sp)->s;
     const model& m = static_cast<model_h*>(mp)->m;
     match start{from_colmajor(T16_in), {}, {}, 0.0};
-    match r = icp(s, m, start, max_iterations, dist_thres, accept_prob, iters);
+    // max_iterations == 0: icp_ returns the incoming match unchanged (scene.hpp:371); the
+    // incoming match is finish_find(t, dist_thres) (scene.hpp:361-364)
+    match r = max_iterations == 0 ? finish_find(s, m, start.transform, accept_prob, dist_thres)
+                                  : icp(s, m, start, max_iterations, dist_thres, accept_prob, iters);
+    if (max_iterations == 0 && iters) *iters = 0;
     to_colmajor(r.transform, T16_out);
     if (score) *score = r.score;
     return (uint32_t)r.scene_corrs.size();

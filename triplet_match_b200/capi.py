@@ -1,0 +1,429 @@
+"""ctypes binding of the C-ABI in include/tm_b200.h (harness side: tests, bench, smoke).
+
+This is a thin mirror: every method maps to one exported function and takes /
+returns numpy arrays living on the HOST.  There is no fallback — if the shared
+library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtriplet_match_b200.so")
+
+TM_OK = 0
+TM_ERR_INVALID, TM_ERR_CUDA, TM_ERR_CAPACITY, TM_ERR_UNINITIALIZED, TM_ERR_NCCL = 1, 2, 3, 4, 5
+
+
+class TmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CloudView(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("nrm", C.c_void_p), ("tgt", C.c_void_p),
+                ("stride", C.c_uint32), ("n", C.c_uint32)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("voxel", C.c_void_p), ("extents", C.c_int32 * 3), ("to_voxel", C.c_float * 16),
+                ("resolution", C.c_float), ("diameter", C.c_float),
+                ("keys", C.c_void_p), ("offsets", C.c_void_p), ("pairs", C.c_void_p),
+                ("n_keys", C.c_uint32),
+                ("feat_min", C.c_float * 4), ("feat_max", C.c_float * 4),
+                ("distance_step_count", C.c_float), ("angle_step", C.c_float)]
+
+
+class QueryParams(C.Structure):
+    _fields_ = [("min_diameter_factor", C.c_float), ("max_diameter_factor", C.c_float),
+                ("force_up", C.c_int32), ("query_limit", C.c_uint32),
+                ("dist_thres", C.c_float), ("accept_prob", C.c_float),
+                ("early_out", C.c_int32), ("icp_top_k", C.c_uint32),
+                ("max_icp_iterations", C.c_uint32),
+                ("max_hypotheses", C.c_uint64), ("hyp_limit", C.c_uint64)]
+
+
+class QueryResult(C.Structure):
+    _fields_ = [("n_pairs_valid", C.c_uint64), ("n_hypotheses", C.c_uint64),
+                ("n_scored", C.c_uint64), ("n_tests", C.c_uint64), ("best_key", C.c_uint64),
+                ("best_hypothesis", C.c_uint32), ("best_inliers", C.c_uint32),
+                ("best_score", C.c_double), ("best_T", C.c_float * 16)]
+
+
+EXPORTS = [
+    "tm_last_error", "tm_version", "tm_ctx_create", "tm_ctx_destroy", "tm_ctx_sync",
+    "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
+    "tm_ctx_kernel_launches", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
+    "tm_scene_upload", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
+    "tm_traits_project", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
+    "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
+    "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
+    "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.tm_last_error.restype = C.c_char_p
+    lib.tm_version.restype = C.c_char_p
+    lib.tm_ctx_stream.restype = C.c_void_p
+    lib.tm_ctx_stream.argtypes = [C.c_void_p]
+    lib.tm_ctx_kernel_launches.restype = C.c_uint64
+    lib.tm_ctx_kernel_launches.argtypes = [C.c_void_p]
+    lib.tm_query_best_key_device.restype = C.c_void_p
+    lib.tm_query_best_key_device.argtypes = [C.c_void_p]
+    for name in ("tm_ctx_destroy", "tm_model_destroy", "tm_scene_destroy", "tm_query_destroy",
+                 "tm_comm_destroy"):
+        getattr(lib, name).restype = None
+        getattr(lib, name).argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _chk(rc: int) -> None:
+    if rc != TM_OK:
+        raise TmError(rc, load().tm_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _view(pos, nrm, tgt):
+    pos, nrm, tgt = _f32(pos), _f32(nrm), _f32(tgt)
+    v = CloudView(pos.ctypes.data, nrm.ctypes.data, tgt.ctypes.data, 3, pos.shape[0])
+    return v, (pos, nrm, tgt)
+
+
+def surfel_view(records: np.ndarray):
+    """View over an (n,12) float32 array laid out like pcl::PointSurfel (48 B)."""
+    assert records.dtype == np.float32 and records.ndim == 2 and records.shape[1] == 12
+    base = records.ctypes.data
+    return CloudView(base, base + 16, base + 36, 12, records.shape[0])
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        _chk(self.lib.tm_ctx_create(C.c_int(device), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.tm_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def sync(self):
+        _chk(self.lib.tm_ctx_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.tm_ctx_stream(self.h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.tm_ctx_sm_count(self.h))
+
+    def timer_start(self):
+        _chk(self.lib.tm_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _chk(self.lib.tm_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        _chk(self.lib.tm_ctx_flush_l2(self.h))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.tm_ctx_kernel_launches(self.h))
+
+    def voxel_fill(self, pos, nrm, tgt, extents, to_voxel16) -> np.ndarray:
+        v, keep = _view(pos, nrm, tgt)
+        ext = (C.c_int32 * 3)(*[int(e) for e in extents])
+        tv = _f32(to_voxel16, (16,))
+        out = np.empty(int(extents[0]) * int(extents[1]) * int(extents[2]), dtype=np.uint32)
+        _chk(self.lib.tm_voxel_fill(self.h, C.byref(v), ext, _p(tv), _p(out)))
+        return out
+
+    def traits_project(self, kind: int, g2l16, radius: float, threshold: float, xyz):
+        xyz = _f32(xyz, (-1, 3))
+        g = _f32(g2l16, (16,))
+        uvw = np.empty_like(xyz)
+        ok = np.empty(xyz.shape[0], dtype=np.uint8)
+        _chk(self.lib.tm_traits_project(self.h, C.c_int(kind), _p(g), C.c_float(radius),
+                                        C.c_float(threshold), _p(xyz), C.c_uint64(xyz.shape[0]),
+                                        _p(uvw), _p(ok)))
+        return uvw, ok
+
+
+class Model:
+    """Resident model: cloud + what model::init produced (include/impl/model.hpp:16-167)."""
+
+    def __init__(self, ctx: Context, pos, nrm, tgt, *, voxel, extents, to_voxel16, resolution,
+                 diameter, keys, offsets, pairs, feat_min, feat_max, distance_step_count,
+                 angle_step, view: CloudView | None = None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        if view is None:
+            v, self._keep = _view(pos, nrm, tgt)
+        else:
+            v, self._keep = view, (pos,)
+        voxel = np.ascontiguousarray(voxel, dtype=np.uint32)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 4)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        d = ModelDesc()
+        d.voxel = voxel.ctypes.data
+        d.extents = (C.c_int32 * 3)(*[int(e) for e in extents])
+        d.to_voxel = (C.c_float * 16)(*[float(x) for x in np.asarray(to_voxel16, dtype=np.float32).ravel()])
+        d.resolution = float(resolution)
+        d.diameter = float(diameter)
+        d.keys = keys.ctypes.data if keys.size else None
+        d.offsets = offsets.ctypes.data if offsets.size else None
+        d.pairs = pairs.ctypes.data if pairs.size else None
+        d.n_keys = keys.shape[0]
+        d.feat_min = (C.c_float * 4)(*[float(x) for x in feat_min])
+        d.feat_max = (C.c_float * 4)(*[float(x) for x in feat_max])
+        d.distance_step_count = float(distance_step_count)
+        d.angle_step = float(angle_step)
+        self.n = int(v.n)
+        self.diameter = float(np.float32(diameter))
+        self.resolution = float(np.float32(resolution))
+        self.h = C.c_void_p()
+        _chk(self.lib.tm_model_upload(ctx.h, C.byref(v), C.byref(d), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.tm_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def probe(self, keys, valid=None, limit: int = 200):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 4)
+        n = keys.shape[0]
+        valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        _chk(self.lib.tm_probe(self.h, _p(keys), _p(valid), C.c_uint64(n), C.c_uint32(limit),
+                               _p(off), None, C.c_uint64(0)))
+        total = int(off[n])
+        hits = np.zeros((total, 2), dtype=np.uint32)
+        if total:
+            _chk(self.lib.tm_probe(self.h, _p(keys), _p(valid), C.c_uint64(n), C.c_uint32(limit),
+                                   _p(off), _p(hits), C.c_uint64(total)))
+        return off, hits
+
+
+class Scene:
+    def __init__(self, ctx: Context, pos, nrm, tgt, tangent_mask, view: CloudView | None = None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        if view is None:
+            v, self._keep = _view(pos, nrm, tgt)
+        else:
+            v, self._keep = view, (pos,)
+        tm = None if tangent_mask is None else np.ascontiguousarray(tangent_mask, dtype=np.uint8)
+        self.n = int(v.n)
+        self.h = C.c_void_p()
+        _chk(self.lib.tm_scene_upload(ctx.h, C.byref(v), _p(tm), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.tm_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_mask(self, mask):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        _chk(self.lib.tm_scene_set_mask(self.h, _p(m)))
+
+    def features(self, model: Model, pair_i, pair_j, min_df: float, max_df: float):
+        pi = np.ascontiguousarray(pair_i, dtype=np.uint32)
+        pj = np.ascontiguousarray(pair_j, dtype=np.uint32)
+        n = pi.shape[0]
+        feats = np.zeros((n, 4), dtype=np.float32)
+        keys = np.zeros((n, 4), dtype=np.uint32)
+        valid = np.zeros(n, dtype=np.uint8)
+        _chk(self.lib.tm_features(self.h, model.h, _p(pi), _p(pj), C.c_uint64(n), C.c_float(min_df),
+                                  C.c_float(max_df), _p(feats), _p(keys), _p(valid)))
+        return feats, keys, valid
+
+    def hypotheses(self, model: Model, pair_i, pair_j, offsets, hits, force_up: bool = False):
+        pi = np.ascontiguousarray(pair_i, dtype=np.uint32)
+        pj = np.ascontiguousarray(pair_j, dtype=np.uint32)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        hits = np.ascontiguousarray(hits, dtype=np.uint32).reshape(-1, 2)
+        n = pi.shape[0]
+        total = int(off[n]) if n else 0
+        T = np.zeros((total, 16), dtype=np.float32)
+        valid = np.zeros(total, dtype=np.uint8)
+        _chk(self.lib.tm_hypotheses(self.h, model.h, _p(pi), _p(pj), C.c_uint64(n), _p(off),
+                                    _p(hits), C.c_int(1 if force_up else 0), _p(T), _p(valid)))
+        return T, valid
+
+    def ball_subsets(self, centres, radius: float):
+        cs = np.ascontiguousarray(centres, dtype=np.uint32)
+        n = cs.shape[0]
+        off = np.zeros(n + 1, dtype=np.uint64)
+        _chk(self.lib.tm_ball_subsets(self.h, _p(cs), C.c_uint32(n), C.c_float(radius), _p(off),
+                                      None, C.c_uint64(0)))
+        total = int(off[n])
+        idx = np.zeros(max(total, 1), dtype=np.int32)
+        _chk(self.lib.tm_ball_subsets(self.h, _p(cs), C.c_uint32(n), C.c_float(radius), _p(off),
+                                      _p(idx), C.c_uint64(total)))
+        return off, idx[:total]
+
+    def score(self, model: Model, T16s, hyp_sub=None, sub_offsets=None, sub_indices=None,
+              dist_thres: float = 1.0, accept_prob: float = 0.5, early_out: bool = False,
+              want_scores: bool = True):
+        T = _f32(T16s, (-1, 16))
+        n = T.shape[0]
+        counts = np.zeros(n, dtype=np.uint32)
+        scores = np.zeros(n, dtype=np.float64) if want_scores else None
+        dropped = np.zeros(n, dtype=np.uint8)
+        hs = so = si = None
+        n_sub = 0
+        if hyp_sub is not None:
+            hs = np.ascontiguousarray(hyp_sub, dtype=np.uint32)
+            so = np.ascontiguousarray(sub_offsets, dtype=np.uint64)
+            si = np.ascontiguousarray(sub_indices, dtype=np.int32)
+            if si.size == 0:
+                si = np.zeros(1, dtype=np.int32)
+            n_sub = so.shape[0] - 1
+        _chk(self.lib.tm_score(self.h, model.h, _p(T), C.c_uint64(n), _p(hs), _p(so), _p(si),
+                               C.c_uint32(n_sub), C.c_float(dist_thres), C.c_float(accept_prob),
+                               C.c_int(1 if early_out else 0), _p(counts), _p(scores), _p(dropped)))
+        return counts, scores, dropped
+
+    def correspondences(self, model: Model, T16, dist_thres: float):
+        T = _f32(T16, (16,))
+        sc = np.zeros(max(self.n, 1), dtype=np.uint32)
+        mc = np.zeros(max(self.n, 1), dtype=np.uint32)
+        n = C.c_uint32()
+        score = C.c_double()
+        _chk(self.lib.tm_correspondences(self.h, model.h, _p(T), C.c_float(dist_thres), _p(sc),
+                                         _p(mc), C.byref(n), C.byref(score)))
+        return sc[:n.value].copy(), mc[:n.value].copy(), float(score.value)
+
+    def icp(self, model: Model, T16s, max_iterations: int, dist_thres: float):
+        T = _f32(T16s, (-1, 16))
+        n = T.shape[0]
+        out = np.zeros_like(T)
+        counts = np.zeros(n, dtype=np.uint32)
+        scores = np.zeros(n, dtype=np.float64)
+        iters = np.zeros(n, dtype=np.uint32)
+        _chk(self.lib.tm_icp(self.h, model.h, _p(T), C.c_uint32(n), C.c_uint32(max_iterations),
+                             C.c_float(dist_thres), _p(out), _p(counts), _p(scores), _p(iters)))
+        return out, counts, scores, iters
+
+
+class Query:
+    """Resident recorded-list search (tm_query_*)."""
+
+    def __init__(self, scene: Scene, model: Model, *, min_df=0.2, max_df=1.0, force_up=False,
+                 query_limit=200, dist_thres=1.0, accept_prob=0.5, early_out=False, icp_top_k=0,
+                 max_icp_iterations=0, max_hypotheses=0, hyp_limit=0):
+        self.lib = scene.lib
+        self.scene, self.model = scene, model
+        p = QueryParams(min_df, max_df, 1 if force_up else 0, query_limit, dist_thres, accept_prob,
+                        1 if early_out else 0, icp_top_k, max_icp_iterations, max_hypotheses,
+                        hyp_limit)
+        self.params = p
+        self.h = C.c_void_p()
+        _chk(self.lib.tm_query_create(scene.h, model.h, C.byref(p), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.tm_query_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_pairs(self, outer, pair_outer, pair_j):
+        o = np.ascontiguousarray(outer, dtype=np.uint32)
+        po = np.ascontiguousarray(pair_outer, dtype=np.uint32)
+        pj = np.ascontiguousarray(pair_j, dtype=np.uint32)
+        _chk(self.lib.tm_query_set_pairs(self.h, _p(o), C.c_uint32(o.shape[0]), _p(po), _p(pj),
+                                         C.c_uint64(po.shape[0])))
+
+    def set_shard(self, rank: int, world: int):
+        _chk(self.lib.tm_query_set_shard(self.h, C.c_uint32(rank), C.c_uint32(world)))
+
+    def run(self):
+        _chk(self.lib.tm_query_run(self.h))
+
+    def result(self) -> QueryResult:
+        r = QueryResult()
+        _chk(self.lib.tm_query_result_get(self.h, C.byref(r)))
+        return r
+
+    def best_key_device_ptr(self) -> int:
+        return int(self.lib.tm_query_best_key_device(self.h))
+
+    def set_global_best(self, key: int):
+        _chk(self.lib.tm_query_set_global_best(self.h, C.c_uint64(key)))
+
+    def download(self):
+        r = self.result()
+        n = int(r.n_scored)
+        counts = np.zeros(n, dtype=np.uint32)
+        scores = np.zeros(n, dtype=np.float64)
+        T = np.zeros((n, 16), dtype=np.float32)
+        valid = np.zeros(n, dtype=np.uint8)
+        hyp_pair = np.zeros(n, dtype=np.uint32)
+        dropped = np.zeros(n, dtype=np.uint8)
+        if n:
+            _chk(self.lib.tm_query_download(self.h, C.c_uint64(n), _p(counts), _p(scores), _p(T),
+                                            _p(valid), _p(hyp_pair), _p(dropped)))
+        return dict(counts=counts, scores=scores, T=T, valid=valid, hyp_pair=hyp_pair,
+                    dropped=dropped, result=r)
+
+    def icp_results(self):
+        k = int(self.params.icp_top_k)
+        ids = np.zeros(k, dtype=np.uint32)
+        T = np.zeros((k, 16), dtype=np.float32)
+        counts = np.zeros(k, dtype=np.uint32)
+        scores = np.zeros(k, dtype=np.float64)
+        iters = np.zeros(k, dtype=np.uint32)
+        _chk(self.lib.tm_query_icp_results(self.h, _p(ids), _p(T), _p(counts), _p(scores), _p(iters)))
+        return ids, T, counts, scores, iters
+
+
+class Comm:
+    def __init__(self, ctx: Context, unique_id: bytes, rank: int, world: int):
+        self.lib = ctx.lib
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self.h = C.c_void_p()
+        _chk(self.lib.tm_comm_create(ctx.h, buf, C.c_int(rank), C.c_int(world), C.byref(self.h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _chk(load().tm_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def allreduce_best(self, q: Query):
+        _chk(self.lib.tm_query_allreduce_best(q.h, self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.tm_comm_destroy(self.h)
+            self.h = C.c_void_p()
