@@ -30,6 +30,10 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_icp.cu", "k_query.cu", "capi.cu"]
+HOST_SOURCES = ["host_model.cpp"]
+CXX = os.environ.get("CXX", "g++")
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+             "-Wall", "-Wno-sign-compare"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -42,6 +46,7 @@ def _newer(target: str, deps: list[str]) -> bool:
 def _headers() -> list[str]:
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hs.append(os.path.join(REPO, "include", "tm_b200.h"))
+    hs.append(os.path.join(REPO, "include", "tm_b200_host.h"))
     return hs
 
 
@@ -66,16 +71,26 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         if force or not _newer(o, [s] + hdrs):
             jobs.append((s, o))
 
+    for src in HOST_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cpp", ".o"))
+        objs.append(o)
+        if force or not _newer(o, [s] + hdrs):
+            jobs.append((s, o))
+
     def compile_one(job):
         s, o = job
-        _run([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
+        if s.endswith(".cpp"):
+            _run([CXX] + CXX_FLAGS + ["-c", s, "-o", o], log=o + ".log")
+        else:
+            _run([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
         if verbose:
             print("compiled", os.path.basename(s))
 
     with ThreadPoolExecutor(max_workers=max(1, min(6, os.cpu_count() or 1))) as ex:
         list(ex.map(compile_one, jobs))
     if force or jobs or not _newer(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-ldl", "-gencode", "arch=compute_100a,code=sm_100a"])
+        _run([NVCC, "-shared", "-o", LIB] + objs + ["-ldl", "-lgomp", "-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
 
 

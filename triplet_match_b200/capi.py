@@ -65,6 +65,11 @@ EXPORTS = [
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
     "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best",
 ]
+HOST_EXPORTS = [
+    "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_destroy",
+    "tm_hostmodel_desc", "tm_hostmodel_counts", "tm_hostmodel_subset", "tm_hostmodel_entry_keys",
+    "tm_hostmodel_entry_pairs", "tm_model_create",
+]
 
 _lib = None
 
@@ -87,8 +92,15 @@ def load() -> C.CDLL:
     lib.tm_ctx_kernel_launches.argtypes = [C.c_void_p]
     lib.tm_query_best_key_device.restype = C.c_void_p
     lib.tm_query_best_key_device.argtypes = [C.c_void_p]
+    lib.tm_host_last_error.restype = C.c_char_p
+    lib.tm_host_resolution.restype = C.c_float
+    for name in ("tm_hostmodel_subset", "tm_hostmodel_entry_keys", "tm_hostmodel_entry_pairs"):
+        getattr(lib, name).restype = C.c_void_p
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.tm_hostmodel_desc.restype = None
+    lib.tm_hostmodel_counts.restype = None
     for name in ("tm_ctx_destroy", "tm_model_destroy", "tm_scene_destroy", "tm_query_destroy",
-                 "tm_comm_destroy"):
+                 "tm_comm_destroy", "tm_hostmodel_destroy"):
         getattr(lib, name).restype = None
         getattr(lib, name).argtypes = [C.c_void_p]
     _lib = lib
@@ -177,6 +189,83 @@ class Context:
                                         C.c_float(threshold), _p(xyz), C.c_uint64(xyz.shape[0]),
                                         _p(uvw), _p(ok)))
         return uvw, ok
+
+
+def host_resolution(pos) -> float:
+    pos = _f32(pos, (-1, 3))
+    v = CloudView(pos.ctypes.data, pos.ctypes.data, pos.ctypes.data, 3, pos.shape[0])
+    return float(load().tm_host_resolution(C.byref(v)))
+
+
+class HostModel:
+    """model::init on the host (+ GPU grid fill when ctx is given): tm_hostmodel_build."""
+
+    def __init__(self, ctx, pos, nrm, tgt, curv_ok=None, distance_step_count=20.0,
+                 angle_step=0.17453292, min_df=0.2, max_df=1.0, resolution=-1.0, cap=200):
+        self.lib = load()
+        v, self._keep = _view(pos, nrm, tgt)
+        self._view = v
+        co = None if curv_ok is None else np.ascontiguousarray(curv_ok, dtype=np.uint8)
+        self.h = C.c_void_p()
+        rc = self.lib.tm_hostmodel_build(ctx.h if ctx is not None else None, C.byref(v), _p(co),
+                                         C.c_float(distance_step_count), C.c_float(angle_step),
+                                         C.c_float(min_df), C.c_float(max_df), C.c_float(resolution),
+                                         C.c_uint32(cap), C.byref(self.h))
+        if rc != TM_OK:
+            raise TmError(rc, self.lib.tm_host_last_error().decode("utf-8", "replace"))
+        d = ModelDesc()
+        self.lib.tm_hostmodel_desc(self.h, C.byref(d))
+        self.desc = d
+        c = (C.c_uint64 * 4)()
+        self.lib.tm_hostmodel_counts(self.h, C.byref(c, 0), C.byref(c, 8), C.byref(c, 16), C.byref(c, 24))
+        self.n_subset, self.n_entries, self.n_keys, self.n_kept = [int(x) for x in c]
+        self.extents = np.array(list(d.extents), dtype=np.int32)
+        self.to_voxel16 = np.array(list(d.to_voxel), dtype=np.float32)
+        self.resolution, self.diameter = float(d.resolution), float(d.diameter)
+        self.feat_min = np.array(list(d.feat_min), dtype=np.float32)
+        self.feat_max = np.array(list(d.feat_max), dtype=np.float32)
+
+    def _arr(self, ptr, n, dtype=np.uint32):
+        if not n:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n,)).copy()
+
+    @property
+    def voxel(self):
+        return self._arr(self.desc.voxel, int(np.prod(self.extents.astype(np.int64))))
+
+    @property
+    def keys(self):
+        return self._arr(self.desc.keys, 4 * self.n_keys).reshape(-1, 4)
+
+    @property
+    def offsets(self):
+        return self._arr(self.desc.offsets, self.n_keys + 1)
+
+    @property
+    def pairs(self):
+        return self._arr(self.desc.pairs, 2 * self.n_kept).reshape(-1, 2)
+
+    @property
+    def subset(self):
+        return self._arr(self.lib.tm_hostmodel_subset(self.h), self.n_subset)
+
+    def upload(self, ctx) -> "Model":
+        m = Model.__new__(Model)
+        m.ctx, m.lib, m._keep = ctx, ctx.lib, self._keep
+        m.n = int(self._view.n)
+        m.diameter, m.resolution = self.diameter, self.resolution
+        m.h = C.c_void_p()
+        rc = self.lib.tm_model_create(ctx.h, C.byref(self._view), self.h, C.byref(m.h))
+        if rc != TM_OK:
+            msg = self.lib.tm_last_error() or self.lib.tm_host_last_error()
+            raise TmError(rc, msg.decode("utf-8", "replace"))
+        return m
+
+    def close(self):
+        if self.h:
+            self.lib.tm_hostmodel_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Model:
