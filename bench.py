@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — hypotheses scored / s of the triplet_match search path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload "C2" (BASELINE.json configs[1]): plane_traits-style model (1 m x 1 m plane patch,
+10 201 points, 12 line-segment feature curves) in a 1 M-point synthetic scene, 2^20 pose
+hypotheses per GPU generated from a recorded, seed-fixed sample list.  One step = one pass
+of the hot path over that batch: radius subsets -> pair features + keys -> hash probe ->
+base_transform_ -> inlier scoring of every hypothesis against its subset (finish_find
+semantics, i.e. no early drop) -> best-pose argmax (+ one NCCL max all-reduce when N > 1).
+Hypotheses are sharded across ranks (weak scaling: 2^20 per GPU), scene + model replicated.
+
+Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pose hypotheses scored/sec"
+UNIT = "hypotheses/s"
+BYTES_PER_TEST = 36  # 16 B scene float4 + 4 B voxel cell + 16 B model float4
+HYP_PER_GPU = 1 << 20
+
+DP = dict(distance_step_count=20.0, angle_step=0.17453292)
+QP = dict(min_df=0.2, max_df=1.0, query_limit=200, dist_thres=1.0, accept_prob=0.5)
+
+
+def build_workload(n_gpus: int, scale: float = 1.0):
+    """Seed-fixed C2 clouds + recorded pair list sized for n_gpus * 2^20 hypotheses."""
+    from triplet_match_b200 import synth
+    n_scene = int(1_000_000 * scale)
+    model = synth.plane_model(seed=2, size=1.0, res=0.01, n_curves=12)
+    scene = synth.make_scene(seed=2, model=model, n_points=n_scene, n_copies=8, extent=10.0 * np.sqrt(scale))
+    scene = scene.take(synth.morton_order(scene.pos))
+    return model, scene
+
+
+def record_list(scene, diameter: float, n_gpus: int):
+    from triplet_match_b200 import synth
+    # ~ 9 k hypotheses per outer sample on this workload; oversample, the query clips
+    # the global list to exactly n_gpus * 2^20 hypotheses (hyp_limit)
+    return synth.record_pairs(2, scene, diameter, n_outer=256 * n_gpus, pairs_per_outer=128)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the scoring kernel from the committed ncu summary, or None."""
+    p = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_reference_run(model, scene, rec, n_hyp_sample: int, steps: int, warmup: int, threads: int):
+    """The reference's CPU path (oracle port) on a bounded sample: pair features -> query ->
+    base_transform_ -> project_ (early_out = false) with `threads` std::threads.
+    Returns (hyps/s, tests/s, ms/step, sample description)."""
+    from oracle import pyoracle as po
+    om = po.OModel(model, **DP, min_df=QP["min_df"], max_df=QP["max_df"])
+    osc = po.OScene(scene)
+    # bounded sample: the first pairs of the recorded list until n_hyp_sample hypotheses
+    npairs = min(rec.pair_j.size, 64)
+    while True:
+        T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i[:npairs], rec.pair_j[:npairs],
+                                           limit=QP["query_limit"])
+        if T.shape[0] >= n_hyp_sample or npairs >= rec.pair_j.size:
+            break
+        npairs = min(rec.pair_j.size, npairs * 2)
+    T, hp = T[:n_hyp_sample], hp[:n_hyp_sample]
+    outers = np.unique(rec.pair_outer[hp])
+    remap = {int(o): k for k, o in enumerate(outers)}
+    subs = [osc.ball_subset(int(rec.outer[o]), om.diameter) for o in outers]
+    off = np.zeros(len(subs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([s.size for s in subs])
+    idx = np.concatenate(subs) if subs else np.zeros(0, np.int32)
+    hyp_sub = np.array([remap[int(o)] for o in rec.pair_outer[hp]], dtype=np.uint32)
+    tests = int(sum(int(off[g + 1] - off[g]) for g in hyp_sub))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        # the whole path for the sample, as the reference runs it per hypothesis
+        osc.pair_features(om, rec.pair_i[:npairs], rec.pair_j[:npairs])
+        osc.hypotheses(om, rec.pair_i[:npairs], rec.pair_j[:npairs], limit=QP["query_limit"])
+        osc.score_batch(om, T, hyp_sub, off, idx, accept_prob=QP["accept_prob"],
+                        dist_thres=QP["dist_thres"], early_out=False, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    sample = (f"first {T.shape[0]} hypotheses of the recorded C2 list ({npairs} pairs, "
+              f"{len(subs)} outer samples, {tests:.3e} hypothesis-point tests per step), "
+              f"project_ early_out=false, {threads} std::threads")
+    return T.shape[0] / sec, tests / sec, sec * 1e3, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("TM_BENCH_SCALE", 1.0)),
+                    help="scene size scale (dev only; 1.0 = the named configuration)")
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TM_CPU_SAMPLE", 16384)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    n_gpus = max(args.gpus, world)
+    threads = os.cpu_count() or 1
+
+    import __graft_entry__ as ge
+    config = {"workload": "C2: plane model 10201 pts / 1M-point synthetic scene / 2^20 hypotheses "
+                          "per GPU from a recorded seed-fixed sample list (BASELINE.json configs[1])",
+              "scene_points": int(1_000_000 * args.scale), "hypotheses_per_gpu": HYP_PER_GPU,
+              "scoring": "finish_find semantics (project_ early_out=false)",
+              "parallelism": f"hypotheses sharded x{n_gpus}, scene+model replicated",
+              "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ge.build()
+        model, scene = build_workload(n_gpus, args.scale)
+        # recorded list needs the model diameter only (no GPU): bbox diagonal in float32
+        lo, hi = model.pos.min(axis=0), model.pos.max(axis=0)
+        d = (hi - lo).astype(np.float32)
+        diam = float(np.sqrt(np.float32(d[0] * d[0]) + (np.float32(d[1] * d[1]) + np.float32(d[2] * d[2]))))
+        rec = record_list(scene, diam, n_gpus)
+        hps, tps, ms, sample = cpu_reference_run(model, scene, rec, args.cpu_sample, args.steps,
+                                                 args.warmup, threads)
+        line = {"impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "tests_per_sec": tps,
+                "cpu_baseline": {"value": hps, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": hps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "reference cannot be built here (PCL/Eigen/range-v3 absent): oracle port of "
+                        "its CPU path on the host cores"}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ ours
+    ge.build()
+    import torch
+    from triplet_match_b200 import capi
+
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(local_rank)
+    model, scene = build_workload(n_gpus, args.scale)
+    hm = capi.HostModel(ctx, model.pos, model.nrm, model.tgt, curv_ok=model.tangent_mask, **DP,
+                        min_df=QP["min_df"], max_df=QP["max_df"], cap=QP["query_limit"])
+    gm = hm.upload(ctx)
+    gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
+    rec = record_list(scene, hm.diameter, n_gpus)
+    total_limit = HYP_PER_GPU * n_gpus
+    q = capi.Query(gs, gm, **QP, hyp_limit=total_limit, max_hypotheses=HYP_PER_GPU)
+    q.set_shard(rank, world)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    comm = None
+    if dist_on:
+        ids = [capi.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = capi.Comm(ctx, ids[0], rank, world)
+
+    def step():
+        q.run()
+        if comm is not None:
+            comm.allreduce_best(q)
+
+    def barrier():
+        ctx.sync()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    r0 = q.result()
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.kernel_launches()
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    step_ms, kern_ms = [], []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        step()
+        step_ms.append(ctx.timer_stop())
+        kern_ms.append(q.score_kernel_ms())
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0 - args.steps  # minus the untimed L2-flush launches
+    r = q.result()
+    total_ms = float(np.sum(step_ms))
+    n_scored = int(r.n_scored)
+    n_tests = int(r.n_tests)
+    if dist_on:
+        t = torch.tensor([total_ms, float(n_scored), float(n_tests)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms = float(tmax[0].item())
+        all_scored = int(tsum[1].item())
+        all_tests = int(tsum[2].item())
+    else:
+        all_scored, all_tests = n_scored, n_tests
+    sec = total_ms * 1e-3
+    value = all_scored * args.steps / sec
+    tests_per_sec = all_tests * args.steps / sec
+
+    # ---- e2e: host buffers in, host results out, through the C-ABI ----------
+    e2e_ms = []
+    for it in range(2 + args.steps):
+        if dist_on:
+            dist.barrier()
+        t0 = time.perf_counter()
+        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # H2D: recorded list (+ sizing pass)
+        q.run()
+        if comm is not None:
+            comm.allreduce_best(q)
+        d = q.download_counts()                              # D2H: result + per-hypothesis counts
+        dt = (time.perf_counter() - t0) * 1e3
+        if it >= 2:
+            e2e_ms.append(dt)
+    e2e_sec = float(np.mean(e2e_ms)) * 1e-3
+    if dist_on:
+        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    h2d = 4 * (rec.outer.size + 2 * rec.pair_j.size)
+    d2h = 4 * n_scored + 152
+    e2e = {"value": all_scored / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3,
+           "call": "tm_query_set_pairs + tm_query_run + tm_query_result_get + tm_query_download "
+                   "(scene + model resident, as in the reference where they are built before find)"}
+
+    # ---- roofline of the dominant kernel (score_full_kernel) ----------------
+    peak, peak_src = measured_peak_gbs()
+    k_ms = float(np.mean(kern_ms))
+    achieved = n_tests * BYTES_PER_TEST / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "kernel": "score_full_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / float(np.sum(step_ms)),
+                "algorithmic_bytes_per_launch": n_tests * BYTES_PER_TEST,
+                "note": "36 B/test is the no-reuse algorithmic figure (SURVEY §8d); the kernel keeps scene "
+                        "points in registers and the grid in L2, so frac > 1 is expected and DRAM traffic "
+                        "is far below it"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config, "tests_per_sec": tests_per_sec,
+            "hypotheses_per_step": all_scored, "tests_per_step": all_tests,
+            "best_inliers": int(r.best_inliers), "best_hypothesis": int(r.best_hypothesis),
+            "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        hps, tps, ms, sample = cpu_reference_run(model, scene, rec, args.cpu_sample, 3, 1, threads)
+        line["cpu_baseline"] = {"value": hps, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": sample, "tests_per_sec": tps, "ms_per_step": ms}
+        # p50 full-query latency incl. ICP of the top 64 (SURVEY §8d metric ii)
+        q2 = capi.Query(gs, gm, **QP, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
+                        icp_top_k=64, max_icp_iterations=5)
+        q2.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        lat = []
+        for it in range(3 + 20):
+            t0 = time.perf_counter()
+            q2.run()
+            q2.result()
+            if it >= 3:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        line["p50_query_ms"] = float(np.median(lat))
+        line["p50_query_def"] = ("resident scene+model; subsets->features->probe->hypotheses(2^20)->"
+                                 "score->argmax->ICP(top 64, 5 iterations); 20 repeats after 3 warm-ups")
+        q2.close()
+    if comm is not None:
+        comm.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,9 @@ int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world);
  * context stream; inputs and outputs stay resident */
 int tm_query_run(tm_query* q);
 int tm_query_result_get(tm_query* q, tm_query_result* out); /* synchronises, small D2H */
+/* device time of the scoring kernel of the last tm_query_run (CUDA events on the context
+ * stream around that one launch) — the roofline numerator's denominator */
+int tm_query_score_kernel_ms(tm_query* q, float* ms);
 void* tm_query_best_key_device(tm_query* q); /* resident u64 for the NCCL max-reduce */
 int tm_query_set_global_best(tm_query* q, uint64_t key); /* after the all-reduce */
 /* full per-hypothesis arrays of this shard (parity tests); any pointer may be NULL */

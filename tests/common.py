@@ -15,6 +15,9 @@ SP = dict(min_df=0.2, max_df=1.0)
 @functools.lru_cache(maxsize=None)
 def config(name: str):
     """(model cloud, scene cloud, oracle model, oracle scene, recorded pairs)."""
+    shuffled = name.endswith("_shuffled")
+    if shuffled:  # scene in seeded random order: the order the early-drop test assumes
+        name = name[: -len("_shuffled")]
     if name == "plane_small":
         m = synth.plane_model(seed=2, size=0.3, res=0.01, n_curves=4)
         s = synth.make_scene(seed=5, model=m, n_points=20000, n_copies=3, extent=1.2)
@@ -31,7 +34,7 @@ def config(name: str):
         n_outer, ppo = 10, 24
     else:
         raise KeyError(name)
-    order = synth.morton_order(s.pos)
+    order = synth.shuffle_perm(13, 3, s.n) if shuffled else synth.morton_order(s.pos)
     s = s.take(order)
     om = po.OModel(m, **DP, **SP)
     osc = po.OScene(s)

@@ -1,0 +1,358 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle
+on the same seeded inputs, against the committed golden fixtures, and — at the full C2 size —
+through size-independent properties.  Bit-exact for keys, hits, transforms, subsets and
+inlier counts; scores to 1e-9 (fixed-point 2^-36 accumulation vs double sum); ICP poses to
+1e-4 (north_star tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIGS = ["plane_small", "cylinder_small", "freeform_small"]
+SHUFFLED = ["plane_small_shuffled", "cylinder_small_shuffled"]
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    from triplet_match_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def _subsets(osc, om, rec):
+    subs = [osc.ball_subset(int(o), om.diameter) for o in rec.outer]
+    off = np.zeros(len(subs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([x.size for x in subs])
+    return off, np.concatenate(subs).astype(np.int32)
+
+
+@pytest.fixture(scope="module", params=CONFIGS + SHUFFLED)
+def setup(request, ctx):
+    m, s, om, osc, rec = common.config(request.param)
+    gm = common.upload_model(ctx, m, om)
+    gs = common.upload_scene(ctx, s)
+    yield request.param, m, s, om, osc, rec, gm, gs
+    gm.close()
+    gs.close()
+
+
+def test_features_keys_valid(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    f, k, v = gs.features(gm, rec.pair_i, rec.pair_j, 0.2, 1.0)
+    fo, ko, vo = osc.pair_features(om, rec.pair_i, rec.pair_j)
+    assert np.array_equal(v, vo) and v.sum() > 10
+    assert np.array_equal(k, ko)
+    ok = v.astype(bool)
+    assert np.array_equal(_bits(f[ok]), _bits(fo[ok]))
+
+
+def test_probe_hits_order_and_limit(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    f, k, v = gs.features(gm, rec.pair_i, rec.pair_j, 0.2, 1.0)
+    for limit in (200, 3):
+        off, hits = gm.probe(k, v, limit)
+        T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i, rec.pair_j, limit=limit)
+        assert hits.shape[0] == T.shape[0]
+        assert np.array_equal(hits, np.stack([mi, mj], 1))
+        assert np.array_equal(np.repeat(np.arange(v.size), np.diff(off.astype(np.int64))), hp)
+
+
+def test_hypotheses_bit_exact(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    f, k, v = gs.features(gm, rec.pair_i, rec.pair_j, 0.2, 1.0)
+    off, hits = gm.probe(k, v, 200)
+    for force_up in (False, True):
+        Tg, vg = gs.hypotheses(gm, rec.pair_i, rec.pair_j, off, hits, force_up=force_up)
+        T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i, rec.pair_j, force_up=force_up)
+        assert np.array_equal(vg, va)
+        ok = va.astype(bool)
+        assert np.array_equal(_bits(Tg[ok]), _bits(T[ok]))
+        if force_up:
+            assert np.isnan(Tg[~ok]).all()  # rejected hypotheses can never score
+
+
+def test_ball_subsets(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    off, idx = gs.ball_subsets(rec.outer, om.diameter)
+    eo, ei = _subsets(osc, om, rec)
+    assert np.array_equal(off, eo) and np.array_equal(idx, ei)
+    o2, i2 = gs.ball_subsets(rec.outer[:1], 0.0)  # empty ball (strict '<')
+    assert o2[-1] == 0 and i2.size == 0
+
+
+def test_scoring_full_and_early_drop(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    off, idx = _subsets(osc, om, rec)
+    hyp_sub = rec.pair_outer[hp]
+    for eo in (False, True):
+        cg, sg, dg = gs.score(gm, T, hyp_sub, off, idx, early_out=eo)
+        co, so, do = osc.score_batch(om, T, hyp_sub, off, idx, early_out=eo, nthreads=4)
+        assert np.array_equal(cg, co), (name, eo)
+        assert np.array_equal(dg, do)
+        assert np.allclose(sg, so, rtol=1e-9, atol=1e-9)
+    if name.endswith("_shuffled"):
+        assert 0 < do.sum() < do.size  # both outcomes of the early-drop rule are exercised
+
+
+def test_scoring_with_mask_and_all_scene(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    T = T[:: max(1, T.shape[0] // 96)]
+    rng = np.random.default_rng(1)
+    mask = (rng.random(s.n) < 0.3).astype(np.uint8)
+    c0, _, _ = gs.score(gm, T)
+    gs.set_mask(mask)
+    osc.set_mask(mask)
+    try:
+        cg, sg, _ = gs.score(gm, T)
+        co, so, _ = osc.score_batch(om, T, nthreads=4)
+        assert np.array_equal(cg, co) and np.allclose(sg, so, rtol=1e-9, atol=1e-9)
+        assert np.all(cg <= c0)  # masking can only remove inliers
+    finally:
+        gs.set_mask(None)
+        osc.set_mask(np.zeros(s.n, dtype=np.uint8))
+    c1, _, _ = gs.score(gm, T)
+    assert np.array_equal(c0, c1)  # idempotent / mask cleared
+
+
+def test_correspondences_and_icp(setup):
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    co, _, _ = osc.score_batch(om, T, nthreads=4)
+    top = np.argsort(-co.astype(np.int64), kind="stable")[:6]
+    for h in top[:2]:
+        sc, mc, score = gs.correspondences(gm, T[h], 1.0)
+        pr = osc.project(om, np.arange(s.n, dtype=np.int32), T[h])
+        assert np.array_equal(sc, pr["scene_corrs"]) and np.array_equal(mc, pr["model_corrs"])
+        assert abs(score - pr["score"]) < 1e-9
+    for iters in (0, 1, 5):
+        To, cnt, scr, it = gs.icp(gm, T[top], iters, 1.0)
+        for r, h in enumerate(top):
+            oT, on, osx, oit = osc.icp(om, T[h], iters, 1.0)
+            # pose tolerance from north_star (1e-4); counts are exact whenever the float
+            # transforms agree bit-for-bit, else within the few points on the threshold
+            assert np.allclose(To[r], oT, atol=1e-4), (name, iters, r)
+            assert int(it[r]) == oit
+            if np.array_equal(_bits(To[r]), _bits(oT)):
+                assert int(cnt[r]) == on
+            else:
+                assert abs(int(cnt[r]) - on) <= max(3, on // 100)
+
+
+def test_resident_query_and_golden(setup, ctx):
+    from triplet_match_b200 import capi
+    name, m, s, om, osc, rec, gm, gs = setup
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    assert np.array_equal(rec.outer, g["outer"]) and np.array_equal(rec.pair_j, g["pair_j"])
+    q = capi.Query(gs, gm, icp_top_k=4, max_icp_iterations=2)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    n0 = ctx.kernel_launches()
+    q.run()
+    assert ctx.kernel_launches() - n0 >= 12
+    d = q.download()
+    r = d["result"]
+    assert r.n_hypotheses == g["T"].shape[0] == r.n_scored
+    assert r.n_pairs_valid == int(g["valid"].sum())
+    assert np.array_equal(_bits(d["T"]), _bits(g["T"]))
+    assert np.array_equal(d["hyp_pair"], g["hyp_pair"])
+    assert np.array_equal(d["counts"], g["counts"])
+    assert np.allclose(d["scores"], g["scores"], rtol=1e-9, atol=1e-9)
+    sizes = np.diff(g["sub_off"].astype(np.int64))
+    assert r.n_tests == int(sizes[rec.pair_outer[g["hyp_pair"]]].sum())
+    assert r.best_inliers == int(g["counts"].max())
+    assert r.best_hypothesis == int(np.argmax(g["counts"]))
+    assert np.array_equal(_bits(np.array(list(r.best_T), dtype=np.float32)), _bits(g["T"][r.best_hypothesis]))
+    ids, Ti, ci, si, it = q.icp_results()
+    order = np.argsort(-g["counts"].astype(np.int64), kind="stable")[:4]
+    assert np.array_equal(ids, order.astype(np.uint32))
+    # early-drop mode of the resident query == golden early-drop outcome
+    q.close()
+    q = capi.Query(gs, gm, early_out=True)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    d = q.download()
+    assert np.array_equal(d["counts"], g["counts_eo"]) and np.array_equal(d["dropped"], g["dropped_eo"])
+    q.close()
+
+
+def test_sharded_query(setup):
+    from triplet_match_b200 import capi
+    name, m, s, om, osc, rec, gm, gs = setup
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for world in (2, 3):
+        parts, keys = [], []
+        for rank in range(world):
+            q = capi.Query(gs, gm)
+            q.set_shard(rank, world)
+            q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+            q.run()
+            d = q.download()
+            hb, he = capi.shard_range(g["T"].shape[0], rank, world)
+            assert d["counts"].shape[0] == he - hb
+            parts.append(d["counts"])
+            keys.append(int(d["result"].best_key))
+            q.close()
+        assert np.array_equal(np.concatenate(parts), g["counts"])
+        inl, gid = capi.unpack_key(max(keys))  # what the NCCL max all-reduce computes
+        assert inl == int(g["counts"].max()) and gid == int(np.argmax(g["counts"]))
+
+
+def test_hyp_limit_and_capacity(setup):
+    from triplet_match_b200 import capi
+    name, m, s, om, osc, rec, gm, gs = setup
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    lim = max(1, g["T"].shape[0] // 3)
+    q = capi.Query(gs, gm, hyp_limit=lim, max_hypotheses=lim)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    d = q.download()
+    assert np.array_equal(d["counts"], g["counts"][:lim])
+    q.close()
+    q = capi.Query(gs, gm, max_hypotheses=max(1, lim // 2))
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    with pytest.raises(capi.TmError) as e:
+        q.result()
+    assert e.value.code == capi.TM_ERR_CAPACITY
+    q.close()
+
+
+def test_model_built_by_product_equals_oracle_model(ctx):
+    """HostModel (host C++ + GPU voxel fill) == oracle model, then the full query on it."""
+    from triplet_match_b200 import capi
+    for name in CONFIGS:
+        m, s, om, osc, rec = common.config(name)
+        hm = capi.HostModel(ctx, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **common.DP, **common.SP)
+        assert np.array_equal(hm.voxel, om.voxel)
+        k, o, p = om.table(200)
+        assert np.array_equal(hm.keys, k) and np.array_equal(hm.pairs, p)
+        gm = hm.upload(ctx)
+        gs = common.upload_scene(ctx, s)
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        q = capi.Query(gs, gm)
+        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        q.run()
+        assert np.array_equal(q.download()["counts"], g["counts"])
+        q.close(); gm.close(); gs.close(); hm.close()
+
+
+def test_surfel_aos_upload_equals_packed(ctx):
+    from triplet_match_b200 import capi
+    m, s, om, osc, rec = common.config("cylinder_small")
+    rec_s = np.zeros((s.n, 12), dtype=np.float32)  # pcl::PointSurfel: xyz1 | nxyz0 | rgba, tangent
+    rec_s[:, 0:3], rec_s[:, 3] = s.pos, 1.0
+    rec_s[:, 4:7] = s.nrm
+    rec_s[:, 9:12] = s.tgt
+    gs_a = capi.Scene(ctx, rec_s, None, None, s.tangent_mask, view=capi.surfel_view(rec_s))
+    gs_p = common.upload_scene(ctx, s)
+    gm = common.upload_model(ctx, m, om)
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    ca, sa, _ = gs_a.score(gm, T[:200])
+    cp, sp, _ = gs_p.score(gm, T[:200])
+    assert np.array_equal(ca, cp) and np.array_equal(sa, sp)
+    gs_a.close(); gs_p.close(); gm.close()
+
+
+def test_traits_project(ctx):
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4)
+    xyz = (rng.standard_normal((4000, 3)) * 0.3).astype(np.float32)
+    ax = rng.standard_normal(3); ax /= np.linalg.norm(ax)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(0.7) * K + (1 - np.cos(0.7)) * K @ K
+    g2l = np.eye(4); g2l[:3, :3] = R; g2l[:3, 3] = [0.1, -0.2, 0.05]
+    g16 = g2l.T.astype(np.float32).ravel()  # column-major
+    for kind, radius, thr in ((0, 0.3, 0.15), (1, 0.0, 0.2), (2, 0.0, 0.0), (3, 0.0, 0.0)):
+        uvw, ok = ctx.traits_project(kind, g16, radius, thr, xyz)
+        uo, oo = po.traits_project(kind, g16, radius, thr, xyz)
+        assert np.array_equal(ok, oo)
+        sel = ok.astype(bool)
+        assert 0 < sel.sum()
+        assert np.array_equal(_bits(uvw[sel]), _bits(uo[sel])), kind
+
+
+def test_empty_inputs(ctx):
+    from triplet_match_b200 import capi
+    m, s, om, osc, rec = common.config("plane_small")
+    gm = common.upload_model(ctx, m, om)
+    gs = common.upload_scene(ctx, s)
+    e = np.zeros(0, dtype=np.uint32)
+    f, k, v = gs.features(gm, e, e, 0.2, 1.0)
+    assert v.size == 0
+    off, hits = gm.probe(np.zeros((0, 4), np.uint32), None, 200)
+    assert off.tolist() == [0] and hits.shape[0] == 0
+    c, sc, d = gs.score(gm, np.zeros((0, 16), np.float32))
+    assert c.size == 0
+    q = capi.Query(gs, gm)
+    q.set_pairs(e, e, e)
+    q.run()
+    r = q.result()
+    assert r.n_hypotheses == 0 and r.best_key == 0
+    q.close()
+    # a pair list whose pairs all fail the filter -> zero hypotheses, no crash
+    q = capi.Query(gs, gm)
+    nt = np.nonzero(s.tangent_mask == 0)[0][:4].astype(np.uint32)
+    q.set_pairs(nt[:1], np.zeros(3, np.uint32), nt[1:4])
+    q.run()
+    assert q.result().n_hypotheses == 0
+    q.close(); gm.close(); gs.close()
+
+
+def test_full_size_properties(ctx):
+    """C2-sized run (1M-point scene): properties that do not need the CPU oracle at full
+    size, plus an oracle spot check on a sample of hypotheses."""
+    import bench
+    from oracle import pyoracle as po
+    from triplet_match_b200 import capi, synth
+    model, scene = bench.build_workload(1, 1.0)
+    hm = capi.HostModel(ctx, model.pos, model.nrm, model.tgt, curv_ok=model.tangent_mask, **common.DP, **common.SP)
+    gm = hm.upload(ctx)
+    gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
+    rec = synth.record_pairs(2, scene, hm.diameter, n_outer=24, pairs_per_outer=64)
+    q = capi.Query(gs, gm)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    d = q.download()
+    n = d["counts"].shape[0]
+    assert n > 20000
+    # (1) two independent kernels agree: register-tiled full scorer vs warp-per-hypothesis scorer
+    off, idx = gs.ball_subsets(rec.outer, hm.diameter)
+    sel = np.linspace(0, n - 1, 3000).astype(np.int64)
+    hyp_sub = rec.pair_outer[d["hyp_pair"][sel]]
+    c2, s2, dr = gs.score(gm, d["T"][sel], hyp_sub, off, idx, early_out=True, accept_prob=0.0)
+    assert not dr.any()  # accept_prob 0 => the drop rule can never fire
+    assert np.array_equal(c2, d["counts"][sel]) and np.allclose(s2, d["scores"][sel], rtol=1e-9, atol=1e-12)
+    # (2) idempotence and (3) sharding invariance
+    q.run()
+    assert np.array_equal(q.download_counts()[0], d["counts"])
+    parts = []
+    for rank in range(2):
+        q2 = capi.Query(gs, gm)
+        q2.set_shard(rank, 2)
+        q2.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        q2.run()
+        parts.append(q2.download_counts()[0])
+        q2.close()
+    assert np.array_equal(np.concatenate(parts), d["counts"])
+    # (4) every hypothesis sees its own pair: p1 -> m_i exactly => at least one inlier
+    assert (d["counts"][d["valid"].astype(bool)] >= 1).all()
+    # (5) oracle spot check at full size
+    om = po.OModel(model, **common.DP, **common.SP, resolution=hm.resolution)
+    assert np.array_equal(om.voxel, hm.voxel)
+    osc = po.OScene(scene)
+    pick = np.concatenate([np.argsort(-d["counts"].astype(np.int64))[:8], sel[::100]])
+    co, so, _ = osc.score_batch(om, d["T"][pick], rec.pair_outer[d["hyp_pair"][pick]], off, idx, nthreads=os.cpu_count())
+    assert np.array_equal(co, d["counts"][pick])
+    q.close(); gm.close(); gs.close(); hm.close()

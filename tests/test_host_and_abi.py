@@ -1,0 +1,99 @@
+"""CPU tests of the product's host side: C-ABI surface, model::init restatement (host C++)
+against the oracle, loud failure without a GPU, synthetic generators."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_library_exports_every_declared_symbol(built):
+    from triplet_match_b200 import capi
+    lib = capi.load()
+    declared = set()
+    for hdr in ("tm_b200.h", "tm_b200_host.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(tm_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 45
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(capi.EXPORTS + capi.HOST_EXPORTS) <= declared
+    assert b"sm_100a" in lib.tm_version()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="box has a GPU")
+def test_no_cpu_fallback(built):
+    from triplet_match_b200 import capi
+    with pytest.raises(capi.TmError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.TM_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("name", ["plane_small", "cylinder_small", "freeform_small"])
+def test_host_model_init_matches_oracle(built, name):
+    from triplet_match_b200 import capi
+    m, s, om, osc, rec = common.config(name)
+    hm = capi.HostModel(None, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **common.DP, **common.SP)
+    k, o, p = om.table(200)
+    assert np.float32(hm.resolution) == np.float32(om.resolution)
+    assert np.float32(hm.diameter) == np.float32(om.diameter)
+    assert np.array_equal(hm.extents, om.extents)
+    assert np.array_equal(hm.to_voxel16.view(np.uint32), om.to_voxel16.view(np.uint32))
+    assert np.array_equal(hm.voxel, om.voxel)
+    assert np.array_equal(hm.subset, om.subset)
+    assert np.array_equal(hm.feat_min.view(np.uint32), om.feat_min.view(np.uint32))
+    assert np.array_equal(hm.feat_max.view(np.uint32), om.feat_max.view(np.uint32))
+    assert hm.n_entries == om.n_entries and hm.n_keys == om.n_keys
+    assert np.array_equal(hm.keys, k) and np.array_equal(hm.offsets, o) and np.array_equal(hm.pairs, p)
+    hm.close()
+
+
+def test_host_resolution_matches_bruteforce(built):
+    from oracle import pyoracle as po
+    from triplet_match_b200 import capi, synth
+    for seed in (1, 2, 3):
+        c = synth.freeform_model(seed=seed, n_points=700, radius=0.2)
+        exp = po.load().orc_resolution(po._p(po._f32(c.pos)), po.C.c_uint32(c.n))
+        assert np.float32(capi.host_resolution(c.pos)) == np.float32(exp)
+
+
+def test_uninitialized_model_error(built):
+    from triplet_match_b200 import capi
+    lib = capi.load()
+    out = capi.C.c_void_p()
+    v = capi.CloudView(None, None, None, 3, 0)
+    rc = lib.tm_model_create(None, capi.C.byref(v), None, capi.C.byref(out))
+    assert rc == capi.TM_ERR_UNINITIALIZED
+    assert b"uninitialized model" in lib.tm_host_last_error()  # include/impl/model.hpp:171-173
+
+
+def test_synth_is_seed_fixed():
+    from triplet_match_b200 import synth
+    a = synth.plane_model(seed=2, size=0.2)
+    b = synth.plane_model(seed=2, size=0.2)
+    c = synth.plane_model(seed=3, size=0.2)
+    assert np.array_equal(a.pos, b.pos) and not np.array_equal(a.pos, c.pos)
+    assert a.pos.dtype == np.float32 and a.tangent_mask.dtype == np.uint8
+    on = a.tangent_mask.astype(bool)
+    assert np.allclose(np.linalg.norm(a.tgt[on], axis=1), 1, atol=1e-6) and not a.tgt[~on].any()
+    s = synth.make_scene(seed=4, model=a, n_points=5000, n_copies=2, extent=0.8)
+    assert s.n == 5000 and len(s.poses) == 2
+    p = synth.morton_order(s.pos)
+    assert sorted(p.tolist()) == list(range(s.n))
+    rec = synth.record_pairs(1, s, 0.3, 4, 10)
+    assert np.all(np.diff(rec.pair_outer.astype(np.int64)) >= 0)
+    assert np.all(s.tangent_mask[rec.pair_j] == 1) and np.all(rec.pair_j != rec.pair_i)

@@ -62,6 +62,7 @@ EXPORTS = [
     "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
     "tm_traits_project", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
+    "tm_query_score_kernel_ms",
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
     "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best",
 ]
@@ -464,6 +465,11 @@ class Query:
         _chk(self.lib.tm_query_result_get(self.h, C.byref(r)))
         return r
 
+    def score_kernel_ms(self) -> float:
+        ms = C.c_float()
+        _chk(self.lib.tm_query_score_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def best_key_device_ptr(self) -> int:
         return int(self.lib.tm_query_best_key_device(self.h))
 
@@ -484,6 +490,16 @@ class Query:
                                             _p(valid), _p(hyp_pair), _p(dropped)))
         return dict(counts=counts, scores=scores, T=T, valid=valid, hyp_pair=hyp_pair,
                     dropped=dropped, result=r)
+
+    def download_counts(self):
+        """result + per-hypothesis inlier counts only (the e2e read-back)."""
+        r = self.result()
+        n = int(r.n_scored)
+        counts = np.zeros(n, dtype=np.uint32)
+        if n:
+            _chk(self.lib.tm_query_download(self.h, C.c_uint64(n), _p(counts), None, None, None,
+                                            None, None))
+        return counts, r
 
     def icp_results(self):
         k = int(self.params.icp_top_k)
@@ -516,3 +532,21 @@ class Comm:
         if self.h:
             self.lib.tm_comm_destroy(self.h)
             self.h = C.c_void_p()
+
+
+# ---- host mirrors of the device-side sharding / key packing (k_query.cu, k_score.cu) ----
+def shard_range(n_hyp: int, rank: int, world: int, hyp_limit: int = 0):
+    """[begin, end) of the global hypothesis list scored by `rank` (shard_range_kernel)."""
+    H = min(n_hyp, hyp_limit) if hyp_limit else n_hyp
+    per = (H + world - 1) // world
+    hb = min(rank * per, H)
+    return hb, min(hb + per, H)
+
+
+def pack_key(inliers: int, global_id: int) -> int:
+    """(inliers << 32) | (0xFFFFFFFF - id): max-reduce picks most inliers, lowest id on ties."""
+    return (int(inliers) << 32) | (0xFFFFFFFF - int(global_id))
+
+
+def unpack_key(key: int):
+    return int(key) >> 32, 0xFFFFFFFF - (int(key) & 0xFFFFFFFF)

@@ -946,6 +946,7 @@ struct tm_query {
     IcpBufs icp;
     QueryOut host_out;
     bool ran = false;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the scoring kernel
 };
 
 static int count_valid_pairs_dev(tm_query* q);
@@ -959,12 +960,17 @@ int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query
     q->m = m;
     q->p = *p;
     memset(&q->host_out, 0, sizeof(QueryOut));
+    TRY(bind(s->ctx));
+    CU(cudaEventCreate(&q->ev_s0));
+    CU(cudaEventCreate(&q->ev_s1));
     *out = q;
     return TM_OK;
 }
 void tm_query_destroy(tm_query* q) {
     if (!q) return;
     cudaSetDevice(q->s->ctx->device);
+    if (q->ev_s0) cudaEventDestroy(q->ev_s0);
+    if (q->ev_s1) cudaEventDestroy(q->ev_s1);
     for (DevBuf* b :
          {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
@@ -1135,7 +1141,9 @@ int tm_query_run(tm_query* q) {
             if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
             int grid = c->sm_count * b;
             if (const char* e = getenv("TM_SCORE_GRID")) grid = std::max(1, atoi(e));
+            CU(cudaEventRecord(q->ev_s0, c->stream));
             launch_score_full(c->stream, a, grid, m->fused, true);
+            CU(cudaEventRecord(q->ev_s1, c->stream));
         } else {
             launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
                                 q->g_of_hyp.as<uint32_t>());
@@ -1156,7 +1164,9 @@ int tm_query_run(tm_query* q) {
             a.scores = q->scores.as<unsigned long long>();
             a.dropped = q->dropped.as<uint8_t>();
             a.tested = nullptr;
+            CU(cudaEventRecord(q->ev_s0, c->stream));
             launch_score_early_drop(c->stream, a, m->fused);
+            CU(cudaEventRecord(q->ev_s1, c->stream));
         }
     }
     launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(), &out->n_local,
@@ -1200,6 +1210,15 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
         r->best_score = o.best_score;
         memcpy(r->best_T, o.best_T16, 64);
     }
+    return TM_OK;
+}
+int tm_query_score_kernel_ms(tm_query* q, float* ms) {
+    REQUIRE(q && ms && q->ran, "tm_query_score_kernel_ms: null/unrun query");
+    TRY(bind(q->s->ctx));
+    *ms = 0.f;
+    if (!q->n_outer) return TM_OK;
+    CU(cudaEventSynchronize(q->ev_s1));
+    CU(cudaEventElapsedTime(ms, q->ev_s0, q->ev_s1));
     return TM_OK;
 }
 void* tm_query_best_key_device(tm_query* q) {
