@@ -16,8 +16,10 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(ROOT)
 CSRC = os.path.join(ROOT, "csrc")
-OBJ = os.path.join(ROOT, "_obj")
-LIB = os.path.join(ROOT, "libtriplet_match_b200.so")
+# dev knob: TM_LIB_SUFFIX=_x TM_NVCC_EXTRA="-DTM_SCORE_MIN_BLOCKS=4" builds a tuning variant
+_SUFFIX = os.environ.get("TM_LIB_SUFFIX", "")
+OBJ = os.path.join(ROOT, "_obj" + _SUFFIX)
+LIB = os.path.join(ROOT, "libtriplet_match_b200" + _SUFFIX + ".so")
 HOSTLIB = os.path.join(ROOT, "libtriplet_match_host.so")
 ORACLE_DIR = os.path.join(REPO, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
@@ -28,7 +30,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
-]
+] + os.environ.get("TM_NVCC_EXTRA", "").split()
 SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_icp.cu", "k_query.cu", "capi.cu"]
 HOST_SOURCES = ["host_model.cpp"]
 CXX = os.environ.get("CXX", "g++")

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtriplet_match_b200.so")
+LIB_PATH = os.path.join(_HERE, "libtriplet_match_b200" + os.environ.get("TM_LIB_SUFFIX", "") + ".so")
 
 TM_OK = 0
 TM_ERR_INVALID, TM_ERR_CUDA, TM_ERR_CAPACITY, TM_ERR_UNINITIALIZED, TM_ERR_NCCL = 1, 2, 3, 4, 5

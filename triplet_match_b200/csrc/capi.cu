@@ -82,7 +82,7 @@ struct tm_ctx {
 
 struct tm_model {
     tm_ctx* ctx;
-    DevBuf pos, nrm, tgt, voxel, vcell, slots, hits;
+    DevBuf pos, nrm, tgt, voxel, vcell, vref, slots, hits;
     ModelDev dev;
     float centre[3];
     float half_diag;
@@ -310,12 +310,14 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
         CU(cudaMemcpyAsync(m->hits.p, d->pairs, sizeof(uint2) * (size_t)n_hits,
                            cudaMemcpyHostToDevice, c->stream));
     // fused grid (cell -> model point) when it stays L2-sized
-    m->fused = cells * sizeof(float4) <= (96ull << 20);
+    m->fused = 2 * cells * sizeof(float4) <= (96ull << 20);
     if (const char* e = getenv("TM_FUSED_GRID")) m->fused = atoi(e) != 0;
     if (m->fused) {
         if ((rc = m->vcell.ensure(cells * sizeof(float4)))) return bail(rc);
+        if ((rc = m->vref.ensure(cells * sizeof(float4)))) return bail(rc);
         launch_fuse_grid(c->stream, m->voxel.as<uint32_t>(), cells, m->pos.as<float4>(),
-                         m->vcell.as<float4>());
+                         m->nrm.as<float4>(), m->tgt.as<float4>(), m->vcell.as<float4>(),
+                         m->vref.as<float4>());
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -323,7 +325,7 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
     dv.cloud = CloudDev{m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n};
     dv.voxel = m->voxel.as<uint32_t>();
     dv.vcell = m->fused ? m->vcell.as<float4>() : nullptr;
-    dv.vcell_idx = nullptr;
+    dv.vref = m->fused ? m->vref.as<float4>() : nullptr;
     dv.ex = d->extents[0];
     dv.ey = d->extents[1];
     dv.ez = d->extents[2];
@@ -365,7 +367,7 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
 void tm_model_destroy(tm_model* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    for (DevBuf* b : {&m->pos, &m->nrm, &m->tgt, &m->voxel, &m->vcell, &m->slots, &m->hits})
+    for (DevBuf* b : {&m->pos, &m->nrm, &m->tgt, &m->voxel, &m->vcell, &m->vref, &m->slots, &m->hits})
         b->release();
     delete m;
 }
@@ -628,6 +630,7 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
     a.counts = d_counts;
     a.scores = d_scores;
     a.sq_thres = sq_thres;
+    a.stats = nullptr;
     static int bps[2][2] = {{0, 0}, {0, 0}};
     int& b = bps[m->fused ? 1 : 0][with_score ? 1 : 0];
     if (!b) b = score_full_max_blocks_per_sm(m->fused, with_score);
@@ -942,7 +945,7 @@ struct tm_query {
     DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
     DevBuf n_items_g, item_off, items, ctrl;
     DevBuf out;  // QueryOut
-    DevBuf topk_ids, icp_T16;
+    DevBuf topk_ids, icp_T16, stats;
     IcpBufs icp;
     QueryOut host_out;
     bool ran = false;
@@ -976,7 +979,7 @@ void tm_query_destroy(tm_query* q) {
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->icp_T16})
+          &q->topk_ids, &q->icp_T16, &q->stats})
         b->release();
     q->icp.release();
     delete q;
@@ -1136,6 +1139,12 @@ int tm_query_run(tm_query* q) {
             a.counts = q->counts.as<uint32_t>();
             a.scores = q->scores.as<unsigned long long>();
             a.sq_thres = sqt;
+            a.stats = nullptr;
+            if (getenv("TM_SCORE_STATS")) {
+                TRY(q->stats.ensure(64));
+                CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
+                a.stats = q->stats.as<unsigned long long>();
+            }
             static int bps[2] = {0, 0};
             int& b = bps[m->fused ? 1 : 0];
             if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
@@ -1197,6 +1206,12 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
     CU(cudaStreamSynchronize(c->stream));
     memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
     const QueryOut& o = q->host_out;
+    if (q->stats.p && getenv("TM_SCORE_STATS")) {
+        unsigned long long st[4] = {0, 0, 0, 0};
+        CU(cudaMemcpy(st, q->stats.p, 32, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)\n",
+                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0);
+    }
     if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
     memset(r, 0, sizeof(*r));
     r->n_pairs_valid = o.n_valid;

@@ -15,6 +15,8 @@
 //   build_work_kernel(s)     device-side work list for the persistent scorer.
 //   argmax_kernel            packed (inliers << 32 | ~id) max — the local half
 //                            of the best-pose all-reduce.
+#include <cstdlib>
+
 #include "tm_kernels.cuh"
 
 namespace tmk {
@@ -72,121 +74,233 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // --------------------------------------------------------------- full scoring
-template <int P, bool FUSED, bool WITH_SCORE>
-__global__ void __launch_bounds__(SCORE_THREADS)
+// v4 (round 1).  Every WARP is an independent worker: it pulls (tile, hypothesis
+// chunk) work items from a global counter — no CTA barrier anywhere — where a
+// tile is SCORE_P*32 CONTIGUOUS subset points (P per lane, kept in registers).
+// The hypotheses of an item are walked 32 at a time in two phases:
+//   cull   lane l loads the rows of hypothesis h0+l (and parks them in a per-warp
+//          shared-memory slab) and bounds it: the tile's bounding box is pushed
+//          through the transform with interval arithmetic (|R| * half-extent, plus a
+//          1e-5 relative guard that dominates every float rounding of the exact path);
+//          if the resulting voxel-coordinate box misses (-1, extent) on any axis no
+//          point of the tile can pass voxel_query and the pair is skipped.  NaN
+//          bounds never cull.  A ballot gives the surviving hypotheses.
+//   test   for each survivor the rows come back from shared memory (broadcast) and
+//          the exact reference arithmetic runs on the P points of every lane: all P
+//          voxel coordinates first, then the P cell gathers back to back (P loads
+//          in flight per lane), then distance / class tests.  Inliers are counted
+//          with REDUX and flushed with one coalesced RED per 32 hypotheses.
+// The per-inlier score term needs the scene point's ref vector (tangent or normal),
+// staged once per item in a per-warp shared-memory slab, and the model point's ref
+// vector, which sits in the second half of the same 32-byte grid cell.
+template <int P, bool FUSED, bool WITH_SCORE, bool CULL>
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     score_full_kernel(ScoreArgs a) {
-    __shared__ float4 sT[SCORE_HSTAGE * 3];
-    __shared__ uint32_t s_item;
+    __shared__ float4 s_ref[WITH_SCORE ? SCORE_THREADS * P : 1];
+    __shared__ float4 s_rows[CULL ? (SCORE_THREADS / 32) * 32 * 3 : 1];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float4* my_ref = s_ref + (WITH_SCORE ? warp * 32 * P : 0);
+    float4* my_rows = s_rows + (CULL ? warp * 32 * 3 : 0);
     const uint32_t n_items = *a.n_items;
+    const ModelDev& m = a.model;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const WorkItem w = a.items[item];
         float px[P], py[P], pz[P];
-        uint32_t pfl[P], pidx[P];
+        uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
+        const float nanv = __int_as_float(0x7fc00000);
+        float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+        if (WITH_SCORE) __syncwarp();  // previous item's readers of my_ref are done
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            uint32_t q = k * SCORE_THREADS + threadIdx.x;
-            const float nanv = __int_as_float(0x7fc00000);
+            const uint32_t q = k * 32 + lane;
             px[k] = py[k] = pz[k] = nanv;  // a NaN point fails every test
-            pfl[k] = 0u;
-            pidx[k] = 0u;
             if (q < w.npts) {
                 uint32_t idx = a.sub_idx ? (uint32_t)a.sub_idx[w.sub_begin + q]
                                          : (uint32_t)(w.sub_begin + q);
                 float4 v = a.scene.pos[idx];
                 uint32_t fl = __float_as_uint(v.w);
-                pidx[k] = idx;
-                pfl[k] = fl;
                 if (!(fl & FLAG_MASKED)) {  // mask_ (scene.hpp:434)
-                    px[k] = v.x;
-                    py[k] = v.y;
-                    pz[k] = v.z;
+                    px[k] = v.x; py[k] = v.y; pz[k] = v.z;
+                    if (fl & FLAG_TANGENT) tflags |= 1u << k;
+                    mnx = fminf(mnx, v.x); mxx = fmaxf(mxx, v.x);
+                    mny = fminf(mny, v.y); mxy = fmaxf(mxy, v.y);
+                    mnz = fminf(mnz, v.z); mxz = fmaxf(mxz, v.z);
+                    if (WITH_SCORE)  // ref = use_tangent ? tangent : normal (scene.hpp:441-442)
+                        my_ref[q] = (fl & FLAG_TANGENT) ? a.scene.tgt[idx] : a.scene.nrm[idx];
                 }
             }
         }
-        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += SCORE_HSTAGE) {
-            const uint32_t nh = min((uint32_t)SCORE_HSTAGE, w.hyp_end - h0);
-            __syncthreads();
-            for (uint32_t t = threadIdx.x; t < nh * 3; t += SCORE_THREADS)
-                sT[t] = a.T[(size_t)h0 * 3 + t];
-            __syncthreads();
+        if (WITH_SCORE) __syncwarp();
+        float cx = 0.f, cy = 0.f, cz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
+        if (CULL) {
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+                mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+                mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+                mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+                mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+                mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+            }
+            if (!(mnx <= mxx)) continue;  // no live (finite, unmasked) point in this tile
+            cx = 0.5f * (mnx + mxx); hx = 0.5f * (mxx - mnx);
+            cy = 0.5f * (mny + mxy); hy = 0.5f * (mxy - mny);
+            cz = 0.5f * (mnz + mxz); hz = 0.5f * (mxz - mnz);
+        }
+        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {
+            const uint32_t h = h0 + lane;
+            uint32_t mask;
+            if (CULL) {
+                bool survive = false;
+                __syncwarp();  // readers of the previous batch's rows are done
+                if (h < w.hyp_end) {
+                    const float4 r0 = __ldg(&a.T[3 * (size_t)h]), r1 = __ldg(&a.T[3 * (size_t)h + 1]),
+                                 r2 = __ldg(&a.T[3 * (size_t)h + 2]);
+                    my_rows[lane] = r0;  // row-major slabs: conflict-free stores, broadcast loads
+                    my_rows[32 + lane] = r1;
+                    my_rows[64 + lane] = r2;
+                    const float acx = fabsf(cx) + hx, acy = fabsf(cy) + hy, acz = fabsf(cz) + hz;
+                    bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                  \
+    {                                                                                           \
+        float cc = r.x * cx + r.y * cy + r.z * cz + r.w;                                        \
+        float ee = fabsf(r.x) * hx + fabsf(r.y) * hy + fabsf(r.z) * hz;                         \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
+        ee += 1e-5f * mag + 1e-30f;                                                             \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
+        float lo = S * (cc - ee) + TV - sl, hi = S * (cc + ee) + TV + sl;                       \
+        out = out || (lo >= EXF) || (hi <= -1.0f);                                              \
+    }
+                    TM_AXIS(r0, m.sx, m.tx, m.exf)
+                    TM_AXIS(r1, m.sy, m.ty, m.eyf)
+                    TM_AXIS(r2, m.sz, m.tz, m.ezf)
+#undef TM_AXIS
+                    survive = !out;
+                }
+                mask = __ballot_sync(0xffffffffu, survive);  // also orders the smem stores
+            } else {
+                const uint32_t left = w.hyp_end - h0;
+                mask = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+            }
+            if (a.stats && lane == 0) {
+                atomicAdd(&a.stats[0], (unsigned long long)min(32u, w.hyp_end - h0));
+                atomicAdd(&a.stats[1], (unsigned long long)__popc(mask));
+            }
             uint32_t mycnt = 0;
             unsigned long long mysc = 0;
-            for (uint32_t hh = 0; hh < nh; ++hh) {
-                const float4 r0 = sT[3 * hh], r1 = sT[3 * hh + 1], r2 = sT[3 * hh + 2];
+            while (mask) {
+                const int hh = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                float4 r0, r1, r2;
+                if (CULL) {
+                    r0 = my_rows[hh]; r1 = my_rows[32 + hh]; r2 = my_rows[64 + hh];
+                } else {
+                    const size_t hb = 3 * (size_t)(h0 + hh);
+                    r0 = __ldg(&a.T[hb]); r1 = __ldg(&a.T[hb + 1]); r2 = __ldg(&a.T[hb + 2]);
+                }
+                // ---- exact path, stage 1: pos = t*pos, ijk = trunc(to_voxel*pos) (scene.hpp:444,
+                // model.hpp:182) for all P points; trunc-toward-zero bounds in the float domain
+                float x[P], y[P], z[P];
+                uint32_t lin[P];
+                uint32_t inb = 0;
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    x[k] = row_apply(r0, px[k], py[k], pz[k]);
+                    y[k] = row_apply(r1, px[k], py[k], pz[k]);
+                    z[k] = row_apply(r2, px[k], py[k], pz[k]);
+                    const float vx = m.sx * x[k] + m.tx, vy = m.sy * y[k] + m.ty, vz = m.sz * z[k] + m.tz;
+                    const bool in = (vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) &
+                                    (vz > -1.f) & (vz < m.ezf);
+                    const int i = (int)vx, j = (int)vy, kk = (int)vz;
+                    lin[k] = in ? (uint32_t)((kk * m.ey + j) * m.ex + i) : 0u;
+                    inb |= in ? (1u << k) : 0u;
+                }
+                if (!__any_sync(0xffffffffu, inb != 0u)) continue;  // nothing reaches the grid
+                // ---- stage 2: P cell gathers in flight (out-of-grid lanes read cell 0, unused)
+                float4 mp[P];
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
+                    else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+                }
+                // ---- stage 3: dist > thres (scene.hpp:464-467), class agreement (:469-478)
                 uint32_t c = 0;
                 unsigned long long sc = 0;
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
-                    float x, y, z;
-                    uint32_t lin;
-                    if (point_test<FUSED>(a.model, r0, r1, r2, px[k], py[k], pz[k], pfl[k],
-                                          a.sq_thres, x, y, z, lin)) {
+                    const float dx = x[k] - mp[k].x, dy = y[k] - mp[k].y, dz = z[k] - mp[k].z;
+                    const float sq = sum3(dx * dx, dy * dy, dz * dz);
+                    const uint32_t pfl = (tflags >> k) & 1u;
+                    const bool inl = ((inb >> k) & 1u) && !(sq > a.sq_thres) &&
+                                     (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
+                    if (inl) {
                         ++c;
-                        if (WITH_SCORE)
-                            sc += inlier_score(a.scene, a.model, r0, r1, r2, pidx[k], pfl[k], lin);
+                        if (WITH_SCORE) {
+                            const f3 ref = mk3(my_ref[k * 32 + lane]);
+                            f3 rn;
+                            if (FUSED) {
+                                rn = mk3(__ldg(&m.vref[lin[k]]));
+                            } else {
+                                const uint32_t mi = m.voxel[lin[k]];
+                                rn = mk3(pfl ? m.cloud.tgt[mi] : m.cloud.nrm[mi]);
+                            }
+                            const f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
+                            sc += score_fixed(fabsf(dot3(rr, rn)));  // scene.hpp:461,483
+                        }
                     }
                 }
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
                 if (tot) {  // warp-uniform
-                    unsigned long long s = WITH_SCORE ? warp_sum_u64(sc) : 0ull;
-                    if (lane == (int)(hh & 31u)) {
+                    if (a.stats && lane == 0) atomicAdd(&a.stats[2], 1ull);
+                    unsigned long long sv = WITH_SCORE ? warp_sum_u64(sc) : 0ull;
+                    if (lane == hh) {
                         mycnt = tot;
-                        mysc = s;
+                        mysc = sv;
                     }
                 }
-                if ((hh & 31u) == 31u || hh == nh - 1) {
-                    if (mycnt) {
-                        uint32_t h = h0 + (hh & ~31u) + lane;
-                        atomicAdd(&a.counts[h], mycnt);
-                        if (WITH_SCORE) atomicAdd(&a.scores[h], mysc);
-                    }
-                    mycnt = 0;
-                    mysc = 0;
-                }
+            }
+            if (mycnt) {
+                atomicAdd(&a.counts[h], mycnt);
+                if (WITH_SCORE) atomicAdd(&a.scores[h], mysc);
             }
         }
     }
 }
 
-template <int P>
-static void launch_score_full_p(cudaStream_t st, const ScoreArgs& a, int grid, bool fused,
-                                bool with_score) {
-    if (fused) {
-        if (with_score) score_full_kernel<P, true, true><<<grid, SCORE_THREADS, 0, st>>>(a);
-        else score_full_kernel<P, true, false><<<grid, SCORE_THREADS, 0, st>>>(a);
-    } else {
-        if (with_score) score_full_kernel<P, false, true><<<grid, SCORE_THREADS, 0, st>>>(a);
-        else score_full_kernel<P, false, false><<<grid, SCORE_THREADS, 0, st>>>(a);
+template <bool FUSED, bool WITH_SCORE, bool CULL>
+static void launch_score_full_v(cudaStream_t st, const ScoreArgs& a, int grid) {
+    score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL><<<grid, SCORE_THREADS, 0, st>>>(a);
+}
+template <bool FUSED, bool WITH_SCORE, bool CULL>
+static int occ_score_full_v() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &nb, score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL>, SCORE_THREADS, 0);
+    return nb > 0 ? nb : 1;
+}
+#define TM_DISPATCH3(FN, f, s, c, ...)                                                       \
+    ((f) ? ((s) ? ((c) ? FN<true, true, true>(__VA_ARGS__) : FN<true, true, false>(__VA_ARGS__))     \
+                : ((c) ? FN<true, false, true>(__VA_ARGS__) : FN<true, false, false>(__VA_ARGS__)))  \
+         : ((s) ? ((c) ? FN<false, true, true>(__VA_ARGS__) : FN<false, true, false>(__VA_ARGS__))   \
+                : ((c) ? FN<false, false, true>(__VA_ARGS__) : FN<false, false, false>(__VA_ARGS__))))
+static bool score_cull_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TM_SCORE_CULL");
+        v = e ? (atoi(e) != 0) : 1;
     }
+    return v != 0;
 }
 void launch_score_full(cudaStream_t st, const ScoreArgs& a, int grid, bool fused, bool with_score) {
-    ++g_launch_count;
-    launch_score_full_p<SCORE_P>(st, a, grid, fused, with_score);
+    TM_DISPATCH3(launch_score_full_v, fused, with_score, score_cull_enabled(), st, a, grid);
 }
 int score_full_max_blocks_per_sm(bool fused, bool with_score) {
-    int nb = 0;
-    if (fused) {
-        if (with_score)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &nb, score_full_kernel<SCORE_P, true, true>, SCORE_THREADS, 0);
-        else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &nb, score_full_kernel<SCORE_P, true, false>, SCORE_THREADS, 0);
-    } else {
-        if (with_score)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &nb, score_full_kernel<SCORE_P, false, true>, SCORE_THREADS, 0);
-        else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &nb, score_full_kernel<SCORE_P, false, false>, SCORE_THREADS, 0);
-    }
-    return nb > 0 ? nb : 1;
+    return TM_DISPATCH3(occ_score_full_v, fused, with_score, score_cull_enabled());
 }
 
 // ------------------------------------------------------------------ work list

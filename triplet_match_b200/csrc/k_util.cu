@@ -239,17 +239,27 @@ void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, 
                                                                       sz, tx, ty, tz, voxel);
 }
 
-// fused grid: cell -> (model pos.xyz, flags) so scoring needs one gather, not two
+// fused grids: cell -> (model pos.xyz, flags) and cell -> ref vector of that model point,
+// so scoring needs one gather per test (and one more per inlier) instead of dependent chains
 __global__ void fuse_grid_kernel(const uint32_t* __restrict__ voxel, size_t total,
-                                 const float4* __restrict__ mpos, float4* __restrict__ vcell) {
+                                 const float4* __restrict__ mpos, const float4* __restrict__ mnrm,
+                                 const float4* __restrict__ mtgt, float4* __restrict__ vcell,
+                                 float4* __restrict__ vref) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) vcell[i] = mpos[voxel[i]];
+    if (i >= total) return;
+    uint32_t mi = voxel[i];
+    float4 p = mpos[mi];
+    // two 16-byte grids: 16-B position cells keep 8 cells per 128-B line (fewer L1 tag
+    // look-ups per gather than one 32-B cell; measured)
+    vcell[i] = p;
+    vref[i] = (__float_as_uint(p.w) & FLAG_TANGENT) ? mtgt[mi] : mnrm[mi];
 }
 void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
-                      float4* vcell) {
+                      const float4* mnrm, const float4* mtgt, float4* vcell, float4* vref) {
     if (!total) return;
     ++g_launch_count;
-    fuse_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(voxel, total, mpos, vcell);
+    fuse_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(voxel, total, mpos, mnrm, mtgt,
+                                                                      vcell, vref);
 }
 
 // ------------------------------------------------------------ traits project

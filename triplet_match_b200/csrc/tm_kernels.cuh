@@ -10,7 +10,11 @@ extern unsigned long long g_launch_count;
 // ---- tuning constants ------------------------------------------------------
 constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_P = 4;                              // scene points per thread
-constexpr int SCORE_TILE = SCORE_THREADS * SCORE_P;     // points per work item
+#ifndef TM_SCORE_MIN_BLOCKS
+#define TM_SCORE_MIN_BLOCKS 4
+#endif
+constexpr int SCORE_MIN_BLOCKS = TM_SCORE_MIN_BLOCKS;   // __launch_bounds__ occupancy target
+constexpr int SCORE_TILE = 32 * SCORE_P;                // points per (warp) work item
 constexpr int SCORE_HSTAGE = 128;                       // hypotheses staged in smem at a time
 constexpr int SCORE_HCHUNK = 2048;                      // hypotheses per work item
 constexpr uint32_t BALL_SEG = 1024;                     // scene points per warp segment
@@ -36,6 +40,8 @@ struct ScoreArgs {
     uint32_t* counts;
     unsigned long long* scores;
     float sq_thres;
+    unsigned long long* stats;  // optional debug counters: [0] (warp,hyp) pairs, [1] survivors,
+                                // [2] warp-tiles with an inlier
 };
 
 struct EarlyArgs {
@@ -84,7 +90,7 @@ void launch_ball_row_offsets(cudaStream_t st, const unsigned long long* seg_offs
 void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
                        float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel);
 void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
-                      float4* vcell);
+                      const float4* mnrm, const float4* mtgt, float4* vcell, float4* vref);
 void launch_traits_project(cudaStream_t st, int kind, float4 r0, float4 r1, float4 r2, float radius,
                            float threshold, const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
 void launch_flush(cudaStream_t st, float4* buf, size_t n, float v);
