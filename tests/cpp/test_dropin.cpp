@@ -1,0 +1,162 @@
+// tests/cpp/test_dropin.cpp — exercises the drop-in C++ API (include/triplet_match/*).
+//   test_dropin cpu                      host-only checks (no GPU): feature / discretize / traits / octree
+//   test_dropin find <model.bin> <scene.bin> <out.txt>
+//        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
+//        the Python harness (n, then n x {pos3, nrm3, tgt3} floats); prints matches.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include <triplet_match/cylinder_traits>
+#include <triplet_match/identity_traits>
+#include <triplet_match/octree>
+#include <triplet_match/plane2_traits>
+#include <triplet_match/plane_traits>
+#include <triplet_match/scene>
+
+namespace tr = triplet_match;
+typedef pcl::PointSurfel point_t;
+typedef tr::pointcloud<point_t> cloud_t;
+
+#define CHECK(c)                                                            \
+    do {                                                                    \
+        if (!(c)) {                                                         \
+            std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            std::exit(1);                                                   \
+        }                                                                   \
+    } while (0)
+
+static cloud_t::Ptr load(const char* path) {
+    std::ifstream f(path, std::ios::binary);
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), 4);
+    cloud_t::Ptr c = cloud_t::empty();
+    for (uint32_t i = 0; i < n; ++i) {
+        float v[9];
+        f.read(reinterpret_cast<char*>(v), sizeof(v));
+        point_t p;
+        p.x = v[0]; p.y = v[1]; p.z = v[2];
+        p.normal_x = v[3]; p.normal_y = v[4]; p.normal_z = v[5];
+        tr::set_tangent(p, tr::vec3f_t(v[6], v[7], v[8]));
+        c->push_back(p);
+    }
+    return c;
+}
+
+static int cpu_checks() {
+    // discretize / murmur known answers (src/discretize.cpp:19-30; MurmurHash3_x86_32 seed 42)
+    CHECK(tr::discretize(-1.f, 0.f, 2.f, 20u) == 0u);
+    CHECK(tr::discretize(5.f, 0.f, 2.f, 20u) == 19u);
+    CHECK(tr::discretize(1.f, 0.f, 2.f, 20u) == 10u);
+    CHECK(tr::discretize(1.5707964f, 0.17453292f) == 9u);
+    tr::discrete_feature_t k(1u, 2u, 3u, 4u);
+    CHECK(std::hash<tr::discrete_feature_t>()(k) == 0x3F7F5D44u);
+    // feature of two points with tangents
+    point_t a, b;
+    a.x = 0; a.y = 0; a.z = 0; b.x = 1; b.y = 0; b.z = 0;
+    tr::set_tangent(a, tr::vec3f_t(1, 0, 0));
+    tr::set_tangent(b, tr::vec3f_t(0, 1, 0));
+    auto f = tr::feature<point_t>(a, b);
+    CHECK(f && (*f)[0] == 1.f && (*f)[1] == 0.f && std::fabs((*f)[2] - 1.5707964f) < 1e-6f && (*f)[3] == (*f)[0]);
+    tr::feature_bounds_t fb;
+    fb.extend(tr::feature_t(0.5f, 0.f, 0.f, 0.5f));
+    fb.extend(tr::feature_t(2.f, 1.f, 1.f, 2.f));
+    CHECK(tr::valid<point_t>(*f, fb));
+    tr::discretization_params dp{20.f, 0.17453292f, 10.f};
+    auto df = tr::discretize_feature<point_t>(*f, fb, dp);
+    CHECK(df[0] == 6u && df[1] == 0u && df[2] == 9u && df[3] == 6u);
+    // traits round trips
+    {
+        auto h = tr::cylinder_traits<point_t>::from_axis(tr::vec3f_t(0.1f, 0.2f, 0.3f), tr::vec3f_t(0.f, 0.f, 1.f), 0.5f, 0.1f);
+        tr::vec3f_t p(0.1f + 0.5f * std::cos(1.f), 0.2f + 0.5f * std::sin(1.f), 0.8f);
+        auto uvw = tr::cylinder_traits<point_t>::project(h, p);
+        CHECK(uvw);
+        tr::vec3f_t q = tr::cylinder_traits<point_t>::unproject(h, *uvw);
+        CHECK((q - p).norm() < 1e-5f);
+        CHECK(!tr::cylinder_traits<point_t>::project(h, tr::vec3f_t(2.f, 2.f, 0.f)));
+        CHECK(std::fabs(tr::cylinder_traits<point_t>::intrinsic_distance(h, tr::vec3f_t(0.05f, 0, 0), tr::vec3f_t(3.1f, 0, 0)) - (float)(2 * M_PI * 0.5 - 3.05)) < 1e-4f);
+    }
+    {
+        cloud_t::Ptr c = cloud_t::empty();
+        for (int i = 0; i < 20; ++i)
+            for (int j = 0; j < 10; ++j) {
+                point_t p;
+                p.x = 0.1f * i; p.y = 0.1f * j; p.z = 0.001f * ((i * 7 + j * 3) % 5);
+                p.normal_z = 1.f;
+                c->push_back(p);
+            }
+        auto h = tr::plane_traits<point_t>::init_from_model(c);
+        CHECK(h->threshold > 0.f && h->threshold < 0.02f);
+        auto uvw = tr::plane_traits<point_t>::project(h, c->points[37].getVector3f());
+        CHECK(uvw && std::fabs((*uvw)[2]) < 0.01f);
+        CHECK((tr::plane_traits<point_t>::unproject(h, *uvw) - c->points[37].getVector3f()).norm() < 1e-5f);
+        CHECK(!tr::plane_traits<point_t>::project(h, tr::vec3f_t(0.5f, 0.5f, 1.f)));
+        auto h2 = tr::plane2_traits<point_t>::init_from_samples(
+            tr::plane2_traits<point_t>::init_from_model(c),
+            std::make_tuple(c->points[0], c->points[50], c->points[199]));
+        CHECK(h2 != nullptr);
+        point_t bad = c->points[50];
+        bad.normal_x = 1.f; bad.normal_z = 0.f;
+        CHECK(tr::plane2_traits<point_t>::init_from_samples(tr::plane2_traits<point_t>::init_from_model(c),
+                                                            std::make_tuple(c->points[0], bad, c->points[199])) == nullptr);
+        auto hi = tr::identity_traits<point_t>::init_from_model(c);
+        CHECK(*tr::identity_traits<point_t>::project(hi, tr::vec3f_t(1, 2, 3)) == tr::vec3f_t(1, 2, 3));
+        // octree: every point lands in exactly one leaf; octant rule; depth limit
+        auto tree = tr::octree<point_t>::from_pointcloud(c, 4, tr::max_point_count{8});
+        size_t total = 0;
+        for (auto n : tree->leaf_traverse()) {
+            const auto& l = std::get<tr::leaf_node>(*n);
+            total += l.points.size();
+            CHECK(l.depth == 4 || l.points.size() <= 8);
+            for (uint32_t idx : l.points) {
+                tr::vec3f_t p = c->points[idx].getVector3f();
+                for (int k = 0; k < 3; ++k) CHECK(p[k] >= l.bbox.min()[k] - 1e-6f && p[k] <= l.bbox.max()[k] + 1e-6f);
+            }
+        }
+        CHECK(total == c->size() && tree->depth() <= 4);
+        CHECK(tree->depth_traverse().size() == tree->breadth_traverse().size());
+        CHECK(tree->level_traverse(0).size() == 1);
+        CHECK(tr::detail::get_octant(tr::vec3f_t(0, 0, 0), tr::vec3f_t(1, -1, 1)) == 5);
+        CHECK(tr::detail::get_octant(tr::vec3f_t(0, 0, 0), tr::vec3f_t(0, 0, 0)) == 0);
+    }
+    // uninitialised model: same exception text as include/impl/model.hpp:171-173
+    {
+        cloud_t::Ptr c = cloud_t::empty();
+        tr::model<point_t> m(c, dp);
+        bool thrown = false;
+        try { m.query(tr::feature_t(1.f, 0.f, 0.f, 1.f)); } catch (const std::runtime_error& e) { thrown = std::string(e.what()) == "Cannot query uninitialized model"; }
+        CHECK(thrown);
+        CHECK(!m.voxel_query(tr::vec4f_t(0, 0, 0, 1)));
+    }
+    std::puts("cpu checks ok");
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc < 5) {
+        std::fprintf(stderr, "usage: %s cpu | find model.bin scene.bin out.txt\n", argv[0]);
+        return 2;
+    }
+    cloud_t::Ptr mc = load(argv[2]), sc = load(argv[3]);
+    tr::discretization_params dp{20.f, 10.f / 180.f * static_cast<float>(M_PI), 10.f};
+    tr::sample_parameters sp{0.f, 0.f, 1.f, 1.f, 0.2f, 1.0f, 0.f, 1.f, false};
+    tr::model<point_t> m(mc, dp);
+    m.init(sp);
+    // API users still get the host-side query()/voxel_query()
+    auto f = tr::feature<point_t>(mc->points[0], mc->points[1]);
+    (void)m.query(*f);
+    tr::scene<point_t> s(sc);
+    auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, 5);
+    std::ofstream out(argv[4]);
+    out << matches.size() << "\n";
+    for (auto& mt : matches) {
+        out << mt.scene_corrs.size() << " " << mt.signed_score;
+        for (int i = 0; i < 16; ++i) out << " " << mt.transform.data()[i];
+        out << "\n";
+    }
+    std::printf("model pts %zu tangent %u pairs %llu | matches %zu\n", mc->size(), m.point_count(),
+                (unsigned long long)m.pair_count(), matches.size());
+    return 0;
+}
