@@ -1,0 +1,228 @@
+// oracle/ref_shim_capi.cpp — TEST INFRASTRUCTURE.  Compiles the REFERENCE's own sources where
+// they lie under /root/reference (nothing is copied into this repository):
+//   src/discretize.cpp + include/impl/discretize.hpp   discretize x2, murmur, std::hash        (a3, a4)
+//   include/impl/feature.hpp                           angle, feature, valid, discretize_feature (a1-a3)
+//   include/impl/model.hpp                             model::init, query, voxel_query          (a5, a9)
+//   include/impl/scene.hpp                             base_transform_, project_, finish_find, icp_ (a6, a10-a12)
+//   include/impl/pointcloud.hpp                        resolution(), curvature()
+// against the header stand-ins in oracle/shim/ (Eigen, PCL/FLANN, boost, fmt and range-v3 are
+// absent from this image and there is no network).  What the stand-ins decide — and the
+// reference therefore does NOT pin — is listed in oracle/oracle.hpp ("parity unpinned"):
+// Eigen's evaluation orders, the 4x4 inverse, umeyama/SVD, kd-tree order and ties, sampling.
+// Everything else (control flow, thresholds, casts, filters, container order, early-drop
+// arithmetic incl. its uint32 casts as gcc/x86-64 compiles them) is the reference's own code.
+// Output: oracle/_ref/libtm_ref.so (git-ignored), used only by tests/test_oracle_vs_ref.py.
+#include <optional>
+#include <variant>
+
+#include "oracle.hpp"             // only for the rigid solve behind the Eigen::umeyama stand-in
+
+#include <common>                 // /root/reference/include/common
+#include <src/discretize.cpp>     // /root/reference/src/discretize.cpp (+ discretize, impl/discretize.hpp)
+#include <scene>                  // /root/reference/include/scene (-> model, feature, pointcloud, octree)
+#include <impl/pointcloud.hpp>
+#include <impl/feature.hpp>
+#include <impl/model.hpp>
+#include <impl/scene.hpp>
+
+namespace Eigen {
+Matrix4f umeyama(const Matrix<float, 3, Dynamic>& src, const Matrix<float, 3, Dynamic>& dst, bool) {
+    std::vector<orc::v3> s(src.cols()), d(dst.cols());
+    for (int i = 0; i < src.cols(); ++i) {
+        s[i] = {src(0, i), src(1, i), src(2, i)};
+        d[i] = {dst(0, i), dst(1, i), dst(2, i)};
+    }
+    orc::m4 t = orc::umeyama(s, d);
+    Matrix4f r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r(i, j) = t.m[i][j];
+    return r;
+}
+}  // namespace Eigen
+
+namespace tr = triplet_match;
+typedef pcl::PointSurfel point_t;
+typedef tr::pointcloud<point_t> cloud_t;
+
+// scene<Point>::impl is a protected nested type: reach it through a derived class
+struct scene_access : tr::scene<point_t> {
+    typedef tr::scene<point_t>::impl impl_t;
+};
+
+static point_t make_point(const float* p, const float* t) {
+    point_t q;
+    q.x = p[0]; q.y = p[1]; q.z = p[2];
+    q.data_c[1] = t[0]; q.data_c[2] = t[1]; q.data_c[3] = t[2];
+    return q;
+}
+static cloud_t::Ptr make_cloud(const float* pos, const float* nrm, const float* tgt, uint32_t n) {
+    cloud_t::Ptr c = cloud_t::empty();
+    for (uint32_t i = 0; i < n; ++i) {
+        point_t q = make_point(pos + 3 * i, tgt + 3 * i);
+        q.normal_x = nrm[3 * i]; q.normal_y = nrm[3 * i + 1]; q.normal_z = nrm[3 * i + 2];
+        c->push_back(q);
+    }
+    return c;
+}
+static tr::feature_bounds_t make_bounds(const float* mn, const float* mx) {
+    tr::feature_bounds_t b;
+    for (int i = 0; i < 4; ++i) { b.min()[i] = mn[i]; b.max()[i] = mx[i]; }
+    return b;
+}
+static tr::mat4f_t mat_from(const float* t16) {
+    tr::mat4f_t m;
+    for (int i = 0; i < 16; ++i) m.data()[i] = t16[i];  // both column-major
+    return m;
+}
+
+struct ref_model {
+    cloud_t::Ptr cloud;
+    std::unique_ptr<tr::model<point_t>> m;
+};
+struct ref_scene {
+    cloud_t::Ptr cloud;
+    std::unique_ptr<scene_access::impl_t> impl;
+};
+
+extern "C" {
+
+uint32_t ref_murmur4(const uint32_t* k) {
+    tr::discrete_feature_t key;
+    for (int i = 0; i < 4; ++i) key[i] = k[i];
+    return tr::detail::murmur<4>(key);
+}
+uint64_t ref_std_hash4(const uint32_t* k) {
+    tr::discrete_feature_t key;
+    for (int i = 0; i < 4; ++i) key[i] = k[i];
+    return std::hash<tr::discrete_feature_t>()(key);
+}
+uint32_t ref_discretize_range(float v, float mn, float range, uint32_t steps) { return tr::discretize(v, mn, range, steps); }
+uint32_t ref_discretize_step(float v, float step) { return tr::discretize(v, step); }
+// in: p0, t0, p1, t1 (12 floats)
+void ref_feature(const float* in, float* f) {
+    point_t a = make_point(in, in + 3), b = make_point(in + 6, in + 9);
+    tr::curv_info_t<point_t> c{};
+    auto r = tr::feature<point_t>(a, b, c, c);
+    for (int i = 0; i < 4; ++i) f[i] = (*r)[i];
+}
+int ref_valid(const float* f, const float* mn, const float* mx) {
+    tr::feature_t ff;
+    for (int i = 0; i < 4; ++i) ff[i] = f[i];
+    return tr::valid<point_t>(ff, make_bounds(mn, mx)) ? 1 : 0;
+}
+void ref_discretize_feature(const float* f, const float* mn, const float* mx, float dist_steps, float angle_step, uint32_t* key) {
+    tr::feature_t ff;
+    for (int i = 0; i < 4; ++i) ff[i] = f[i];
+    tr::discretization_params dp{dist_steps, angle_step, 10.f};
+    tr::discrete_feature_t df = tr::discretize_feature<point_t>(ff, make_bounds(mn, mx), dp);
+    for (int i = 0; i < 4; ++i) key[i] = df[i];
+}
+void ref_valid_bounds(const float* mn, const float* mx, float min_rel, float max_rel, float* omn, float* omx) {
+    tr::feature_bounds_t b = tr::valid_bounds(make_bounds(mn, mx), 0.f, 0.f, min_rel, max_rel);
+    for (int i = 0; i < 4; ++i) { omn[i] = b.min()[i]; omx[i] = b.max()[i]; }
+}
+
+// ---- model: the reference's model<PointSurfel>::init / query / voxel_query ----------------
+void* ref_model_create(const float* pos, const float* nrm, const float* tgt, uint32_t n,
+                       float dist_steps, float angle_step, float min_df, float max_df) {
+    auto* h = new ref_model();
+    h->cloud = make_cloud(pos, nrm, tgt, n);
+    tr::discretization_params dp{dist_steps, angle_step, 10.f};
+    h->m.reset(new tr::model<point_t>(h->cloud, dp));
+    tr::sample_parameters sp{0.f, 0.f, 1.f, 1.f, min_df, max_df, 0.f, 1.f, false};
+    h->m->init(sp);
+    return h;
+}
+void ref_model_destroy(void* p) { delete static_cast<ref_model*>(p); }
+// f: resolution, diameter, feat_min[4], feat_max[4] (10); to_voxel16 column-major; ints: extents[3], margin, point_count
+void ref_model_info(void* p, float* f10, float* to_voxel16, int* i5) {
+    auto* h = static_cast<ref_model*>(p);
+    f10[0] = h->cloud->resolution();
+    f10[1] = h->m->diameter();
+    for (int k = 0; k < 4; ++k) {
+        f10[2 + k] = h->m->feature_bounds().min()[k];
+        f10[6 + k] = h->m->feature_bounds().max()[k];
+    }
+    for (int k = 0; k < 16; ++k) to_voxel16[k] = h->m->voxel_transform().data()[k];
+    for (int k = 0; k < 3; ++k) i5[k] = h->m->extents()[k];
+    i5[3] = h->m->margin();
+    i5[4] = (int)h->m->point_count();
+}
+int ref_model_voxel_query(void* p, const float* pos4, uint32_t* out) {
+    auto* h = static_cast<ref_model*>(p);
+    auto r = h->m->voxel_query(tr::vec4f_t(pos4[0], pos4[1], pos4[2], pos4[3]));
+    if (!r) return 0;
+    *out = (*r)[0];
+    return 1;
+}
+// model::query + the caller's query_limit loop (scene.hpp:304-311)
+uint32_t ref_model_query(void* p, const float* f, uint32_t limit, uint32_t* pairs_out) {
+    auto* h = static_cast<ref_model*>(p);
+    tr::feature_t ff;
+    for (int i = 0; i < 4; ++i) ff[i] = f[i];
+    auto range = h->m->query(ff);
+    uint32_t query = 0, cnt = 0;
+    for (auto it = range.first; it != range.second; ++it) {
+        if (limit > 0 && (++query) > limit) break;
+        auto&& [m_i, m_j] = it->second;
+        pairs_out[2 * cnt] = m_i;
+        pairs_out[2 * cnt + 1] = m_j;
+        ++cnt;
+    }
+    return cnt;
+}
+
+// ---- scene: the reference's scene<PointSurfel>::impl ---------------------------------------
+void* ref_scene_create(const float* pos, const float* nrm, const float* tgt, uint32_t n,
+                       const uint8_t* tangent_mask, const uint8_t* mask) {
+    auto* h = new ref_scene();
+    h->cloud = make_cloud(pos, nrm, tgt, n);
+    h->impl.reset(new scene_access::impl_t(h->cloud));
+    h->impl->mask_.assign(n, 0);
+    h->impl->fp_mask_.assign(n, 0);
+    h->impl->tangent_mask_.assign(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        h->impl->tangent_mask_[i] = tangent_mask[i];
+        h->impl->mask_[i] = mask ? mask[i] : 0;
+    }
+    return h;
+}
+void ref_scene_destroy(void* p) { delete static_cast<ref_scene*>(p); }
+// in: src_i, src_j, src_t, tgt_i, tgt_j, tgt_t (18 floats) -> column-major 4x4
+void ref_base_transform(void* sp, const float* in, float* out16) {
+    auto* h = static_cast<ref_scene*>(sp);
+    auto v = [&](int k) { return tr::vec3f_t(in[3 * k], in[3 * k + 1], in[3 * k + 2]); };
+    tr::mat4f_t t = h->impl->base_transform_(v(0), v(1), v(2), v(3), v(4), v(5));
+    for (int i = 0; i < 16; ++i) out16[i] = t.data()[i];
+}
+uint32_t ref_project(void* sp, void* mp, const int* subset, uint64_t nsub, const float* T16,
+                     float accept_prob, float dist_thres, int early_out, uint32_t* scene_corrs,
+                     uint32_t* model_corrs, double* score, uint32_t* saved) {
+    auto* h = static_cast<ref_scene*>(sp);
+    auto* m = static_cast<ref_model*>(mp);
+    std::vector<int> sub(subset, subset + nsub);
+    uint32_t sv = 0;
+    auto r = h->impl->project_(sv, *m->m, sub, mat_from(T16), accept_prob, dist_thres, early_out != 0);
+    const auto& sc = std::get<0>(r);
+    const auto& mc = std::get<1>(r);
+    for (size_t i = 0; i < sc.size(); ++i) { scene_corrs[i] = sc[i]; model_corrs[i] = mc[i]; }
+    *score = std::get<2>(r);
+    *saved = sv;
+    return (uint32_t)sc.size();
+}
+uint32_t ref_icp(void* sp, void* mp, const float* T16_in, uint32_t max_iterations, float dist_thres,
+                 float accept_prob, float* T16_out, double* score) {
+    auto* h = static_cast<ref_scene*>(sp);
+    auto* m = static_cast<ref_model*>(mp);
+    // the incoming match of icp_ is finish_find(t, dist_thres) (scene.hpp:361-364)
+    auto start = h->impl->finish_find(*m->m, mat_from(T16_in), accept_prob, dist_thres);
+    auto r = h->impl->icp_(*m->m, start, max_iterations, dist_thres, accept_prob);
+    for (int i = 0; i < 16; ++i) T16_out[i] = r.transform.data()[i];
+    *score = r.signed_score;
+    return (uint32_t)r.scene_corrs.size();
+}
+float ref_resolution(const float* pos, uint32_t n) {
+    std::vector<float> z(3 * (size_t)n, 0.f);
+    return make_cloud(pos, z.data(), z.data(), n)->resolution();
+}
+}  // extern "C"

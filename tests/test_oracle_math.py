@@ -63,25 +63,48 @@ def test_discretize_edges():
         assert L.orc_discretize_range(float(x), 0.25, 1.75, 20) == exp
 
 
-def test_atan2f_is_correctly_rounded_and_libm_report():
+def test_atan2f_restatement_equals_libm():
+    """The oracle's atan2f restates glibc 2.39's binary32 algorithm (the reference platform's
+    libm, include/impl/feature.hpp:7).  It was pinned against this image's libm on 10^8 inputs;
+    this test repeats the comparison on the host it runs on."""
     rng = np.random.default_rng(0)
-    n = 400000
+    n = 2_000_000
     y = np.abs(rng.standard_normal(n)).astype(np.float32)
     x = np.abs(rng.standard_normal(n)).astype(np.float32)
     y[:100] = 0
     x[100:200] = 0
     y[200:300] *= 1e-20
     x[300:400] *= 1e-20
+    y[400:500] = np.inf
+    x[500:600] = np.inf
+    x[600:700] = 1.0
+    # raw bit patterns (every exponent, denormals, NaN) for the first quadrant
+    yb = rng.integers(0, 0x7FC00001, size=n // 4, dtype=np.int64).astype(np.uint32).view(np.float32)
+    xb = rng.integers(0, 0x7FC00001, size=n // 4, dtype=np.int64).astype(np.uint32).view(np.float32)
+    y, x = np.concatenate([y, yb]), np.concatenate([x, xb])
     ours, libm = po.atan2f_q1_batch(y, x)
-    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
-    assert np.array_equal(ours, ref)
-    # libm differs by at most 1 ulp and never flips a 10-degree bin on this sample
-    d = np.abs(ours.view(np.int32).astype(np.int64) - libm.view(np.int32).astype(np.int64))
+    nan = np.isnan(ours) & np.isnan(libm)
+    same = (ours.view(np.uint32) == libm.view(np.uint32)) | nan
+    assert same.all(), f"{int((~same).sum())} of {y.size} inputs differ from this host's libm atan2f"
+    # accuracy: within 1 ulp of the correctly rounded value
+    fin = np.isfinite(ours) & np.isfinite(x) & np.isfinite(y)
+    cr = np.arctan2(y[fin].astype(np.float64), x[fin].astype(np.float64)).astype(np.float32)
+    d = np.abs(ours[fin].view(np.int32).astype(np.int64) - cr.view(np.int32).astype(np.int64))
     assert d.max() <= 1
-    step = np.float32(0.17453292)
-    flips = int(((ours / step).astype(np.uint32) != (libm / step).astype(np.uint32)).sum())
-    print(f"atan2f vs libm: {int((d > 0).sum())}/{n} differ by 1 ulp, {flips} bin flips")
-    assert flips <= n // 10000
+
+
+def test_atan2f_all_quadrants_equals_libm():
+    rng = np.random.default_rng(1)
+    n = 500000
+    y = rng.standard_normal(n).astype(np.float32)
+    x = rng.standard_normal(n).astype(np.float32)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 3e38, -3e38, 1e-30], np.float32)
+    yy, xx = np.meshgrid(sp, sp)
+    y, x = np.concatenate([y, yy.ravel()]), np.concatenate([x, xx.ravel()])
+    ours, libm = po.atan2f_q1_batch(y, x)  # atan2f_q1 is the full four-quadrant restatement
+    nan = np.isnan(ours) & np.isnan(libm)
+    same = (ours.view(np.uint32) == libm.view(np.uint32)) | nan
+    assert same.all(), f"{int((~same).sum())} of {y.size} inputs differ from this host's libm atan2f"
 
 
 def _upper_x86(tried, nsub, corrs):

@@ -1,0 +1,295 @@
+"""Pins rows a1-a4 of the oracle against the REFERENCE's own sources: src/discretize.cpp,
+include/impl/discretize.hpp and include/impl/feature.hpp compiled where they lie against the
+header stand-ins of oracle/shim/ (recipe: oracle/Makefile target `ref` -> oracle/_ref/).
+The shared library is built in the authoring container (where /root/reference exists) and
+travels with the snapshot; the test skips when it is absent."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libtm_ref.so")
+
+
+@pytest.fixture(scope="module")
+def ref(built):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libtm_ref.so not built (no /root/reference in this environment)")
+    L = C.CDLL(REF)
+    L.ref_murmur4.restype = C.c_uint32
+    L.ref_std_hash4.restype = C.c_uint64
+    L.ref_discretize_range.restype = C.c_uint32
+    L.ref_discretize_range.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint32]
+    L.ref_discretize_step.restype = C.c_uint32
+    L.ref_discretize_step.argtypes = [C.c_float, C.c_float]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_murmur_and_hash(ref):
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 2**32, size=(3000, 4), dtype=np.uint64).astype(np.uint32)
+    keys[:20] = rng.integers(0, 20, size=(20, 4))  # realistic small keys
+    for k in keys:
+        h = ref.ref_murmur4(_p(k))
+        assert h == po.murmur4(k)
+        assert ref.ref_std_hash4(_p(k)) == h  # std::hash widens the 32-bit murmur to size_t
+
+
+def test_discretize(ref):
+    L = po.load()
+    rng = np.random.default_rng(1)
+    for _ in range(4000):
+        v, mn, rg = (np.float32(x) for x in rng.standard_normal(3) * 2)
+        rg = np.float32(abs(rg) + 1e-3)
+        steps = int(rng.integers(1, 64))
+        assert ref.ref_discretize_range(v, mn, rg, steps) == L.orc_discretize_range(v, mn, rg, steps)
+        a, st = np.float32(abs(v)), np.float32(abs(mn) + 0.01)
+        assert ref.ref_discretize_step(a, st) == L.orc_discretize_step(a, st)
+
+
+def test_feature_valid_discretize_feature(ref):
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        p0, p1 = rng.standard_normal(3), rng.standard_normal(3)
+        t0 = rng.standard_normal(3); t0 /= np.linalg.norm(t0)
+        t1 = rng.standard_normal(3); t1 /= np.linalg.norm(t1)
+        if rng.random() < 0.1:
+            t1 = t0  # parallel tangents
+        if rng.random() < 0.05:
+            t0 = (p1 - p0) / np.linalg.norm(p1 - p0)  # tangent along the pair direction
+        inp = np.concatenate([p0, t0, p1, t1]).astype(np.float32)
+        f_ref = np.zeros(4, dtype=np.float32)
+        ref.ref_feature(_p(inp), _p(f_ref))
+        # the reference calls libm atan2f; the oracle in libm mode must agree bit for bit
+        f_orc = po.feature(inp[0:3], inp[3:6], inp[6:9], inp[9:12], use_libm=True)
+        assert np.array_equal(f_ref.view(np.uint32), f_orc.view(np.uint32))
+        # ... and so must the restated atan2f every kernel shares (glibc's binary32 algorithm)
+        f_sw = po.feature(inp[0:3], inp[3:6], inp[6:9], inp[9:12])
+        assert np.array_equal(f_sw.view(np.uint32), f_ref.view(np.uint32))
+        mn = np.array([0.3, 0, 0, 0.3], dtype=np.float32) * np.float32(rng.random() + 0.5)
+        mx = mn + np.array([2.5, 3.2, 3.2, 2.5], dtype=np.float32) * np.float32(rng.random() + 0.2)
+        # oracle side through the same public helpers the pipeline uses
+        nb_mn, nb_mx = np.zeros(4, np.float32), np.zeros(4, np.float32)
+        ref.ref_valid_bounds(_p(mn), _p(mx), C.c_float(0.0), C.c_float(1.0), _p(nb_mn), _p(nb_mx))
+        d0 = np.float32(mx[0] - mn[0]); d3 = np.float32(mx[3] - mn[3])
+        assert nb_mn[0] == np.float32(mn[0] + np.float32(0.0) * d0) and nb_mx[0] == np.float32(mn[0] + np.float32(1.0) * d0)
+        assert nb_mx[3] == np.float32(mn[3] + np.float32(1.0) * d3) and nb_mn[1] == mn[1] and nb_mx[2] == mx[2]
+        v_ref = ref.ref_valid(_p(f_ref), _p(mn), _p(mx))
+        v_exp = int((mn[0] <= f_ref[0] <= mx[0]) and 0 <= f_ref[1] <= np.float32(np.pi) and 0 <= f_ref[2] <= np.float32(np.pi))
+        assert v_ref == v_exp
+        key = np.zeros(4, dtype=np.uint32)
+        ref.ref_discretize_feature(_p(f_ref), _p(mn), _p(mx), C.c_float(20.0), C.c_float(0.17453292), _p(key))
+        L = po.load()
+        exp = [L.orc_discretize_range(f_ref[0], mn[0], d0, 20), L.orc_discretize_step(f_ref[1], 0.17453292),
+               L.orc_discretize_step(f_ref[2], 0.17453292), L.orc_discretize_range(f_ref[3], mn[0], d0, 20)]
+        assert key.tolist() == exp
+
+
+# ---- rows a5-a12: the reference's model::init / query / voxel_query and scene::impl::
+# base_transform_ / project_ / icp_, compiled from /root/reference against oracle/shim ----
+import common  # noqa: E402
+
+CONFIGS = ["plane_small", "cylinder_small", "freeform_small"]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class RefModel:
+    def __init__(self, L, m):
+        L.ref_model_create.restype = C.c_void_p
+        L.ref_model_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float,
+                                       C.c_float, C.c_float]
+        L.ref_model_query.restype = C.c_uint32
+        self.L = L
+        self.pos, self.nrm, self.tgt = _f32(m.pos), _f32(m.nrm), _f32(m.tgt)
+        self.h = C.c_void_p(L.ref_model_create(_p(self.pos), _p(self.nrm), _p(self.tgt), m.n, 20.0, 0.17453292, 0.2, 1.0))
+        f10, tv, i5 = np.zeros(10, np.float32), np.zeros(16, np.float32), np.zeros(5, np.int32)
+        L.ref_model_info(self.h, _p(f10), _p(tv), _p(i5))
+        self.resolution, self.diameter = f10[0], f10[1]
+        self.feat_min, self.feat_max = f10[2:6].copy(), f10[6:10].copy()
+        self.to_voxel16, self.extents, self.margin, self.point_count = tv, i5[:3].copy(), int(i5[3]), int(i5[4])
+
+    def query(self, f, limit=200):
+        out = np.zeros((max(limit, 1), 2), dtype=np.uint32)
+        n = self.L.ref_model_query(self.h, _p(_f32(f)), C.c_uint32(limit), _p(out))
+        return out[:n]
+
+    def voxel_query(self, p4):
+        o = C.c_uint32()
+        return int(o.value) if self.L.ref_model_voxel_query(self.h, _p(_f32(p4)), C.byref(o)) else None
+
+
+class RefScene:
+    def __init__(self, L, s, mask=None):
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_scene_create.argtypes = [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p]
+        L.ref_project.restype = C.c_uint32
+        L.ref_icp.restype = C.c_uint32
+        self.L = L
+        self.pos, self.nrm, self.tgt = _f32(s.pos), _f32(s.nrm), _f32(s.tgt)
+        tm = np.ascontiguousarray(s.tangent_mask, dtype=np.uint8)
+        mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.h = C.c_void_p(L.ref_scene_create(_p(self.pos), _p(self.nrm), _p(self.tgt), s.n, _p(tm),
+                                               None if mk is None else _p(mk)))
+
+    def project(self, rm, subset, T16, accept=0.5, dist_thres=1.0, early_out=False):
+        sub = np.ascontiguousarray(subset, dtype=np.int32)
+        sc, mc = np.zeros(max(sub.size, 1), np.uint32), np.zeros(max(sub.size, 1), np.uint32)
+        score, saved = C.c_double(), C.c_uint32()
+        n = self.L.ref_project(self.h, rm.h, _p(sub), C.c_uint64(sub.size), _p(_f32(T16)), C.c_float(accept),
+                               C.c_float(dist_thres), C.c_int(int(early_out)), _p(sc), _p(mc), C.byref(score),
+                               C.byref(saved))
+        return dict(count=int(n), scene_corrs=sc[:n].copy(), model_corrs=mc[:n].copy(), score=score.value,
+                    saved=int(saved.value))
+
+
+@pytest.fixture(scope="module", params=CONFIGS)
+def refcfg(request, ref):
+    m, s, om, osc, rec = common.config(request.param)
+    rm = RefModel(ref, m)
+    rs = RefScene(ref, s)
+    return request.param, m, s, om, osc, rec, rm, rs
+
+
+def test_reference_model_init(refcfg):
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    assert np.float32(rm.resolution) == np.float32(om.resolution)
+    assert np.float32(rm.diameter) == np.float32(om.diameter)
+    assert np.array_equal(rm.extents, om.extents) and rm.margin == om.margin
+    assert np.array_equal(rm.to_voxel16.view(np.uint32), om.to_voxel16.view(np.uint32))
+    assert np.array_equal(rm.feat_min.view(np.uint32), om.feat_min.view(np.uint32))
+    assert np.array_equal(rm.feat_max.view(np.uint32), om.feat_max.view(np.uint32))
+    assert rm.point_count == om.n_subset
+    # voxel grid through the reference's voxel_query at every cell (+ outside positions).
+    # The reference places voxel centres with Matrix4f::inverse() (stand-in: Gauss-Jordan), the
+    # oracle with (index - t)/s: centres differ by rounding, so only exact near-ties may differ.
+    ex = om.extents.astype(np.int64)
+    rng = np.random.default_rng(0)
+    cells = rng.choice(int(ex.prod()), size=min(4000, int(ex.prod())), replace=False)
+    diff = 0
+    for lin in cells:
+        k, r = divmod(int(lin), int(ex[0] * ex[1]))
+        j, i = divmod(r, int(ex[0]))
+        centre = (np.array([i, j, k], np.float32) + np.float32(0.25) - om.trans) / om.scale
+        got = rm.voxel_query([centre[0], centre[1], centre[2], 1.0])
+        exp = om.voxel_query([centre[0], centre[1], centre[2], 1.0])
+        assert (got is None) == (exp is None)
+        if got != exp:
+            d = np.linalg.norm(m.pos[[got, exp]].astype(np.float64) - ((np.array([i, j, k]) - om.trans) / om.scale), axis=1)
+            assert abs(d[0] - d[1]) < 1e-5
+            diff += 1
+    assert diff <= len(cells) // 500
+    for p in ([1e3, 0, 0, 1], [-1e3, 0, 0, 1], [np.nan, 0, 0, 1]):
+        assert rm.voxel_query(p) is None and om.voxel_query(p) is None
+
+
+def test_reference_query_order_and_limit(refcfg):
+    """Hash-hit order of the reference's own unordered_multimap + std::hash + query_limit loop."""
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    feats, keys, valid = osc.pair_features(om, rec.pair_i, rec.pair_j)
+    n = 0
+    for f in feats[valid.astype(bool)][:60]:
+        for limit in (200, 7):
+            a, b = rm.query(f, limit), om.query(f, limit)
+            assert np.array_equal(a, b)
+            n += a.shape[0]
+    assert n > 100
+
+
+def test_reference_base_transform(refcfg):
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    rng = np.random.default_rng(3)
+    T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    for h in rng.choice(T.shape[0], size=min(300, T.shape[0]), replace=False):
+        i, j = rec.pair_i[hp[h]], rec.pair_j[hp[h]]
+        inp = _f32(np.concatenate([s.pos[i], s.pos[j], s.tgt[i], m.pos[mi[h]], m.pos[mj[h]], m.tgt[mi[h]]]))
+        out = np.zeros(16, np.float32)
+        rs.L.ref_base_transform(rs.h, _p(inp), _p(out))
+        assert np.array_equal(out.view(np.uint32), T[h].view(np.uint32))
+    for _ in range(200):  # arbitrary (incl. degenerate) inputs
+        inp = _f32(rng.standard_normal(18))
+        if rng.random() < 0.1:
+            inp[6:9] = inp[3:6] - inp[0:3]  # tangent parallel to the pair direction -> singular frame
+        out = np.zeros(16, np.float32)
+        rs.L.ref_base_transform(rs.h, _p(inp), _p(out))
+        exp = po.base_transform(inp[0:3], inp[3:6], inp[6:9], inp[9:12], inp[12:15], inp[15:18])
+        assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+
+
+def test_reference_project(refcfg):
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T, nthreads=4)
+    rng = np.random.default_rng(4)
+    pick = np.unique(np.concatenate([np.argsort(-cnt.astype(np.int64))[:12],
+                                     rng.choice(T.shape[0], size=min(40, T.shape[0]), replace=False)]))
+    for h in pick:
+        sub = osc.ball_subset(int(rec.outer[rec.pair_outer[hp[h]]]), om.diameter)
+        for eo in (False, True):
+            a = rs.project(rm, sub, T[h], early_out=eo)
+            b = osc.project(om, sub, T[h], early_out=eo)
+            assert a["count"] == b["count"], (name, int(h), eo)
+            assert np.array_equal(a["scene_corrs"], b["scene_corrs"])
+            assert np.array_equal(a["model_corrs"], b["model_corrs"])
+            assert a["score"] == b["score"] and a["saved"] == b["saved"]
+    # early-drop on short / shuffled subsets (checkpoint chaining, UB casts as compiled by gcc)
+    sub_full = osc.ball_subset(int(rec.outer[0]), om.diameter)
+    perm = rng.permutation(sub_full)
+    for n in (0, 1, 2, 7, 19, 20, 21, 40, 333, len(perm)):
+        for h in pick[:6]:
+            a = rs.project(rm, perm[:n], T[h], early_out=True)
+            b = osc.project(om, perm[:n], T[h], early_out=True)
+            assert (a["count"], a["saved"], a["score"]) == (b["count"], b["saved"], b["score"]), (n, int(h))
+
+
+def test_reference_project_with_mask(refcfg, ref):
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    rng = np.random.default_rng(5)
+    mask = (rng.random(s.n) < 0.25).astype(np.uint8)
+    rs2 = RefScene(ref, s, mask)
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T, nthreads=4)
+    osc.set_mask(mask)
+    try:
+        for h in np.argsort(-cnt.astype(np.int64))[:10]:
+            sub = osc.ball_subset(int(rec.outer[rec.pair_outer[hp[h]]]), om.diameter)
+            for eo in (False, True):
+                a, b = rs2.project(rm, sub, T[h], early_out=eo), osc.project(om, sub, T[h], early_out=eo)
+                assert (a["count"], a["saved"], a["score"]) == (b["count"], b["saved"], b["score"])
+    finally:
+        osc.set_mask(np.zeros(s.n, dtype=np.uint8))
+
+
+def test_reference_icp_control_flow(refcfg):
+    """icp_ loop / stop rule / 2*dist_thres of the reference vs the oracle (the rigid solve is
+    the same stand-in on both sides, so counts and poses must agree exactly)."""
+    name, m, s, om, osc, rec, rm, rs = refcfg
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T, nthreads=4)
+    for h in np.argsort(-cnt.astype(np.int64), kind="stable")[:3]:
+        for iters in (1, 5):
+            out, score = np.zeros(16, np.float32), C.c_double()
+            n = rs.L.ref_icp(rs.h, rm.h, _p(_f32(T[h])), C.c_uint32(iters), C.c_float(1.0), C.c_float(0.5), _p(out),
+                             C.byref(score))
+            oT, on, osx, oit = osc.icp(om, T[h], iters, 1.0)
+            assert n == on and np.array_equal(out.view(np.uint32), oT.view(np.uint32))
+            assert score.value == osx
+
+
+def test_reference_resolution(ref):
+    from triplet_match_b200 import synth
+    ref.ref_resolution.restype = C.c_float
+    c = synth.freeform_model(seed=9, n_points=400, radius=0.2)
+    pos = _f32(c.pos)
+    assert np.float32(ref.ref_resolution(_p(pos), C.c_uint32(c.n))) == np.float32(
+        po.load().orc_resolution(_p(pos), C.c_uint32(c.n)))

@@ -17,6 +17,7 @@
 
 #include "../../include/tm_b200.h"
 #include "../../include/tm_b200_host.h"
+#include "../../include/triplet_match/tm_atan2f.h"
 
 namespace {
 
@@ -35,48 +36,8 @@ inline float sqdist_seq(v3 a, v3 b) {  // FLANN L2_Simple accumulation order
     return (dx * dx + dy * dy) + dz * dz;
 }
 
-// shared software atan2f (first quadrant) — identical to tm_device.cuh / DESIGN.md
-double atan_pos(double x) {
-    static const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01,
-                                 9.82793723247329054082e-01, 1.57079632679489655800e+00};
-    static const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17,
-                                 1.39033110312309984516e-17, 6.12323399573676603587e-17};
-    static const double aT[11] = {
-        3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
-        -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
-        6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
-        -3.65315727442169155270e-02, 1.62858201153657823623e-02};
-    int id;
-    if (x >= 1.8446744073709552e19) return hi[3] + lo[3];
-    if (x < 0.4375) {
-        if (x < 1.862645149230957e-09) return x;
-        id = -1;
-    } else if (x < 1.1875) {
-        if (x < 0.6875) {
-            id = 0;
-            x = (2.0 * x - 1.0) / (2.0 + x);
-        } else {
-            id = 1;
-            x = (x - 1.0) / (x + 1.0);
-        }
-    } else if (x < 2.4375) {
-        id = 2;
-        x = (x - 1.5) / (1.0 + 1.5 * x);
-    } else {
-        id = 3;
-        x = -1.0 / x;
-    }
-    double z = x * x, w = z * z;
-    double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
-    double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
-    if (id < 0) return x - x * (s1 + s2);
-    return hi[id] - ((x * (s1 + s2) - lo[id]) - x);
-}
-float atan2f_q1(float y, float x) {
-    if (y == 0.f) return 0.f;
-    if (x == 0.f) return (float)(1.57079632679489655800e+00 + 6.12323399573676603587e-17);
-    return (float)atan_pos((double)y / (double)x);
-}
+// atan2f of the reference platform's libm, restated (include/triplet_match/tm_atan2f.h)
+float atan2f_q1(float y, float x) { return tm_math::atan2f_libm(y, x); }
 float angle(v3 a, v3 b) { return atan2f_q1(norm(cross(a, b)), fabsf(dot(a, b))); }
 
 uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/triplet_match/tm_atan2f.h"
+
 namespace tmk {
 
 // ---- resident layouts ----------------------------------------------------
@@ -89,67 +91,9 @@ __host__ __device__ __forceinline__ float row_rot(float4 r, f3 v) {
     return sum3(r.x * v.x, r.y * v.y, r.z * v.z);
 }
 
-// ---- shared software atan (first quadrant), see DESIGN.md "atan2f" --------
-// Same algorithm, constants and operation order as the oracle's restatement:
-// IEEE double +,*,/ only, rounded once to float.
-__host__ __device__ inline double atan_pos(double x) {
-    const double hi0 = 4.63647609000806093515e-01, hi1 = 7.85398163397448278999e-01,
-                 hi2 = 9.82793723247329054082e-01, hi3 = 1.57079632679489655800e+00;
-    const double lo0 = 2.26987774529616870924e-17, lo1 = 3.06161699786838301793e-17,
-                 lo2 = 1.39033110312309984516e-17, lo3 = 6.12323399573676603587e-17;
-    const double a0 = 3.33333333333329318027e-01, a1 = -1.99999999998764832476e-01,
-                 a2 = 1.42857142725034663711e-01, a3 = -1.11111104054623557880e-01,
-                 a4 = 9.09088713343650656196e-02, a5 = -7.69187620504482999495e-02,
-                 a6 = 6.66107313738753120669e-02, a7 = -5.83357013379057348645e-02,
-                 a8 = 4.97687799461593236017e-02, a9 = -3.65315727442169155270e-02,
-                 a10 = 1.62858201153657823623e-02;
-    double hi, lo;
-    int id;
-    if (x >= 1.8446744073709552e19) return hi3 + lo3;
-    if (x < 0.4375) {
-        if (x < 1.862645149230957e-09) return x;
-        id = -1;
-        hi = 0.0;
-        lo = 0.0;
-    } else if (x < 1.1875) {
-        if (x < 0.6875) {
-            id = 0; hi = hi0; lo = lo0;
-            x = (2.0 * x - 1.0) / (2.0 + x);
-        } else {
-            id = 1; hi = hi1; lo = lo1;
-            x = (x - 1.0) / (x + 1.0);
-        }
-    } else if (x < 2.4375) {
-        id = 2; hi = hi2; lo = lo2;
-        x = (x - 1.5) / (1.0 + 1.5 * x);
-    } else {
-        id = 3; hi = hi3; lo = lo3;
-        x = -1.0 / x;
-    }
-    double z = x * x;
-    double w = z * z;
-    double s1 = z * (a0 + w * (a2 + w * (a4 + w * (a6 + w * (a8 + w * a10)))));
-    double s2 = w * (a1 + w * (a3 + w * (a5 + w * (a7 + w * a9))));
-    if (id < 0) return x - x * (s1 + s2);
-    return hi - ((x * (s1 + s2) - lo) - x);
-}
-__host__ __device__ inline float atan2f_q1(float y, float x) {  // y >= 0, x >= 0
-    if (y == 0.f) return 0.f;
-    if (x == 0.f) return (float)(1.57079632679489655800e+00 + 6.12323399573676603587e-17);
-    double q = (double)y / (double)x;
-    return (float)atan_pos(q);
-}
-__host__ __device__ inline float atan2f_full(float y, float x) {
-    const double pi_d = 3.14159265358979311600e+00;
-    double ay = y < 0.f ? -(double)y : (double)y, ax = x < 0.f ? -(double)x : (double)x;
-    double q;
-    if (ay == 0.0) q = 0.0;
-    else if (ax == 0.0) q = 1.57079632679489655800e+00 + 6.12323399573676603587e-17;
-    else q = atan_pos(ay / ax);
-    bool sx = signbit(x), sy = signbit(y);
-    double a = sx ? pi_d - q : q;
-    return (float)(sy ? -a : a);
-}
+// ---- atan2f: the reference platform's libm algorithm in binary32 (include/triplet_match/tm_atan2f.h)
+__host__ __device__ inline float atan2f_q1(float y, float x) { return tm_math::atan2f_libm(y, x); }
+__host__ __device__ inline float atan2f_full(float y, float x) { return tm_math::atan2f_libm(y, x); }
 
 // ---- discretise + murmur (src/discretize.cpp:19-30, impl/discretize.hpp:10-45)
 __host__ __device__ __forceinline__ uint32_t discretize_range(float value, float min_value,
