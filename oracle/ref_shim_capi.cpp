@@ -12,7 +12,9 @@
 // Everything else (control flow, thresholds, casts, filters, container order, early-drop
 // arithmetic incl. its uint32 casts as gcc/x86-64 compiles them) is the reference's own code.
 // Output: oracle/_ref/libtm_ref.so (git-ignored), used only by tests/test_oracle_vs_ref.py.
+#include <atomic>
 #include <optional>
+#include <thread>
 #include <variant>
 
 #include "oracle.hpp"             // only for the rigid solve behind the Eigen::umeyama stand-in
@@ -220,6 +222,67 @@ uint32_t ref_icp(void* sp, void* mp, const float* T16_in, uint32_t max_iteration
     for (int i = 0; i < 16; ++i) T16_out[i] = r.transform.data()[i];
     *score = r.signed_score;
     return (uint32_t)r.scene_corrs.size();
+}
+// bench.py --impl reference: the reference's project_ (scene.hpp:411-510) for a batch of
+// hypotheses over their recorded radius subsets, fanned out over std::threads the way
+// find_parallel fans find_in_subset out over std::async tasks (scene.hpp:146-166)
+void ref_project_batch(void* sp, void* mp, const float* T16s, uint64_t n_hyp, const uint32_t* hyp_sub,
+                       const uint64_t* sub_off, const int* sub_idx, uint32_t n_sub, float accept_prob,
+                       float dist_thres, int early_out, int nthreads, uint32_t* counts, double* scores) {
+    auto* h = static_cast<ref_scene*>(sp);
+    auto* m = static_cast<ref_model*>(mp);
+    std::vector<std::vector<int>> subs(n_sub);
+    for (uint32_t g = 0; g < n_sub; ++g) subs[g].assign(sub_idx + sub_off[g], sub_idx + sub_off[g + 1]);
+    (void)m->cloud->resolution();  // computed once, as in a real run (cached behind its mutex afterwards)
+    std::atomic<uint64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            uint64_t b = next.fetch_add(16);
+            if (b >= n_hyp) break;
+            for (uint64_t q = b; q < std::min<uint64_t>(b + 16, n_hyp); ++q) {
+                uint32_t sv = 0;
+                auto r = h->impl->project_(sv, *m->m, subs[hyp_sub[q]], mat_from(T16s + 16 * q), accept_prob,
+                                           dist_thres, early_out != 0);
+                counts[q] = (uint32_t)std::get<0>(r).size();
+                scores[q] = std::get<2>(r);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < std::max(1, nthreads); ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+}
+// the per-pair part of find_in_subset's loop body for pairs that passed the caller's filters:
+// feature -> valid -> query (<= limit hits) -> base_transform_ (scene.hpp:299-315).  Returns the
+// number of hypotheses written (column-major 4x4 each); hyp_pair[k] = index of the producing pair.
+uint64_t ref_hypotheses_batch(void* sp, void* mp, const uint32_t* pair_i, const uint32_t* pair_j, uint64_t n_pairs,
+                              uint32_t limit, uint64_t cap, float* T16s, uint32_t* hyp_pair) {
+    auto* h = static_cast<ref_scene*>(sp);
+    auto* m = static_cast<ref_model*>(mp);
+    uint64_t n = 0;
+    tr::curv_info_t<point_t> c{};
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        const point_t& p1 = h->cloud->points[pair_i[k]];
+        const point_t& p2 = h->cloud->points[pair_j[k]];
+        auto f = tr::feature<point_t>(p1, p2, c, c);
+        if (!f || !tr::valid<point_t>(*f, m->m->feature_bounds())) continue;
+        auto range = m->m->query(*f);
+        uint32_t query = 0;
+        for (auto it = range.first; it != range.second; ++it) {
+            if (limit > 0 && (++query) > limit) break;
+            auto&& [m_i, m_j] = it->second;
+            if (n >= cap) return n;
+            const point_t& q1 = m->cloud->points[m_i];
+            const point_t& q2 = m->cloud->points[m_j];
+            tr::mat4f_t t = h->impl->base_transform_(p1.getVector3fMap(), p2.getVector3fMap(), tr::tangent(p1),
+                                                     q1.getVector3fMap(), q2.getVector3fMap(), tr::tangent(q1));
+            for (int e = 0; e < 16; ++e) T16s[16 * n + e] = t.data()[e];
+            hyp_pair[n] = (uint32_t)k;
+            ++n;
+        }
+    }
+    return n;
 }
 float ref_resolution(const float* pos, uint32_t n) {
     std::vector<float> z(3 * (size_t)n, 0.f);

@@ -27,6 +27,26 @@ public:
         return (dx * dx + dy * dy) + dz * dz;
     }
     int nearestKSearch(const P& q, int k, std::vector<int>& is, std::vector<float>& ds) const {
+        if (k <= 2) {  // same (distance, index) order as below, without materialising all candidates
+            float bd[2] = {0.f, 0.f};
+            int bi[2] = {-1, -1};
+            for (int i : idx_) {
+                const P& p = (*pts_)[i];
+                if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+                float d = d2(p, q);
+                if (bi[0] < 0 || d < bd[0] || (d == bd[0] && i < bi[0])) {
+                    bd[1] = bd[0]; bi[1] = bi[0];
+                    bd[0] = d; bi[0] = i;
+                } else if (bi[1] < 0 || d < bd[1] || (d == bd[1] && i < bi[1])) {
+                    bd[1] = d; bi[1] = i;
+                }
+            }
+            int kk = (bi[0] >= 0) + (bi[1] >= 0);
+            kk = std::min(kk, k);
+            is.resize(kk); ds.resize(kk);
+            for (int j = 0; j < kk; ++j) { is[j] = bi[j]; ds[j] = bd[j]; }
+            return kk;
+        }
         std::vector<std::pair<float, int>> all;
         all.reserve(idx_.size());
         for (int i : idx_) {
