@@ -142,6 +142,27 @@ int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max
 int tm_traits_project(tm_ctx* ctx, int kind, const float g2l[16], float radius, float threshold,
                       const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
 
+/* The orphaned OpenCL ICP path (a15).  tm_uvicp_projection = opencl/icp.cl:1-53 icp_projection
+ * with the projector of opencl/cylinder.cl:1-25 (projector 0) or a linear projector
+ * uv = mat_proj * loc (projector 1): per scene point pnts[i] (float4), nearest model sample =
+ * the float4 stored in the pixel of the model's n_img = img_size[0]*img_size[1] "uv image".
+ * Outputs as the kernel writes them: model_indices / scene_indices (-1 when rejected),
+ * out_positions (uv_nrm, or (0,0,0,dist)); n_corr = number of emitted correspondences (what the
+ * absent host would have counted).  Matrices are 16 floats, column-major (opencl/util.cl:1-9). */
+int tm_uvicp_projection(tm_ctx* ctx, int projector, const float* pnts4, int32_t n, const float* image4,
+                        const int32_t img_size[2], const int32_t img_margin[2], const float mat_align[16],
+                        const float mat_uvw[16], const float mat_proj[16], const float mat_norm[16],
+                        float max_corr_dist, float* out_positions4, int32_t* model_indices,
+                        int32_t* scene_indices, uint32_t* n_corr);
+/* opencl/icp.cl:55-86 icp_correlation fused with the reduction its host never had: cov9 =
+ * sum over k of the nine float terms (scene[is[k]]-c_s) (x) (model[im[k]]-c_m) / (n-1), summed
+ * in double (column-major 3x3: cov9[3*j+i] = scene_i * model_j).  records16 (n x 16 floats, the
+ * kernel's float16 output) may be NULL. */
+int tm_uvicp_correlation(tm_ctx* ctx, const float* scene4, uint32_t n_scene, const float* model4,
+                         uint32_t n_model, const int32_t* indices_scene, const int32_t* indices_model, int32_t n,
+                         const float centroid_scene[4], const float centroid_model[4], float* records16,
+                         double cov9[9]);
+
 /* ---- resident query: the whole recorded-list search in one call --------- */
 typedef struct tm_query_params {
     float min_diameter_factor; /* sample_parameters (include/common:72-82) */

@@ -819,6 +819,85 @@ inline bool identity_project(v3 xyz, float uvw[3]) {
     return true;
 }
 
+// ------------------------------------------------------- opencl/*.cl (row a15)
+// The reference ships these OpenCL kernels without host code; restated per work-item.
+// [parity unpinned: OpenCL builtins atan2pi / length / convert_int and the device compiler's
+// contraction choices are third-party; fixed here as: no FMA, atan2pi(y,x) = atan2f(y,x)/pi_f32,
+// length = sqrtf of the left-to-right sum of squares, convert_int = round toward zero,
+// saturating, NaN -> 0, integer adds wrap.]
+// opencl/util.cl:1-9
+inline void cl_mat44_multiply(const float p[4], const float* mat, float out[4]) {
+    for (int r = 0; r < 4; ++r) out[r] = ((mat[r] * p[0] + mat[4 + r] * p[1]) + mat[8 + r] * p[2]) + mat[12 + r] * p[3];
+}
+// opencl/cylinder.cl:1-25
+inline void cl_uv_project(const float loc[4], const float* cyl2ncoord, float out[4]) {
+    float nc[4];
+    cl_mat44_multiply(loc, cyl2ncoord, nc);
+    float u = atan2f_full(nc[1], nc[0]) / 3.14159274101257324219f;
+    if (u < 0.f) u += 2.f;
+    u /= 2.f;
+    out[0] = u;
+    out[1] = nc[2];
+    out[2] = sqrtf(nc[0] * nc[0] + nc[1] * nc[1]) - 1.0f;
+    out[3] = 1.f;
+}
+inline int32_t cl_convert_int(float v) {
+    if (!(v == v)) return 0;
+    if (v >= 2147483648.f) return INT32_MAX;
+    if (v <= -2147483648.f) return INT32_MIN;
+    return (int32_t)v;
+}
+// opencl/icp.cl:1-53, one work-item.  projector 0 = cylinder.cl's uv_project, 1 = linear.
+inline void cl_icp_projection(int projector, const float* pnts4, int index, const float* image4,
+                              const int32_t img_size[2], const int32_t img_margin[2], const float* mat_align,
+                              const float* mat_uvw, const float* mat_proj, const float* mat_norm,
+                              float max_corr_dist, float* out_positions4, int32_t* model_indices,
+                              int32_t* scene_indices) {
+    const float* pnt = pnts4 + 4 * (size_t)index;
+    float loc[4], uv[4], tmp[4], uv_nrm[4];
+    cl_mat44_multiply(pnt, mat_align, loc);
+    if (projector == 0) cl_uv_project(loc, mat_proj, uv);
+    else cl_mat44_multiply(loc, mat_proj, uv);
+    cl_mat44_multiply(uv, mat_norm, tmp);
+    cl_mat44_multiply(tmp, mat_uvw, uv_nrm);
+    float ext[2] = {(float)(img_size[0] - 2 * img_margin[0] - 1), (float)(img_size[1] - 2 * img_margin[1] - 1)};
+    int32_t px[2];
+    for (int a = 0; a < 2; ++a)
+        px[a] = (int32_t)((uint32_t)cl_convert_int(uv_nrm[a] * ext[a]) + (uint32_t)img_margin[a]);
+    if (px[1] == img_size[1]) px[1] = img_size[1] - 1;
+    model_indices[index] = -1;
+    scene_indices[index] = -1;
+    float* op = out_positions4 + 4 * (size_t)index;
+    op[0] = op[1] = op[2] = op[3] = 0.f;
+    if (px[0] >= 0 && px[0] < img_size[0] && px[1] >= 0 && px[1] < img_size[1]) {
+        int idx = px[1] * img_size[0] + px[0];
+        float dx = image4[4 * (size_t)idx] - uv_nrm[0], dy = image4[4 * (size_t)idx + 1] - uv_nrm[1];
+        float dist = sqrtf(dx * dx + dy * dy);
+        op[3] = dist;
+        if (dist < max_corr_dist) {
+            model_indices[index] = idx;
+            scene_indices[index] = index;
+            for (int a = 0; a < 4; ++a) op[a] = uv_nrm[a];
+        }
+    }
+}
+// opencl/icp.cl:55-86, one work-item -> 16 floats
+inline void cl_icp_correlation(const float* scene4, const float* model4, const int32_t* indices_scene,
+                               const int32_t* indices_model, int n, int index, const float* centroid_scene,
+                               const float* centroid_model, float out16[16]) {
+    const float* s = scene4 + 4 * (size_t)indices_scene[index];
+    const float* m = model4 + 4 * (size_t)indices_model[index];
+    float spt[3], mpt[3];
+    for (int a = 0; a < 3; ++a) {
+        spt[a] = s[a] - centroid_scene[a];
+        mpt[a] = m[a] - centroid_model[a];
+    }
+    float norm = 1.f / (float)(n - 1);
+    for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) out16[3 * j + i] = spt[i] * mpt[j] * norm;
+    for (int a = 9; a < 16; ++a) out16[a] = 0.f;
+}
+
 // --------------------------------------------------------------------- octree
 // include/impl/octree.hpp:11-17 — octant bit i = pos[i] > center[i]
 inline uint8_t get_octant(v3 center, v3 pos) {

@@ -110,6 +110,30 @@ int orc_traits_project(int kind, const float* g2l16, float radius, float thresho
         default: return identity_project(p, uvw) ? 1 : 0;
     }
 }
+// opencl/icp.cl restated over all work-items; returns the number of emitted correspondences
+uint32_t orc_cl_icp_projection(int projector, const float* pnts4, int n, const float* image4, const int32_t* img_size,
+                               const int32_t* img_margin, const float* mat_align, const float* mat_uvw,
+                               const float* mat_proj, const float* mat_norm, float max_corr_dist,
+                               float* out_positions4, int32_t* model_indices, int32_t* scene_indices) {
+    uint32_t c = 0;
+    for (int i = 0; i < n; ++i) {
+        cl_icp_projection(projector, pnts4, i, image4, img_size, img_margin, mat_align, mat_uvw, mat_proj, mat_norm,
+                          max_corr_dist, out_positions4, model_indices, scene_indices);
+        c += model_indices[i] >= 0;
+    }
+    return c;
+}
+// per-correspondence float16 records + their sum in double (index order)
+void orc_cl_icp_correlation(const float* scene4, const float* model4, const int32_t* is, const int32_t* im, int n,
+                            const float* cs, const float* cm, float* records16, double* cov9) {
+    for (int k = 0; k < 9; ++k) cov9[k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float o[16];
+        cl_icp_correlation(scene4, model4, is, im, n, i, cs, cm, o);
+        if (records16) std::memcpy(records16 + 16 * (size_t)i, o, 64);
+        for (int k = 0; k < 9; ++k) cov9[k] += (double)o[k];
+    }
+}
 uint32_t orc_get_octant(const float* center, const float* pos) {
     return get_octant({center[0], center[1], center[2]}, {pos[0], pos[1], pos[2]});
 }

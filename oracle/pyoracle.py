@@ -118,6 +118,38 @@ def traits_project(kind, g2l16, radius, threshold, xyz):
     return uvw, ok
 
 
+def cl_icp_projection(projector, pnts4, image4, img_size, img_margin, mat_align, mat_uvw, mat_proj, mat_norm,
+                      max_corr_dist):
+    """opencl/icp.cl:1-53 (+ cylinder.cl / util.cl) over all work-items."""
+    pn = _f32(pnts4, (-1, 4))
+    im = _f32(image4, (-1, 4))
+    n = pn.shape[0]
+    sz = np.ascontiguousarray(img_size, dtype=np.int32)
+    mg = np.ascontiguousarray(img_margin, dtype=np.int32)
+    op = np.zeros((n, 4), dtype=np.float32)
+    mi = np.zeros(n, dtype=np.int32)
+    si = np.zeros(n, dtype=np.int32)
+    L = load()
+    L.orc_cl_icp_projection.restype = C.c_uint32
+    c = L.orc_cl_icp_projection(C.c_int(projector), _p(pn), C.c_int(n), _p(im), _p(sz), _p(mg), _p(_f32(mat_align, (16,))),
+                                _p(_f32(mat_uvw, (16,))), _p(_f32(mat_proj, (16,))), _p(_f32(mat_norm, (16,))),
+                                C.c_float(max_corr_dist), _p(op), _p(mi), _p(si))
+    return op, mi, si, int(c)
+
+
+def cl_icp_correlation(scene4, model4, indices_scene, indices_model, centroid_scene, centroid_model):
+    """opencl/icp.cl:55-86 over all work-items + the sum of the records in double."""
+    sc, md = _f32(scene4, (-1, 4)), _f32(model4, (-1, 4))
+    is_ = np.ascontiguousarray(indices_scene, dtype=np.int32)
+    im_ = np.ascontiguousarray(indices_model, dtype=np.int32)
+    n = is_.shape[0]
+    rec = np.zeros((max(n, 1), 16), dtype=np.float32)
+    cov = np.zeros(9, dtype=np.float64)
+    load().orc_cl_icp_correlation(_p(sc), _p(md), _p(is_), _p(im_), C.c_int(n), _p(_f32(centroid_scene, (4,))),
+                                  _p(_f32(centroid_model, (4,))), _p(rec), _p(cov))
+    return rec[:n], cov
+
+
 class OModel:
     def __init__(self, cloud, distance_step_count=20.0, angle_step=0.17453292, min_df=0.2,
                  max_df=1.0, resolution=-1.0, curv_ok=None):

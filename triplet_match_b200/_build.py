@@ -31,7 +31,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
 ] + os.environ.get("TM_NVCC_EXTRA", "").split()
-SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_icp.cu", "k_query.cu", "capi.cu"]
+SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_icp.cu", "k_uvicp.cu", "k_query.cu", "capi.cu"]
 HOST_SOURCES = ["host_model.cpp"]
 CXX = os.environ.get("CXX", "g++")
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
@@ -49,6 +49,7 @@ def _headers() -> list[str]:
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hs.append(os.path.join(REPO, "include", "tm_b200.h"))
     hs.append(os.path.join(REPO, "include", "tm_b200_host.h"))
+    hs.append(os.path.join(REPO, "include", "triplet_match", "tm_atan2f.h"))
     return hs
 
 

@@ -60,7 +60,7 @@ EXPORTS = [
     "tm_ctx_kernel_launches", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
     "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
-    "tm_traits_project", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
+    "tm_traits_project", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
@@ -190,6 +190,38 @@ class Context:
                                         C.c_float(threshold), _p(xyz), C.c_uint64(xyz.shape[0]),
                                         _p(uvw), _p(ok)))
         return uvw, ok
+
+
+    def uvicp_projection(self, projector, pnts4, image4, img_size, img_margin, mat_align, mat_uvw, mat_proj,
+                         mat_norm, max_corr_dist):
+        """tm_uvicp_projection (opencl/icp.cl icp_projection)."""
+        pn, im = _f32(pnts4, (-1, 4)), _f32(image4, (-1, 4))
+        n = pn.shape[0]
+        sz = np.ascontiguousarray(img_size, dtype=np.int32)
+        mg = np.ascontiguousarray(img_margin, dtype=np.int32)
+        op = np.zeros((max(n, 1), 4), dtype=np.float32)
+        mi = np.zeros(max(n, 1), dtype=np.int32)
+        si = np.zeros(max(n, 1), dtype=np.int32)
+        nc = C.c_uint32()
+        _chk(self.lib.tm_uvicp_projection(self.h, C.c_int(projector), _p(pn), C.c_int32(n), _p(im), _p(sz), _p(mg),
+                                          _p(_f32(mat_align, (16,))), _p(_f32(mat_uvw, (16,))),
+                                          _p(_f32(mat_proj, (16,))), _p(_f32(mat_norm, (16,))),
+                                          C.c_float(max_corr_dist), _p(op), _p(mi), _p(si), C.byref(nc)))
+        return op[:n], mi[:n], si[:n], int(nc.value)
+
+    def uvicp_correlation(self, scene4, model4, indices_scene, indices_model, centroid_scene, centroid_model,
+                          want_records=True):
+        """tm_uvicp_correlation (opencl/icp.cl icp_correlation + fused reduction)."""
+        sc, md = _f32(scene4, (-1, 4)), _f32(model4, (-1, 4))
+        is_ = np.ascontiguousarray(indices_scene, dtype=np.int32)
+        im_ = np.ascontiguousarray(indices_model, dtype=np.int32)
+        n = is_.shape[0]
+        rec = np.zeros((max(n, 1), 16), dtype=np.float32) if want_records else None
+        cov = np.zeros(9, dtype=np.float64)
+        _chk(self.lib.tm_uvicp_correlation(self.h, _p(sc), C.c_uint32(sc.shape[0]), _p(md), C.c_uint32(md.shape[0]),
+                                           _p(is_), _p(im_), C.c_int32(n), _p(_f32(centroid_scene, (4,))),
+                                           _p(_f32(centroid_model, (4,))), _p(rec), _p(cov)))
+        return (rec[:n] if rec is not None else None), cov
 
 
 def host_resolution(pos) -> float:

@@ -915,6 +915,78 @@ int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, fl
     return TM_OK;
 }
 
+// ------------------------------------------------------------ opencl/icp.cl path (a15)
+int tm_uvicp_projection(tm_ctx* c, int projector, const float* pnts4, int32_t n, const float* image4,
+                        const int32_t img_size[2], const int32_t img_margin[2], const float mat_align[16],
+                        const float mat_uvw[16], const float mat_proj[16], const float mat_norm[16],
+                        float max_corr_dist, float* out_positions4, int32_t* model_indices,
+                        int32_t* scene_indices, uint32_t* n_corr) {
+    REQUIRE(c && img_size && img_margin && mat_align && mat_uvw && mat_proj && mat_norm,
+            "tm_uvicp_projection: null argument");
+    REQUIRE(projector == 0 || projector == 1, "tm_uvicp_projection: unknown projector");
+    REQUIRE(n >= 0 && img_size[0] > 0 && img_size[1] > 0, "tm_uvicp_projection: bad sizes");
+    REQUIRE(n == 0 || (pnts4 && image4 && out_positions4 && model_indices && scene_indices),
+            "tm_uvicp_projection: null buffer");
+    TRY(bind(c));
+    if (n_corr) *n_corr = 0;
+    if (!n) return TM_OK;
+    const size_t n_img = (size_t)img_size[0] * (size_t)img_size[1];
+    DevBuf &dp = c->scratch[0], &di = c->scratch[1], &dop = c->scratch[2], &dmi = c->scratch[3],
+           &dsi = c->scratch[4], &dn = c->scratch[5];
+    TRY(dp.ensure((size_t)n * 16)); TRY(di.ensure(n_img * 16)); TRY(dop.ensure((size_t)n * 16));
+    TRY(dmi.ensure((size_t)n * 4)); TRY(dsi.ensure((size_t)n * 4)); TRY(dn.ensure(4));
+    CU(cudaMemcpyAsync(dp.p, pnts4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(di.p, image4, n_img * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(dn.p, 0, 4, c->stream));
+    launch_uvicp_projection(c->stream, projector, dp.as<float4>(), n, di.as<float4>(), img_size, img_margin,
+                            mat_align, mat_uvw, mat_proj, mat_norm, max_corr_dist, dop.as<float4>(),
+                            dmi.as<int>(), dsi.as<int>(), dn.as<unsigned int>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_positions4, dop.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(model_indices, dmi.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(scene_indices, dsi.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t nc = 0;
+    CU(cudaMemcpyAsync(&nc, dn.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_corr) *n_corr = nc;
+    return TM_OK;
+}
+
+int tm_uvicp_correlation(tm_ctx* c, const float* scene4, uint32_t n_scene, const float* model4,
+                         uint32_t n_model, const int32_t* indices_scene, const int32_t* indices_model, int32_t n,
+                         const float centroid_scene[4], const float centroid_model[4], float* records16,
+                         double cov9[9]) {
+    REQUIRE(c && centroid_scene && centroid_model && cov9, "tm_uvicp_correlation: null argument");
+    REQUIRE(n >= 0, "tm_uvicp_correlation: negative n");
+    REQUIRE(n == 0 || (scene4 && model4 && indices_scene && indices_model), "tm_uvicp_correlation: null buffer");
+    for (int32_t k = 0; k < n; ++k)
+        REQUIRE(indices_scene[k] >= 0 && (uint32_t)indices_scene[k] < n_scene && indices_model[k] >= 0 &&
+                    (uint32_t)indices_model[k] < n_model,
+                "tm_uvicp_correlation: index out of range");
+    TRY(bind(c));
+    DevBuf &ds = c->scratch[0], &dm = c->scratch[1], &dis = c->scratch[2], &dim = c->scratch[3],
+           &drec = c->scratch[4], &dpart = c->scratch[5], &dcov = c->scratch[6];
+    const int blocks = uvicp_correlation_blocks(n);
+    TRY(ds.ensure((size_t)n_scene * 16 + 16)); TRY(dm.ensure((size_t)n_model * 16 + 16));
+    TRY(dis.ensure((size_t)n * 4 + 4)); TRY(dim.ensure((size_t)n * 4 + 4));
+    TRY(dpart.ensure((size_t)blocks * 72 + 72)); TRY(dcov.ensure(72));
+    if (records16) TRY(drec.ensure((size_t)n * 64 + 64));
+    if (n) {
+        CU(cudaMemcpyAsync(ds.p, scene4, (size_t)n_scene * 16, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dm.p, model4, (size_t)n_model * 16, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dis.p, indices_scene, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dim.p, indices_model, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    launch_uvicp_correlation(c->stream, ds.as<float4>(), dm.as<float4>(), dis.as<int>(), dim.as<int>(), n,
+                             centroid_scene, centroid_model, records16 ? drec.as<float>() : nullptr,
+                             dpart.as<double>(), dcov.as<double>());
+    CU(cudaGetLastError());
+    if (records16 && n) CU(cudaMemcpyAsync(records16, drec.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(cov9, dcov.p, 72, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
 // ------------------------------------------------------------ resident query
 struct QueryOut {  // one contiguous device block, read back in one copy
     unsigned long long shard[3];  // h_begin, h_end, H

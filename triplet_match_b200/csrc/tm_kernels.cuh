@@ -141,6 +141,17 @@ void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& mo
                       float sq_thres, uint32_t n_seg, const uint32_t* seg_off,
                       uint32_t* scene_corrs, uint32_t* model_corrs, bool fused);
 
+// k_uvicp.cu (the opencl/icp.cl path, a15)
+void launch_uvicp_projection(cudaStream_t st, int projector, const float4* pnts, int n, const float4* image,
+                             const int img_size[2], const int img_margin[2], const float* mat_align,
+                             const float* mat_uvw, const float* mat_proj, const float* mat_norm,
+                             float max_corr_dist, float4* out_positions, int* model_indices, int* scene_indices,
+                             unsigned int* n_corr);
+int uvicp_correlation_blocks(int n);
+void launch_uvicp_correlation(cudaStream_t st, const float4* scene, const float4* model, const int* indices_scene,
+                              const int* indices_model, int n, const float* centroid_scene,
+                              const float* centroid_model, float* records, double* partials, double* cov9);
+
 // k_query.cu (device-side glue of the resident query)
 void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
                         unsigned long long hyp_limit, uint32_t rank, uint32_t world,
