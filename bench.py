@@ -426,6 +426,24 @@ def main():
                         "points in registers and the grid in L2, so frac > 1 is expected and DRAM traffic "
                         "is far below it"}
 
+    # the limit that actually binds (ncu, profiles/r1_score_full_v4_ncu_summary.txt): L2 -> L1 gather
+    # sectors.  Bytes per launch come from the committed ncu capture of this exact workload (they
+    # depend on the data, not on the run); time is this run's live kernel time.
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
+            tj = json.load(f)
+        l2_bytes = float(tj["l2_to_l1_bytes_per_launch"])
+        sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
+        l2_peak = 6300.0 * sm_mhz * 1e6 / 1e9  # ~6300 B/cycle full-chip LTS cap (B300_MICROARCH.md) at the sampled SM clock
+        if args.scale == 1.0 and k_ms > 0:
+            roofline["l2_gather"] = {"achieved": l2_bytes / (k_ms * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                                     "frac": l2_bytes / (k_ms * 1e-3) / 1e9 / l2_peak,
+                                     "l1_sector_requests_per_launch": tj.get("l1_sector_requests_per_launch"),
+                                     "peak_source": "guide: LTS throughput cap ~6300 B/cycle x sampled SM clock",
+                                     "bytes_source": tj.get("source")}
+    except Exception:
+        pass
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
