@@ -220,6 +220,19 @@ int tm_comm_create(tm_ctx* ctx, const uint8_t id[128], int rank, int world, tm_c
 void tm_comm_destroy(tm_comm* c);
 /* ncclAllReduce(max) of the packed best key, then broadcast of the winner's pose */
 int tm_query_allreduce_best(tm_query* q, tm_comm* c);
+/* icp_ with the SCENE sharded across ranks (BASELINE configs[4]: top-64 hypotheses refined
+ * against a 10 M-point scene on 8 GPUs): this rank accumulates n, sum s, sum m, sum s m^T and
+ * the score over its resident points [pt_begin, pt_end) as 64-bit fixed point; one
+ * ncclAllReduce(sum, int64) of n x 17 values per iteration makes every rank solve the same
+ * rigid fit, so all ranks return identical transforms and the result equals tm_icp's on the
+ * whole scene bit for bit.  n_scene_total = scene points over all ranks (it fixes the
+ * fixed-point scale and must be the same everywhere).  comm == NULL runs single-process;
+ * emulate_parts > 1 then accumulates the range as that many consecutive sub-ranges (how the
+ * split-invariance is tested on one GPU). */
+int tm_icp_sharded(tm_scene* s, tm_model* m, tm_comm* comm, const float* T16s, uint32_t n,
+                   uint32_t max_iterations, float dist_thres, uint32_t pt_begin, uint32_t pt_end,
+                   uint64_t n_scene_total, uint32_t emulate_parts, float* T16s_out, uint32_t* counts,
+                   double* scores, uint32_t* iters);
 
 #ifdef __cplusplus
 }

@@ -152,6 +152,23 @@ def test_correspondences_and_icp(setup):
                 assert abs(int(cnt[r]) - on) <= max(3, on // 100)
 
 
+def test_scene_sharded_icp_is_split_invariant(setup):
+    """tm_icp_sharded: any split of the scene points gives tm_icp's result bit for bit (64-bit
+    fixed-point sums); the NCCL leg of the same call is exercised by tools/mgpu_check.py."""
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T, nthreads=4)
+    top = np.argsort(-cnt.astype(np.int64), kind="stable")[:5]
+    To, co, so, io = gs.icp(gm, T[top], 4, 1.0)
+    for parts in (1, 2, 7):
+        Ts, cs, ss, is_ = gs.icp_sharded(gm, T[top], 4, 1.0, 0, s.n, s.n, emulate_parts=parts)
+        assert np.array_equal(_bits(Ts), _bits(To)) and np.array_equal(cs, co) and np.array_equal(is_, io)
+        assert np.array_equal(ss, so)
+    # a proper sub-range sees fewer correspondences
+    Th, ch, *_ = gs.icp_sharded(gm, T[top], 1, 1.0, 0, s.n // 2, s.n)
+    assert (ch <= co).all() and ch.sum() < co.sum()
+
+
 def test_resident_query_and_golden(setup, ctx):
     from triplet_match_b200 import capi
     name, m, s, om, osc, rec, gm, gs = setup

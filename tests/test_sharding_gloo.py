@@ -76,3 +76,66 @@ def test_shard_range_properties():
     assert capi.shard_range(100, 1, 2, hyp_limit=50) == (25, 50)
     assert capi.unpack_key(capi.pack_key(17, 5)) == (17, 5)
     assert capi.pack_key(3, 9) > capi.pack_key(3, 10) > capi.pack_key(2, 0)
+
+
+# ---- scene-sharded ICP (tm_icp_sharded): integer sums all-reduce exactly ---------------------
+def _icp_sums(scene_pos, model_pos, corr_s, corr_m, centre, scale):
+    """64-bit fixed-point n, sum s, sum m, sum s m^T of the pairs (the quantities icp_accumulate
+    reduces), quantised per term as round(v * scale)."""
+    s = scene_pos[corr_s].astype(np.float64) - centre
+    m = model_pos[corr_m].astype(np.float64) - centre
+    out = np.zeros(16, dtype=np.int64)
+    out[0] = corr_s.size
+    out[1:4] = np.rint(s * scale).astype(np.int64).sum(0)
+    out[4:7] = np.rint(m * scale).astype(np.int64).sum(0)
+    out[7:16] = np.rint((s[:, :, None] * m[:, None, :]).reshape(-1, 9) * scale).astype(np.int64).sum(0)
+    return out
+
+
+def _icp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, s, om, osc, rec = common.config("cylinder_small")
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T[:64], nthreads=2)
+    Tb = T[int(np.argmax(cnt))]
+    b, e = capi.point_range(s.n, rank, world)
+    r = osc.project(om, np.arange(b, e, dtype=np.int32), Tb, dist_thres=2.0)  # this rank's scene shard
+    centre = m.pos.mean(0).astype(np.float64)
+    sums = _icp_sums(s.pos, m.pos, r["scene_corrs"], r["model_corrs"], centre, 2.0 ** 30)
+    t = torch.from_numpy(sums.copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put((t.numpy().copy(), (b, e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_scene_sharded_icp_sums():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_icp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    total, rng0 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m, s, om, osc, rec = common.config("cylinder_small")
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T[:64], nthreads=2)
+    Tb = T[int(np.argmax(cnt))]
+    full = osc.project(om, np.arange(s.n, dtype=np.int32), Tb, dist_thres=2.0)
+    exp = _icp_sums(s.pos, m.pos, full["scene_corrs"], full["model_corrs"], m.pos.mean(0).astype(np.float64), 2.0 ** 30)
+    assert rng0 == (0, s.n // 2)
+    assert np.array_equal(total, exp) and total[0] == full["count"] > 100  # exact: integer sums commute
+
+
+def test_point_range_properties():
+    for n in (0, 1, 9, 1000, 10_000_019):
+        for world in (1, 2, 3, 8):
+            r = [capi.point_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))

@@ -64,7 +64,7 @@ EXPORTS = [
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
-    "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best",
+    "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best", "tm_icp_sharded",
 ]
 HOST_EXPORTS = [
     "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_destroy",
@@ -459,6 +459,22 @@ class Scene:
         return out, counts, scores, iters
 
 
+    def icp_sharded(self, model: Model, T16s, max_iterations: int, dist_thres: float, pt_begin: int,
+                    pt_end: int, n_scene_total: int, comm=None, emulate_parts: int = 1):
+        """tm_icp_sharded: this process accumulates scene points [pt_begin, pt_end)."""
+        T = _f32(T16s, (-1, 16))
+        n = T.shape[0]
+        out = np.zeros_like(T)
+        counts = np.zeros(n, dtype=np.uint32)
+        scores = np.zeros(n, dtype=np.float64)
+        iters = np.zeros(n, dtype=np.uint32)
+        _chk(self.lib.tm_icp_sharded(self.h, model.h, comm.h if comm is not None else None, _p(T),
+                                     C.c_uint32(n), C.c_uint32(max_iterations), C.c_float(dist_thres),
+                                     C.c_uint32(pt_begin), C.c_uint32(pt_end), C.c_uint64(n_scene_total),
+                                     C.c_uint32(emulate_parts), _p(out), _p(counts), _p(scores), _p(iters)))
+        return out, counts, scores, iters
+
+
 class Query:
     """Resident recorded-list search (tm_query_*)."""
 
@@ -573,6 +589,11 @@ def shard_range(n_hyp: int, rank: int, world: int, hyp_limit: int = 0):
     per = (H + world - 1) // world
     hb = min(rank * per, H)
     return hb, min(hb + per, H)
+
+
+def point_range(n_points: int, rank: int, world: int):
+    """Scene points of `rank` when an ICP pass is sharded over the scene (tm_icp_sharded)."""
+    return (n_points * rank) // world, (n_points * (rank + 1)) // world
 
 
 def pack_key(inliers: int, global_id: int) -> int:

@@ -823,21 +823,43 @@ static double icp_fix_scale(const tm_model* m, uint32_t n_scene, float thres) {
     bits = std::max(8, std::min(40, bits));
     return std::ldexp(1.0, bits);
 }
+struct tm_comm;
+static int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st);  // NCCL section
+// how the scene points of one ICP pass are split: this process accumulates [pt_begin, pt_end)
+// (as `emulate` consecutive sub-ranges when emulate > 1) and, with a communicator, the 64-bit
+// fixed-point sums are all-reduced — integer sums, so any split gives the same bits.
+struct IcpSplit {
+    uint32_t pt_begin = 0, pt_end = 0;
+    uint64_t n_total = 0;  // scene points over all ranks (fixes the fixed-point scale)
+    tm_comm* comm = nullptr;
+    uint32_t emulate = 1;
+};
 // enqueue the ICP loop for k transforms already in b.Tcur with b.active set
 static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpBufs& b, uint32_t k,
-                       uint32_t max_iterations, float dist_thres) {
+                       uint32_t max_iterations, float dist_thres, const IcpSplit* split = nullptr) {
     const float thres = (2 * dist_thres) * m->dev.resolution;  // scene.hpp:373 + :413
     const float sqt = sq_threshold(thres);
-    const double fs = icp_fix_scale(m, scene.n, thres);
+    IcpSplit sp;
+    if (split) sp = *split;
+    else { sp.pt_end = scene.n; sp.n_total = scene.n; }
+    const double fs = icp_fix_scale(m, (uint32_t)std::min<uint64_t>(sp.n_total, 0xffffffffull), thres);
     CU(cudaMemsetAsync(b.sums_cur.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
     CU(cudaMemsetAsync(b.sums_best.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
     CU(cudaMemsetAsync(b.iters.p, 0, (size_t)k * 4, c->stream));
     const int grid = c->sm_count * 4;
     IcpState st = b.state();
+    const uint32_t parts = std::max(1u, sp.emulate);
+    const uint64_t span = sp.pt_end - sp.pt_begin;
     for (uint32_t it = 0; it <= max_iterations; ++it) {
-        launch_icp_accumulate(c->stream, scene, m->dev, st.Tcur, st.active, k, 0, scene.n, sqt,
-                              m->centre[0], m->centre[1], m->centre[2], fs, st.sums_cur, grid,
-                              m->fused);
+        for (uint32_t w = 0; w < parts; ++w) {
+            const uint32_t b0 = sp.pt_begin + (uint32_t)(span * w / parts);
+            const uint32_t b1 = sp.pt_begin + (uint32_t)(span * (w + 1) / parts);
+            if (b1 > b0)
+                launch_icp_accumulate(c->stream, scene, m->dev, st.Tcur, st.active, k, b0, b1, sqt,
+                                      m->centre[0], m->centre[1], m->centre[2], fs, st.sums_cur, grid,
+                                      m->fused);
+        }
+        if (sp.comm) TRY(comm_allreduce_sum_i64(sp.comm, st.sums_cur, (size_t)k * ICP_NSUM, c->stream));
         launch_icp_step(c->stream, st, k, it == 0 ? 1 : 0, max_iterations, 1.0 / fs, m->centre[0],
                         m->centre[1], m->centre[2]);
     }
@@ -845,14 +867,15 @@ static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpB
     return TM_OK;
 }
 
-int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
-           float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters) {
+static int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
+                   float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters,
+                   const IcpSplit* split) {
     REQUIRE(s && m, "null handle");
     REQUIRE(n == 0 || (T16s && T16s_out && counts), "tm_icp: null buffer");
     tm_ctx* c = s->ctx;
     TRY(bind(c));
     if (!n) return TM_OK;
-    if (max_iterations == 0) {  // scene.hpp:371: the match is returned unchanged
+    if (max_iterations == 0 && !split) {  // scene.hpp:371: the match is returned unchanged
         memcpy(T16s_out, T16s, (size_t)n * 64);
         if (iters) memset(iters, 0, (size_t)n * 4);
         return tm_score(s, m, T16s, n, nullptr, nullptr, nullptr, 0, dist_thres, 0.f, 0, counts,
@@ -874,7 +897,7 @@ int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max
         e = cudaMemcpyAsync(b.active.p, ones.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) return done(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
     launch_rows_from_colmajor(c->stream, d16.as<float>(), n, b.Tcur.as<float4>());
-    if ((rc = icp_enqueue(c, s->dev, m, b, n, max_iterations, dist_thres))) return done(rc);
+    if ((rc = icp_enqueue(c, s->dev, m, b, n, max_iterations, dist_thres, split))) return done(rc);
     launch_colmajor_from_rows(c->stream, b.Tbest.as<float4>(), n, d16.as<float>());
     std::vector<long long> sums((size_t)n * ICP_NSUM);
     e = cudaMemcpyAsync(T16s_out, d16.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream);
@@ -891,6 +914,11 @@ int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max
             scores[h] = (double)sums[(size_t)h * ICP_NSUM + 16] / SCORE_SCALE / (double)m->dev.cloud.n;
     }
     return done(TM_OK);
+}
+
+int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
+           float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters) {
+    return icp_run(s, m, T16s, n, max_iterations, dist_thres, T16s_out, counts, scores, iters, nullptr);
 }
 
 int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, float threshold,
@@ -1400,7 +1428,7 @@ int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess_ = 0 };
-enum { ncclUint8_ = 1, ncclUint64_ = 5 };  // ncclDataType_t
+enum { ncclUint8_ = 1, ncclInt64_ = 4, ncclUint64_ = 5 };  // ncclDataType_t
 enum { ncclSum_ = 0, ncclMax_ = 2 };       // ncclRedOp_t
 struct NcclApi {
     void* lib = nullptr;
@@ -1472,6 +1500,25 @@ void tm_comm_destroy(tm_comm* cm) {
     cudaSetDevice(cm->ctx->device);
     if (cm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm->comm);
     delete cm;
+}
+static int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st) {
+    NC(g_nccl.AllReduce(buf, buf, count, ncclInt64_, ncclSum_, cm->comm, st));
+    return TM_OK;
+}
+int tm_icp_sharded(tm_scene* s, tm_model* m, tm_comm* cm, const float* T16s, uint32_t n,
+                   uint32_t max_iterations, float dist_thres, uint32_t pt_begin, uint32_t pt_end,
+                   uint64_t n_scene_total, uint32_t emulate_parts, float* T16s_out, uint32_t* counts,
+                   double* scores, uint32_t* iters) {
+    REQUIRE(s && m, "null handle");
+    REQUIRE(pt_begin <= pt_end && pt_end <= s->dev.n, "tm_icp_sharded: bad point range");
+    REQUIRE(n_scene_total >= (uint64_t)(pt_end - pt_begin), "tm_icp_sharded: n_scene_total too small");
+    REQUIRE(!cm || cm->ctx == s->ctx, "communicator belongs to another context");
+    REQUIRE(!(cm && emulate_parts > 1), "tm_icp_sharded: emulate_parts is for single-process runs");
+    REQUIRE(max_iterations > 0, "tm_icp_sharded: max_iterations must be > 0");
+    IcpSplit sp;
+    sp.pt_begin = pt_begin; sp.pt_end = pt_end; sp.n_total = n_scene_total; sp.comm = cm;
+    sp.emulate = std::max(1u, emulate_parts);
+    return icp_run(s, m, T16s, n, max_iterations, dist_thres, T16s_out, counts, scores, iters, &sp);
 }
 int tm_query_allreduce_best(tm_query* q, tm_comm* cm) {
     REQUIRE(q && cm && q->ran, "tm_query_allreduce_best: bad argument");
