@@ -220,6 +220,9 @@ int tm_comm_create(tm_ctx* ctx, const uint8_t id[128], int rank, int world, tm_c
 void tm_comm_destroy(tm_comm* c);
 /* ncclAllReduce(max) of the packed best key, then broadcast of the winner's pose */
 int tm_query_allreduce_best(tm_query* q, tm_comm* c);
+/* the same for n queries at once (BASELINE configs[3]: 16 models x one scene): one max
+ * all-reduce over the n keys and one over the n (score, pose) records. */
+int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* c);
 /* icp_ with the SCENE sharded across ranks (BASELINE configs[4]: top-64 hypotheses refined
  * against a 10 M-point scene on 8 GPUs): this rank accumulates n, sum s, sum m, sum s m^T and
  * the score over its resident points [pt_begin, pt_end) as 64-bit fixed point; one

@@ -64,7 +64,7 @@ EXPORTS = [
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
-    "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best", "tm_icp_sharded",
+    "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best", "tm_queries_allreduce_best", "tm_icp_sharded",
 ]
 HOST_EXPORTS = [
     "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_destroy",
@@ -572,6 +572,10 @@ class Comm:
         buf = (C.c_uint8 * 128)()
         _chk(load().tm_nccl_unique_id(buf))
         return bytes(buf)
+
+    def allreduce_best_many(self, queries):
+        arr = (C.c_void_p * len(queries))(*[q.h.value for q in queries])
+        _chk(self.lib.tm_queries_allreduce_best(arr, C.c_uint32(len(queries)), self.h))
 
     def allreduce_best(self, q: Query):
         _chk(self.lib.tm_query_allreduce_best(q.h, self.h))

@@ -1469,6 +1469,7 @@ struct tm_comm {
     tm_ctx* ctx;
     ncclComm_t comm;
     int rank, world;
+    DevBuf stage;  // batched best-pose reduce: n keys, then n x (score, pose)
 };
 
 int tm_nccl_unique_id(uint8_t out[128]) {
@@ -1485,7 +1486,7 @@ int tm_comm_create(tm_ctx* c, const uint8_t idb[128], int rank, int world, tm_co
     TRY(bind(c));
     ncclUniqueId id;
     memcpy(id.internal, idb, 128);
-    tm_comm* cm = new tm_comm{c, nullptr, rank, world};
+    tm_comm* cm = new tm_comm{c, nullptr, rank, world, DevBuf()};
     int r = g_nccl.CommInitRank(&cm->comm, world, id, rank);
     if (r != 0) {
         delete cm;
@@ -1499,7 +1500,42 @@ void tm_comm_destroy(tm_comm* cm) {
     if (!cm) return;
     cudaSetDevice(cm->ctx->device);
     if (cm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm->comm);
+    cm->stage.release();
     delete cm;
+}
+// batched form for several queries over the same scene (BASELINE configs[3]: 16 models x one
+// scene): ONE max all-reduce over the n packed keys and ONE sum all-reduce over the n x 72-byte
+// (score, pose) records instead of 2n collectives
+int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* cm) {
+    REQUIRE(cm && (n == 0 || qs), "tm_queries_allreduce_best: null argument");
+    if (!n) return TM_OK;
+    tm_ctx* c = cm->ctx;
+    for (uint32_t i = 0; i < n; ++i)
+        REQUIRE(qs[i] && qs[i]->ran && qs[i]->s->ctx == c, "tm_queries_allreduce_best: bad query");
+    TRY(bind(c));
+    TRY(cm->stage.ensure((size_t)n * 8 + (size_t)n * 72));
+    unsigned long long* keys = cm->stage.as<unsigned long long>();
+    uint8_t* recs = reinterpret_cast<uint8_t*>(keys + n);
+    for (uint32_t i = 0; i < n; ++i)
+        CU(cudaMemcpyAsync(keys + i, &qs[i]->out.as<QueryOut>()->best, 8, cudaMemcpyDeviceToDevice, c->stream));
+    NC(g_nccl.AllReduce(keys, keys, n, ncclUint64_, ncclMax_, cm->comm, c->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        tm_query* q = qs[i];
+        QueryOut* out = q->out.as<QueryOut>();
+        CU(cudaMemcpyAsync(&out->best, keys + i, 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
+        CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
+        launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
+                             q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
+                             &out->best_score);
+        CU(cudaMemcpyAsync(recs + 72 * (size_t)i, &out->best_score, 72, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaGetLastError());
+    NC(g_nccl.AllReduce(recs, recs, (size_t)n * 72, ncclUint8_, ncclSum_, cm->comm, c->stream));
+    for (uint32_t i = 0; i < n; ++i)
+        CU(cudaMemcpyAsync(&qs[i]->out.as<QueryOut>()->best_score, recs + 72 * (size_t)i, 72,
+                           cudaMemcpyDeviceToDevice, c->stream));
+    return TM_OK;
 }
 static int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st) {
     NC(g_nccl.AllReduce(buf, buf, count, ncclInt64_, ncclSum_, cm->comm, st));

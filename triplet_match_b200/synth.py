@@ -197,16 +197,18 @@ def _rot(axis: np.ndarray, angle: float) -> np.ndarray:
 
 def make_scene(seed: int, model: Cloud, n_points: int, n_copies: int = 3, extent: float = 3.0,
                res: float = 0.01, clutter_frac: float = 0.1, flat_copies: bool = True,
-               noise_tangent_frac: float = 0.002, walls: bool = True) -> Cloud:
+               noise_tangent_frac: float = 0.002, walls: bool = True, models=None) -> Cloud:
     """Ground plane (+ walls) + posed model copies + uniform clutter, exactly n_points.
 
     Roughly half of the copies lie flat (rotation about z, small lift), the rest are tilted.
     A fraction of floor points get random in-plane tangents ("false" feature points)."""
     parts_pos, parts_nrm, parts_tgt, parts_tm = [], [], [], []
     poses = []
-    mc = model.pos.astype(np.float64).mean(axis=0)
     rp = uniform(seed, 51, 6 * n_copies).reshape(n_copies, 6)
     for c in range(n_copies):
+        if models is not None:  # batched search: copy c is an instance of models[c % len(models)]
+            model = models[c % len(models)]
+        mc = model.pos.astype(np.float64).mean(axis=0)
         yaw = 2 * np.pi * rp[c, 0]
         R = _rot(np.array([0, 0, 1.0]), yaw)
         if not (flat_copies and c % 2 == 0):
