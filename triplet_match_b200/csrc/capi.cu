@@ -91,7 +91,7 @@ struct tm_model {
 
 struct tm_scene {
     tm_ctx* ctx;
-    DevBuf pos, nrm, tgt, mask_tmp;
+    DevBuf pos, nrm, tgt, mask_tmp, seg_lo, seg_hi;
     CloudDev dev;
 };
 
@@ -408,6 +408,24 @@ int tm_scene_upload(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangen
         return rc;
     }
     s->dev = CloudDev{s->pos.as<float4>(), s->nrm.as<float4>(), s->tgt.as<float4>(), cloud->n};
+    // bounding boxes of the BALL_SEG-point segments: lets the radius search (a8) skip whole
+    // segments; tight when the caller supplies the scene in a space-filling-curve order
+    const uint32_t n_seg = (cloud->n + BALL_SEG - 1) / BALL_SEG;
+    if (n_seg) {
+        if ((rc = s->seg_lo.ensure((size_t)n_seg * 16)) || (rc = s->seg_hi.ensure((size_t)n_seg * 16))) {
+            tm_scene_destroy(s);
+            return rc;
+        }
+        launch_seg_bbox(c->stream, s->dev.pos, cloud->n, s->seg_lo.as<float4>(), s->seg_hi.as<float4>());
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            tm_scene_destroy(s);
+            return fail(TM_ERR_CUDA, cudaGetErrorString(e));
+        }
+        s->dev.seg_lo = s->seg_lo.as<float4>();
+        s->dev.seg_hi = s->seg_hi.as<float4>();
+    }
     *out = s;
     return TM_OK;
 }
@@ -538,33 +556,33 @@ int tm_hypotheses(tm_scene* s, tm_model* m, const uint32_t* pi, const uint32_t* 
 }
 
 // device-side ball subsets into (row offsets u64, indices); returns total via host sync
+// counts: [centre][segment] u32 (becomes in-row offsets), row_tot: per-centre totals,
+// row_off: CSR offsets.  active_ranges (device, n_centres + 1, or null): centre c is searched
+// only when active_ranges[c + 1] > active_ranges[c]; skipped centres get an empty row.
 static int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t* d_centres,
-                            uint32_t n_centres, float radius, DevBuf& counts, DevBuf& seg_off,
-                            DevBuf& row_off, DevBuf* indices, uint64_t* total_out) {
+                            uint32_t n_centres, const uint32_t* active_ranges, float radius, DevBuf& counts,
+                            DevBuf& row_tot, DevBuf& row_off, DevBuf* indices, uint64_t* total_out) {
     const uint32_t n_seg = (scene.n + BALL_SEG - 1) / BALL_SEG;
     const size_t nc = (size_t)n_centres * n_seg;
     TRY(counts.ensure(std::max<size_t>(nc, 1) * 4));
-    TRY(seg_off.ensure((nc + 1) * 8));
+    TRY(row_tot.ensure(((size_t)n_centres + 1) * 4));
     TRY(row_off.ensure(((size_t)n_centres + 1) * 8));
     float r2 = radius * radius;
-    launch_ball_count(c->stream, scene.pos, scene.n, d_centres, n_centres, r2, n_seg,
-                      counts.as<uint32_t>());
-    launch_exclusive_scan_u64(c->stream, counts.as<uint32_t>(), seg_off.as<unsigned long long>(),
-                              nc);
-    launch_ball_row_offsets(c->stream, seg_off.as<unsigned long long>(), n_centres, n_seg,
-                            row_off.as<unsigned long long>());
+    launch_ball_count(c->stream, scene, d_centres, n_centres, active_ranges, r2, n_seg, counts.as<uint32_t>());
+    launch_ball_seg_scan(c->stream, counts.as<uint32_t>(), n_centres, n_seg, row_tot.as<uint32_t>());
+    launch_exclusive_scan_u64(c->stream, row_tot.as<uint32_t>(), row_off.as<unsigned long long>(), n_centres);
     CU(cudaGetLastError());
     if (total_out) {
         unsigned long long t = 0;
-        CU(cudaMemcpyAsync(&t, seg_off.as<unsigned long long>() + nc, 8, cudaMemcpyDeviceToHost,
+        CU(cudaMemcpyAsync(&t, row_off.as<unsigned long long>() + n_centres, 8, cudaMemcpyDeviceToHost,
                            c->stream));
         CU(cudaStreamSynchronize(c->stream));
         *total_out = t;
         if (indices) TRY(indices->ensure(std::max<uint64_t>(t, 1) * 4));
     }
     if (indices && indices->p) {
-        launch_ball_fill(c->stream, scene.pos, scene.n, d_centres, n_centres, r2, n_seg,
-                         seg_off.as<unsigned long long>(), indices->as<int32_t>());
+        launch_ball_fill(c->stream, scene, d_centres, n_centres, active_ranges, r2, n_seg, counts.as<uint32_t>(),
+                         row_off.as<unsigned long long>(), indices->as<int32_t>());
         CU(cudaGetLastError());
     }
     return TM_OK;
@@ -585,7 +603,7 @@ int tm_ball_subsets(tm_scene* s, const uint32_t* centres, uint32_t n_centres, fl
     TRY(dc.ensure((size_t)n_centres * 4));
     CU(cudaMemcpyAsync(dc.p, centres, (size_t)n_centres * 4, cudaMemcpyHostToDevice, c->stream));
     uint64_t total = 0;
-    TRY(ball_subsets_dev(c, s->dev, dc.as<uint32_t>(), n_centres, radius, cnt, so, ro,
+    TRY(ball_subsets_dev(c, s->dev, dc.as<uint32_t>(), n_centres, nullptr, radius, cnt, so, ro,
                          indices ? &idx : nullptr, &total));
     CU(cudaMemcpyAsync(offsets, ro.p, ((size_t)n_centres + 1) * 8, cudaMemcpyDeviceToHost,
                        c->stream));
@@ -1139,7 +1157,8 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     uint64_t total = 0;
     std::vector<unsigned long long> so(n_outer + 1, 0);
     if (n_outer) {
-        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, q->m->dev.diameter,
+        // sizing pass over ALL outer samples (a rank's shard is only known per run)
+        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, nullptr, q->m->dev.diameter,
                              q->ball_counts, q->ball_seg_off, q->sub_off, &q->sub_idx, &total));
         CU(cudaMemcpyAsync(so.data(), q->sub_off.p, (n_outer + 1) * 8ull, cudaMemcpyDeviceToHost,
                            c->stream));
@@ -1179,20 +1198,6 @@ int tm_query_run(tm_query* q) {
     CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
     CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
     CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
-    const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
-    // (a8) radius subsets of the outer samples
-    if (q->n_outer) {
-        const float r2 = m->dev.diameter * m->dev.diameter;
-        const size_t nc = (size_t)q->n_outer * n_seg;
-        launch_ball_count(c->stream, sc.pos, sc.n, q->outer.as<uint32_t>(), q->n_outer, r2, n_seg,
-                          q->ball_counts.as<uint32_t>());
-        launch_exclusive_scan_u64(c->stream, q->ball_counts.as<uint32_t>(),
-                                  q->ball_seg_off.as<unsigned long long>(), nc);
-        launch_ball_row_offsets(c->stream, q->ball_seg_off.as<unsigned long long>(), q->n_outer,
-                                n_seg, q->sub_off.as<unsigned long long>());
-        launch_ball_fill(c->stream, sc.pos, sc.n, q->outer.as<uint32_t>(), q->n_outer, r2, n_seg,
-                         q->ball_seg_off.as<unsigned long long>(), q->sub_idx.as<int32_t>());
-    }
     // (a1-a5) pair filter, feature, key, probe
     float lower, upper;
     pair_window(m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
@@ -1211,6 +1216,21 @@ int tm_query_run(tm_query* q) {
     launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
                             q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
                             q->g_hyp.as<uint32_t>());
+    // (a8) radius subsets, only of the outer samples that own hypotheses of this rank's shard
+    // (g_hyp); the others get empty rows, so N ranks do not repeat each other's searches
+    if (q->n_outer) {
+        const float r2 = m->dev.diameter * m->dev.diameter;
+        const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
+        launch_ball_count(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
+                          q->ball_counts.as<uint32_t>());
+        launch_ball_seg_scan(c->stream, q->ball_counts.as<uint32_t>(), q->n_outer, n_seg,
+                             q->ball_seg_off.as<uint32_t>());
+        launch_exclusive_scan_u64(c->stream, q->ball_seg_off.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
+                                  q->n_outer);
+        launch_ball_fill(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
+                         q->ball_counts.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
+                         q->sub_idx.as<int32_t>());
+    }
     // (a6, a7) hypotheses
     launch_hypotheses(c->stream, sc, m->dev, q->outer.as<uint32_t>(), q->pair_outer.as<uint32_t>(),
                       q->pair_j.as<uint32_t>(), q->n_pairs, q->hyp_off.as<unsigned long long>(),

@@ -124,69 +124,174 @@ void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned lon
 }
 
 // -------------------------------------------------------------- ball subsets
-// One warp owns a segment of BALL_SEG consecutive scene points and walks all
-// centres; lane l visits points seg*BALL_SEG + k*32 + l, so ballot order is
-// ascending index order and the compaction is deterministic.  Predicate
-// (FLANN L2_Simple order): (dx*dx + dy*dy) + dz*dz < r^2.
-// counts layout: [centre][segment].
-template <bool FILL>
+// One warp owns a segment of BALL_SEG consecutive scene points; lane l visits points
+// seg*BALL_SEG + k*32 + l, so ballot order is ascending index order and the compaction is
+// deterministic.  Predicate (FLANN L2_Simple order): (dx*dx + dy*dy) + dz*dz < r^2.
+// Centres are walked 32 at a time: lane l decides whether centre c0+l can touch the segment at
+// all — the centre is active (has hypotheses in this rank's shard) and the segment's bounding
+// box (computed once per scene, seg_bbox_kernel) comes within r of it, with a 1e-5 relative
+// guard that dominates the rounding of the exact predicate — and only the surviving
+// (segment, centre) pairs run the per-point loop.  On Morton-ordered scenes a ball touches a
+// few percent of the segments.  counts layout: [centre][segment], zero-initialised by the host.
 __global__ void __launch_bounds__(256)
-    ball_kernel(const float4* __restrict__ pos, uint32_t n, const uint32_t* __restrict__ centres,
-                uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* __restrict__ counts,
-                const unsigned long long* __restrict__ seg_offsets, int32_t* __restrict__ indices) {
+    seg_bbox_kernel(const float4* __restrict__ pos, uint32_t n, uint32_t n_seg, float4* __restrict__ lo,
+                    float4* __restrict__ hi) {
     const int lane = threadIdx.x & 31;
     const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (seg >= n_seg) return;
     const uint32_t base = seg * BALL_SEG;
-    for (uint32_t c = 0; c < n_centres; ++c) {
-        float4 cp = pos[centres[c]];
-        unsigned long long off = FILL ? seg_offsets[(size_t)c * n_seg + seg] : 0ull;
-        uint32_t cnt = 0;
-#pragma unroll 4
-        for (uint32_t k = 0; k < BALL_SEG / 32; ++k) {
-            uint32_t i = base + k * 32 + lane;
-            bool in = false;
-            if (i < n) {
-                float4 p = pos[i];
-                float dx = p.x - cp.x, dy = p.y - cp.y, dz = p.z - cp.z;
-                in = ((dx * dx + dy * dy) + dz * dz) < r2;
+    float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+    for (uint32_t k = 0; k < BALL_SEG / 32; ++k) {
+        const uint32_t i = base + k * 32 + lane;
+        if (i < n) {
+            const float4 p = pos[i];
+            if (p.x == p.x && p.y == p.y && p.z == p.z) {  // NaN points never pass the predicate
+                mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x);
+                mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
+                mnz = fminf(mnz, p.z); mxz = fmaxf(mxz, p.z);
             }
-            uint32_t b = __ballot_sync(0xffffffffu, in);
-            if (FILL) {
-                if (in) indices[off + cnt + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
-            }
-            cnt += __popc(b);
         }
-        if (!FILL && lane == 0) counts[(size_t)c * n_seg + seg] = cnt;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+    }
+    if (lane == 0) {
+        lo[seg] = make_float4(mnx, mny, mnz, 0.f);
+        hi[seg] = make_float4(mxx, mxy, mxz, 0.f);
     }
 }
-void launch_ball_count(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
-                       uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* counts) {
+void launch_seg_bbox(cudaStream_t st, const float4* pos, uint32_t n, float4* lo, float4* hi) {
+    const uint32_t n_seg = (n + BALL_SEG - 1) / BALL_SEG;
+    if (!n_seg) return;
+    ++g_launch_count;
+    seg_bbox_kernel<<<(n_seg + 7) / 8, 256, 0, st>>>(pos, n, n_seg, lo, hi);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+    ball_kernel(const float4* __restrict__ pos, uint32_t n, const float4* __restrict__ seg_lo,
+                const float4* __restrict__ seg_hi, const uint32_t* __restrict__ centres, uint32_t n_centres,
+                const uint32_t* __restrict__ active_ranges, float r2, uint32_t n_seg,
+                uint32_t* __restrict__ counts, const unsigned long long* __restrict__ row_off,
+                int32_t* __restrict__ indices) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= n_seg) return;
+    const uint32_t base = seg * BALL_SEG;
+    float4 blo = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f), bhi = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+    if (seg_lo) {
+        blo = seg_lo[seg];
+        bhi = seg_hi[seg];
+    }
+    for (uint32_t c0 = 0; c0 < n_centres; c0 += 32) {
+        const uint32_t cl = c0 + lane;
+        bool cand = false;
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cl < n_centres && (!active_ranges || active_ranges[cl + 1] > active_ranges[cl])) {
+            mine = pos[centres[cl]];
+            // squared distance from the centre to the segment box (0 inside); NaN never culls
+            const float dx = fmaxf(fmaxf(blo.x - mine.x, mine.x - bhi.x), 0.f);
+            const float dy = fmaxf(fmaxf(blo.y - mine.y, mine.y - bhi.y), 0.f);
+            const float dz = fmaxf(fmaxf(blo.z - mine.z, mine.z - bhi.z), 0.f);
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            cand = !(d2 > r2 * 1.00002f + 1e-30f);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, cand);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t c = c0 + src;
+            const float cx = __shfl_sync(0xffffffffu, mine.x, src), cy = __shfl_sync(0xffffffffu, mine.y, src),
+                        cz = __shfl_sync(0xffffffffu, mine.z, src);
+            unsigned long long off = 0ull;
+            if (FILL) off = row_off[c] + counts[(size_t)c * n_seg + seg];  // counts hold in-row offsets here
+            uint32_t cnt = 0;
+#pragma unroll 4
+            for (uint32_t k = 0; k < BALL_SEG / 32; ++k) {
+                const uint32_t i = base + k * 32 + lane;
+                bool in = false;
+                if (i < n) {
+                    const float4 p = pos[i];
+                    const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+                    in = ((dx * dx + dy * dy) + dz * dz) < r2;
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, in);
+                if (FILL) {
+                    if (in) indices[off + cnt + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
+                }
+                cnt += __popc(b);
+            }
+            if (!FILL && lane == 0 && cnt) counts[(size_t)c * n_seg + seg] = cnt;
+        }
+    }
+}
+void launch_ball_count(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
+                       const uint32_t* active_ranges, float r2, uint32_t n_seg, uint32_t* counts) {
+    if (!n_seg || !n_centres) return;
+    cudaMemsetAsync(counts, 0, (size_t)n_centres * n_seg * 4, st);
+    ++g_launch_count;
+    ball_kernel<false><<<(n_seg + 7) / 8, 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
+                                                       n_centres, active_ranges, r2, n_seg, counts, nullptr, nullptr);
+}
+void launch_ball_fill(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
+                      const uint32_t* active_ranges, float r2, uint32_t n_seg, const uint32_t* seg_local_off,
+                      const unsigned long long* row_off, int32_t* indices) {
     if (!n_seg || !n_centres) return;
     ++g_launch_count;
-    ball_kernel<false><<<(n_seg + 7) / 8, 256, 0, st>>>(pos, n, centres, n_centres, r2, n_seg,
-                                                       counts, nullptr, nullptr);
+    ball_kernel<true><<<(n_seg + 7) / 8, 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
+                                                      n_centres, active_ranges, r2, n_seg,
+                                                      const_cast<uint32_t*>(seg_local_off), row_off, indices);
 }
-void launch_ball_fill(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
-                      uint32_t n_centres, float r2, uint32_t n_seg,
-                      const unsigned long long* seg_offsets, int32_t* indices) {
-    if (!n_seg || !n_centres) return;
+// per-centre exclusive scan of the segment counts, in place (one CTA per centre), + row totals
+__global__ void __launch_bounds__(1024)
+    ball_seg_scan_kernel(uint32_t* __restrict__ counts, uint32_t n_seg, uint32_t* __restrict__ row_total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* row = counts + (size_t)blockIdx.x * n_seg;
+    if (threadIdx.x == 0) carry_s = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_seg; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_seg ? row[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + warp_sums[warp] + (incl - v);
+        if (i < n_seg) row[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_total[blockIdx.x] = carry_s;
+}
+void launch_ball_seg_scan(cudaStream_t st, uint32_t* counts, uint32_t n_centres, uint32_t n_seg,
+                          uint32_t* row_total) {
+    if (!n_centres) return;
     ++g_launch_count;
-    ball_kernel<true><<<(n_seg + 7) / 8, 256, 0, st>>>(pos, n, centres, n_centres, r2, n_seg,
-                                                      nullptr, seg_offsets, indices);
-}
-// per-centre CSR offsets = flattened scan sampled at segment 0 of each centre
-__global__ void ball_row_offsets_kernel(const unsigned long long* __restrict__ seg_offsets,
-                                        uint32_t n_centres, uint32_t n_seg,
-                                        unsigned long long* __restrict__ row_offsets) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c <= n_centres) row_offsets[c] = seg_offsets[(size_t)c * n_seg];
-}
-void launch_ball_row_offsets(cudaStream_t st, const unsigned long long* seg_offsets,
-                             uint32_t n_centres, uint32_t n_seg, unsigned long long* row_offsets) {
-    ++g_launch_count;
-    ball_row_offsets_kernel<<<(n_centres + 1 + 255) / 256, 256, 0, st>>>(seg_offsets, n_centres,
-                                                                         n_seg, row_offsets);
+    ball_seg_scan_kernel<<<n_centres, 1024, 0, st>>>(counts, n_seg, row_total);
 }
 
 // ---------------------------------------------------------------- voxel_fill

@@ -24,6 +24,8 @@ struct CloudDev {
     const float4* nrm;
     const float4* tgt;
     uint32_t n;
+    const float4* seg_lo = nullptr;  // scenes: bounding box of every BALL_SEG-point segment
+    const float4* seg_hi = nullptr;
 };
 
 struct HashSlot {  // open addressing, linear probing, home = murmur4(key) & mask

@@ -80,13 +80,14 @@ void launch_set_mask(cudaStream_t st, float4* pos, uint32_t n, const uint8_t* ma
 void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n);
 void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned long long* out,
                                uint64_t n);
-void launch_ball_count(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
-                       uint32_t n_centres, float r2, uint32_t n_seg, uint32_t* counts);
-void launch_ball_fill(cudaStream_t st, const float4* pos, uint32_t n, const uint32_t* centres,
-                      uint32_t n_centres, float r2, uint32_t n_seg,
-                      const unsigned long long* seg_offsets, int32_t* indices);
-void launch_ball_row_offsets(cudaStream_t st, const unsigned long long* seg_offsets,
-                             uint32_t n_centres, uint32_t n_seg, unsigned long long* row_offsets);
+void launch_seg_bbox(cudaStream_t st, const float4* pos, uint32_t n, float4* lo, float4* hi);
+void launch_ball_count(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
+                       const uint32_t* active_ranges, float r2, uint32_t n_seg, uint32_t* counts);
+void launch_ball_seg_scan(cudaStream_t st, uint32_t* counts, uint32_t n_centres, uint32_t n_seg,
+                          uint32_t* row_total);
+void launch_ball_fill(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
+                      const uint32_t* active_ranges, float r2, uint32_t n_seg, const uint32_t* seg_local_off,
+                      const unsigned long long* row_off, int32_t* indices);
 void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
                        float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel);
 void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
