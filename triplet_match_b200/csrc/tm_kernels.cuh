@@ -9,7 +9,10 @@ extern unsigned long long g_launch_count;
 
 // ---- tuning constants ------------------------------------------------------
 constexpr int SCORE_THREADS = 256;
-constexpr int SCORE_P = 4;                              // scene points per thread
+#ifndef TM_SCORE_P
+#define TM_SCORE_P 4
+#endif
+constexpr int SCORE_P = TM_SCORE_P;                     // scene points per thread
 #ifndef TM_SCORE_MIN_BLOCKS
 #define TM_SCORE_MIN_BLOCKS 4
 #endif
