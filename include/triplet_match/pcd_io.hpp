@@ -1,0 +1,178 @@
+// triplet_match/pcd_io.hpp — PCD (Point Cloud Data, v0.7) reader / writer for the 48-byte
+// PointSurfel record, so the CLI works without PCL (the reference loads clouds with
+// pcl::io::loadPCDFile, apps/triplet_match.cpp:14-15,33-34 and include/impl/pointcloud.hpp:60-64).
+// Fields are matched by name: x y z | normal_x normal_y normal_z | rgba (or rgb) | radius
+// confidence curvature (the tangent overlays the last three, include/common:62-70);
+// tangent_x/y/z are accepted as aliases.  Missing fields stay zero.  DATA ascii and binary are
+// supported; binary_compressed (LZF) is reported as an error.  SIZE 4 / 8 floats, 1 / 2 / 4 byte
+// integers.
+#ifndef TRIPLET_MATCH_PCD_IO_HPP_
+#define TRIPLET_MATCH_PCD_IO_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "compat.hpp"
+
+namespace triplet_match {
+namespace pcd {
+
+struct field_t {
+    std::string name;
+    int size = 4;
+    char type = 'F';
+    int count = 1;
+    int offset = 0;  // byte offset inside a binary record
+};
+
+inline int surfel_slot(const std::string& n) {  // float index inside the 12-float record, -1 = ignore
+    static const char* names[] = {"x", "y", "z", nullptr, "normal_x", "normal_y", "normal_z", nullptr,
+                                  "rgba", "radius", "confidence", "curvature"};
+    for (int i = 0; i < 12; ++i)
+        if (names[i] && n == names[i]) return i;
+    if (n == "rgb") return 8;
+    if (n == "tangent_x") return 9;
+    if (n == "tangent_y") return 10;
+    if (n == "tangent_z") return 11;
+    return -1;
+}
+
+inline double read_scalar(const char* p, const field_t& f) {
+    switch (f.type) {
+        case 'F':
+            if (f.size == 4) { float v; std::memcpy(&v, p, 4); return v; }
+            if (f.size == 8) { double v; std::memcpy(&v, p, 8); return v; }
+            break;
+        case 'U':
+            if (f.size == 1) { uint8_t v; std::memcpy(&v, p, 1); return v; }
+            if (f.size == 2) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+            if (f.size == 4) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+            break;
+        case 'I':
+            if (f.size == 1) { int8_t v; std::memcpy(&v, p, 1); return v; }
+            if (f.size == 2) { int16_t v; std::memcpy(&v, p, 2); return v; }
+            if (f.size == 4) { int32_t v; std::memcpy(&v, p, 4); return v; }
+            break;
+    }
+    throw std::runtime_error("pcd: unsupported field type/size for '" + f.name + "'");
+}
+
+inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out) {
+    std::ifstream in(filename, std::ios::binary);
+    if (!in) throw std::runtime_error("pcd: cannot open '" + filename + "'");
+    std::vector<field_t> fields;
+    uint64_t width = 0, height = 1, points = 0;
+    bool have_points = false;
+    std::string data_kind, line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == '#') continue;
+        std::istringstream ls(line);
+        std::string key;
+        ls >> key;
+        auto fill = [&](auto setter) {
+            std::string tok;
+            size_t i = 0;
+            while (ls >> tok) {
+                if (fields.size() <= i) fields.resize(i + 1);
+                setter(fields[i], tok);
+                ++i;
+            }
+        };
+        if (key == "FIELDS") fill([](field_t& f, const std::string& t) { f.name = t; });
+        else if (key == "SIZE") fill([](field_t& f, const std::string& t) { f.size = std::stoi(t); });
+        else if (key == "TYPE") fill([](field_t& f, const std::string& t) { f.type = t[0]; });
+        else if (key == "COUNT") fill([](field_t& f, const std::string& t) { f.count = std::stoi(t); });
+        else if (key == "WIDTH") ls >> width;
+        else if (key == "HEIGHT") ls >> height;
+        else if (key == "POINTS") { ls >> points; have_points = true; }
+        else if (key == "DATA") { ls >> data_kind; break; }
+        // VERSION, VIEWPOINT: ignored
+    }
+    if (fields.empty()) throw std::runtime_error("pcd: no FIELDS line in '" + filename + "'");
+    if (!have_points) points = width * height;
+    int rec = 0;
+    for (auto& f : fields) {
+        f.offset = rec;
+        rec += f.size * f.count;
+    }
+    out.assign(points, pcl::PointSurfel());
+    auto store = [](pcl::PointSurfel& p, int slot, const field_t& f, double v, const char* raw) {
+        float* rec12 = reinterpret_cast<float*>(&p);
+        if (slot == 8) {  // rgba / rgb keep their bit pattern
+            if (raw && f.size == 4) std::memcpy(&p.rgba, raw, 4);
+            else p.rgba = static_cast<uint32_t>(v);
+        } else {
+            rec12[slot] = static_cast<float>(v);
+        }
+    };
+    if (data_kind == "ascii") {
+        for (uint64_t i = 0; i < points; ++i) {
+            if (!std::getline(in, line)) throw std::runtime_error("pcd: truncated ascii data in '" + filename + "'");
+            std::istringstream ls(line);
+            for (const auto& f : fields) {
+                const int slot = surfel_slot(f.name);
+                for (int c = 0; c < f.count; ++c) {
+                    std::string tok;
+                    if (!(ls >> tok)) throw std::runtime_error("pcd: short ascii record in '" + filename + "'");
+                    if (slot < 0 || c > 0) continue;
+                    if (slot == 8 && f.type == 'F') {  // PCL writes packed rgb as a float literal
+                        float fv = std::stof(tok);
+                        std::memcpy(&out[i].rgba, &fv, 4);
+                    } else {
+                        store(out[i], slot, f, f.type == 'F' ? std::stod(tok) : static_cast<double>(std::stoll(tok)), nullptr);
+                    }
+                }
+            }
+        }
+    } else if (data_kind == "binary") {
+        std::vector<char> buf(static_cast<size_t>(rec) * points);
+        in.read(buf.data(), static_cast<std::streamsize>(buf.size()));
+        if (static_cast<size_t>(in.gcount()) != buf.size())
+            throw std::runtime_error("pcd: truncated binary data in '" + filename + "'");
+        for (const auto& f : fields) {
+            const int slot = surfel_slot(f.name);
+            if (slot < 0) continue;
+            for (uint64_t i = 0; i < points; ++i) {
+                const char* p = buf.data() + static_cast<size_t>(rec) * i + f.offset;
+                store(out[i], slot, f, slot == 8 && f.size == 4 ? 0.0 : read_scalar(p, f), p);
+            }
+        }
+    } else {
+        throw std::runtime_error("pcd: DATA '" + data_kind + "' is not supported (ascii and binary are)");
+    }
+    for (auto& p : out) p.data[3] = 1.f;
+}
+
+// writes the full surfel record (x y z normal_x normal_y normal_z rgba radius confidence curvature)
+inline void save(const std::string& filename, const std::vector<pcl::PointSurfel>& pts, bool binary = true) {
+    std::ofstream o(filename, std::ios::binary);
+    if (!o) throw std::runtime_error("pcd: cannot write '" + filename + "'");
+    o << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\n"
+      << "FIELDS x y z normal_x normal_y normal_z rgba radius confidence curvature\n"
+      << "SIZE 4 4 4 4 4 4 4 4 4 4\nTYPE F F F F F F U F F F\nCOUNT 1 1 1 1 1 1 1 1 1 1\n"
+      << "WIDTH " << pts.size() << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << pts.size() << "\n"
+      << "DATA " << (binary ? "binary" : "ascii") << "\n";
+    for (const auto& p : pts) {
+        if (binary) {
+            float r[10] = {p.x, p.y, p.z, p.normal_x, p.normal_y, p.normal_z, 0.f, p.radius, p.confidence, p.curvature};
+            std::memcpy(&r[6], &p.rgba, 4);
+            o.write(reinterpret_cast<const char*>(r), sizeof(r));
+        } else {
+            char line[512];
+            std::snprintf(line, sizeof(line), "%.9g %.9g %.9g %.9g %.9g %.9g %u %.9g %.9g %.9g\n", p.x, p.y, p.z,
+                          p.normal_x, p.normal_y, p.normal_z, p.rgba, p.radius, p.confidence, p.curvature);
+            o << line;
+        }
+    }
+}
+
+}  // namespace pcd
+}  // namespace triplet_match
+
+#endif  // TRIPLET_MATCH_PCD_IO_HPP_

@@ -1,5 +1,6 @@
 // tests/cpp/test_dropin.cpp — exercises the drop-in C++ API (include/triplet_match/*).
 //   test_dropin cpu                      host-only checks (no GPU): feature / discretize / traits / octree
+//   test_dropin pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]   PCD reader / writer round trip
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
 //        the Python harness (n, then n x {pos3, nrm3, tgt3} floats); prints matches.
@@ -135,6 +136,19 @@ static int cpu_checks() {
 
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc >= 4 && std::string(argv[1]) == "pcd") {  // pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]
+        cloud_t::Ptr c;
+        try {
+            c = cloud_t::from_pcd(argv[2]);
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 3;
+        }
+        std::ofstream out(argv[3], std::ios::binary);
+        out.write(reinterpret_cast<const char*>(c->points.data()), (std::streamsize)(c->size() * sizeof(point_t)));
+        if (argc >= 6) tr::pcd::save(argv[4], c->points, std::string(argv[5]) == "binary");
+        return 0;
+    }
     if (argc < 5) {
         std::fprintf(stderr, "usage: %s cpu | find model.bin scene.bin out.txt\n", argv[0]);
         return 2;

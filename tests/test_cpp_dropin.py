@@ -57,3 +57,110 @@ def test_cpp_find_all_parallel(exe, tmp_path):
         assert int(v[0]) >= 0.5 * m.n
         found.add(k)
     assert len(found) == n  # no instance is reported twice (overlap-free acceptance)
+
+
+# ---- PCD I/O + the CLI ------------------------------------------------------
+def _pcd_header(fields, sizes, types, n, data):
+    return ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS " + " ".join(fields) + "\nSIZE " +
+            " ".join(map(str, sizes)) + "\nTYPE " + " ".join(types) + "\nCOUNT " + " ".join(["1"] * len(fields)) +
+            f"\nWIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA {data}\n").encode()
+
+
+def write_pcd(cloud, path, binary=True):
+    """x y z normal_x normal_y normal_z rgba radius confidence curvature (tangent in the last three)."""
+    n = cloud.n
+    rec = np.zeros((n, 10), dtype=np.float32)
+    rec[:, 0:3], rec[:, 3:6], rec[:, 7:10] = cloud.pos, cloud.nrm, cloud.tgt
+    rec[:, 6] = (np.arange(n, dtype=np.uint32) * 2654435761 & 0xFFFFFF).astype(np.uint32).view(np.float32)
+    fields = ["x", "y", "z", "normal_x", "normal_y", "normal_z", "rgba", "radius", "confidence", "curvature"]
+    with open(path, "wb") as f:
+        f.write(_pcd_header(fields, [4] * 10, ["F"] * 6 + ["U"] + ["F"] * 3, n, "binary" if binary else "ascii"))
+        if binary:
+            f.write(rec.tobytes())
+        else:
+            rg = rec[:, 6].view(np.uint32)
+            for i in range(n):
+                v = rec[i]
+                f.write((" ".join(repr(float(x)) for x in v[:6]) + f" {int(rg[i])} " +
+                         " ".join(repr(float(x)) for x in v[7:]) + "\n").encode())
+    return rec
+
+
+def _surfels(path, n):
+    raw = np.fromfile(path, dtype=np.float32).reshape(n, 12)
+    return raw
+
+
+def test_pcd_reader_and_writer(exe, tmp_path):
+    m, *_ = common.config("plane_small")
+    for binary in (True, False):
+        src, out, re_a = str(tmp_path / "a.pcd"), str(tmp_path / "a.bin"), str(tmp_path / "b.pcd")
+        rec = write_pcd(m, src, binary)
+        r = subprocess.run([exe, "pcd", src, out, re_a, "ascii" if binary else "binary"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        s = _surfels(out, m.n)
+        assert np.array_equal(s[:, 0:3].view(np.uint32), rec[:, 0:3].view(np.uint32))
+        assert (s[:, 3] == 1).all()
+        assert np.array_equal(s[:, 4:7].view(np.uint32), rec[:, 3:6].view(np.uint32))
+        assert np.array_equal(s[:, 8].view(np.uint32), rec[:, 6].view(np.uint32))      # rgba bits
+        assert np.array_equal(s[:, 9:12].view(np.uint32), rec[:, 7:10].view(np.uint32))  # tangent overlay
+        # what the writer produced reads back identically (other encoding)
+        out2 = str(tmp_path / "b.bin")
+        assert subprocess.run([exe, "pcd", re_a, out2], capture_output=True).returncode == 0
+        assert np.array_equal(np.fromfile(out2, np.uint32), np.fromfile(out, np.uint32))
+    # other layouts: reordered / extra / double / missing fields, tangent_* aliases
+    n = 5
+    pts = np.arange(n * 3, dtype=np.float64).reshape(n, 3) * 0.25
+    p = str(tmp_path / "c.pcd")
+    with open(p, "wb") as f:
+        f.write(_pcd_header(["intensity", "z", "y", "x", "tangent_x"], [2, 8, 8, 8, 4], ["U", "F", "F", "F", "F"], n, "binary"))
+        for i in range(n):
+            f.write(np.uint16(i).tobytes() + pts[i, ::-1].astype(np.float64).tobytes() + np.float32(0.5 + i).tobytes())
+    out = str(tmp_path / "c.bin")
+    assert subprocess.run([exe, "pcd", p, out], capture_output=True).returncode == 0
+    s = _surfels(out, n)
+    assert np.array_equal(s[:, 0:3], pts.astype(np.float32)) and np.array_equal(s[:, 9], np.arange(n, dtype=np.float32) + 0.5)
+    assert (s[:, 4:7] == 0).all() and (s[:, 10:12] == 0).all()
+    # errors: compressed data, truncated file, missing file
+    bad = str(tmp_path / "d.pcd")
+    with open(bad, "wb") as f:
+        f.write(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, 4, "binary_compressed"))
+    assert subprocess.run([exe, "pcd", bad, out], capture_output=True).returncode == 3
+    with open(bad, "wb") as f:
+        f.write(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, 4, "binary") + b"\0" * 20)
+    assert subprocess.run([exe, "pcd", bad, out], capture_output=True).returncode == 3
+    assert subprocess.run([exe, "pcd", str(tmp_path / "nope.pcd"), out], capture_output=True).returncode == 3
+
+
+@pytest.fixture(scope="module")
+def cli(built, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cli") / "triplet_match")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "apps", "triplet_match.cpp"), "-o", out, "-L" + LIBDIR,
+                           "-ltriplet_match_b200", "-Wl,-rpath," + LIBDIR])
+    return out
+
+
+def test_cli_usage_and_errors(cli, tmp_path):
+    assert subprocess.run([cli], capture_output=True).returncode == 2
+    r = subprocess.run([cli, str(tmp_path / "no.pcd"), str(tmp_path / "no2.pcd")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_finds_instances_from_pcd(cli, tmp_path):
+    m, s, om, osc, rec = common.config("cylinder_small")
+    mp, sp = str(tmp_path / "model.pcd"), str(tmp_path / "scene.pcd")
+    write_pcd(m, mp, binary=True)
+    write_pcd(s, sp, binary=False)
+    r = subprocess.run([cli, mp, sp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    lines = [ln for ln in r.stdout.split("\n") if ln.startswith("match ")]
+    assert len(lines) >= 1, r.stdout
+    mpts = m.pos.astype(np.float64)
+    for ln in lines:
+        tok = ln.split()
+        T = np.array([float(x) for x in tok[tok.index("T") + 1:]]).reshape(4, 4).T
+        placed = mpts @ T[:3, :3].T + T[:3, 3]
+        errs = [np.abs(placed - (mpts @ P[:3, :3].T + P[:3, 3])).max() for P in s.poses]
+        assert min(errs) < 3 * om.resolution, (errs, r.stdout)
