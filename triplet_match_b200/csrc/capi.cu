@@ -735,7 +735,16 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
     } else {
         TRY(w0.ensure(n_hyp * 4)); TRY(ddrop.ensure(n_hyp));
         launch_group_of_hyp(c->stream, dgh.as<uint32_t>(), n_groups, w0.as<uint32_t>());
+        // boxes of every 32 subset positions: lets the walker skip steps that cannot reach the grid
+        uint64_t max_sub = 0;
+        for (uint32_t g = 0; g < n_groups; ++g) max_sub = std::max<uint64_t>(max_sub, soff[g + 1] - soff[g]);
+        const size_t n_tiles = (size_t)(soff[n_groups] / 32) + n_groups + 2;
+        TRY(w1.ensure(n_tiles * 16)); TRY(w2.ensure(n_tiles * 16));
+        launch_subset_tile_boxes(c->stream, s->dev, d_idx, dso.as<unsigned long long>(), n_groups,
+                                 (uint32_t)max_sub, w1.as<float4>(), w2.as<float4>());
         EarlyArgs a;
+        a.tile_lo = w1.as<float4>();
+        a.tile_hi = w2.as<float4>();
         a.scene = s->dev;
         a.model = m->dev;
         a.sub_idx = d_idx;
@@ -1063,7 +1072,8 @@ struct tm_query {
     DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
     DevBuf n_items_g, item_off, items, ctrl;
     DevBuf out;  // QueryOut
-    DevBuf topk_ids, icp_T16, stats;
+    DevBuf topk_ids, icp_T16, stats, tile_lo, tile_hi;
+    uint32_t max_sub = 0;
     IcpBufs icp;
     QueryOut host_out;
     bool ran = false;
@@ -1097,7 +1107,7 @@ void tm_query_destroy(tm_query* q) {
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->icp_T16, &q->stats})
+          &q->topk_ids, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
         b->release();
     q->icp.release();
     delete q;
@@ -1169,8 +1179,10 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     CU(cudaStreamSynchronize(c->stream));
     q->sub_total = total;
     uint64_t items = 0;
+    q->max_sub = 0;
     for (uint32_t o = 0; o < n_outer; ++o) {
         uint64_t np = so[o + 1] - so[o];
+        q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
         uint64_t nh = std::min<uint64_t>((uint64_t)(opo[o + 1] - opo[o]) * limit, cap);
         items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
     }
@@ -1179,6 +1191,10 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
     TRY(q->item_off.ensure((n_outer + 1) * 4ull));
     TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
+    if (q->p.early_out) {
+        const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
+        TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
+    }
     if (q->p.icp_top_k) {
         TRY(q->icp.ensure(q->p.icp_top_k));
         TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
@@ -1276,7 +1292,11 @@ int tm_query_run(tm_query* q) {
         } else {
             launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
                                 q->g_of_hyp.as<uint32_t>());
+            launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                                     q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
             EarlyArgs a;
+            a.tile_lo = q->tile_lo.as<float4>();
+            a.tile_hi = q->tile_hi.as<float4>();
             a.scene = sc;
             a.model = m->dev;
             a.sub_idx = q->sub_idx.as<int32_t>();

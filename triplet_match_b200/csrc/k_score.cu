@@ -370,6 +370,52 @@ __device__ __forceinline__ uint32_t early_drop_upper(uint32_t tried, uint32_t ns
 
 // One warp per hypothesis, subset walked in order 32 elements at a time.
 // g_of_hyp: subset row of each hypothesis (null => row 0); sub_idx null => identity.
+// bounding box of every 32 consecutive positions of every subset row (mask_ ignored: a
+// superset box is still conservative).  One warp per tile; grid.y = group.
+__global__ void __launch_bounds__(256)
+    subset_tile_boxes_kernel(CloudDev scene, const int32_t* __restrict__ sub_idx,
+                             const unsigned long long* __restrict__ sub_off, float4* __restrict__ tile_lo,
+                             float4* __restrict__ tile_hi) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.y;
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long sb = sub_off[g];
+    const uint32_t nsub = (uint32_t)(sub_off[g + 1] - sb);
+    if ((unsigned long long)t * 32ull >= nsub) return;
+    const uint32_t q = t * 32u + lane;
+    float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+    if (q < nsub) {
+        const uint32_t idx = sub_idx ? (uint32_t)sub_idx[sb + q] : (uint32_t)(sb + q);
+        const float4 v = scene.pos[idx];
+        if (v.x == v.x && v.y == v.y && v.z == v.z) {
+            mnx = mxx = v.x; mny = mxy = v.y; mnz = mxz = v.z;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+    }
+    if (lane == 0) {
+        const size_t e = (size_t)(sb / 32ull) + g + t;
+        tile_lo[e] = make_float4(mnx, mny, mnz, 0.f);
+        tile_hi[e] = make_float4(mxx, mxy, mxz, 0.f);
+    }
+}
+void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
+                              const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
+                              float4* tile_lo, float4* tile_hi) {
+    if (!n_groups || !max_sub) return;
+    const uint32_t tiles = (max_sub + 31) / 32;
+    ++g_launch_count;
+    dim3 grid((tiles + 7) / 8, n_groups);
+    subset_tile_boxes_kernel<<<grid, 256, 0, st>>>(scene, sub_idx, sub_off, tile_lo, tile_hi);
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(256)
     score_early_drop_kernel(EarlyArgs a) {
@@ -392,53 +438,98 @@ __global__ void __launch_bounds__(256)
         return (uint32_t)(0.05f * (float)(i + 1u) * (float)nsub);
     };
     uint32_t cur_test = test_at(0);
-    for (uint32_t base = 0; base < nsub && !dropped; base += 32) {
-        uint32_t q = base + lane;
-        bool reach = false, inl = false;
-        unsigned long long term = 0;
-        if (q < nsub) {
-            uint32_t idx = a.sub_idx ? (uint32_t)a.sub_idx[sb + q] : (uint32_t)(sb + q);
-            float4 v = a.scene.pos[idx];
-            uint32_t fl = __float_as_uint(v.w);
-            if (!(fl & FLAG_MASKED)) {
-                float x, y, z;
-                uint32_t lin = 0xffffffffu;
-                inl = point_test<FUSED>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z,
-                                        lin);
-                reach = lin != 0xffffffffu;  // voxel_query succeeded (scene.hpp:458-460)
-                if (inl) term = inlier_score(a.scene, a.model, r0, r1, r2, idx, fl, lin);
-            }
-        }
-        const uint32_t reach_mask = __ballot_sync(0xffffffffu, reach);
-        const uint32_t inl_mask = __ballot_sync(0xffffffffu, inl);
-        if (a.early_out && next_test < 18u && base + 32u >= cur_test) {
-            int last_l = -1;
-            while (next_test < 18u) {
-                // first reaching element at or after position cur_test, one checkpoint per element
-                int lmin = (cur_test > base + 1u) ? (int)(cur_test - base - 1u) : 0;
-                int lstart = max(lmin, last_l + 1);
-                if (lstart >= 32) break;
-                uint32_t cand = reach_mask & (0xffffffffu << lstart);
-                if (!cand) break;
-                int l = __ffs(cand) - 1;
-                uint32_t tried = base + (uint32_t)l + 1u;
-                uint32_t c_here = corrs + __popc(inl_mask & (0xffffffffu >> (31 - l)));
-                uint32_t upper = early_drop_upper(tried, nsub, c_here);
-                if ((float)upper < accept_bound) {
-                    dropped = true;
-                    drop_corrs = c_here;
-                    drop_tried = tried;
-                    unsigned long long part = lane_score + ((lane <= l) ? term : 0ull);
-                    drop_score = warp_sum_u64(part);
-                    break;
+    // Positions are walked in steps of 32.  With tile boxes, 32 steps are screened at once: lane l
+    // pushes the box of step s0+l through the transform (interval arithmetic, same guard as the
+    // full scorer); a step whose box misses the grid has no reaching element, so it changes neither
+    // the counts nor the checkpoint state and is skipped.
+    const ModelDev& m = a.model;
+    const uint32_t n_steps = (nsub + 31u) / 32u;
+    const size_t tile_base = (size_t)(sb / 32ull) + g;
+    for (uint32_t s0 = 0; s0 < n_steps && !dropped; s0 += 32) {
+        uint32_t live = 0xffffffffu;
+        if (a.tile_lo) {
+            bool survive = false;
+            const uint32_t st = s0 + lane;
+            if (st < n_steps) {
+                const float4 lo = a.tile_lo[tile_base + st], hi = a.tile_hi[tile_base + st];
+                if (lo.x <= hi.x) {  // at least one finite point
+                    const float cx = 0.5f * (lo.x + hi.x), hx = 0.5f * (hi.x - lo.x);
+                    const float cy = 0.5f * (lo.y + hi.y), hy = 0.5f * (hi.y - lo.y);
+                    const float cz = 0.5f * (lo.z + hi.z), hz = 0.5f * (hi.z - lo.z);
+                    const float acx = fabsf(cx) + hx, acy = fabsf(cy) + hy, acz = fabsf(cz) + hz;
+                    bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                  \
+    {                                                                                           \
+        float cc = r.x * cx + r.y * cy + r.z * cz + r.w;                                        \
+        float ee = fabsf(r.x) * hx + fabsf(r.y) * hy + fabsf(r.z) * hz;                         \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
+        ee += 1e-5f * mag + 1e-30f;                                                             \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
+        float lo_ = S * (cc - ee) + TV - sl, hi_ = S * (cc + ee) + TV + sl;                     \
+        out = out || (lo_ >= EXF) || (hi_ <= -1.0f);                                            \
+    }
+                    TM_AXIS(r0, m.sx, m.tx, m.exf)
+                    TM_AXIS(r1, m.sy, m.ty, m.eyf)
+                    TM_AXIS(r2, m.sz, m.tz, m.ezf)
+#undef TM_AXIS
+                    survive = !out;
                 }
-                ++next_test;
-                last_l = l;
-                cur_test = next_test < 18u ? test_at(next_test) : 0u;
             }
+            live = __ballot_sync(0xffffffffu, survive);
+        } else {
+            const uint32_t left = n_steps - s0;
+            live = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
         }
-        corrs += __popc(inl_mask);
-        lane_score += term;
+        while (live && !dropped) {
+            const uint32_t base = (s0 + (uint32_t)(__ffs(live) - 1)) * 32u;
+            live &= live - 1u;
+            uint32_t q = base + lane;
+            bool reach = false, inl = false;
+            unsigned long long term = 0;
+            if (q < nsub) {
+                uint32_t idx = a.sub_idx ? (uint32_t)a.sub_idx[sb + q] : (uint32_t)(sb + q);
+                float4 v = a.scene.pos[idx];
+                uint32_t fl = __float_as_uint(v.w);
+                if (!(fl & FLAG_MASKED)) {
+                    float x, y, z;
+                    uint32_t lin = 0xffffffffu;
+                    inl = point_test<FUSED>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z,
+                                            lin);
+                    reach = lin != 0xffffffffu;  // voxel_query succeeded (scene.hpp:458-460)
+                    if (inl) term = inlier_score(a.scene, a.model, r0, r1, r2, idx, fl, lin);
+                }
+            }
+            const uint32_t reach_mask = __ballot_sync(0xffffffffu, reach);
+            const uint32_t inl_mask = __ballot_sync(0xffffffffu, inl);
+            if (a.early_out && next_test < 18u && base + 32u >= cur_test) {
+                int last_l = -1;
+                while (next_test < 18u) {
+                    // first reaching element at or after position cur_test, one checkpoint per element
+                    int lmin = (cur_test > base + 1u) ? (int)(cur_test - base - 1u) : 0;
+                    int lstart = max(lmin, last_l + 1);
+                    if (lstart >= 32) break;
+                    uint32_t cand = reach_mask & (0xffffffffu << lstart);
+                    if (!cand) break;
+                    int l = __ffs(cand) - 1;
+                    uint32_t tried = base + (uint32_t)l + 1u;
+                    uint32_t c_here = corrs + __popc(inl_mask & (0xffffffffu >> (31 - l)));
+                    uint32_t upper = early_drop_upper(tried, nsub, c_here);
+                    if ((float)upper < accept_bound) {
+                        dropped = true;
+                        drop_corrs = c_here;
+                        drop_tried = tried;
+                        unsigned long long part = lane_score + ((lane <= l) ? term : 0ull);
+                        drop_score = warp_sum_u64(part);
+                        break;
+                    }
+                    ++next_test;
+                    last_l = l;
+                    cur_test = next_test < 18u ? test_at(next_test) : 0u;
+                }
+            }
+            corrs += __popc(inl_mask);
+            lane_score += term;
+        }
     }
     unsigned long long total = dropped ? drop_score : warp_sum_u64(lane_score);
     if (lane == 0) {

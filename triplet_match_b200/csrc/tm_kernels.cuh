@@ -64,6 +64,10 @@ struct EarlyArgs {
     unsigned long long* scores;
     uint8_t* dropped;
     uint32_t* tested;
+    // optional bounding boxes of every 32 consecutive subset positions (subset_tile_boxes):
+    // tile t of group g is entry sub_off[g]/32 + g + t
+    const float4* tile_lo = nullptr;
+    const float4* tile_hi = nullptr;
 };
 
 struct IcpState {
@@ -127,6 +131,9 @@ void launch_work_count(cudaStream_t st, const unsigned long long* sub_off, const
 void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
                       uint32_t n_groups, const uint32_t* item_off, WorkItem* items);
 void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
+void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
+                              const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
+                              float4* tile_lo, float4* tile_hi);
 void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
                    const uint32_t* n_local, const unsigned long long* h_begin,
                    unsigned long long* best, int grid);
