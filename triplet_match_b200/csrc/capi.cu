@@ -1072,7 +1072,7 @@ struct tm_query {
     DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
     DevBuf n_items_g, item_off, items, ctrl;
     DevBuf out;  // QueryOut
-    DevBuf topk_ids, icp_T16, stats, tile_lo, tile_hi;
+    DevBuf topk_ids, topk_keys, icp_T16, stats, tile_lo, tile_hi;
     uint32_t max_sub = 0;
     IcpBufs icp;
     QueryOut host_out;
@@ -1107,7 +1107,7 @@ void tm_query_destroy(tm_query* q) {
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
+          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
         b->release();
     q->icp.release();
     delete q;
@@ -1198,6 +1198,7 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     if (q->p.icp_top_k) {
         TRY(q->icp.ensure(q->p.icp_top_k));
         TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
+        TRY(q->topk_keys.ensure(topk_scratch_bytes(q->cap_hyp, q->p.icp_top_k)));
         TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
     }
     q->ran = false;
@@ -1323,7 +1324,8 @@ int tm_query_run(tm_query* q) {
     // (a12) ICP of the local top-k
     if (q->p.icp_top_k && q->p.max_icp_iterations) {
         launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
-                           &out->n_local, q->p.icp_top_k, q->topk_ids.as<uint32_t>(), nullptr);
+                           &out->n_local, q->cap_hyp, q->p.icp_top_k, q->topk_ids.as<uint32_t>(),
+                           q->topk_keys.as<unsigned long long>());
         launch_gather_rows(c->stream, q->T.as<float4>(), q->topk_ids.as<uint32_t>(), q->p.icp_top_k,
                            q->icp.Tcur.as<float4>(), q->icp.active.as<uint32_t>());
         TRY(icp_enqueue(c, sc, m, q->icp, q->p.icp_top_k, q->p.max_icp_iterations, q->p.dist_thres));

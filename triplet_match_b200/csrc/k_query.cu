@@ -2,6 +2,8 @@
 // range, per-outer hypothesis ranges, top-k selection for the ICP stage and the
 // best-pose read-out.  Everything stays on the device so the whole pipeline is
 // one stream-ordered sequence with no host round trip.
+#include <algorithm>
+
 #include "tm_kernels.cuh"
 
 namespace tmk {
@@ -68,55 +70,90 @@ void launch_group_of_hyp(cudaStream_t st, const uint32_t* g_hyp, uint32_t n_grou
     group_of_hyp_kernel<<<n_groups, 128, 0, st>>>(g_hyp, n_groups, g_of_hyp);
 }
 
-// top-k by (inliers desc, id asc): k rounds of a strictly-decreasing key search
-// in a single CTA (keys are unique because the id is embedded).
-__global__ void __launch_bounds__(1024)
-    select_topk_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
-                       const uint32_t* __restrict__ n_local, uint32_t k,
-                       uint32_t* __restrict__ topk_ids) {
-    __shared__ unsigned long long wbest[32];
-    __shared__ unsigned long long last_s;
-    const uint32_t n = *n_local;
-    if (threadIdx.x == 0) last_s = ~0ull;
+// top-k by (inliers desc, id asc).  Keys (count << 32 | ~id) are unique, so "the largest key below
+// the previous one" enumerates them in order.  Two levels: every CTA takes a slice of TOPK_SLICE
+// hypotheses into shared memory and emits its own top k (phase A, whole GPU); one CTA then picks
+// the global top k from those candidates (phase B).  The global top k is a subset of the union
+// of the slice top k's, so the result equals the single-pass selection.
+constexpr uint32_t TOPK_SLICE = 4096;
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* wbest) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o > v ? o : v;
+    }
+    __syncthreads();  // previous readers of wbest are done
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = v;
     __syncthreads();
+    unsigned long long r = wbest[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = wbest[w] > r ? wbest[w] : r;
+    return r;
+}
+__global__ void __launch_bounds__(1024)
+    topk_slice_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
+                      const uint32_t* __restrict__ n_local, uint32_t k, unsigned long long* __restrict__ cand) {
+    __shared__ unsigned long long keys[TOPK_SLICE];
+    __shared__ unsigned long long wbest[32];
+    const uint32_t n = *n_local;
+    const uint32_t base = blockIdx.x * TOPK_SLICE;
+    for (uint32_t t = threadIdx.x; t < TOPK_SLICE; t += blockDim.x) {
+        const uint32_t i = base + t;
+        unsigned long long key = 0;
+        if (i < n && (!valid || valid[i]) && counts[i])
+            key = ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+        keys[t] = key;
+    }
+    __syncthreads();
+    unsigned long long last = ~0ull;
     for (uint32_t r = 0; r < k; ++r) {
-        const unsigned long long last = last_s;
         unsigned long long best = 0;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            if (valid && !valid[i]) continue;
-            if (!counts[i]) continue;
-            unsigned long long key =
-                ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+        for (uint32_t t = threadIdx.x; t < TOPK_SLICE; t += blockDim.x) {
+            const unsigned long long key = keys[t];
             if (key < last && key > best) best = key;
         }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-            best = o > best ? o : best;
-        }
-        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < 32; ++w) best = wbest[w] > best ? wbest[w] : best;
-            // best == 0 only when no candidate is left (a real key always has ~id bits set
-            // unless id == 0xFFFFFFFF, which never occurs for n < 2^32 - 1)
-            topk_ids[r] = best ? (0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) : 0xFFFFFFFFu;
-            last_s = best;
-        }
-        __syncthreads();
-        if (last_s == 0ull) {
-            for (uint32_t rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x)
-                topk_ids[rr] = 0xFFFFFFFFu;
+        best = block_max_u64(best, wbest);
+        if (threadIdx.x == 0) cand[(size_t)blockIdx.x * k + r] = best;
+        last = best;
+        if (best == 0ull) {  // slice exhausted (uniform across the CTA)
+            for (uint32_t rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x) cand[(size_t)blockIdx.x * k + rr] = 0ull;
             break;
         }
     }
 }
+__global__ void __launch_bounds__(1024)
+    topk_final_kernel(const unsigned long long* __restrict__ cand, uint32_t n_cand, uint32_t k,
+                      uint32_t* __restrict__ topk_ids) {
+    __shared__ unsigned long long wbest[32];
+    unsigned long long last = ~0ull;
+    for (uint32_t r = 0; r < k; ++r) {
+        unsigned long long best = 0;
+        for (uint32_t i = threadIdx.x; i < n_cand; i += blockDim.x) {
+            const unsigned long long key = cand[i];
+            if (key < last && key > best) best = key;
+        }
+        best = block_max_u64(best, wbest);
+        // best == 0 only when no candidate is left (a real key always has ~id bits set
+        // unless id == 0xFFFFFFFF, which never occurs for n < 2^32 - 1)
+        if (threadIdx.x == 0) topk_ids[r] = best ? (0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) : 0xFFFFFFFFu;
+        last = best;
+        if (best == 0ull) {
+            for (uint32_t rr = r + 1 + threadIdx.x; rr < k; rr += blockDim.x) topk_ids[rr] = 0xFFFFFFFFu;
+            break;
+        }
+    }
+}
+// capacity = upper bound of *n_local (sizes the grid); scratch_keys: ceil(capacity / TOPK_SLICE) * k u64
+size_t topk_scratch_bytes(uint64_t capacity, uint32_t k) {
+    return (size_t)((capacity + TOPK_SLICE - 1) / TOPK_SLICE) * k * 8 + 8;
+}
 void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
-                        const uint32_t* n_local, uint32_t k, uint32_t* topk_ids,
-                        unsigned long long*) {
+                        const uint32_t* n_local, uint64_t capacity, uint32_t k, uint32_t* topk_ids,
+                        unsigned long long* scratch_keys) {
     if (!k) return;
-    ++g_launch_count;
-    select_topk_kernel<<<1, 1024, 0, st>>>(counts, valid, n_local, k, topk_ids);
+    const uint32_t slices = (uint32_t)std::max<uint64_t>(1, (capacity + TOPK_SLICE - 1) / TOPK_SLICE);
+    g_launch_count += 2;
+    topk_slice_kernel<<<slices, 1024, 0, st>>>(counts, valid, n_local, k, scratch_keys);
+    topk_final_kernel<<<1, 1024, 0, st>>>(scratch_keys, slices * k, k, topk_ids);
 }
 
 __global__ void gather_rows_kernel(const float4* __restrict__ T, const uint32_t* __restrict__ ids,
