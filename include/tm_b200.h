@@ -142,6 +142,25 @@ int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max
 int tm_traits_project(tm_ctx* ctx, int kind, const float g2l[16], float radius, float threshold,
                       const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
 
+/* ---- pre-processing the reference does with PCL/FLANN ----------------
+ * Exact k nearest neighbours (k <= 32) of the resident cloud's points query_idx[0..n_query), the
+ * query point included (pointcloud::knn_inclusive, include/impl/pointcloud.hpp:138-152).  Order:
+ * ascending (d^2, index), d^2 = (dx*dx + dy*dy) + dz*dz.  out_idx: n_query x k (-1 pads clouds
+ * smaller than k); out_d2 may be NULL.  Any cloud can be uploaded with tm_scene_upload for this. */
+int tm_scene_knn(tm_scene* s, const uint32_t* query_idx, uint32_t n_query, uint32_t k, int32_t* out_idx,
+                 float* out_d2);
+/* pointcloud::curvature(k, idx) (include/impl/pointcloud.hpp:200-204 -> principal_curvatures
+ * :3-44 + pcl::eigen33): pc_min = evs[1] / k, pc_max = evs[2] / k per query point.  cov9 (optional,
+ * n_query x 9, row-major) returns the covariance of the projected normals. */
+int tm_scene_curvature(tm_scene* s, const uint32_t* query_idx, uint32_t n_query, uint32_t k, float* pc_min,
+                       float* pc_max, float* cov9);
+/* The tangent criterion of scene.hpp:50 / model.hpp:98: mask[i] = ||tangent_i|| > 0.7 and
+ * pc_min / pc_max < ratio (0.2) with k-NN curvature (k = detail::curvature_k = 30).  mask_out
+ * (scene n bytes, may be NULL) receives the mask; apply != 0 also makes it the resident
+ * tangent_mask_ of the scene (replacing the one given at upload).  n_tangent (optional) = popcount. */
+int tm_scene_tangent_mask(tm_scene* s, uint32_t k, float ratio, uint8_t* mask_out, int apply,
+                          uint32_t* n_tangent);
+
 /* The orphaned OpenCL ICP path (a15).  tm_uvicp_projection = opencl/icp.cl:1-53 icp_projection
  * with the projector of opencl/cylinder.cl:1-25 (projector 0) or a linear projector
  * uv = mat_proj * loc (projector 1): per scene point pnts[i] (float4), nearest model sample =

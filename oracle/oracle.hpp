@@ -819,6 +819,108 @@ inline bool identity_project(v3 xyz, float uvw[3]) {
     return true;
 }
 
+// --------------------------------------- k-NN + principal curvatures (8f rank 2)
+// pointcloud::knn_inclusive (include/impl/pointcloud.hpp:138-152) by brute force, ascending
+// (d^2, index) with d^2 = (dx*dx + dy*dy) + dz*dz.  [parity unpinned: FLANN's order among equal
+// distances]
+inline void knn_inclusive(const cloud& c, uint32_t q, uint32_t k, std::vector<int32_t>& idx, std::vector<float>& d2) {
+    std::vector<std::pair<float, uint32_t>> all;
+    all.reserve(c.n);
+    for (uint32_t i = 0; i < c.n; ++i) {
+        float d = sqdist_seq(ld3(c.pos, i), ld3(c.pos, q));
+        if (d == d) all.push_back({d, i});
+    }
+    uint32_t kk = std::min<uint32_t>(k, (uint32_t)all.size());
+    std::partial_sort(all.begin(), all.begin() + kk, all.end());
+    idx.assign(k, -1);
+    d2.assign(k, 3.4e38f);
+    for (uint32_t j = 0; j < kk; ++j) {
+        idx[j] = (int32_t)all[j].second;
+        d2[j] = all[j].first;
+    }
+}
+// pcl::eigen33 (pcl/common/impl/eigen.hpp; third-party, restated from the published algorithm):
+// closed-form eigenvalues of a symmetric 3x3, ascending.  [parity unpinned: PCL version, libm cos/sin]
+inline void pcl_roots2(float b, float c, float r[3]) {
+    r[0] = 0.f;
+    float d = (float)((double)(b * b) - 4.0 * (double)c);
+    if (d < 0.f) d = 0.f;
+    float sd = std::sqrt(d);
+    r[2] = 0.5f * (b + sd);
+    r[1] = 0.5f * (b - sd);
+}
+inline void pcl_eigen33(const float cov[3][3], float evals[3]) {
+    float scale = 0.f;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(cov[i][j]));
+    if (scale <= std::numeric_limits<float>::min()) scale = 1.f;
+    float m[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) m[i][j] = cov[i][j] / scale;
+    float c0 = m[0][0] * m[1][1] * m[2][2] + 2.f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+               m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+    float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+               m[1][2] * m[1][2];
+    float c2 = m[0][0] + m[1][1] + m[2][2];
+    float r[3];
+    if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+        pcl_roots2(c2, c1, r);
+    } else {
+        const float s_inv3 = (float)(1.0 / 3.0);
+        const float s_sqrt3 = std::sqrt(3.0f);
+        float c2_over_3 = c2 * s_inv3;
+        float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+        if (a_over_3 > 0.f) a_over_3 = 0.f;
+        float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+        float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+        if (q > 0.f) q = 0.f;
+        float rho = std::sqrt(-a_over_3);
+        float theta = atan2f_full(std::sqrt(-q), half_b) * s_inv3;
+        float cos_theta = std::cos(theta);
+        float sin_theta = std::sin(theta);
+        r[0] = c2_over_3 + 2.f * rho * cos_theta;
+        r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+        r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+        if (r[0] >= r[1]) std::swap(r[0], r[1]);
+        if (r[1] >= r[2]) {
+            std::swap(r[1], r[2]);
+            if (r[0] >= r[1]) std::swap(r[0], r[1]);
+        }
+        if (r[0] <= 0.f) pcl_roots2(c2, c1, r);
+    }
+    for (int i = 0; i < 3; ++i) evals[i] = r[i] * scale;
+}
+// include/impl/pointcloud.hpp:3-44 — principal_curvatures over the given neighbours
+inline void principal_curvatures(const cloud& c, uint32_t p_idx, const int32_t* indices, uint32_t n_idx,
+                                 float cov[3][3], float& pc_min, float& pc_max) {
+    v3 n = ld3(c.nrm, p_idx);
+    float nv[3] = {n.x, n.y, n.z};
+    float M[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[i][j] = (i == j ? 1.f : 0.f) - nv[i] * nv[j];
+    std::vector<std::array<float, 3>> proj(n_idx);
+    float cen[3] = {0.f, 0.f, 0.f};
+    for (uint32_t k = 0; k < n_idx; ++k) {
+        v3 nn = ld3(c.nrm, (uint32_t)indices[k]);
+        for (int a = 0; a < 3; ++a) proj[k][a] = M[a][0] * nn.x + (M[a][1] * nn.y + M[a][2] * nn.z);
+        for (int a = 0; a < 3; ++a) cen[a] = cen[a] + (proj[k][a] - cen[a]) / (float)(k + 1);
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) cov[i][j] = 0.f;
+    for (uint32_t k = 0; k < n_idx; ++k) {
+        float d[3] = {proj[k][0] - cen[0], proj[k][1] - cen[1], proj[k][2] - cen[2]};
+        double xy = d[0] * d[1], xz = d[0] * d[2], yz = d[1] * d[2];
+        cov[0][0] += d[0] * d[0]; cov[0][1] += (float)xy; cov[0][2] += (float)xz;
+        cov[1][0] += (float)xy; cov[1][1] += d[1] * d[1]; cov[1][2] += (float)yz;
+        cov[2][0] += (float)xz; cov[2][1] += (float)yz; cov[2][2] += d[2] * d[2];
+    }
+    float ev[3];
+    pcl_eigen33(cov, ev);
+    float area_inv = 1.0f / (float)n_idx;
+    pc_min = ev[1] * area_inv;
+    pc_max = ev[2] * area_inv;
+}
+
 // ------------------------------------------------------- opencl/*.cl (row a15)
 // The reference ships these OpenCL kernels without host code; restated per work-item.
 // [parity unpinned: OpenCL builtins atan2pi / length / convert_int and the device compiler's

@@ -110,6 +110,38 @@ int orc_traits_project(int kind, const float* g2l16, float radius, float thresho
         default: return identity_project(p, uvw) ? 1 : 0;
     }
 }
+// k-NN (inclusive), principal curvatures and the tangent criterion of scene.hpp:50 / model.hpp:98
+void orc_knn(const float* pos, uint32_t n, const uint32_t* query, uint32_t n_query, uint32_t k, int32_t* out_idx,
+             float* out_d2) {
+    cloud c{pos, pos, pos, n};
+    std::vector<int32_t> idx;
+    std::vector<float> d2;
+    for (uint32_t w = 0; w < n_query; ++w) {
+        knn_inclusive(c, query[w], k, idx, d2);
+        for (uint32_t j = 0; j < k; ++j) {
+            out_idx[(size_t)w * k + j] = idx[j];
+            if (out_d2) out_d2[(size_t)w * k + j] = d2[j];
+        }
+    }
+}
+void orc_curvature(const float* pos, const float* nrm, uint32_t n, const uint32_t* query, uint32_t n_query, uint32_t k,
+                   const int32_t* nbr, float* pc_min, float* pc_max, float* cov9) {
+    cloud c{pos, nrm, nrm, n};
+    for (uint32_t w = 0; w < n_query; ++w) {
+        const int32_t* my = nbr + (size_t)w * k;
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < k; ++j) cnt += my[j] >= 0;
+        float cov[3][3];
+        principal_curvatures(c, query[w], my, cnt, cov, pc_min[w], pc_max[w]);
+        if (cov9)
+            for (int i = 0; i < 9; ++i) cov9[(size_t)w * 9 + i] = cov[i / 3][i % 3];
+    }
+}
+void orc_eigen33(const float* cov9, float* evals) {
+    float cov[3][3];
+    for (int i = 0; i < 9; ++i) cov[i / 3][i % 3] = cov9[i];
+    pcl_eigen33(cov, evals);
+}
 // opencl/icp.cl restated over all work-items; returns the number of emitted correspondences
 uint32_t orc_cl_icp_projection(int projector, const float* pnts4, int n, const float* image4, const int32_t* img_size,
                                const int32_t* img_margin, const float* mat_align, const float* mat_uvw,

@@ -118,6 +118,49 @@ def traits_project(kind, g2l16, radius, threshold, xyz):
     return uvw, ok
 
 
+def knn(pos, query, k):
+    """pointcloud::knn_inclusive by brute force: ascending (d^2, index)."""
+    pos = _f32(pos, (-1, 3))
+    q = np.ascontiguousarray(query, dtype=np.uint32)
+    idx = np.zeros((q.size, k), dtype=np.int32)
+    d2 = np.zeros((q.size, k), dtype=np.float32)
+    load().orc_knn(_p(pos), C.c_uint32(pos.shape[0]), _p(q), C.c_uint32(q.size), C.c_uint32(k), _p(idx), _p(d2))
+    return idx, d2
+
+
+def curvature(pos, nrm, query, k, nbr=None):
+    """pointcloud::curvature(k, idx): (pc_min, pc_max, cov 3x3) per query point."""
+    pos, nrm = _f32(pos, (-1, 3)), _f32(nrm, (-1, 3))
+    q = np.ascontiguousarray(query, dtype=np.uint32)
+    if nbr is None:
+        nbr, _ = knn(pos, q, k)
+    nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+    mn = np.zeros(q.size, dtype=np.float32)
+    mx = np.zeros(q.size, dtype=np.float32)
+    cov = np.zeros((q.size, 9), dtype=np.float32)
+    load().orc_curvature(_p(pos), _p(nrm), C.c_uint32(pos.shape[0]), _p(q), C.c_uint32(q.size), C.c_uint32(k),
+                         _p(nbr), _p(mn), _p(mx), _p(cov))
+    return mn, mx, cov.reshape(-1, 3, 3)
+
+
+def eigen33(cov):
+    ev = np.zeros(3, dtype=np.float32)
+    load().orc_eigen33(_p(_f32(cov, (9,))), _p(ev))
+    return ev
+
+
+def tangent_mask(cloud, k=30, ratio=0.2):
+    """scene.hpp:50 / model.hpp:98: ||tangent|| > 0.7 and pc_min / pc_max < ratio."""
+    t = _f32(cloud.tgt, (-1, 3))
+    nrm = np.sqrt((t[:, 0] * t[:, 0] + (t[:, 1] * t[:, 1] + t[:, 2] * t[:, 2])).astype(np.float32)).astype(np.float32)
+    cand = np.flatnonzero(nrm > np.float32(0.7)).astype(np.uint32)
+    mn, mx, _ = curvature(cloud.pos, cloud.nrm, cand, k)
+    mask = np.zeros(t.shape[0], dtype=np.uint8)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mask[cand] = ((mn / mx) < np.float32(ratio)).astype(np.uint8)
+    return mask, cand, mn, mx
+
+
 def cl_icp_projection(projector, pnts4, image4, img_size, img_margin, mat_align, mat_uvw, mat_proj, mat_norm,
                       max_corr_dist):
     """opencl/icp.cl:1-53 (+ cylinder.cl / util.cl) over all work-items."""

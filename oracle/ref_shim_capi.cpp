@@ -284,6 +284,22 @@ uint64_t ref_hypotheses_batch(void* sp, void* mp, const uint32_t* pair_i, const 
     }
     return n;
 }
+// pointcloud::curvature(k, idx) = principal_curvatures(knn_inclusive(k, idx)) (pointcloud.hpp:200-204)
+void ref_curvature(const float* pos, const float* nrm, uint32_t n, const uint32_t* query, uint32_t n_query, uint32_t k,
+                   float* pc_min, float* pc_max, int32_t* nbr_out) {
+    std::vector<float> z(3 * (size_t)n, 0.f);
+    cloud_t::Ptr c = make_cloud(pos, nrm, z.data(), n);
+    struct mode_guard { mode_guard() { pcl::eigen33_mode() = 1; } ~mode_guard() { pcl::eigen33_mode() = 0; } } guard;
+    for (uint32_t w = 0; w < n_query; ++w) {
+        auto ci = c->curvature(k, query[w]);
+        pc_min[w] = ci.pc_min;
+        pc_max[w] = ci.pc_max;
+        if (nbr_out) {
+            auto nn = c->knn_inclusive(k, query[w]).first;
+            for (uint32_t j = 0; j < k; ++j) nbr_out[(size_t)w * k + j] = j < nn.size() ? nn[j] : -1;
+        }
+    }
+}
 float ref_resolution(const float* pos, uint32_t n) {
     std::vector<float> z(3 * (size_t)n, 0.f);
     return make_cloud(pos, z.data(), z.data(), n)->resolution();

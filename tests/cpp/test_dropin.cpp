@@ -154,14 +154,19 @@ int main(int argc, char** argv) {
         return 2;
     }
     cloud_t::Ptr mc = load(argv[2]), sc = load(argv[3]);
+    // argv[5] == "curv": keep the reference's curvature-ratio criterion (clouds with estimated, i.e.
+    // noisy, normals); default for the analytic synthetic clouds: norm test only
+    const bool curv = argc >= 6 && std::string(argv[5]) == "curv";
     tr::discretization_params dp{20.f, 10.f / 180.f * static_cast<float>(M_PI), 10.f};
     tr::sample_parameters sp{0.f, 0.f, 1.f, 1.f, 0.2f, 1.0f, 0.f, 1.f, false};
     tr::model<point_t> m(mc, dp);
+    m.set_curvature_test(curv);
     m.init(sp);
     // API users still get the host-side query()/voxel_query()
     auto f = tr::feature<point_t>(mc->points[0], mc->points[1]);
     (void)m.query(*f);
     tr::scene<point_t> s(sc);
+    s.set_curvature_test(curv);
     auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, 5);
     std::ofstream out(argv[4]);
     out << matches.size() << "\n";

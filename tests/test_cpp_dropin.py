@@ -34,13 +34,31 @@ def _write(cloud, path):
         f.write(np.ascontiguousarray(rec).tobytes())
 
 
+def _noisy_normals(cloud, seed, sigma=0.05):
+    from triplet_match_b200 import synth
+    rng = np.random.default_rng(seed)
+    nrm = cloud.nrm.astype(np.float64) + sigma * rng.standard_normal(cloud.nrm.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    return synth.Cloud(cloud.pos, nrm.astype(np.float32), cloud.tgt, cloud.tangent_mask, cloud.poses)
+
+
 @pytest.mark.gpu
-def test_cpp_find_all_parallel(exe, tmp_path):
+@pytest.mark.parametrize("curv", [False, True])
+def test_cpp_find_all_parallel(exe, tmp_path, curv):
+    """curv=True: raw clouds with estimated (noisy) normals, tangent masks from the GPU 30-NN
+    curvature criterion on both model and scene, as the reference does with PCL."""
+    from triplet_match_b200 import synth
     m, s, om, osc, rec = common.config("freeform_small")
+    res = om.resolution
+    if curv:  # a model with genuine creases: the criterion keeps its edge points and rejects the floor's fake tangents
+        m = synth.pyramid_model(seed=7, size=0.4, height=0.16, res=0.005)
+        s = synth.make_scene(seed=8, model=m, n_points=60000, n_copies=3, extent=1.5, flat_copies=False, res=0.005)
+        s = s.take(synth.morton_order(s.pos))
+        res = 0.005
     mp, sp, op = str(tmp_path / "m.bin"), str(tmp_path / "s.bin"), str(tmp_path / "o.txt")
     _write(m, mp)
     _write(s, sp)
-    r = subprocess.run([exe, "find", mp, sp, op], capture_output=True, text=True)
+    r = subprocess.run([exe, "find", mp, sp, op] + (["curv"] if curv else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     lines = open(op).read().strip().split("\n")
     n = int(lines[0])
@@ -53,7 +71,7 @@ def test_cpp_find_all_parallel(exe, tmp_path):
         placed = mpts @ T[:3, :3].T + T[:3, 3]
         errs = [np.abs(placed - (mpts @ P[:3, :3].T + P[:3, 3])).max() for P in s.poses]
         k = int(np.argmin(errs))
-        assert errs[k] < 3 * om.resolution, (errs, r.stdout)  # every reported instance is a real one
+        assert errs[k] < 3 * res, (errs, r.stdout)  # every reported instance is a real one
         assert int(v[0]) >= 0.5 * m.n
         found.add(k)
     assert len(found) == n  # no instance is reported twice (overlap-free acceptance)
@@ -153,7 +171,7 @@ def test_cli_finds_instances_from_pcd(cli, tmp_path):
     mp, sp = str(tmp_path / "model.pcd"), str(tmp_path / "scene.pcd")
     write_pcd(m, mp, binary=True)
     write_pcd(s, sp, binary=False)
-    r = subprocess.run([cli, mp, sp], capture_output=True, text=True)
+    r = subprocess.run([cli, mp, sp, "1.0", "0.5", "5", "0"], capture_output=True, text=True)  # analytic normals
     assert r.returncode == 0, r.stderr + r.stdout
     lines = [ln for ln in r.stdout.split("\n") if ln.startswith("match ")]
     assert len(lines) >= 1, r.stdout

@@ -60,7 +60,7 @@ EXPORTS = [
     "tm_ctx_kernel_launches", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
     "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
-    "tm_traits_project", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
+    "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
     "tm_query_set_global_best", "tm_query_download", "tm_query_icp_results",
@@ -458,6 +458,28 @@ class Scene:
                              C.c_float(dist_thres), _p(out), _p(counts), _p(scores), _p(iters)))
         return out, counts, scores, iters
 
+
+    def knn(self, query_idx, k: int):
+        q = np.ascontiguousarray(query_idx, dtype=np.uint32)
+        idx = np.zeros((max(q.size, 1), k), dtype=np.int32)
+        d2 = np.zeros((max(q.size, 1), k), dtype=np.float32)
+        _chk(self.lib.tm_scene_knn(self.h, _p(q), C.c_uint32(q.size), C.c_uint32(k), _p(idx), _p(d2)))
+        return idx[:q.size], d2[:q.size]
+
+    def curvature(self, query_idx, k: int):
+        q = np.ascontiguousarray(query_idx, dtype=np.uint32)
+        mn = np.zeros(max(q.size, 1), dtype=np.float32)
+        mx = np.zeros(max(q.size, 1), dtype=np.float32)
+        cov = np.zeros((max(q.size, 1), 9), dtype=np.float32)
+        _chk(self.lib.tm_scene_curvature(self.h, _p(q), C.c_uint32(q.size), C.c_uint32(k), _p(mn), _p(mx), _p(cov)))
+        return mn[:q.size], mx[:q.size], cov[:q.size].reshape(-1, 3, 3)
+
+    def compute_tangent_mask(self, k: int = 30, ratio: float = 0.2, apply: bool = True):
+        mask = np.zeros(max(self.n, 1), dtype=np.uint8)
+        cnt = C.c_uint32()
+        _chk(self.lib.tm_scene_tangent_mask(self.h, C.c_uint32(k), C.c_float(ratio), _p(mask), C.c_int(int(apply)),
+                                            C.byref(cnt)))
+        return mask[:self.n], int(cnt.value)
 
     def icp_sharded(self, model: Model, T16s, max_iterations: int, dist_thres: float, pt_begin: int,
                     pt_end: int, n_scene_total: int, comm=None, emulate_parts: int = 1):

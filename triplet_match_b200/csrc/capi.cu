@@ -970,6 +970,102 @@ int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, fl
     return TM_OK;
 }
 
+// ------------------------------------------------------------ pre-processing (k-NN, curvature)
+static int knn_dev(tm_ctx* c, tm_scene* s, const uint32_t* d_query, uint32_t n_query, uint32_t k, DevBuf& idx,
+                   DevBuf* d2) {
+    TRY(idx.ensure((size_t)std::max(n_query, 1u) * k * 4));
+    if (d2) TRY(d2->ensure((size_t)std::max(n_query, 1u) * k * 4));
+    launch_knn(c->stream, s->dev, d_query, n_query, k, idx.as<int32_t>(), d2 ? d2->as<float>() : nullptr);
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+int tm_scene_knn(tm_scene* s, const uint32_t* query_idx, uint32_t n_query, uint32_t k, int32_t* out_idx,
+                 float* out_d2) {
+    REQUIRE(s, "null scene");
+    REQUIRE(k >= 1 && k <= 32, "tm_scene_knn: k must be in [1, 32]");
+    REQUIRE(n_query == 0 || (query_idx && out_idx), "tm_scene_knn: null buffer");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n_query) return TM_OK;
+    for (uint32_t i = 0; i < n_query; ++i) REQUIRE(query_idx[i] < s->dev.n, "tm_scene_knn: query index out of range");
+    DevBuf &dq = c->scratch[0], &di = c->scratch[1], &dd = c->scratch[2];
+    TRY(dq.ensure((size_t)n_query * 4));
+    CU(cudaMemcpyAsync(dq.p, query_idx, (size_t)n_query * 4, cudaMemcpyHostToDevice, c->stream));
+    TRY(knn_dev(c, s, dq.as<uint32_t>(), n_query, k, di, out_d2 ? &dd : nullptr));
+    CU(cudaMemcpyAsync(out_idx, di.p, (size_t)n_query * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_d2) CU(cudaMemcpyAsync(out_d2, dd.p, (size_t)n_query * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+int tm_scene_curvature(tm_scene* s, const uint32_t* query_idx, uint32_t n_query, uint32_t k, float* pc_min,
+                       float* pc_max, float* cov9) {
+    REQUIRE(s, "null scene");
+    REQUIRE(k >= 1 && k <= 32, "tm_scene_curvature: k must be in [1, 32]");
+    REQUIRE(n_query == 0 || (query_idx && pc_min && pc_max), "tm_scene_curvature: null buffer");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    if (!n_query) return TM_OK;
+    for (uint32_t i = 0; i < n_query; ++i)
+        REQUIRE(query_idx[i] < s->dev.n, "tm_scene_curvature: query index out of range");
+    DevBuf &dq = c->scratch[0], &di = c->scratch[1], &dmn = c->scratch[2], &dmx = c->scratch[3], &dcov = c->scratch[4];
+    TRY(dq.ensure((size_t)n_query * 4)); TRY(dmn.ensure((size_t)n_query * 4)); TRY(dmx.ensure((size_t)n_query * 4));
+    if (cov9) TRY(dcov.ensure((size_t)n_query * 36));
+    CU(cudaMemcpyAsync(dq.p, query_idx, (size_t)n_query * 4, cudaMemcpyHostToDevice, c->stream));
+    TRY(knn_dev(c, s, dq.as<uint32_t>(), n_query, k, di, nullptr));
+    launch_curvature(c->stream, s->dev, dq.as<uint32_t>(), n_query, k, di.as<int32_t>(), dmn.as<float>(),
+                     dmx.as<float>(), cov9 ? dcov.as<float>() : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pc_min, dmn.p, (size_t)n_query * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(pc_max, dmx.p, (size_t)n_query * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cov9) CU(cudaMemcpyAsync(cov9, dcov.p, (size_t)n_query * 36, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+int tm_scene_tangent_mask(tm_scene* s, uint32_t k, float ratio, uint8_t* mask_out, int apply,
+                          uint32_t* n_tangent) {
+    REQUIRE(s, "null scene");
+    REQUIRE(k >= 1 && k <= 32, "tm_scene_tangent_mask: k must be in [1, 32]");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    const uint32_t n = s->dev.n;
+    if (n_tangent) *n_tangent = 0;
+    if (!n) return TM_OK;
+    DevBuf &fl = c->scratch[0], &off = c->scratch[1], &cand = c->scratch[2], &di = c->scratch[3],
+           &dmn = c->scratch[4], &dmx = c->scratch[5], &dmask = c->scratch[6];
+    TRY(fl.ensure((size_t)n * 4)); TRY(off.ensure(((size_t)n + 1) * 4)); TRY(dmask.ensure(n));
+    launch_tangent_candidates(c->stream, s->dev.tgt, n, fl.as<uint32_t>());
+    launch_exclusive_scan_u32(c->stream, fl.as<uint32_t>(), off.as<uint32_t>(), n);
+    uint32_t n_cand = 0;
+    CU(cudaMemcpyAsync(&n_cand, off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemsetAsync(dmask.p, 0, n, c->stream));
+    TRY(cand.ensure((size_t)std::max(n_cand, 1u) * 4));
+    TRY(dmn.ensure((size_t)std::max(n_cand, 1u) * 4)); TRY(dmx.ensure((size_t)std::max(n_cand, 1u) * 4));
+    if (n_cand) {
+        launch_compact(c->stream, fl.as<uint32_t>(), off.as<uint32_t>(), n, cand.as<uint32_t>());
+        TRY(knn_dev(c, s, cand.as<uint32_t>(), n_cand, k, di, nullptr));
+        launch_curvature(c->stream, s->dev, cand.as<uint32_t>(), n_cand, k, di.as<int32_t>(), dmn.as<float>(),
+                         dmx.as<float>(), nullptr);
+    }
+    launch_tangent_mask(c->stream, s->pos.as<float4>(), n, cand.as<uint32_t>(), n_cand, dmn.as<float>(),
+                        dmx.as<float>(), ratio, dmask.as<uint8_t>(), apply);
+    CU(cudaGetLastError());
+    std::vector<uint8_t> tmp;
+    uint8_t* dst = mask_out;
+    if (!dst && n_tangent) {
+        tmp.resize(n);
+        dst = tmp.data();
+    }
+    if (dst) CU(cudaMemcpyAsync(dst, dmask.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_tangent && dst) {
+        uint32_t cnt = 0;
+        for (uint32_t i = 0; i < n; ++i) cnt += dst[i];
+        *n_tangent = cnt;
+    }
+    return TM_OK;
+}
+
 // ------------------------------------------------------------ opencl/icp.cl path (a15)
 int tm_uvicp_projection(tm_ctx* c, int projector, const float* pnts4, int32_t n, const float* image4,
                         const int32_t img_size[2], const int32_t img_margin[2], const float mat_align[16],

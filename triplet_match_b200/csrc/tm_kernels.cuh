@@ -163,6 +163,16 @@ void launch_uvicp_correlation(cudaStream_t st, const float4* scene, const float4
                               const int* indices_model, int n, const float* centroid_scene,
                               const float* centroid_model, float* records, double* partials, double* cov9);
 
+// k_knn.cu (pre-processing: exact k-NN, principal-curvature tangent masks)
+void launch_knn(cudaStream_t st, const CloudDev& cloud, const uint32_t* query, uint32_t n_query, uint32_t k,
+                int32_t* out_idx, float* out_d2);
+void launch_curvature(cudaStream_t st, const CloudDev& cloud, const uint32_t* query, uint32_t n_query, uint32_t k,
+                      const int32_t* nbr, float* pc_min, float* pc_max, float* cov_out);
+void launch_tangent_candidates(cudaStream_t st, const float4* tgt, uint32_t n, uint32_t* flags);
+void launch_compact(cudaStream_t st, const uint32_t* flags, const uint32_t* offsets, uint32_t n, uint32_t* out);
+void launch_tangent_mask(cudaStream_t st, float4* pos, uint32_t n, const uint32_t* cand, uint32_t n_cand,
+                         const float* pc_min, const float* pc_max, float ratio, uint8_t* mask, int apply);
+
 // k_query.cu (device-side glue of the resident query)
 void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
                         unsigned long long hyp_limit, uint32_t rank, uint32_t world,

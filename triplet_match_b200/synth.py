@@ -189,6 +189,39 @@ def freeform_model(seed: int = 3, n_points: int = 50000, radius: float = 0.5, n_
     return Cloud(_f32(pos), _f32(d), _f32(tgt), on.astype(np.uint8))
 
 
+def pyramid_model(seed: int = 7, size: float = 0.3, height: float = 0.12, res: float = 0.01,
+                  normal_noise: float = 0.02, blend: float = 1.5) -> Cloud:
+    """Square pyramid whose four slanted edges are genuine creases: the normal field turns across
+    an edge within ~`blend` * res (and carries a little isotropic noise), so the reference's
+    principal-curvature criterion pc_min / pc_max < 0.2 (scene.hpp:50, model.hpp:98) selects the
+    edge points — unlike the analytic clouds above, whose exact normals give 0/0."""
+    half = 0.5 * size
+    n1 = int(round(size / res)) + 1
+    g = np.linspace(-half, half, n1)
+    x, y = np.meshgrid(g, g, indexing="xy")
+    x, y = x.ravel(), y.ravel()
+    n = x.size
+    x = x + 0.1 * res * normal(seed, 1, n)
+    y = y + 0.1 * res * normal(seed, 2, n)
+    ax, ay = np.abs(x), np.abs(y)
+    z = height * (1.0 - np.maximum(ax, ay) / half) + 0.05 * res * normal(seed, 3, n)
+    # smooth max for the normal field only
+    w = blend * res
+    root = np.sqrt((ax - ay) ** 2 + w * w)
+    dmx = (0.5 + 0.5 * (ax - ay) / root) * np.sign(x)
+    dmy = (0.5 - 0.5 * (ax - ay) / root) * np.sign(y)
+    slope = height / half
+    nrm = _unit(np.stack([slope * dmx, slope * dmy, np.ones(n)], 1))
+    nrm = _unit(nrm + normal_noise * np.stack([normal(seed, 4, n), normal(seed, 5, n), normal(seed, 6, n)], 1))
+    d_edge = np.abs(ax - ay) / np.sqrt(2.0)
+    m = np.maximum(ax, ay)
+    on = (d_edge <= 0.5 * res) & (m > 0.1 * half) & (m < 0.95 * half)
+    tgt = np.zeros((n, 3))
+    e = _unit(np.stack([np.sign(x) * half, np.sign(y) * half, -height * np.ones(n)], 1))
+    tgt[on] = e[on]
+    return Cloud(_f32(np.stack([x, y, z], 1)), _f32(nrm), _f32(tgt), on.astype(np.uint8))
+
+
 def _rot(axis: np.ndarray, angle: float) -> np.ndarray:
     a = axis / np.linalg.norm(axis)
     K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
