@@ -173,6 +173,7 @@ int main(int argc, char** argv) {
     for (auto& mt : matches) {
         out << mt.scene_corrs.size() << " " << mt.signed_score;
         for (int i = 0; i < 16; ++i) out << " " << mt.transform.data()[i];
+        for (size_t i = 0; i < mt.scene_corrs.size() && i < 400; i += 4) out << " " << mt.scene_corrs[i];
         out << "\n";
     }
     std::printf("model pts %zu tangent %u pairs %llu | matches %zu\n", mc->size(), m.point_count(),

@@ -43,8 +43,8 @@ def _noisy_normals(cloud, seed, sigma=0.05):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("curv", [False, True])
-def test_cpp_find_all_parallel(exe, tmp_path, curv):
+@pytest.mark.parametrize("curv,shuffled", [(False, False), (True, False), (False, True)])
+def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
     """curv=True: raw clouds with estimated (noisy) normals, tangent masks from the GPU 30-NN
     curvature criterion on both model and scene, as the reference does with PCL."""
     from triplet_match_b200 import synth
@@ -55,6 +55,8 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv):
         s = synth.make_scene(seed=8, model=m, n_points=60000, n_copies=3, extent=1.5, flat_copies=False, res=0.005)
         s = s.take(synth.morton_order(s.pos))
         res = 0.005
+    if shuffled:  # the caller's cloud in random order: the drop-in sorts its device copy itself
+        s = s.take(synth.shuffle_perm(5, 1, s.n))
     mp, sp, op = str(tmp_path / "m.bin"), str(tmp_path / "s.bin"), str(tmp_path / "o.txt")
     _write(m, mp)
     _write(s, sp)
@@ -74,6 +76,11 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv):
         assert errs[k] < 3 * res, (errs, r.stdout)  # every reported instance is a real one
         assert int(v[0]) >= 0.5 * m.n
         found.add(k)
+        # correspondences are reported in the caller's index space: the matched scene points lie on the instance
+        corr = [int(x) for x in ln.split()[18:]]
+        if corr:
+            dmin = np.abs(s.pos[corr].astype(np.float64)[:, None, :] - placed[None, ::7, :]).sum(-1).min(1)
+            assert np.median(dmin) < 6 * res
     assert len(found) == n  # no instance is reported twice (overlap-free acceptance)
 
 
