@@ -72,8 +72,55 @@ __global__ void __launch_bounds__(256)
             const float nanv = __int_as_float(0x7fc00000);
             v[k] = i < pt_end ? scene.pos[i] : make_float4(nanv, nanv, nanv, 0.f);
         }
-        for (uint32_t h = 0; h < n_hyp; ++h) {
-            if (active && !active[h]) continue;
+        // the chunk's points lie in at most two BALL_SEG segments: their boxes (scenes only) bound it
+        float blx = -3.0e38f, bly = -3.0e38f, blz = -3.0e38f, bhx = 3.0e38f, bhy = 3.0e38f, bhz = 3.0e38f;
+        const bool have_box = scene.seg_lo != nullptr;
+        if (have_box) {
+            const uint64_t end_ = base + 32ull * ICP_P < (uint64_t)pt_end ? base + 32ull * ICP_P : (uint64_t)pt_end;
+            const uint64_t last = end_ - 1;
+            const uint32_t sa = (uint32_t)(base / BALL_SEG), sb = (uint32_t)(last / BALL_SEG);
+            const float4 la = scene.seg_lo[sa], ha = scene.seg_hi[sa], lb = scene.seg_lo[sb], hb = scene.seg_hi[sb];
+            blx = fminf(la.x, lb.x); bly = fminf(la.y, lb.y); blz = fminf(la.z, lb.z);
+            bhx = fmaxf(ha.x, hb.x); bhy = fmaxf(ha.y, hb.y); bhz = fmaxf(ha.z, hb.z);
+        }
+        const float cx_ = 0.5f * (blx + bhx), hx_ = 0.5f * (bhx - blx);
+        const float cy_ = 0.5f * (bly + bhy), hy_ = 0.5f * (bhy - bly);
+        const float cz_ = 0.5f * (blz + bhz), hz_ = 0.5f * (bhz - blz);
+        for (uint32_t h0 = 0; h0 < n_hyp; h0 += 32) {
+          // lane l screens transform h0 + l: skip (chunk, transform) pairs whose box misses the grid
+          bool live = false;
+          {
+            const uint32_t hl = h0 + lane;
+            if (hl < n_hyp && (!active || active[hl])) {
+                live = true;
+                if (have_box && blx <= bhx) {
+                    const float4 q0 = __ldg(&T[3 * hl]), q1 = __ldg(&T[3 * hl + 1]), q2 = __ldg(&T[3 * hl + 2]);
+                    const float acx = fabsf(cx_) + hx_, acy = fabsf(cy_) + hy_, acz = fabsf(cz_) + hz_;
+                    bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                  \
+    {                                                                                           \
+        float cc = r.x * cx_ + r.y * cy_ + r.z * cz_ + r.w;                                     \
+        float ee = fabsf(r.x) * hx_ + fabsf(r.y) * hy_ + fabsf(r.z) * hz_;                      \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
+        ee += 1e-5f * mag + 1e-30f;                                                             \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
+        float lo_ = S * (cc - ee) + TV - sl, hi_ = S * (cc + ee) + TV + sl;                     \
+        out = out || (lo_ >= EXF) || (hi_ <= -1.0f);                                            \
+    }
+                    TM_AXIS(q0, model.sx, model.tx, model.exf)
+                    TM_AXIS(q1, model.sy, model.ty, model.eyf)
+                    TM_AXIS(q2, model.sz, model.tz, model.ezf)
+#undef TM_AXIS
+                    live = !out;
+                } else if (have_box) {
+                    live = false;  // no finite point in either segment
+                }
+            }
+          }
+          uint32_t todo = __ballot_sync(0xffffffffu, live);
+          while (todo) {
+            const uint32_t h = h0 + (uint32_t)(__ffs(todo) - 1);
+            todo &= todo - 1u;
             const float4 r0 = __ldg(&T[3 * h]), r1 = __ldg(&T[3 * h + 1]), r2 = __ldg(&T[3 * h + 2]);
             long long acc[ICP_NSUM];
 #pragma unroll
@@ -117,6 +164,7 @@ __global__ void __launch_bounds__(256)
                                   (unsigned long long)t);
                 }
             }
+          }
         }
     }
 }
