@@ -470,6 +470,18 @@ def main():
             if it >= 3:
                 eo_ms.append(t_ms)
         r3 = q3.result()
+        q3.close()
+        q3 = capi.Query(gs, gm, **QP, early_out=True, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
+                        icp_top_k=64, max_icp_iterations=5)
+        q3.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        lat3 = []
+        for it in range(3 + 20):
+            t0 = time.perf_counter()
+            q3.run()
+            q3.result()
+            if it >= 3:
+                lat3.append((time.perf_counter() - t0) * 1e3)
+        line["p50_query_early_drop_ms"] = float(np.median(lat3))
         line["early_drop_mode"] = {"value": r3.n_scored / (float(np.mean(eo_ms)) * 1e-3), "unit": UNIT,
                                    "ms_per_step": float(np.mean(eo_ms)), "tests_per_step": int(r3.n_tests),
                                    "note": "project_(early_out=true) semantics, bit-exact with the reference incl. drop points; "
