@@ -1,4 +1,4 @@
-"""In-tree build of the CUDA library (sm_100a) and of the CPU oracle.
+"""In-tree build of the CUDA library (sm_100a).
 
 `build_native()` compiles triplet_match_b200/csrc/*.cu with nvcc into
 triplet_match_b200/libtriplet_match_b200.so (git-ignored, travels with gpurun).
@@ -21,8 +21,6 @@ _SUFFIX = os.environ.get("TM_LIB_SUFFIX", "")
 OBJ = os.path.join(ROOT, "_obj" + _SUFFIX)
 LIB = os.path.join(ROOT, "libtriplet_match_b200" + _SUFFIX + ".so")
 HOSTLIB = os.path.join(ROOT, "libtriplet_match_host.so")
-ORACLE_DIR = os.path.join(REPO, "oracle")
-ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -97,15 +95,5 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_oracle(force: bool = False) -> str:
-    deps = [os.path.join(ORACLE_DIR, f) for f in ("oracle.hpp", "oracle_capi.cpp", "Makefile")]
-    if force or not _newer(ORACLE_LIB, deps):
-        _run(["make", "-C", ORACLE_DIR, "-s", "all"])
-    elif os.path.isdir("/root/reference"):
-        _run(["make", "-C", ORACLE_DIR, "-s", "ref"])
-    return ORACLE_LIB
-
-
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
-    print(build_oracle(force="--force" in sys.argv))
