@@ -123,7 +123,11 @@ int tm_ball_subsets(tm_scene* s, const uint32_t* centres, uint32_t n_centres, fl
 /* project_ per hypothesis (include/impl/scene.hpp:411-510): inlier count
  * (= scene_corrs.size()), score, and (early_out != 0) the reference's early-drop
  * outcome.  hyp_sub[h] selects subset CSR row; hyp_sub == NULL scores against all
- * scene points (finish_find, scene.hpp:100-106).  scores/dropped may be NULL. */
+ * scene points (finish_find, scene.hpp:100-106).  scores/dropped may be NULL.
+ * Scores are accumulated as 2^-36 fixed point (order-independent, reproducible across tilings
+ * and GPUs): exact for per-point terms |ref . ref_n| < 2^27, i.e. for every rigid transform
+ * (terms <= 1); a matrix that scales vectors by more than that is outside the score's domain
+ * (inlier counts are unaffected). */
 int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const uint32_t* hyp_sub,
              const uint64_t* sub_offsets, const int32_t* sub_indices, uint32_t n_sub,
              float dist_thres, float accept_prob, int early_out, uint32_t* counts, double* scores,

@@ -1,0 +1,178 @@
+"""Adversarial parity cases (-m gpu): the CUDA path against the oracle on inputs chosen to sit on
+every decision boundary of the path — voxel cell edges and the (-1, 0) truncation band of
+voxel_query (model.hpp:182-189), points exactly at the distance threshold, non-finite points and
+transforms, duplicate points, zero tangents, and a table with thousands of keys (open-addressing
+collisions)."""
+import numpy as np
+import pytest
+
+import common
+from oracle import pyoracle as po
+from triplet_match_b200 import synth
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    from triplet_match_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _boundary_scene(m, om, seed):
+    """Scene points that map (under identity-like transforms) onto voxel-coordinate integers, into the
+    (-1, 0) band, just outside the grid, and onto model points +- the distance threshold."""
+    rng = np.random.default_rng(seed)
+    sc, tr, ex = om.scale.astype(np.float64), om.trans.astype(np.float64), om.extents
+    pts = []
+    # voxel coordinates exactly on / next to integers, incl. the truncation band and both grid faces
+    for _ in range(3000):
+        v = np.array([rng.integers(-2, ex[0] + 2), rng.integers(-2, ex[1] + 2), rng.integers(-2, ex[2] + 2)], np.float64)
+        v += rng.choice([0.0, 1e-7, -1e-7, 0.5, -0.5, 0.999999, -0.999999], size=3)
+        pts.append((v - tr) / sc)
+    # model points displaced by almost exactly the threshold
+    thres = om.resolution
+    for i in rng.integers(0, m.n, 2000):
+        d = rng.standard_normal(3)
+        d /= np.linalg.norm(d)
+        pts.append(m.pos[i].astype(np.float64) + d * thres * rng.choice([0.999999, 1.0, 1.000001, 0.5, 0.0]))
+    pts = np.array(pts, F)
+    # non-finite and huge coordinates, duplicates
+    bad = np.array([[np.nan, 0, 0], [0, np.inf, 0], [0, 0, -np.inf], [1e30, 1e30, 1e30], [-1e30, 0, 0], [0, 0, 0]], F)
+    pts = np.concatenate([pts, bad, pts[:50]])
+    n = pts.shape[0]
+    nrm = rng.standard_normal((n, 3)).astype(F)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    tgt = np.zeros((n, 3), F)
+    tm = (rng.random(n) < 0.3).astype(np.uint8)
+    t = rng.standard_normal((n, 3)).astype(F)
+    tgt[tm == 1] = (t / np.linalg.norm(t, axis=1, keepdims=True))[tm == 1]
+    return synth.Cloud(pts, nrm, tgt, tm)
+
+
+@pytest.mark.parametrize("name", ["plane_small", "cylinder_small", "freeform_small"])
+def test_scoring_on_decision_boundaries(ctx, name):
+    from triplet_match_b200 import capi
+    m, s0, om, osc0, rec = common.config(name)
+    s = _boundary_scene(m, om, 1)
+    osc = po.OScene(s)
+    gm = common.upload_model(ctx, m, om)
+    gs = capi.Scene(ctx, s.pos, s.nrm, s.tgt, s.tangent_mask)
+    rng = np.random.default_rng(2)
+    Ts = [np.eye(4)]
+    for _ in range(40):  # tiny perturbations of identity keep the points on the boundaries "almost"
+        a = rng.standard_normal(3) * 1e-6
+        T = np.eye(4)
+        T[:3, :3] += np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        T[:3, 3] = rng.standard_normal(3) * 1e-7
+        Ts.append(T)
+    for k in range(3):  # axis permutations / reflections: exact arithmetic, other cells
+        P = np.eye(4)
+        P[:3, :3] = np.roll(np.eye(3), k, axis=0) * (-1 if k == 2 else 1)
+        Ts.append(P)
+    nanT = np.eye(4); nanT[0, 0] = np.nan
+    infT = np.eye(4); infT[1, 3] = np.inf
+    hugeT = np.eye(4) * 1e20; hugeT[3, 3] = 1
+    zeroT = np.zeros((4, 4)); zeroT[3, 3] = 1
+    Ts += [nanT, infT, hugeT, zeroT]
+    T16 = np.stack([T.T.reshape(-1) for T in Ts]).astype(F)  # column-major
+    for eo in (False, True):
+        cg, sg, dg = gs.score(gm, T16, early_out=eo)
+        co, so, do = osc.score_batch(om, T16, early_out=eo, nthreads=4)
+        assert np.array_equal(cg, co), (name, eo, np.flatnonzero(cg != co))
+        assert np.array_equal(dg, do)
+        # scores are 2^-36 fixed point: exact for |ref . ref_n| terms below 2^27, i.e. for any rigid
+        # transform (terms <= 1); the 1e20-scaled matrix is outside that domain (counts still agree)
+        rigid = np.array([abs(np.linalg.det(T[:3, :3])) < 10 if np.isfinite(T).all() else True for T in Ts])
+        assert np.allclose(sg[rigid], so[rigid], rtol=1e-9, atol=1e-9)
+    assert co[0] > 0
+    for h in (0, 5, len(Ts) - 8):
+        a = osc.project(om, np.arange(s.n, dtype=np.int32), T16[h])
+        scn, mdl, score = gs.correspondences(gm, T16[h], 1.0)
+        assert np.array_equal(scn, a["scene_corrs"]) and np.array_equal(mdl, a["model_corrs"])
+    # ICP from these transforms (incl. the degenerate ones) follows the oracle's control flow
+    To, cnt, scr, it = gs.icp(gm, T16[:6], 3, 1.0)
+    for h in range(6):
+        oT, on, osx, oit = osc.icp(om, T16[h], 3, 1.0)
+        assert cnt[h] == on and it[h] == oit and np.abs(To[h] - oT).max() < 1e-4
+    gs.close(); gm.close()
+
+
+def test_features_on_degenerate_pairs(ctx):
+    """Zero / non-finite tangents, coincident points, tangent parallel to the pair direction, distance
+    exactly at the window ends."""
+    from triplet_match_b200 import capi
+    m, s0, om, osc0, rec = common.config("plane_small")
+    rng = np.random.default_rng(3)
+    n = 600
+    pos = (rng.random((n, 3)) * om.diameter).astype(F)
+    tgt = rng.standard_normal((n, 3)).astype(F)
+    tgt /= np.linalg.norm(tgt, axis=1, keepdims=True)
+    pos[1] = pos[0]                                   # coincident pair (0, 1)
+    tgt[2] = 0                                        # zero tangent
+    tgt[3] = [np.nan, 0, 0]
+    pos[5] = pos[4] + tgt[4] * F(0.5 * om.diameter)   # tangent exactly along the pair direction
+    lower, upper = F(0.2) * F(om.diameter), F(1.0) * F(om.diameter)
+    pos[7] = pos[6] + np.array([lower, 0, 0], F)      # window ends
+    pos[9] = pos[8] + np.array([upper, 0, 0], F)
+    pos[10] = [np.inf, 0, 0]
+    nrm = np.tile(np.array([0, 0, 1], F), (n, 1))
+    tm = np.ones(n, np.uint8)
+    tm[11] = 0                                        # not a tangent point: pair filtered (scene.hpp:290)
+    s = synth.Cloud(pos, nrm, tgt, tm)
+    osc = po.OScene(s)
+    gm = common.upload_model(ctx, m, om)
+    gs = capi.Scene(ctx, s.pos, s.nrm, s.tgt, s.tangent_mask)
+    pi = np.concatenate([[0, 2, 3, 4, 6, 8, 10, 11, 12, 12], rng.integers(0, n, 3000)]).astype(np.uint32)
+    pj = np.concatenate([[1, 12, 12, 5, 7, 9, 12, 12, 11, 12], rng.integers(0, n, 3000)]).astype(np.uint32)
+    f, k, v = gs.features(gm, pi, pj, 0.2, 1.0)
+    fo, ko, vo = osc.pair_features(om, pi, pj)
+    assert np.array_equal(v, vo) and np.array_equal(k[v.astype(bool)], ko[vo.astype(bool)])
+    ok = v.astype(bool)
+    assert np.array_equal(f[ok].view(np.uint32), fo[ok].view(np.uint32)) and ok.sum() > 100
+    off, hits = gm.probe(k, v, 200)
+    Tg, vg = gs.hypotheses(gm, pi, pj, off, hits)
+    T, hp, mi, mj, va = osc.hypotheses(om, pi, pj)
+    assert np.array_equal(vg, va) and np.array_equal(Tg[va.astype(bool)].view(np.uint32), T[va.astype(bool)].view(np.uint32))
+    gs.close(); gm.close()
+
+
+def test_table_with_thousands_of_keys(ctx):
+    """distance_step_count = 400 and 2-degree angle bins: ~10^4 distinct keys -> long probe sequences
+    in the open-addressing table; hits and their order must still equal equal_range's."""
+    from triplet_match_b200 import capi
+    m = synth.freeform_model(seed=3, n_points=1500, radius=0.12, n_bumps=6, n_curves=5)
+    s = synth.make_scene(seed=7, model=m, n_points=24000, n_copies=4, extent=1.2, flat_copies=False)
+    s = s.take(synth.morton_order(s.pos))
+    dp = dict(distance_step_count=400.0, angle_step=float(np.deg2rad(2.0)))
+    om = po.OModel(m, **dp, **common.SP)
+    assert om.n_keys > 3000
+    osc = po.OScene(s)
+    rec = synth.record_pairs(11, s, om.diameter, 10, 48)
+    keys, offsets, pairs = om.table(200)
+    gm = capi.Model(ctx, m.pos, m.nrm, m.tgt, voxel=om.voxel, extents=om.extents, to_voxel16=om.to_voxel16,
+                    resolution=om.resolution, diameter=om.diameter, keys=keys, offsets=offsets, pairs=pairs,
+                    feat_min=om.feat_min, feat_max=om.feat_max, **dp)
+    gs = common.upload_scene(ctx, s)
+    f, k, v = gs.features(gm, rec.pair_i, rec.pair_j, 0.2, 1.0)
+    fo, ko, vo = osc.pair_features(om, rec.pair_i, rec.pair_j)
+    assert np.array_equal(v, vo) and np.array_equal(k, ko)
+    off, hits = gm.probe(k, v, 200)
+    T, hp, mi, mj, va = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    assert hits.shape[0] == T.shape[0] > 50 and np.array_equal(hits, np.stack([mi, mj], 1))
+    # keys that are absent from the table (probe runs into an empty slot) give no hits
+    absent = np.array([[399, 89, 89, 399], [0, 0, 0, 1], [123456, 1, 1, 123456]], np.uint32)
+    o2, h2 = gm.probe(absent, None, 200)
+    assert o2[-1] == 0 and h2.shape[0] == 0
+    # the product's own host build produces the same table
+    hm = capi.HostModel(ctx, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **dp, **common.SP)
+    assert hm.n_keys == om.n_keys
+    order = lambda kk: np.lexsort(kk.T[::-1])
+    a, b = order(hm.keys), order(keys)
+    assert np.array_equal(hm.keys[a], keys[b])
+    for x, y in zip(a[:200], b[:200]):
+        assert np.array_equal(hm.pairs[hm.offsets[x]:hm.offsets[x + 1]], pairs[offsets[y]:offsets[y + 1]])
+    hm.close(); gs.close(); gm.close()
