@@ -146,6 +146,19 @@ int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max
 int tm_traits_project(tm_ctx* ctx, int kind, const float g2l[16], float radius, float threshold,
                       const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
 
+/* ---- model::init pair enumeration (include/impl/model.hpp:100-149) on the device -------------
+ * pos3 / tgt3: packed T x 3 positions and tangents of the tangent subset, in subset order.
+ * tm_model_pair_bounds = pass 1: feat_min / feat_max over all ordered pairs that pass the
+ * distance-window and collinearity filters (components 0..2; component 3 equals 0) and their
+ * number.  tm_model_pair_keys = pass 2: for pair (a, b) at keys[a * T + b] the discretised key
+ * packed as k0 | k1 << 24 | k2 << 44 (k3 == k0), or ~0 when the pair is filtered or not valid();
+ * fmn0 / fmx0 = the distance bounds after valid_bounds(). */
+int tm_model_pair_bounds(tm_ctx* ctx, const float* pos3, const float* tgt3, uint32_t T, float lower,
+                         float upper, float feat_min[3], float feat_max[3], uint64_t* n_pass);
+int tm_model_pair_keys(tm_ctx* ctx, const float* pos3, const float* tgt3, uint32_t T, float lower,
+                       float upper, float fmn0, float fmx0, uint32_t steps, float angle_step,
+                       uint64_t* keys);
+
 /* ---- pre-processing the reference does with PCL/FLANN ----------------
  * Exact k nearest neighbours (k <= 32) of the resident cloud's points query_idx[0..n_query), the
  * query point included (pointcloud::knn_inclusive, include/impl/pointcloud.hpp:138-152).  Order:

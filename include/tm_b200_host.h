@@ -29,6 +29,12 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* c
                        float max_diameter_factor, float resolution, uint32_t cap,
                        tm_hostmodel** out);
 void tm_hostmodel_destroy(tm_hostmodel* m);
+/* Model blob: serialises what model::init produced (grid, hash table in insertion and in
+ * equal_range order, bounds) so a model is built once and reloaded — the reference rebuilds both
+ * on every run.  n_cloud_points ties the blob to its cloud; load verifies magic, version, an
+ * FNV-1a checksum and every index before anything reaches the device. */
+int tm_hostmodel_save(const tm_hostmodel* m, uint32_t n_cloud_points, const char* path);
+int tm_hostmodel_load(const char* path, uint32_t n_cloud_points, tm_hostmodel** out);
 /* pointers in *d stay valid while the host model lives */
 void tm_hostmodel_desc(const tm_hostmodel* m, tm_model_desc* d);
 void tm_hostmodel_counts(const tm_hostmodel* m, uint64_t* n_subset, uint64_t* n_entries,

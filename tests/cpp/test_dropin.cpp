@@ -162,6 +162,20 @@ int main(int argc, char** argv) {
     tr::model<point_t> m(mc, dp);
     m.set_curvature_test(curv);
     m.init(sp);
+    if (argc >= 7) {  // argv[6]: blob path — save, reload into a fresh model and search with that one
+        m.save(argv[6]);
+        tr::model<point_t> m2(mc, dp);
+        m2.load(argv[6]);
+        CHECK(m2.point_count() == m.point_count() && m2.pair_count() == m.pair_count() && m2.diameter() == m.diameter());
+        auto f2 = tr::feature<point_t>(mc->points[m.point_count() ? 0 : 0], mc->points[1]);
+        auto ra = m.query(*f2), rb = m2.query(*f2);
+        CHECK(std::distance(ra.first, ra.second) == std::distance(rb.first, rb.second));
+        tr::scene<point_t> s2(sc);
+        s2.set_curvature_test(curv);
+        auto mm = s2.find_all_parallel(m2, 1.0f, 0.5f, 0.9f, sp, 5);
+        std::printf("blob round trip: %zu matches with the reloaded model\n", mm.size());
+        CHECK(!mm.empty());
+    }
     // API users still get the host-side query()/voxel_query()
     auto f = tr::feature<point_t>(mc->points[0], mc->points[1]);
     (void)m.query(*f);

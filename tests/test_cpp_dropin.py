@@ -60,7 +60,8 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
     mp, sp, op = str(tmp_path / "m.bin"), str(tmp_path / "s.bin"), str(tmp_path / "o.txt")
     _write(m, mp)
     _write(s, sp)
-    r = subprocess.run([exe, "find", mp, sp, op] + (["curv"] if curv else []), capture_output=True, text=True)
+    extra = ["curv" if curv else "nocurv"] + ([str(tmp_path / "model.tmb")] if not curv and not shuffled else [])
+    r = subprocess.run([exe, "find", mp, sp, op] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     lines = open(op).read().strip().split("\n")
     n = int(lines[0])

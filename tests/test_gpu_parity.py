@@ -266,6 +266,62 @@ def test_model_built_by_product_equals_oracle_model(ctx):
         q.close(); gm.close(); gs.close(); hm.close()
 
 
+def test_device_pair_enumeration_equals_host(ctx):
+    """model::init's O(T^2) passes on the device (k_model.cu) vs the host loops: identical bounds,
+    insertion-order entries and capped table."""
+    import os
+    from triplet_match_b200 import capi, synth
+    clouds = [common.config(n)[0] for n in ("plane_small", "cylinder_small", "freeform_small")]
+    clouds.append(synth.freeform_model(seed=5, n_points=20000, radius=0.01 * np.sqrt(20000 / (4 * np.pi)), n_bumps=9, n_curves=6))
+    for m in clouds:
+        for dp in (common.DP, dict(distance_step_count=400.0, angle_step=float(np.deg2rad(2.0)))):
+            os.environ["TM_MODEL_PAIRS_HOST"] = "1"
+            try:
+                h = capi.HostModel(ctx, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **dp, **common.SP)
+            finally:
+                os.environ.pop("TM_MODEL_PAIRS_HOST")
+            d = capi.HostModel(ctx, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **dp, **common.SP)
+            assert (d.n_subset, d.n_entries, d.n_keys, d.n_kept) == (h.n_subset, h.n_entries, h.n_keys, h.n_kept)
+            assert d.n_entries > 1000
+            for a in ("feat_min", "feat_max", "keys", "offsets", "pairs"):
+                assert np.array_equal(getattr(d, a), getattr(h, a)), a
+            ek = lambda x: x._arr(x.lib.tm_hostmodel_entry_keys(x.h), 4 * x.n_entries)
+            ep = lambda x: x._arr(x.lib.tm_hostmodel_entry_pairs(x.h), 2 * x.n_entries)
+            assert np.array_equal(ek(d), ek(h)) and np.array_equal(ep(d), ep(h))
+            h.close(); d.close()
+
+
+def test_pruned_voxel_fill_equals_brute_force(ctx):
+    """The block-pruned two-pass grid fill picks exactly the brute-force winners (incl. ties ->
+    lowest index), on grids with partial border blocks, duplicate points and a thin (planar) model."""
+    import os
+    from triplet_match_b200 import synth
+    models = [common.config(n)[0] for n in ("plane_small", "cylinder_small", "freeform_small")]
+    models.append(synth.freeform_model(seed=5, n_points=20000, radius=0.01 * np.sqrt(20000 / (4 * np.pi)), n_bumps=9, n_curves=6))
+    dup = models[1]
+    models.append(synth.Cloud(np.concatenate([dup.pos, dup.pos[::3]]), np.concatenate([dup.nrm, dup.nrm[::3]]),
+                              np.concatenate([dup.tgt, dup.tgt[::3]]), np.concatenate([dup.tangent_mask, dup.tangent_mask[::3]])))
+    for m in models:
+        from triplet_match_b200 import capi
+        res = capi.host_resolution(m.pos)
+        lo, hi = m.pos.min(0), m.pos.max(0)
+        rng_ = (hi - lo).astype(np.float32)
+        ext_f = np.maximum(rng_ / np.float32(0.5 * res), 1).astype(np.float32)
+        extents = (ext_f + 10).astype(np.int32)
+        scale = np.where(rng_ < 1e-5, 1, ext_f / np.where(rng_ < 1e-5, 1, rng_)).astype(np.float32)
+        trans = ((scale * (-lo) + np.float32(5)) - np.float32(0.5)).astype(np.float32)
+        tv = np.zeros(16, np.float32)
+        tv[0], tv[5], tv[10], tv[15] = scale[0], scale[1], scale[2], 1
+        tv[12:15] = trans
+        os.environ["TM_VOXEL_FILL_BRUTE"] = "1"
+        try:
+            brute = ctx.voxel_fill(m.pos, m.nrm, m.tgt, extents, tv)
+        finally:
+            os.environ.pop("TM_VOXEL_FILL_BRUTE")
+        pruned = ctx.voxel_fill(m.pos, m.nrm, m.tgt, extents, tv)
+        assert np.array_equal(brute, pruned), (m.n, extents, int((brute != pruned).sum()))
+
+
 def test_surfel_aos_upload_equals_packed(ctx):
     from triplet_match_b200 import capi
     m, s, om, osc, rec = common.config("cylinder_small")

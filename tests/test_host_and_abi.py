@@ -97,3 +97,36 @@ def test_synth_is_seed_fixed():
     rec = synth.record_pairs(1, s, 0.3, 4, 10)
     assert np.all(np.diff(rec.pair_outer.astype(np.int64)) >= 0)
     assert np.all(s.tangent_mask[rec.pair_j] == 1) and np.all(rec.pair_j != rec.pair_i)
+
+
+def test_model_blob_round_trip_and_corruption(built, tmp_path):
+    """tm_hostmodel_save / tm_hostmodel_load: identical tables after a reload; magic, version, cloud
+    size, checksum and index checks reject damaged files (CPU only: ctx = None build)."""
+    from triplet_match_b200 import capi
+    m, s, om, osc, rec = common.config("cylinder_small")
+    hm = capi.HostModel(None, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **common.DP, **common.SP)
+    path = str(tmp_path / "model.tmb")
+    hm.save(path)
+    h2 = capi.HostModel.load(path, m.pos, m.nrm, m.tgt)
+    assert (h2.n_subset, h2.n_entries, h2.n_keys, h2.n_kept) == (hm.n_subset, hm.n_entries, hm.n_keys, hm.n_kept)
+    for a in ("voxel", "keys", "offsets", "pairs", "subset", "extents", "to_voxel16", "feat_min", "feat_max"):
+        assert np.array_equal(getattr(h2, a), getattr(hm, a)), a
+    assert h2.resolution == hm.resolution and h2.diameter == hm.diameter
+    h2.close()
+    raw = bytearray(open(path, "rb").read())
+    def expect_fail(data, n_pts=m.n, what=""):
+        p = str(tmp_path / "bad.tmb")
+        open(p, "wb").write(bytes(data))
+        with pytest.raises(capi.TmError) as e:
+            capi.HostModel.load(p, m.pos[:n_pts], m.nrm[:n_pts], m.tgt[:n_pts])
+        assert what in str(e.value)
+    flipped = bytearray(raw); flipped[len(raw) // 2] ^= 0x40
+    expect_fail(flipped, what="checksum")
+    expect_fail(raw[: len(raw) // 3], what="truncated")
+    expect_fail(b"NOTABLOB" + bytes(raw[8:]), what="not a model blob")
+    v2 = bytearray(raw); v2[8] = 9
+    expect_fail(v2, what="version")
+    expect_fail(raw, n_pts=m.n - 1, what="points")
+    with pytest.raises(capi.TmError):
+        capi.HostModel.load(str(tmp_path / "missing.tmb"), m.pos, m.nrm, m.tgt)
+    hm.close()

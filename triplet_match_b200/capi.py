@@ -69,7 +69,7 @@ EXPORTS = [
 HOST_EXPORTS = [
     "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_destroy",
     "tm_hostmodel_desc", "tm_hostmodel_counts", "tm_hostmodel_subset", "tm_hostmodel_entry_keys",
-    "tm_hostmodel_entry_pairs", "tm_model_create",
+    "tm_hostmodel_entry_pairs", "tm_model_create", "tm_hostmodel_save", "tm_hostmodel_load",
 ]
 
 _lib = None
@@ -257,6 +257,37 @@ class HostModel:
         self.resolution, self.diameter = float(d.resolution), float(d.diameter)
         self.feat_min = np.array(list(d.feat_min), dtype=np.float32)
         self.feat_max = np.array(list(d.feat_max), dtype=np.float32)
+
+    def _read_desc(self):
+        d = ModelDesc()
+        self.lib.tm_hostmodel_desc(self.h, C.byref(d))
+        self.desc = d
+        c = (C.c_uint64 * 4)()
+        self.lib.tm_hostmodel_counts(self.h, C.byref(c, 0), C.byref(c, 8), C.byref(c, 16), C.byref(c, 24))
+        self.n_subset, self.n_entries, self.n_keys, self.n_kept = [int(x) for x in c]
+        self.extents = np.array(list(d.extents), dtype=np.int32)
+        self.to_voxel16 = np.array(list(d.to_voxel), dtype=np.float32)
+        self.resolution, self.diameter = float(d.resolution), float(d.diameter)
+        self.feat_min = np.array(list(d.feat_min), dtype=np.float32)
+        self.feat_max = np.array(list(d.feat_max), dtype=np.float32)
+
+    def save(self, path: str):
+        rc = self.lib.tm_hostmodel_save(self.h, C.c_uint32(int(self._view.n)), path.encode())
+        if rc != TM_OK:
+            raise TmError(rc, self.lib.tm_host_last_error().decode("utf-8", "replace"))
+
+    @classmethod
+    def load(cls, path: str, pos, nrm, tgt) -> "HostModel":
+        """Reload a blob written by save(); pos/nrm/tgt are the cloud it was built for."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self._view, self._keep = _view(pos, nrm, tgt)
+        self.h = C.c_void_p()
+        rc = self.lib.tm_hostmodel_load(path.encode(), C.c_uint32(int(self._view.n)), C.byref(self.h))
+        if rc != TM_OK:
+            raise TmError(rc, self.lib.tm_host_last_error().decode("utf-8", "replace"))
+        self._read_desc()
+        return self
 
     def _arr(self, ptr, n, dtype=np.uint32):
         if not n:

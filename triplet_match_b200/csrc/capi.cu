@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -381,18 +382,23 @@ int tm_voxel_fill(tm_ctx* c, const tm_cloud_view* cloud, const int32_t extents[3
     TRY(check_to_voxel(to_voxel, s, tr));
     const size_t cells = (size_t)extents[0] * extents[1] * extents[2];
     REQUIRE(cells > 0 && cells < (1ull << 31), "bad extents");
-    DevBuf pos, nrm, tgt, vox;
+    DevBuf pos, nrm, tgt, vox, blk;
     int rc = upload_cloud(c, cloud, nullptr, 1, pos, nrm, tgt);
     if (!rc) rc = vox.ensure(cells * sizeof(uint32_t));
+    // pruned two-pass fill unless TM_VOXEL_FILL_BRUTE=1 (the brute-force kernel is kept as its cross-check)
+    const char* brute_env = getenv("TM_VOXEL_FILL_BRUTE");
+    const bool brute = brute_env && atoi(brute_env) != 0;
+    if (!rc && !brute) rc = blk.ensure(voxel_fill_scratch_bytes(extents[0], extents[1], extents[2]));
     if (!rc) {
         launch_voxel_fill(c->stream, pos.as<float4>(), cloud->n, extents[0], extents[1], extents[2],
-                          s[0], s[1], s[2], tr[0], tr[1], tr[2], vox.as<uint32_t>());
+                          s[0], s[1], s[2], tr[0], tr[1], tr[2], vox.as<uint32_t>(),
+                          brute ? nullptr : blk.as<float>());
         cudaError_t e = cudaMemcpyAsync(voxel_out, vox.p, cells * sizeof(uint32_t),
                                         cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(TM_ERR_CUDA, cudaGetErrorString(e));
     }
-    pos.release(); nrm.release(); tgt.release(); vox.release();
+    pos.release(); nrm.release(); tgt.release(); vox.release(); blk.release();
     return rc;
 }
 
@@ -966,6 +972,60 @@ int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, fl
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(uvw, out.p, n * 12, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+// ------------------------------------------------------------ model::init pair enumeration
+int tm_model_pair_bounds(tm_ctx* c, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
+                         float feat_min[3], float feat_max[3], uint64_t* n_pass) {
+    REQUIRE(c && feat_min && feat_max, "tm_model_pair_bounds: null argument");
+    REQUIRE(T == 0 || (pos3 && tgt3), "tm_model_pair_bounds: null buffer");
+    TRY(bind(c));
+    for (int k = 0; k < 3; ++k) {
+        feat_min[k] = std::numeric_limits<float>::max();
+        feat_max[k] = std::numeric_limits<float>::lowest();
+    }
+    if (n_pass) *n_pass = 0;
+    if (!T) return TM_OK;
+    DevBuf &dp = c->scratch[0], &dt = c->scratch[1], &db = c->scratch[2];
+    TRY(dp.ensure((size_t)T * 12)); TRY(dt.ensure((size_t)T * 12)); TRY(db.ensure(64));
+    CU(cudaMemcpyAsync(dp.p, pos3, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dt.p, tgt3, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t init[8] = {0x7f7fffffu, 0x7f7fffffu, 0x7f7fffffu, 0u, 0u, 0u, 0u, 0u};  // min: FLT_MAX bits, max: +0
+    CU(cudaMemcpyAsync(db.p, init, 32, cudaMemcpyHostToDevice, c->stream));
+    launch_model_pair_bounds(c->stream, dp.as<float>(), dt.as<float>(), T, lower, upper, db.as<uint32_t>(),
+                             reinterpret_cast<unsigned long long*>(db.as<uint32_t>() + 6), c->sm_count * 8);
+    CU(cudaGetLastError());
+    uint32_t out[8];
+    CU(cudaMemcpyAsync(out, db.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long cnt;
+    memcpy(&cnt, &out[6], 8);
+    if (n_pass) *n_pass = cnt;
+    if (cnt) {
+        memcpy(feat_min, &out[0], 12);
+        memcpy(feat_max, &out[3], 12);
+    }
+    return TM_OK;
+}
+int tm_model_pair_keys(tm_ctx* c, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
+                       float fmn0, float fmx0, uint32_t steps, float angle_step, uint64_t* keys) {
+    REQUIRE(c, "tm_model_pair_keys: null context");
+    REQUIRE(T == 0 || (pos3 && tgt3 && keys), "tm_model_pair_keys: null buffer");
+    REQUIRE((uint64_t)T * T <= (1ull << 28), "tm_model_pair_keys: too many pairs for one call");
+    REQUIRE(steps < (1u << 24), "tm_model_pair_keys: distance_step_count too large for the packed key");
+    TRY(bind(c));
+    if (!T) return TM_OK;
+    const size_t n = (size_t)T * T;
+    DevBuf &dp = c->scratch[0], &dt = c->scratch[1], &dk = c->scratch[2];
+    TRY(dp.ensure((size_t)T * 12)); TRY(dt.ensure((size_t)T * 12)); TRY(dk.ensure(n * 8));
+    CU(cudaMemcpyAsync(dp.p, pos3, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dt.p, tgt3, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    launch_model_pair_keys(c->stream, dp.as<float>(), dt.as<float>(), T, lower, upper, fmn0, fmx0, steps, angle_step,
+                           dk.as<unsigned long long>(), c->sm_count * 8);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keys, dk.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return TM_OK;
 }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -40,26 +41,6 @@ inline float sqdist_seq(v3 a, v3 b) {  // FLANN L2_Simple accumulation order
 float atan2f_q1(float y, float x) { return tm_math::atan2f_libm(y, x); }
 float angle(v3 a, v3 b) { return atan2f_q1(norm(cross(a, b)), fabsf(dot(a, b))); }
 
-uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-uint32_t murmur4(const uint32_t* key) {  // include/impl/discretize.hpp:10-45
-    uint32_t h1 = 42u;
-    for (int i = 0; i < 4; ++i) {
-        uint32_t k1 = key[i];
-        k1 *= 0xcc9e2d51u;
-        k1 = rotl32(k1, 15);
-        k1 *= 0x1b873593u;
-        h1 ^= k1;
-        h1 = rotl32(h1, 13);
-        h1 = h1 * 5u + 0xe6546b64u;
-    }
-    h1 ^= 16u;
-    h1 ^= h1 >> 16;
-    h1 *= 0x85ebca6bu;
-    h1 ^= h1 >> 13;
-    h1 *= 0xc2b2ae35u;
-    h1 ^= h1 >> 16;
-    return h1;
-}
 uint32_t discretize_range(float value, float mn, float range, uint32_t steps) {
     float nval = (value - mn) / range;
     if (nval < 0.f) return 0;
@@ -68,14 +49,7 @@ uint32_t discretize_range(float value, float mn, float range, uint32_t steps) {
 }
 uint32_t discretize_step(float value, float step) { return static_cast<uint32_t>(value / step); }
 
-struct key4 {
-    uint32_t k[4];
-    bool operator==(const key4& o) const { return !memcmp(k, o.k, 16); }
-};
-struct key4_hash {
-    size_t operator()(const key4& k) const { return murmur4(k.k); }
-};
-typedef std::unordered_multimap<key4, std::pair<uint32_t, uint32_t>, key4_hash> hash_map_t;
+
 
 // exact nearest neighbour on a uniform bucket grid; lowest index wins ties
 struct NNGrid {
@@ -337,15 +311,44 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
         f[3] = f[0];
         return true;
     };
-    for (uint32_t i : m->subset)
-        for (uint32_t j : m->subset) {
-            float f[4];
-            if (!pair_feature(i, j, f)) continue;
-            for (int k = 0; k < 4; ++k) {
-                fmn[k] = std::min(fmn[k], f[k]);
-                fmx[k] = std::max(fmx[k], f[k]);
-            }
+    // The O(T^2) pair enumeration runs on the device when a context is given (k_model.cu: same
+    // filters, feature and discretisation; packed key per pair in insertion order); the host then
+    // only does the integer bookkeeping.  TM_MODEL_PAIRS_HOST=1 forces the host loops (cross-check).
+    const uint32_t Tn = (uint32_t)m->subset.size();
+    const char* host_env = getenv("TM_MODEL_PAIRS_HOST");
+    const uint32_t steps = static_cast<uint32_t>(distance_step_count);
+    const bool on_device = ctx && Tn > 0 && (uint64_t)Tn * Tn <= (1ull << 28) && steps < (1u << 24) &&
+                           !(host_env && atoi(host_env) != 0);
+    std::vector<float> sp3, st3;
+    if (on_device) {
+        sp3.resize((size_t)Tn * 3);
+        st3.resize((size_t)Tn * 3);
+        for (uint32_t a = 0; a < Tn; ++a) {
+            v3 p = P(m->subset[a]), t = T(m->subset[a]);
+            sp3[3 * a] = p.x; sp3[3 * a + 1] = p.y; sp3[3 * a + 2] = p.z;
+            st3[3 * a] = t.x; st3[3 * a + 1] = t.y; st3[3 * a + 2] = t.z;
         }
+        float mn3[3], mx3[3];
+        uint64_t n_pass = 0;
+        int rc = tm_model_pair_bounds(ctx, sp3.data(), st3.data(), Tn, lower_bound, upper_bound, mn3, mx3, &n_pass);
+        if (rc) {
+            g_host_err = std::string("tm_model_pair_bounds: ") + tm_last_error();
+            delete m;
+            return rc;
+        }
+        for (int k = 0; k < 3; ++k) { fmn[k] = mn3[k]; fmx[k] = mx3[k]; }
+        fmn[3] = fmn[0]; fmx[3] = fmx[0];
+    } else {
+        for (uint32_t i : m->subset)
+            for (uint32_t j : m->subset) {
+                float f[4];
+                if (!pair_feature(i, j, f)) continue;
+                for (int k = 0; k < 4; ++k) {
+                    fmn[k] = std::min(fmn[k], f[k]);
+                    fmx[k] = std::max(fmx[k], f[k]);
+                }
+            }
+    }
     // valid_bounds(bounds, ., ., 0, 1), feature.hpp:90-114
     float d0 = fmx[0] - fmn[0], d3 = fmx[3] - fmn[3];
     float nmn0 = fmn[0] + 0.0f * d0, nmx0 = fmn[0] + 1.f * d0;
@@ -353,44 +356,76 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
     fmn[0] = nmn0; fmx[0] = nmx0; fmn[3] = nmn3; fmx[3] = nmx3;
     memcpy(m->feat_min, fmn, 16);
     memcpy(m->feat_max, fmx, 16);
-    hash_map_t map;
-    const uint32_t steps = static_cast<uint32_t>(distance_step_count);
     const float pi = static_cast<float>(M_PI);
-    for (uint32_t i : m->subset)  // model.hpp:125-149
-        for (uint32_t j : m->subset) {
-            float f[4];
-            if (!pair_feature(i, j, f)) continue;
-            if (f[0] < fmn[0] || f[0] > fmx[0]) continue;  // valid(), feature.hpp:48-88
-            if (!((f[1] >= 0.f && f[1] <= pi) && (f[2] >= 0.f && f[2] <= pi))) continue;
-            key4 k;
-            float diag0 = fmx[0] - fmn[0];
-            k.k[0] = discretize_range(f[0], fmn[0], diag0, steps);
-            k.k[1] = discretize_step(f[1], angle_step);
-            k.k[2] = discretize_step(f[2], angle_step);
-            k.k[3] = discretize_range(f[3], fmn[0], diag0, steps);
-            map.insert({k, {i, j}});
-            m->entry_keys.insert(m->entry_keys.end(), k.k, k.k + 4);
-            m->entry_pairs.push_back(i);
-            m->entry_pairs.push_back(j);
-        }
-    m->n_entries = map.size();
-    // flatten: keys in lexicographic order (deterministic), values in equal_range order, capped
+    // per key: the (i, j) values in insertion order.  equal_range of libstdc++'s unordered_multimap
+    // walks equal keys newest-first (each insert lands at the front of its group), so the table keeps
+    // the LAST `cap` insertions of a key, reversed — checked against the real container in the tests.
+    std::unordered_map<uint64_t, uint32_t> key_id;
     std::vector<std::array<uint32_t, 4>> uk;
-    for (auto it = map.begin(); it != map.end(); it = map.equal_range(it->first).second)
-        uk.push_back({it->first.k[0], it->first.k[1], it->first.k[2], it->first.k[3]});
-    std::sort(uk.begin(), uk.end());
-    m->offsets.push_back(0);
-    for (auto& k : uk) {
-        key4 kk{{k[0], k[1], k[2], k[3]}};
-        auto r = map.equal_range(kk);
-        uint32_t cnt = 0;
-        for (auto e = r.first; e != r.second; ++e) {
-            if (cap && cnt >= cap) break;
-            m->pairs.push_back(e->second.first);
-            m->pairs.push_back(e->second.second);
-            ++cnt;
+    std::vector<std::vector<uint32_t>> vals;  // flattened (i, j) per key
+    auto add_entry = [&](uint32_t k0, uint32_t k1, uint32_t k2, uint32_t i, uint32_t j) {
+        const uint64_t pk = (uint64_t)k0 | ((uint64_t)k1 << 24) | ((uint64_t)k2 << 44);
+        auto it = key_id.find(pk);
+        uint32_t id;
+        if (it == key_id.end()) {
+            id = (uint32_t)uk.size();
+            key_id.emplace(pk, id);
+            uk.push_back({k0, k1, k2, k0});
+            vals.emplace_back();
+        } else {
+            id = it->second;
         }
-        m->keys.insert(m->keys.end(), k.begin(), k.end());
+        vals[id].push_back(i);
+        vals[id].push_back(j);
+        const uint32_t k4[4] = {k0, k1, k2, k0};
+        m->entry_keys.insert(m->entry_keys.end(), k4, k4 + 4);
+        m->entry_pairs.push_back(i);
+        m->entry_pairs.push_back(j);
+    };
+    if (on_device) {
+        std::vector<uint64_t> pk((size_t)Tn * Tn);
+        int rc = tm_model_pair_keys(ctx, sp3.data(), st3.data(), Tn, lower_bound, upper_bound, fmn[0], fmx[0], steps,
+                                    angle_step, pk.data());
+        if (rc) {
+            g_host_err = std::string("tm_model_pair_keys: ") + tm_last_error();
+            delete m;
+            return rc;
+        }
+        for (uint32_t a = 0; a < Tn; ++a)
+            for (uint32_t b = 0; b < Tn; ++b) {
+                const uint64_t k = pk[(size_t)a * Tn + b];
+                if (k == ~0ull) continue;
+                add_entry((uint32_t)(k & 0xffffffu), (uint32_t)((k >> 24) & 0xfffffu), (uint32_t)(k >> 44), m->subset[a],
+                          m->subset[b]);
+            }
+    } else {
+        for (uint32_t i : m->subset)  // model.hpp:125-149
+            for (uint32_t j : m->subset) {
+                float f[4];
+                if (!pair_feature(i, j, f)) continue;
+                if (f[0] < fmn[0] || f[0] > fmx[0]) continue;  // valid(), feature.hpp:48-88
+                if (!((f[1] >= 0.f && f[1] <= pi) && (f[2] >= 0.f && f[2] <= pi))) continue;
+                float diag0 = fmx[0] - fmn[0];
+                const uint32_t k0 = discretize_range(f[0], fmn[0], diag0, steps);
+                // k3 = discretize_range(f[3], ...) with f[3] == f[0] and identical bounds: equals k0
+                add_entry(k0, discretize_step(f[1], angle_step), discretize_step(f[2], angle_step), i, j);
+            }
+    }
+    m->n_entries = m->entry_pairs.size() / 2;
+    // flatten: keys in lexicographic order (deterministic), values newest-first, capped
+    std::vector<uint32_t> order(uk.size());
+    for (uint32_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return uk[a] < uk[b]; });
+    m->offsets.push_back(0);
+    for (uint32_t id : order) {
+        const std::vector<uint32_t>& v = vals[id];
+        const size_t n_val = v.size() / 2;
+        const size_t take = cap ? std::min<size_t>(cap, n_val) : n_val;
+        for (size_t e = 0; e < take; ++e) {
+            m->pairs.push_back(v[2 * (n_val - 1 - e)]);
+            m->pairs.push_back(v[2 * (n_val - 1 - e) + 1]);
+        }
+        m->keys.insert(m->keys.end(), uk[id].begin(), uk[id].end());
         m->offsets.push_back((uint32_t)(m->pairs.size() / 2));
     }
     *out = m;
@@ -398,6 +433,121 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
 }
 
 void tm_hostmodel_destroy(tm_hostmodel* m) { delete m; }
+
+// ---- model blob: what model::init produced, serialised (the reference rebuilds the hash table and
+// the grid on every run, SURVEY section 5 "checkpoint / resume: none").  Layout, little endian:
+//   "TMB200M\0" | u32 version = 1 | u32 n_cloud_points | 16 header floats/ints | 7 x (u64 count + payload)
+//   | u64 FNV-1a of everything before it.
+namespace {
+const char kBlobMagic[8] = {'T', 'M', 'B', '2', '0', '0', 'M', '\0'};
+struct Fnv {
+    uint64_t h = 1469598103934665603ull;
+    void add(const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    }
+};
+struct BlobWriter {
+    FILE* f;
+    Fnv fnv;
+    bool ok = true;
+    void put(const void* p, size_t n) {
+        if (n && fwrite(p, 1, n, f) != n) ok = false;
+        fnv.add(p, n);
+    }
+    void vec(const std::vector<uint32_t>& v) {
+        uint64_t n = v.size();
+        put(&n, 8);
+        put(v.data(), n * 4);
+    }
+};
+struct BlobReader {
+    FILE* f;
+    Fnv fnv;
+    bool ok = true;
+    void get(void* p, size_t n) {
+        if (n && fread(p, 1, n, f) != n) { ok = false; return; }
+        fnv.add(p, n);
+    }
+    void vec(std::vector<uint32_t>& v, uint64_t limit) {
+        uint64_t n = 0;
+        get(&n, 8);
+        if (!ok || n > limit) { ok = false; return; }
+        v.resize(n);
+        get(v.data(), n * 4);
+    }
+};
+}  // namespace
+
+int tm_hostmodel_save(const tm_hostmodel* m, uint32_t n_cloud_points, const char* path) {
+    if (!m || !path) { g_host_err = "tm_hostmodel_save: null argument"; return TM_ERR_INVALID; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { g_host_err = std::string("tm_hostmodel_save: cannot write '") + path + "'"; return TM_ERR_INVALID; }
+    BlobWriter w{f};
+    const uint32_t version = 1;
+    w.put(kBlobMagic, 8);
+    w.put(&version, 4);
+    w.put(&n_cloud_points, 4);
+    w.put(m->extents, sizeof(m->extents));
+    w.put(m->to_voxel, sizeof(m->to_voxel));
+    w.put(&m->resolution, 4); w.put(&m->diameter, 4);
+    w.put(m->feat_min, 16); w.put(m->feat_max, 16);
+    w.put(&m->distance_step_count, 4); w.put(&m->angle_step, 4);
+    w.put(&m->n_entries, 8);
+    w.vec(m->voxel); w.vec(m->subset); w.vec(m->entry_keys); w.vec(m->entry_pairs);
+    w.vec(m->keys); w.vec(m->offsets); w.vec(m->pairs);
+    const uint64_t sum = w.fnv.h;
+    if (fwrite(&sum, 1, 8, f) != 8) w.ok = false;
+    if (fclose(f) != 0) w.ok = false;
+    if (!w.ok) { g_host_err = std::string("tm_hostmodel_save: write error on '") + path + "'"; return TM_ERR_INVALID; }
+    return TM_OK;
+}
+
+int tm_hostmodel_load(const char* path, uint32_t n_cloud_points, tm_hostmodel** out) {
+    if (!path || !out) { g_host_err = "tm_hostmodel_load: null argument"; return TM_ERR_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { g_host_err = std::string("tm_hostmodel_load: cannot open '") + path + "'"; return TM_ERR_INVALID; }
+    tm_hostmodel* m = new tm_hostmodel();
+    BlobReader r{f};
+    auto bad = [&](const std::string& why) {
+        fclose(f);
+        delete m;
+        g_host_err = "tm_hostmodel_load: '" + std::string(path) + "': " + why;
+        return TM_ERR_INVALID;
+    };
+    char magic[8];
+    uint32_t version = 0, n_pts = 0;
+    r.get(magic, 8); r.get(&version, 4); r.get(&n_pts, 4);
+    if (!r.ok || memcmp(magic, kBlobMagic, 8) != 0) return bad("not a model blob");
+    if (version != 1) return bad("unsupported version " + std::to_string(version));
+    if (n_pts != n_cloud_points) return bad("built for a cloud of " + std::to_string(n_pts) + " points, not " + std::to_string(n_cloud_points));
+    r.get(m->extents, sizeof(m->extents));
+    r.get(m->to_voxel, sizeof(m->to_voxel));
+    r.get(&m->resolution, 4); r.get(&m->diameter, 4);
+    r.get(m->feat_min, 16); r.get(m->feat_max, 16);
+    r.get(&m->distance_step_count, 4); r.get(&m->angle_step, 4);
+    r.get(&m->n_entries, 8);
+    const uint64_t lim = 1ull << 31;
+    r.vec(m->voxel, lim); r.vec(m->subset, lim); r.vec(m->entry_keys, 4 * lim); r.vec(m->entry_pairs, 2 * lim);
+    r.vec(m->keys, lim); r.vec(m->offsets, lim); r.vec(m->pairs, lim);
+    if (!r.ok) return bad("truncated");
+    uint64_t sum = 0;
+    if (fread(&sum, 1, 8, f) != 8 || sum != r.fnv.h) return bad("checksum mismatch");
+    // structural checks: everything the device upload will index with
+    bool sane = m->extents[0] > 0 && m->extents[1] > 0 && m->extents[2] > 0 &&
+                m->voxel.size() == (size_t)m->extents[0] * m->extents[1] * m->extents[2] &&
+                m->keys.size() % 4 == 0 && m->offsets.size() == m->keys.size() / 4 + 1 && m->pairs.size() % 2 == 0 &&
+                (m->offsets.empty() || m->offsets.back() == m->pairs.size() / 2) &&
+                m->entry_keys.size() == 4 * m->n_entries && m->entry_pairs.size() == 2 * m->n_entries;
+    for (size_t i = 0; sane && i < m->voxel.size(); ++i) sane = m->voxel[i] < n_pts;
+    for (size_t i = 0; sane && i < m->pairs.size(); ++i) sane = m->pairs[i] < n_pts;
+    for (size_t i = 0; sane && i < m->subset.size(); ++i) sane = m->subset[i] < n_pts;
+    for (size_t i = 0; sane && i + 1 < m->offsets.size(); ++i) sane = m->offsets[i] <= m->offsets[i + 1];
+    if (!sane) return bad("inconsistent contents");
+    fclose(f);
+    *out = m;
+    return TM_OK;
+}
 
 void tm_hostmodel_desc(const tm_hostmodel* m, tm_model_desc* d) {
     memset(d, 0, sizeof(*d));

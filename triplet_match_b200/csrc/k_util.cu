@@ -334,14 +334,146 @@ __global__ void __launch_bounds__(256)
     }
     if (live) voxel[lin] = bi;
 }
+// Pruned fill for larger grids.  Cells are grouped in 8x8x8 blocks.  Pass A: the distance d_b from
+// every block centre c_b to its nearest model point (one warp per block, brute force).  For a cell
+// centre q of the block, with h = the largest |q - c_b|, the nearest point of q is no farther than
+// |q - p_b| <= h + d_b, so every point that can be nearest to (or tie at) any cell of the block
+// lies within R = 2h + d_b of c_b.  Pass B: one CTA per block streams the model through shared
+// memory, keeps (order-preserving ballot compaction) the points inside that ball — with a 1e-4
+// relative guard that dominates every float rounding — and each thread runs the exact reference
+// scan over the survivors for its two cells: same arithmetic, same ascending order, same strict
+// '<', hence the same winners as the brute-force kernel.
+constexpr int VB = 8;  // block edge in cells
+__global__ void __launch_bounds__(256)
+    voxel_block_radius_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, float sx, float sy,
+                              float sz, float tx, float ty, float tz, int bx, int by, int bz,
+                              float* __restrict__ radius2) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nb = (uint32_t)bx * by * bz;
+    if (b >= nb) return;
+    const int bi = b % bx, bj = (b / bx) % by, bk = b / (bx * by);
+    // centre of the block's lattice of cell centres (cells bi*8 .. bi*8+7, clipped to the grid)
+    const float i0 = (float)(bi * VB), i1 = (float)min(bi * VB + VB - 1, ex - 1);
+    const float j0 = (float)(bj * VB), j1 = (float)min(bj * VB + VB - 1, ey - 1);
+    const float k0 = (float)(bk * VB), k1 = (float)min(bk * VB + VB - 1, ez - 1);
+    const float cx = (0.5f * (i0 + i1) - tx) / sx, cy = (0.5f * (j0 + j1) - ty) / sy, cz = (0.5f * (k0 + k1) - tz) / sz;
+    const float hx = 0.5f * (i1 - i0) / sx, hy = 0.5f * (j1 - j0) / sy, hz = 0.5f * (k1 - k0) / sz;
+    float best = 3.0e38f;
+    for (uint32_t t = lane; t < n; t += 32) {
+        const float4 p = mpos[t];
+        const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) best = d;  // NaN never wins
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0) {
+        const float h = sqrtf(hx * hx + hy * hy + hz * hz);
+        const float R = (2.f * h + sqrtf(best)) * 1.0001f + 1e-30f;
+        radius2[b] = best < 3.0e38f ? R * R : 3.0e38f;  // no finite point: keep everything
+    }
+}
+constexpr int VF2_TILE = 1024;
+__global__ void __launch_bounds__(256)
+    voxel_fill_pruned_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, float sx, float sy,
+                             float sz, float tx, float ty, float tz, int bx, int by,
+                             const float* __restrict__ radius2, uint32_t* __restrict__ voxel) {
+    __shared__ float4 cand[VF2_TILE];  // xyz + index bits in w
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t n_cand_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x;
+    const int bi = b % bx, bj = (b / bx) % by, bk = b / (bx * by);
+    const float i0 = (float)(bi * VB), i1 = (float)min(bi * VB + VB - 1, ex - 1);
+    const float j0 = (float)(bj * VB), j1 = (float)min(bj * VB + VB - 1, ey - 1);
+    const float k0 = (float)(bk * VB), k1 = (float)min(bk * VB + VB - 1, ez - 1);
+    const float cx = (0.5f * (i0 + i1) - tx) / sx, cy = (0.5f * (j0 + j1) - ty) / sy, cz = (0.5f * (k0 + k1) - tz) / sz;
+    const float R2 = radius2[b];
+    // this thread's two cells: local ids threadIdx.x and threadIdx.x + 256 of the 8x8x8 block
+    float qx[2], qy[2], qz[2], best[2];
+    uint32_t bidx[2];
+    bool live[2];
+    size_t lin[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int l = threadIdx.x + 256 * c;
+        const int i = bi * VB + (l & 7), j = bj * VB + ((l >> 3) & 7), k = bk * VB + (l >> 6);
+        live[c] = i < ex && j < ey && k < ez;
+        lin[c] = ((size_t)k * ey + j) * ex + i;
+        qx[c] = ((float)i - tx) / sx;
+        qy[c] = ((float)j - ty) / sy;
+        qz[c] = ((float)k - tz) / sz;
+        best[c] = 3.402823466e+38f;
+        bidx[c] = 0;
+    }
+    for (uint32_t base = 0; base < n; base += VF2_TILE) {
+        __syncthreads();  // previous tile's candidates are consumed
+        uint32_t tile_count = 0;
+        // 4 rounds of 256 points: order-preserving compaction into cand[]
+        for (int r = 0; r < VF2_TILE / 256; ++r) {
+            const uint32_t t = base + r * 256 + threadIdx.x;
+            bool in = false;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < n) {
+                p = mpos[t];
+                const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+                in = !(dx * dx + dy * dy + dz * dz > R2);  // NaN points stay (they never win anyway)
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t off = tile_count;
+            for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+            uint32_t round_total = 0;
+            for (int w = 0; w < 8; ++w) round_total += warp_cnt[w];
+            if (in) {
+                p.w = __uint_as_float(t);
+                cand[off + __popc(bal & ((1u << lane) - 1u))] = p;
+            }
+            tile_count += round_total;
+            __syncthreads();
+        }
+        // exact scan (reference arithmetic) over the surviving points, ascending index
+        for (uint32_t t = 0; t < tile_count; ++t) {
+            const float4 p = cand[t];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float dx = p.x - qx[c], dy = p.y - qy[c], dz = p.z - qz[c];
+                const float d = (dx * dx + dy * dy) + dz * dz;
+                if (d < best[c]) {
+                    best[c] = d;
+                    bidx[c] = __float_as_uint(p.w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (live[c]) voxel[lin[c]] = bidx[c];
+    (void)n_cand_s;
+}
 void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
                        float sx, float sy, float sz, float tx, float ty, float tz,
-                       uint32_t* voxel) {
-    ++g_launch_count;
+                       uint32_t* voxel, float* block_scratch) {
     size_t total = (size_t)ex * ey * ez;
     if (!total) return;
-    voxel_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy,
-                                                                      sz, tx, ty, tz, voxel);
+    if (!block_scratch) {  // brute force (small grids, and the cross-check of the pruned kernel)
+        ++g_launch_count;
+        voxel_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy,
+                                                                          sz, tx, ty, tz, voxel);
+        return;
+    }
+    const int bx = (ex + VB - 1) / VB, by = (ey + VB - 1) / VB, bz = (ez + VB - 1) / VB;
+    const uint32_t nb = (uint32_t)bx * by * bz;
+    g_launch_count += 2;
+    voxel_block_radius_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy, sz, tx, ty, tz, bx, by, bz,
+                                                           block_scratch);
+    voxel_fill_pruned_kernel<<<nb, 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy, sz, tx, ty, tz, bx, by,
+                                                 block_scratch, voxel);
+}
+size_t voxel_fill_scratch_bytes(int ex, int ey, int ez) {
+    return (size_t)((ex + VB - 1) / VB) * ((ey + VB - 1) / VB) * ((ez + VB - 1) / VB) * sizeof(float);
 }
 
 // fused grids: cell -> (model pos.xyz, flags) and cell -> ref vector of that model point,

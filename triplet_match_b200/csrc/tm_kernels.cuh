@@ -95,8 +95,11 @@ void launch_ball_seg_scan(cudaStream_t st, uint32_t* counts, uint32_t n_centres,
 void launch_ball_fill(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
                       const uint32_t* active_ranges, float r2, uint32_t n_seg, const uint32_t* seg_local_off,
                       const unsigned long long* row_off, int32_t* indices);
+// block_scratch == nullptr: brute force; else the pruned two-pass fill (voxel_fill_scratch_bytes floats)
 void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, int ey, int ez,
-                       float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel);
+                       float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel,
+                       float* block_scratch);
+size_t voxel_fill_scratch_bytes(int ex, int ey, int ez);
 void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
                       const float4* mnrm, const float4* mtgt, float4* vcell, float4* vref);
 void launch_traits_project(cudaStream_t st, int kind, float4 r0, float4 r1, float4 r2, float radius,
@@ -162,6 +165,12 @@ int uvicp_correlation_blocks(int n);
 void launch_uvicp_correlation(cudaStream_t st, const float4* scene, const float4* model, const int* indices_scene,
                               const int* indices_model, int n, const float* centroid_scene,
                               const float* centroid_model, float* records, double* partials, double* cov9);
+
+// k_model.cu (model::init pair enumeration)
+void launch_model_pair_bounds(cudaStream_t st, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
+                              uint32_t* bounds, unsigned long long* count, int grid);
+void launch_model_pair_keys(cudaStream_t st, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
+                            float fmn0, float fmx0, uint32_t steps, float angle_step, unsigned long long* keys, int grid);
 
 // k_knn.cu (pre-processing: exact k-NN, principal-curvature tangent masks)
 void launch_knn(cudaStream_t st, const CloudDev& cloud, const uint32_t* query, uint32_t n_query, uint32_t k,
