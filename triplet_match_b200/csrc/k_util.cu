@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(256)
         blo = seg_lo[seg];
         bhi = seg_hi[seg];
     }
-    for (uint32_t c0 = 0; c0 < n_centres; c0 += 32) {
+    // blockIdx.y selects a batch of 32 centres: (segment, batch) pairs spread over the whole GPU
+    {
+        const uint32_t c0 = blockIdx.y * 32u;
         const uint32_t cl = c0 + lane;
         bool cand = false;
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,7 +238,7 @@ void launch_ball_count(cudaStream_t st, const CloudDev& scene, const uint32_t* c
     if (!n_seg || !n_centres) return;
     cudaMemsetAsync(counts, 0, (size_t)n_centres * n_seg * 4, st);
     ++g_launch_count;
-    ball_kernel<false><<<(n_seg + 7) / 8, 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
+    ball_kernel<false><<<dim3((n_seg + 7) / 8, (n_centres + 31) / 32), 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
                                                        n_centres, active_ranges, r2, n_seg, counts, nullptr, nullptr);
 }
 void launch_ball_fill(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
@@ -244,7 +246,7 @@ void launch_ball_fill(cudaStream_t st, const CloudDev& scene, const uint32_t* ce
                       const unsigned long long* row_off, int32_t* indices) {
     if (!n_seg || !n_centres) return;
     ++g_launch_count;
-    ball_kernel<true><<<(n_seg + 7) / 8, 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
+    ball_kernel<true><<<dim3((n_seg + 7) / 8, (n_centres + 31) / 32), 256, 0, st>>>(scene.pos, scene.n, scene.seg_lo, scene.seg_hi, centres,
                                                       n_centres, active_ranges, r2, n_seg,
                                                       const_cast<uint32_t*>(seg_local_off), row_off, indices);
 }
