@@ -257,7 +257,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
                 if (tot) {  // warp-uniform
                     if (a.stats && lane == 0) atomicAdd(&a.stats[2], 1ull);
-                    unsigned long long sv = WITH_SCORE ? warp_sum_u64(sc) : 0ull;
+                    // per-lane partial < 2^39 for rigid transforms (P terms <= ~2^36): two 32-bit REDUX
+                    // (low 24 bits, the rest) instead of a 5-step 64-bit shuffle tree
+                    unsigned long long sv = 0ull;
+                    if (WITH_SCORE) {
+                        const uint32_t lo = __reduce_add_sync(0xffffffffu, (uint32_t)(sc & 0xffffffull));
+                        const uint32_t hi = __reduce_add_sync(0xffffffffu, (uint32_t)(sc >> 24));
+                        sv = ((unsigned long long)hi << 24) + lo;
+                    }
                     if (lane == hh) {
                         mycnt = tot;
                         mysc = sv;

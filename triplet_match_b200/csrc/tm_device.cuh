@@ -140,7 +140,9 @@ __host__ __device__ __forceinline__ uint32_t murmur4(uint32_t k0, uint32_t k1, u
 // any tiling, launch order or multi-GPU sharding.
 constexpr double SCORE_SCALE = 68719476736.0;  // 2^36
 __device__ __forceinline__ unsigned long long score_fixed(float term) {
-    return (unsigned long long)((double)term * SCORE_SCALE);
+    // == (unsigned long long)((double)term * 2^36): scaling by a power of two is exact in binary32 too,
+    // and the conversion truncates toward zero either way
+    return __float2ull_rz(term * 68719476736.0f);
 }
 
 }  // namespace tmk
