@@ -81,6 +81,11 @@ struct tm_ctx {
     size_t pinned_cap = 0;
 };
 
+struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
+    float thres = -1.f;
+    DevBuf bits;
+    bool useful = false;  // enough empty blocks to pay for the extra look-up
+};
 struct tm_model {
     tm_ctx* ctx;
     DevBuf pos, nrm, tgt, voxel, vcell, vref, slots, hits;
@@ -88,6 +93,8 @@ struct tm_model {
     float centre[3];
     float half_diag;
     bool fused;
+    OccMask occ[2];  // scoring threshold and the ICP one (2 x dist_thres); replaced round-robin
+    int occ_next = 0;
 };
 
 struct tm_scene {
@@ -98,6 +105,47 @@ struct tm_scene {
 
 static int bind(tm_ctx* c) {
     CU(cudaSetDevice(c->device));
+    return TM_OK;
+}
+// ModelDev for kernels that test against `thres`: the resident description plus, when it pays, the
+// block-occupancy mask of that threshold (built on first use, cached per model).  TM_OCC=0 disables.
+static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
+    *out = m->dev;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("TM_OCC");
+        enabled = e ? (atoi(e) != 0) : 1;
+    }
+    if (!enabled || !(thres >= 0.f)) return TM_OK;
+    OccMask* hit = nullptr;
+    for (OccMask& o : m->occ)
+        if (o.thres == thres) hit = &o;
+    if (!hit) {
+        hit = &m->occ[m->occ_next];
+        m->occ_next ^= 1;
+        const ModelDev& d = m->dev;
+        const int obx = (d.ex + 7) >> 3, oby = (d.ey + 7) >> 3, obz = (d.ez + 7) >> 3;
+        const size_t nb = (size_t)obx * oby * obz, words = (nb + 31) / 32;
+        TRY(hit->bits.ensure(words * 4));
+        CU(cudaMemsetAsync(hit->bits.p, 0, words * 4, c->stream));
+        const double D = std::sqrt(1.0 / ((double)d.sx * d.sx) + 1.0 / ((double)d.sy * d.sy) + 1.0 / ((double)d.sz * d.sz));
+        const double reach = ((double)thres + D * 1.001) * 1.0001 + 1e-30;
+        launch_occupancy(c->stream, d.voxel, d.cloud.pos, d.ex, d.ey, d.ez, d.sx, d.sy, d.sz, d.tx, d.ty, d.tz,
+                         (float)(reach * reach * 1.00001), obx, oby, hit->bits.as<uint32_t>());
+        CU(cudaGetLastError());
+        std::vector<uint32_t> hbits(words);
+        CU(cudaMemcpyAsync(hbits.data(), hit->bits.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        size_t set = 0;
+        for (uint32_t w : hbits) set += (size_t)__builtin_popcount(w);
+        hit->thres = thres;
+        hit->useful = set * 2 < nb;  // at least half of the blocks are empty
+    }
+    if (hit->useful) {
+        out->occ = hit->bits.as<uint32_t>();
+        out->obx = (m->dev.ex + 7) >> 3;
+        out->oby = (m->dev.ey + 7) >> 3;
+    }
     return TM_OK;
 }
 static int pinned_ensure(tm_ctx* c, size_t bytes) {
@@ -368,7 +416,8 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
 void tm_model_destroy(tm_model* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
-    for (DevBuf* b : {&m->pos, &m->nrm, &m->tgt, &m->voxel, &m->vcell, &m->vref, &m->slots, &m->hits})
+    for (DevBuf* b : {&m->pos, &m->nrm, &m->tgt, &m->voxel, &m->vcell, &m->vref, &m->slots, &m->hits,
+                      &m->occ[0].bits, &m->occ[1].bits})
         b->release();
     delete m;
 }
@@ -631,7 +680,7 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
                           const int32_t* d_sub_idx, const unsigned long long* d_sub_off,
                           const uint32_t* d_g_hyp, uint32_t n_groups, uint32_t items_capacity,
                           DevBuf& n_items_g, DevBuf& item_off, DevBuf& items, DevBuf& ctrl,
-                          float sq_thres, uint32_t* d_counts, unsigned long long* d_scores,
+                          float thres, float sq_thres, uint32_t* d_counts, unsigned long long* d_scores,
                           bool with_score) {
     // ctrl: [0] work counter (u32) [1] pad, [2..3] n_tests (u64)
     TRY(n_items_g.ensure(std::max<size_t>(n_groups, 1) * 4));
@@ -645,7 +694,7 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
                      items.as<WorkItem>());
     ScoreArgs a;
     a.scene = scene;
-    a.model = m->dev;
+    TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
     a.sub_idx = d_sub_idx;
     a.items = items.as<WorkItem>();
     a.n_items = item_off.as<uint32_t>() + n_groups;
@@ -736,7 +785,7 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
     std::vector<uint8_t> drop_l(n_hyp, 0);
     if (!early_out) {
         TRY(score_full_dev(c, s->dev, m, dT.as<float4>(), d_idx, dso.as<unsigned long long>(),
-                           dgh.as<uint32_t>(), n_groups, (uint32_t)items_cap, w0, w1, w2, ctrl, sqt,
+                           dgh.as<uint32_t>(), n_groups, (uint32_t)items_cap, w0, w1, w2, ctrl, thres, sqt,
                            dcnt.as<uint32_t>(), dsc.as<unsigned long long>(), scores != nullptr));
     } else {
         TRY(w0.ensure(n_hyp * 4)); TRY(ddrop.ensure(n_hyp));
@@ -752,7 +801,7 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
         a.tile_lo = w1.as<float4>();
         a.tile_hi = w2.as<float4>();
         a.scene = s->dev;
-        a.model = m->dev;
+        TRY(model_dev_for(c, m, thres, &a.model));
         a.sub_idx = d_idx;
         a.sub_off = dso.as<unsigned long long>();
         a.g_of_hyp = w0.as<uint32_t>();
@@ -876,6 +925,8 @@ static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpB
     if (split) sp = *split;
     else { sp.pt_end = scene.n; sp.n_total = scene.n; }
     const double fs = icp_fix_scale(m, (uint32_t)std::min<uint64_t>(sp.n_total, 0xffffffffull), thres);
+    ModelDev mdev;
+    TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &mdev));
     CU(cudaMemsetAsync(b.sums_cur.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
     CU(cudaMemsetAsync(b.sums_best.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
     CU(cudaMemsetAsync(b.iters.p, 0, (size_t)k * 4, c->stream));
@@ -888,7 +939,7 @@ static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpB
             const uint32_t b0 = sp.pt_begin + (uint32_t)(span * w / parts);
             const uint32_t b1 = sp.pt_begin + (uint32_t)(span * (w + 1) / parts);
             if (b1 > b0)
-                launch_icp_accumulate(c->stream, scene, m->dev, st.Tcur, st.active, k, b0, b1, sqt,
+                launch_icp_accumulate(c->stream, scene, mdev, st.Tcur, st.active, k, b0, b1, sqt,
                                       m->centre[0], m->centre[1], m->centre[2], fs, st.sums_cur, grid,
                                       m->fused);
         }
@@ -1423,7 +1474,7 @@ int tm_query_run(tm_query* q) {
                              q->n_outer, q->item_off.as<uint32_t>(), q->items.as<WorkItem>());
             ScoreArgs a;
             a.scene = sc;
-            a.model = m->dev;
+            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
             a.sub_idx = q->sub_idx.as<int32_t>();
             a.items = q->items.as<WorkItem>();
             a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
@@ -1455,7 +1506,7 @@ int tm_query_run(tm_query* q) {
             a.tile_lo = q->tile_lo.as<float4>();
             a.tile_hi = q->tile_hi.as<float4>();
             a.scene = sc;
-            a.model = m->dev;
+            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
             a.sub_idx = q->sub_idx.as<int32_t>();
             a.sub_off = q->sub_off.as<unsigned long long>();
             a.g_of_hyp = q->g_of_hyp.as<uint32_t>();

@@ -32,6 +32,7 @@ __device__ __forceinline__ bool icp_point_test(const ModelDev& m, float4 r0, flo
     if (!inb) return false;
     int i = (int)vx, j = (int)vy, k = (int)vz;
     lin = (uint32_t)((k * m.ey + j) * m.ex + i);
+    if (m.occ && !occ_test(m, i, j, k)) return false;
     if (FUSED) {
         mp = __ldg(&m.vcell[lin]);
     } else {

@@ -22,7 +22,7 @@
 namespace tmk {
 
 // one hypothesis-point test; returns true for an inlier.  mi_out = model index.
-template <bool FUSED>
+template <bool FUSED, bool OCC = false>
 __device__ __forceinline__ bool point_test(const ModelDev& m, float4 r0, float4 r1, float4 r2,
                                            float px, float py, float pz, uint32_t pflags,
                                            float sq_thres, float& x, float& y, float& z,
@@ -37,7 +37,8 @@ __device__ __forceinline__ bool point_test(const ModelDev& m, float4 r0, float4 
     if (!inb) return false;
     int i = (int)vx, j = (int)vy, k = (int)vz;
     uint32_t lin = (uint32_t)((k * m.ey + j) * m.ex + i);
-    lin_out = lin;
+    lin_out = lin;  // voxel_query succeeded ("reaching" element), whatever the mask says
+    if (OCC && !occ_test(m, i, j, k)) return false;  // provably farther than the threshold
     float4 mp;
     if (FUSED) {
         mp = __ldg(&m.vcell[lin]);
@@ -93,7 +94,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // The per-inlier score term needs the scene point's ref vector (tangent or normal),
 // staged once per item in a per-warp shared-memory slab, and the model point's ref
 // vector, which sits in the second half of the same 32-byte grid cell.
-template <int P, bool FUSED, bool WITH_SCORE, bool CULL>
+template <int P, bool FUSED, bool WITH_SCORE, bool CULL, bool OCC>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     score_full_kernel(ScoreArgs a) {
     __shared__ float4 s_ref[WITH_SCORE ? SCORE_THREADS * P : 1];
@@ -214,9 +215,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     y[k] = row_apply(r1, px[k], py[k], pz[k]);
                     z[k] = row_apply(r2, px[k], py[k], pz[k]);
                     const float vx = m.sx * x[k] + m.tx, vy = m.sy * y[k] + m.ty, vz = m.sz * z[k] + m.tz;
-                    const bool in = (vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) &
-                                    (vz > -1.f) & (vz < m.ezf);
+                    bool in = (vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) &
+                              (vz > -1.f) & (vz < m.ezf);
                     const int i = (int)vx, j = (int)vy, kk = (int)vz;
+                    if (OCC) {
+                        if (in) in = occ_test(m, i, j, kk);  // empty block: no inlier possible, skip the gathers
+                    }
                     lin[k] = in ? (uint32_t)((kk * m.ey + j) * m.ex + i) : 0u;
                     inb |= in ? (1u << k) : 0u;
                 }
@@ -281,13 +285,17 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
 
 template <bool FUSED, bool WITH_SCORE, bool CULL>
 static void launch_score_full_v(cudaStream_t st, const ScoreArgs& a, int grid) {
-    score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL><<<grid, SCORE_THREADS, 0, st>>>(a);
+    if (a.model.occ) score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL, true><<<grid, SCORE_THREADS, 0, st>>>(a);
+    else score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL, false><<<grid, SCORE_THREADS, 0, st>>>(a);
 }
 template <bool FUSED, bool WITH_SCORE, bool CULL>
 static int occ_score_full_v() {
-    int nb = 0;
+    int nb = 0, nb2 = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &nb, score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL>, SCORE_THREADS, 0);
+        &nb, score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL, false>, SCORE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &nb2, score_full_kernel<SCORE_P, FUSED, WITH_SCORE, CULL, true>, SCORE_THREADS, 0);
+    nb = nb < nb2 ? nb : nb2;
     return nb > 0 ? nb : 1;
 }
 #define TM_DISPATCH3(FN, f, s, c, ...)                                                       \
@@ -500,8 +508,8 @@ __global__ void __launch_bounds__(256)
                 if (!(fl & FLAG_MASKED)) {
                     float x, y, z;
                     uint32_t lin = 0xffffffffu;
-                    inl = point_test<FUSED>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z,
-                                            lin);
+                    inl = a.model.occ ? point_test<FUSED, true>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z, lin)
+                                      : point_test<FUSED, false>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z, lin);
                     reach = lin != 0xffffffffu;  // voxel_query succeeded (scene.hpp:458-460)
                     if (inl) term = inlier_score(a.scene, a.model, r0, r1, r2, idx, fl, lin);
                 }

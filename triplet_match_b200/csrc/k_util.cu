@@ -478,6 +478,37 @@ size_t voxel_fill_scratch_bytes(int ex, int ey, int ez) {
     return (size_t)((ex + VB - 1) / VB) * ((ey + VB - 1) / VB) * ((ez + VB - 1) / VB) * sizeof(float);
 }
 
+// Block-occupancy mask for one distance threshold.  A position p that voxel_query maps to cell c has
+// voxel coordinates within one cell of c's fill point q_c per axis (truncation toward zero makes cell
+// 0 two cells wide), i.e. |p - q_c| <= D = the cell diagonal, so |p - nn(c)| >= |q_c - nn(c)| - D:
+// cell c can hold an inlier only if |q_c - nn(c)| <= thres + D.  reach2 = that bound squared (with a
+// relative guard).  A block's bit is set when any of its cells can.
+__global__ void __launch_bounds__(256)
+    occupancy_kernel(const uint32_t* __restrict__ voxel, const float4* __restrict__ mpos, int ex, int ey, int ez,
+                     float sx, float sy, float sz, float tx, float ty, float tz, float reach2, int obx, int oby,
+                     uint32_t* __restrict__ occ) {
+    const size_t total = (size_t)ex * ey * ez;
+    const size_t lin = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lin >= total) return;
+    const int i = (int)(lin % ex), j = (int)((lin / ex) % ey), k = (int)(lin / ((size_t)ex * ey));
+    const float qx = ((float)i - tx) / sx, qy = ((float)j - ty) / sy, qz = ((float)k - tz) / sz;
+    const float4 p = mpos[voxel[lin]];
+    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 > reach2)) {  // NaN keeps the block
+        const uint32_t b = (uint32_t)(((k >> OCC_SHIFT) * oby + (j >> OCC_SHIFT)) * obx + (i >> OCC_SHIFT));
+        atomicOr(&occ[b >> 5], 1u << (b & 31u));
+    }
+}
+void launch_occupancy(cudaStream_t st, const uint32_t* voxel, const float4* mpos, int ex, int ey, int ez, float sx,
+                      float sy, float sz, float tx, float ty, float tz, float reach2, int obx, int oby, uint32_t* occ) {
+    const size_t total = (size_t)ex * ey * ez;
+    if (!total) return;
+    ++g_launch_count;
+    occupancy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(voxel, mpos, ex, ey, ez, sx, sy, sz, tx, ty, tz,
+                                                                    reach2, obx, oby, occ);
+}
+
 // fused grids: cell -> (model pos.xyz, flags) and cell -> ref vector of that model point,
 // so scoring needs one gather per test (and one more per inlier) instead of dependent chains
 __global__ void fuse_grid_kernel(const uint32_t* __restrict__ voxel, size_t total,

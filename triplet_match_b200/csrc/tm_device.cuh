@@ -52,7 +52,17 @@ struct ModelDev {
     uint32_t dist_steps;
     float angle_step;
     float resolution, diameter;
+    // optional block-occupancy mask for one distance threshold (occupancy_kernel): bit b of 8x8x8-cell
+    // block b is clear when no position inside the block can be within the threshold of its cell's
+    // nearest model point, so the cell gathers can be skipped there without changing any result
+    const uint32_t* occ = nullptr;
+    int obx = 0, oby = 0;
 };
+constexpr int OCC_SHIFT = 3;  // 8 cells per block edge
+__device__ __forceinline__ bool occ_test(const ModelDev& m, int i, int j, int k) {
+    const uint32_t b = (uint32_t)(((k >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx + (i >> OCC_SHIFT));
+    return (__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u;
+}
 
 // hypothesis transform: rows 0..2 of the 4x4 (row 3 is 0,0,0,1)
 struct Rows {
