@@ -124,7 +124,8 @@ static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
         hit = &m->occ[m->occ_next];
         m->occ_next ^= 1;
         const ModelDev& d = m->dev;
-        const int obx = (d.ex + 7) >> 3, oby = (d.ey + 7) >> 3, obz = (d.ez + 7) >> 3;
+        const int ob = (1 << OCC_SHIFT) - 1;
+        const int obx = (d.ex + ob) >> OCC_SHIFT, oby = (d.ey + ob) >> OCC_SHIFT, obz = (d.ez + ob) >> OCC_SHIFT;
         const size_t nb = (size_t)obx * oby * obz, words = (nb + 31) / 32;
         TRY(hit->bits.ensure(words * 4));
         CU(cudaMemsetAsync(hit->bits.p, 0, words * 4, c->stream));
@@ -143,8 +144,8 @@ static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
     }
     if (hit->useful) {
         out->occ = hit->bits.as<uint32_t>();
-        out->obx = (m->dev.ex + 7) >> 3;
-        out->oby = (m->dev.ey + 7) >> 3;
+        out->obx = (m->dev.ex + (1 << OCC_SHIFT) - 1) >> OCC_SHIFT;
+        out->oby = (m->dev.ey + (1 << OCC_SHIFT) - 1) >> OCC_SHIFT;
     }
     return TM_OK;
 }

@@ -58,7 +58,10 @@ struct ModelDev {
     const uint32_t* occ = nullptr;
     int obx = 0, oby = 0;
 };
-constexpr int OCC_SHIFT = 3;  // 8 cells per block edge
+#ifndef TM_OCC_SHIFT
+#define TM_OCC_SHIFT 3
+#endif
+constexpr int OCC_SHIFT = TM_OCC_SHIFT;  // 2^OCC_SHIFT cells per block edge
 __device__ __forceinline__ bool occ_test(const ModelDev& m, int i, int j, int k) {
     const uint32_t b = (uint32_t)(((k >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx + (i >> OCC_SHIFT));
     return (__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u;
