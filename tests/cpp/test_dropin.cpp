@@ -4,6 +4,7 @@
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
 //        the Python harness (n, then n x {pos3, nrm3, tgt3} floats); prints matches.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -153,7 +154,11 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "usage: %s cpu | find model.bin scene.bin out.txt\n", argv[0]);
         return 2;
     }
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = now();
     cloud_t::Ptr mc = load(argv[2]), sc = load(argv[3]);
+    auto t1 = now();
     // argv[5] == "curv": keep the reference's curvature-ratio criterion (clouds with estimated, i.e.
     // noisy, normals); default for the analytic synthetic clouds: norm test only
     const bool curv = argc >= 6 && std::string(argv[5]) == "curv";
@@ -162,6 +167,7 @@ int main(int argc, char** argv) {
     tr::model<point_t> m(mc, dp);
     m.set_curvature_test(curv);
     m.init(sp);
+    auto t2 = now();
     if (argc >= 7) {  // argv[6]: blob path — save, reload into a fresh model and search with that one
         m.save(argv[6]);
         tr::model<point_t> m2(mc, dp);
@@ -181,7 +187,11 @@ int main(int argc, char** argv) {
     (void)m.query(*f);
     tr::scene<point_t> s(sc);
     s.set_curvature_test(curv);
+    auto t3 = now();
     auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, 5);
+    auto t4 = now();
+    std::printf("timing: load %.0f ms, model::init (incl. CUDA context) %.0f ms, find_all_parallel %.0f ms\n", ms(t0, t1),
+                ms(t1, t2), ms(t3, t4));
     std::ofstream out(argv[4]);
     out << matches.size() << "\n";
     for (auto& mt : matches) {
