@@ -81,7 +81,11 @@ int tm_ctx_sm_count(tm_ctx* ctx);
 int tm_timer_start(tm_ctx* ctx);               /* CUDA event on the context stream */
 int tm_timer_stop(tm_ctx* ctx, float* ms);     /* records, synchronises, elapsed ms */
 int tm_ctx_flush_l2(tm_ctx* ctx);              /* overwrites a 256 MiB scratch buffer */
-uint64_t tm_ctx_kernel_launches(tm_ctx* ctx);  /* kernels launched so far on this context */
+uint64_t tm_ctx_kernel_launches(tm_ctx* ctx);
+/* Micro-benchmark for the scorer's roofline: random 16-byte cell gathers (one 32-byte sector each)
+ * over a working set of `working_set_bytes` (rounded down to a power of two; keep it below L2),
+ * 8 loads in flight per lane.  Returns sector traffic in GB/s (32 B per load). */
+int tm_ctx_measure_l2_gather(tm_ctx* ctx, uint64_t working_set_bytes, double* gb_per_s);  /* kernels launched so far on this context */
 
 /* ---- resident model / scene -------------------------------------------- */
 /* replaces the CPU-resident state probed by model::query / model::voxel_query

@@ -1028,6 +1028,34 @@ int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, fl
     return TM_OK;
 }
 
+int tm_ctx_measure_l2_gather(tm_ctx* c, uint64_t working_set_bytes, double* gb_per_s) {
+    REQUIRE(c && gb_per_s, "tm_ctx_measure_l2_gather: null argument");
+    REQUIRE(working_set_bytes >= (1u << 20), "tm_ctx_measure_l2_gather: working set too small");
+    TRY(bind(c));
+    uint64_t cells = 1;
+    while (cells * 2 * 16 <= working_set_bytes && cells < (1ull << 31)) cells *= 2;
+    DevBuf &buf = c->scratch[0], &out = c->scratch[1];
+    TRY(buf.ensure(cells * 16)); TRY(out.ensure(16));
+    CU(cudaMemsetAsync(buf.p, 0, cells * 16, c->stream));
+    const int grid = c->sm_count * 8;
+    const uint32_t iters = 256;
+    launch_l2_gather(c->stream, buf.as<float4>(), (uint32_t)(cells - 1), iters, out.as<float>(), grid);  // warm-up: fills L2
+    CU(cudaGetLastError());
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < 3; ++r)
+        launch_l2_gather(c->stream, buf.as<float4>(), (uint32_t)(cells - 1), iters, out.as<float>(), grid);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double loads = 3.0 * (double)grid * 256.0 * iters * 8.0;
+    *gb_per_s = ms > 0.f ? loads * 32.0 / (ms * 1e-3) / 1e9 : 0.0;
+    return TM_OK;
+}
+
 // ------------------------------------------------------------ model::init pair enumeration
 int tm_model_pair_bounds(tm_ctx* c, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
                          float feat_min[3], float feat_max[3], uint64_t* n_pass) {

@@ -509,6 +509,30 @@ void launch_occupancy(cudaStream_t st, const uint32_t* voxel, const float4* mpos
                                                                     reach2, obx, oby, occ);
 }
 
+// ---- L2 gather micro-benchmark: the roofline the scorer is measured against --------------------
+// Every lane reads independent pseudo-random 16-byte cells (one 32-byte sector each, like the fused
+// grid gathers) from a working set that fits L2; 8 loads in flight per lane.
+__global__ void __launch_bounds__(256)
+    l2_gather_kernel(const float4* __restrict__ buf, uint32_t n_cells_mask, uint32_t iters, float* __restrict__ out) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (uint32_t it = 0; it < iters; ++it) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s = s * 1664525u + 1013904223u;
+            v[u] = __ldg(&buf[(s >> 7) & n_cells_mask]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u].x + v[u].w;
+    }
+    if (acc == 123.456f) out[0] = acc;  // never true: keeps the loads alive
+}
+void launch_l2_gather(cudaStream_t st, const float4* buf, uint32_t n_cells_mask, uint32_t iters, float* out, int grid) {
+    ++g_launch_count;
+    l2_gather_kernel<<<grid, 256, 0, st>>>(buf, n_cells_mask, iters, out);
+}
+
 // fused grids: cell -> (model pos.xyz, flags) and cell -> ref vector of that model point,
 // so scoring needs one gather per test (and one more per inlier) instead of dependent chains
 __global__ void fuse_grid_kernel(const uint32_t* __restrict__ voxel, size_t total,

@@ -100,6 +100,7 @@ void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, 
                        float sx, float sy, float sz, float tx, float ty, float tz, uint32_t* voxel,
                        float* block_scratch);
 size_t voxel_fill_scratch_bytes(int ex, int ey, int ez);
+void launch_l2_gather(cudaStream_t st, const float4* buf, uint32_t n_cells_mask, uint32_t iters, float* out, int grid);
 void launch_occupancy(cudaStream_t st, const uint32_t* voxel, const float4* mpos, int ex, int ey, int ez, float sx,
                       float sy, float sz, float tx, float ty, float tz, float reach2, int obx, int oby, uint32_t* occ);
 void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
