@@ -360,22 +360,22 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
         CU(cudaMemcpyAsync(m->hits.p, d->pairs, sizeof(uint2) * (size_t)n_hits,
                            cudaMemcpyHostToDevice, c->stream));
     // fused grid (cell -> model point) when it stays L2-sized
-    m->fused = 2 * cells * sizeof(float4) <= (96ull << 20);
+    m->fused = cells * sizeof(float4) <= (96ull << 20);
     if (const char* e = getenv("TM_FUSED_GRID")) m->fused = atoi(e) != 0;
     if (m->fused) {
         if ((rc = m->vcell.ensure(cells * sizeof(float4)))) return bail(rc);
-        if ((rc = m->vref.ensure(cells * sizeof(float4)))) return bail(rc);
-        launch_fuse_grid(c->stream, m->voxel.as<uint32_t>(), cells, m->pos.as<float4>(),
-                         m->nrm.as<float4>(), m->tgt.as<float4>(), m->vcell.as<float4>(),
-                         m->vref.as<float4>());
+        launch_fuse_grid(c->stream, m->voxel.as<uint32_t>(), cells, m->pos.as<float4>(), m->vcell.as<float4>());
     }
+    if ((rc = m->vref.ensure((size_t)cloud->n * sizeof(float4)))) return bail(rc);
+    launch_model_ref(c->stream, m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n,
+                     m->vref.as<float4>());
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     ModelDev& dv = m->dev;
     dv.cloud = CloudDev{m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n};
     dv.voxel = m->voxel.as<uint32_t>();
     dv.vcell = m->fused ? m->vcell.as<float4>() : nullptr;
-    dv.vref = m->fused ? m->vref.as<float4>() : nullptr;
+    dv.mref = m->vref.as<float4>();
     dv.ex = d->extents[0];
     dv.ey = d->extents[1];
     dv.ez = d->extents[2];

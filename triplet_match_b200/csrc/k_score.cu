@@ -63,7 +63,7 @@ __device__ __forceinline__ unsigned long long inlier_score(const CloudDev& scene
     bool use_t = (pflags & FLAG_TANGENT) != 0u;
     f3 ref = mk3(use_t ? scene.tgt[sidx] : scene.nrm[sidx]);
     uint32_t mi = m.voxel[lin];
-    f3 rn = mk3(use_t ? m.cloud.tgt[mi] : m.cloud.nrm[mi]);  // classes agree for an inlier
+    f3 rn = mk3(m.mref[mi]);  // classes agree for an inlier: tangent or normal of the model point
     f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
     return score_fixed(fabsf(dot3(rr, rn)));
 }
@@ -247,12 +247,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                         if (WITH_SCORE) {
                             const f3 ref = mk3(my_ref[k * 32 + lane]);
                             f3 rn;
-                            if (FUSED) {
-                                rn = mk3(__ldg(&m.vref[lin[k]]));
-                            } else {
-                                const uint32_t mi = m.voxel[lin[k]];
-                                rn = mk3(pfl ? m.cloud.tgt[mi] : m.cloud.nrm[mi]);
-                            }
+                            // the model point's ref vector (its class agrees with the scene point's)
+                            const uint32_t mi = FUSED ? (__float_as_uint(mp[k].w) >> 1) : __ldg(&m.voxel[lin[k]]);
+                            rn = mk3(__ldg(&m.mref[mi]));
                             const f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
                             sc += score_fixed(fabsf(dot3(rr, rn)));  // scene.hpp:461,483
                         }

@@ -38,9 +38,10 @@ struct HashSlot {  // open addressing, linear probing, home = murmur4(key) & mas
 struct ModelDev {
     CloudDev cloud;
     const uint32_t* voxel;  // lin = k*ex*ey + j*ex + i
-    const float4* vcell;    // optional fused grid (or null): nearest model point pos.xyz + class flag
-    const float4* vref;     // fused grid: that point's ref vector (tangent if ||tangent|| > 0.7
-                            // else normal), read only for inliers
+    const float4* vcell;    // optional fused grid (or null): nearest model point pos.xyz; .w bits =
+                            // (model index << 1) | class flag
+    const float4* mref;     // per model point: its ref vector (tangent if ||tangent|| > 0.7 else normal),
+                            // read only for inliers; n_model x 16 B, small enough to live in L1
     int ex, ey, ez;
     float exf, eyf, ezf;
     float sx, sy, sz, tx, ty, tz;  // to_voxel_ = diag(s) + t

@@ -103,8 +103,9 @@ size_t voxel_fill_scratch_bytes(int ex, int ey, int ez);
 void launch_l2_gather(cudaStream_t st, const float4* buf, uint32_t n_cells_mask, uint32_t iters, float* out, int grid);
 void launch_occupancy(cudaStream_t st, const uint32_t* voxel, const float4* mpos, int ex, int ey, int ez, float sx,
                       float sy, float sz, float tx, float ty, float tz, float reach2, int obx, int oby, uint32_t* occ);
-void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos,
-                      const float4* mnrm, const float4* mtgt, float4* vcell, float4* vref);
+void launch_fuse_grid(cudaStream_t st, const uint32_t* voxel, size_t total, const float4* mpos, float4* vcell);
+void launch_model_ref(cudaStream_t st, const float4* mpos, const float4* mnrm, const float4* mtgt, uint32_t n,
+                      float4* mref);
 void launch_traits_project(cudaStream_t st, int kind, float4 r0, float4 r1, float4 r2, float radius,
                            float threshold, const float* xyz, uint64_t n, float* uvw, uint8_t* ok);
 void launch_flush(cudaStream_t st, float4* buf, size_t n, float v);
