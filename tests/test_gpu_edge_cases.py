@@ -176,3 +176,47 @@ def test_table_with_thousands_of_keys(ctx):
     for x, y in zip(a[:200], b[:200]):
         assert np.array_equal(hm.pairs[hm.offsets[x]:hm.offsets[x + 1]], pairs[offsets[y]:offsets[y + 1]])
     hm.close(); gs.close(); gm.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_irregular_clouds(ctx, seed):
+    """Unstructured random clouds (the generator of tests/test_oracle_vs_ref_fuzz.py, on which the
+    oracle equals the reference's own code): product-built model, every stage vs the oracle."""
+    from triplet_match_b200 import capi
+    from test_oracle_vs_ref_fuzz import _cloud
+    rng = np.random.default_rng(seed)
+    m = _cloud(rng, 260 + 40 * seed, 0.25, 60 + 5 * seed, dup=3)
+    s = _cloud(rng, 2500, 0.6, 300)
+    s.pos[:m.n] = m.pos + F(0.17)
+    om = po.OModel(m, **common.DP, **common.SP)
+    osc = po.OScene(s)
+    hm = capi.HostModel(ctx, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, **common.DP, **common.SP)
+    assert np.array_equal(hm.voxel, om.voxel) and np.array_equal(hm.feat_min.view(np.uint32), om.feat_min.view(np.uint32))
+    gm = hm.upload(ctx)
+    gs = capi.Scene(ctx, s.pos, s.nrm, s.tgt, s.tangent_mask)
+    tidx = np.flatnonzero(s.tangent_mask)
+    pi = rng.choice(tidx, 600).astype(np.uint32)
+    pj = rng.choice(tidx, 600).astype(np.uint32)
+    f, k, v = gs.features(gm, pi, pj, 0.2, 1.0)
+    fo, ko, vo = osc.pair_features(om, pi, pj)
+    assert np.array_equal(v, vo) and np.array_equal(k[v.astype(bool)], ko[vo.astype(bool)])
+    off, hits = gm.probe(k, v, 200)
+    Tg, vg = gs.hypotheses(gm, pi, pj, off, hits)
+    T, hp, mi, mj, va = osc.hypotheses(om, pi, pj)
+    assert np.array_equal(hits, np.stack([mi, mj], 1)) and np.array_equal(vg, va)
+    ok = va.astype(bool)
+    assert np.array_equal(Tg[ok].view(np.uint32), T[ok].view(np.uint32))
+    Ts = [T[h] for h in np.flatnonzero(ok)[:40]]
+    for _ in range(12):  # near the planted pose: many inliers
+        M = np.eye(4)
+        a = rng.standard_normal(3) * 0.02
+        M[:3, :3] += np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        M[:3, 3] = -0.17 + rng.standard_normal(3) * 0.003
+        Ts.append(M.T.reshape(-1).astype(F))
+    T16 = np.stack(Ts).astype(F)
+    for eo in (False, True):
+        cg, sg, dg = gs.score(gm, T16, early_out=eo)
+        co, so, do = osc.score_batch(om, T16, early_out=eo, nthreads=4)
+        assert np.array_equal(cg, co) and np.array_equal(dg, do) and np.allclose(sg, so, rtol=1e-9, atol=1e-9)
+    assert co.max() > 50
+    gs.close(); gm.close(); hm.close()
