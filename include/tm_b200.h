@@ -101,6 +101,13 @@ int tm_voxel_fill(tm_ctx* ctx, const tm_cloud_view* cloud, const int32_t extents
 /* scene cloud + tangent_mask_ (include/impl/scene.hpp:46-58); mask_ starts 0 */
 int tm_scene_upload(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
                     tm_scene** out);
+/* Same, but the device copy is put into Z-curve (Morton) order first: 30-bit codes over the cloud's
+ * bounding box, stable radix sort on the device.  to_user[d] (scene n entries, may be NULL) = index in
+ * the caller's cloud of device point d.  EVERY index exchanged with this scene afterwards (outer
+ * samples, pair lists, masks, correspondences, k-NN) is a device index.  Results do not depend on the
+ * order; run time does (radius search, k-NN and tile culling want consecutive points close in space). */
+int tm_scene_upload_sorted(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
+                           uint32_t* to_user, tm_scene** out);
 int tm_scene_set_mask(tm_scene* s, const uint8_t* mask); /* mask_ (scene.hpp:87-90); NULL clears */
 void tm_scene_destroy(tm_scene* s);
 

@@ -188,3 +188,58 @@ def test_gpu_knn_edge_cases(ctx):
     with pytest.raises(capi.TmError):
         gs.knn(np.array([0], np.uint32), 33)
     gs.close()
+
+
+# ---- Z-curve ordering on the device (tm_scene_upload_sorted) ---------------------------------
+def _morton30(pos):
+    p = pos.astype(np.float32)
+    fin = np.isfinite(p).all(1)
+    lo = p[fin].min(0)
+    hi = p[fin].max(0)
+    d = (hi - lo).astype(np.float32)
+    inv = np.where(d > 0, np.float32(1) / np.where(d > 0, d, 1), 0).astype(np.float32)
+    t = ((p - lo) * inv).astype(np.float32)
+    t = np.where(t >= 0, t, 0)  # also NaN
+    t = np.minimum(t, 1).astype(np.float32)
+    q = (t * np.float32(1023)).astype(np.uint32)
+
+    def spread(v):
+        v = v & 0x3FF
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    return spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 50000, 300001])
+def test_gpu_sorted_upload_is_a_stable_morton_sort(ctx, n):
+    from triplet_match_b200 import capi
+    rng = np.random.default_rng(n)
+    pos = rng.random((n, 3)).astype(F) * np.array([3.0, 1.0, 0.2], F)
+    if n > 100:
+        pos[5] = pos[6]                 # equal codes: stability
+        pos[7, 0] = np.nan              # non-finite point: code of the clamped coordinates, still present
+    nrm = rng.standard_normal((n, 3)).astype(F)
+    tgt = rng.standard_normal((n, 3)).astype(F)
+    tm = (rng.random(n) < 0.3).astype(np.uint8)
+    gs = capi.Scene(ctx, pos, nrm, tgt, tm, sort=True)
+    perm = gs.to_user
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+    codes = _morton30(pos)
+    exp = np.argsort(codes, kind="stable").astype(np.uint32)
+    assert np.array_equal(perm, exp)
+    # the resident arrays are the permuted cloud: k-NN of device point d == k-NN of user point perm[d]
+    if n >= 255:
+        q = rng.integers(0, n, 40).astype(np.uint32)
+        gi, gd = gs.knn(q, 4)
+        ref = capi.Scene(ctx, pos[perm], nrm[perm], tgt[perm], tm[perm])
+        ri, rd = ref.knn(q, 4)
+        assert np.array_equal(gi, ri) and np.array_equal(gd.view(np.uint32), rd.view(np.uint32))
+        m1, c1 = gs.compute_tangent_mask(8, 0.2, apply=False)
+        m2, c2 = ref.compute_tangent_mask(8, 0.2, apply=False)
+        assert np.array_equal(m1, m2)
+        ref.close()
+    gs.close()

@@ -58,7 +58,7 @@ EXPORTS = [
     "tm_last_error", "tm_version", "tm_ctx_create", "tm_ctx_destroy", "tm_ctx_sync",
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
-    "tm_scene_upload", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
+    "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
     "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
@@ -394,7 +394,11 @@ class Model:
 
 
 class Scene:
-    def __init__(self, ctx: Context, pos, nrm, tgt, tangent_mask, view: CloudView | None = None):
+    def __init__(self, ctx: Context, pos, nrm, tgt, tangent_mask, view: CloudView | None = None,
+                 sort: bool = False):
+        """sort=True: tm_scene_upload_sorted — the device copy is put into Z-curve order on the device;
+        self.to_user[d] is the caller's index of device point d and every index exchanged with the
+        scene afterwards is a device index."""
         self.ctx = ctx
         self.lib = ctx.lib
         if view is None:
@@ -404,7 +408,13 @@ class Scene:
         tm = None if tangent_mask is None else np.ascontiguousarray(tangent_mask, dtype=np.uint8)
         self.n = int(v.n)
         self.h = C.c_void_p()
-        _chk(self.lib.tm_scene_upload(ctx.h, C.byref(v), _p(tm), C.byref(self.h)))
+        self.to_user = None
+        if sort:
+            self.to_user = np.zeros(max(self.n, 1), dtype=np.uint32)
+            _chk(self.lib.tm_scene_upload_sorted(ctx.h, C.byref(v), _p(tm), _p(self.to_user), C.byref(self.h)))
+            self.to_user = self.to_user[:self.n]
+        else:
+            _chk(self.lib.tm_scene_upload(ctx.h, C.byref(v), _p(tm), C.byref(self.h)))
 
     def close(self):
         if self.h:

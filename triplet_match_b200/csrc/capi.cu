@@ -452,38 +452,97 @@ int tm_voxel_fill(tm_ctx* c, const tm_cloud_view* cloud, const int32_t extents[3
     return rc;
 }
 
-int tm_scene_upload(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
-                    tm_scene** out) {
+// segment boxes of a resident scene (radius search, k-NN, ICP screening)
+static int scene_seg_boxes(tm_ctx* c, tm_scene* s) {
+    const uint32_t n_seg = (s->dev.n + BALL_SEG - 1) / BALL_SEG;
+    if (!n_seg) return TM_OK;
+    TRY(s->seg_lo.ensure((size_t)n_seg * 16));
+    TRY(s->seg_hi.ensure((size_t)n_seg * 16));
+    launch_seg_bbox(c->stream, s->dev.pos, s->dev.n, s->seg_lo.as<float4>(), s->seg_hi.as<float4>());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    s->dev.seg_lo = s->seg_lo.as<float4>();
+    s->dev.seg_hi = s->seg_hi.as<float4>();
+    return TM_OK;
+}
+static int scene_upload_impl(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangent_mask, bool sorted,
+                             uint32_t* to_user, tm_scene** out) {
     REQUIRE(c && cloud && out, "tm_scene_upload: null argument");
     TRY(bind(c));
     tm_scene* s = new tm_scene();
     s->ctx = c;
-    int rc = upload_cloud(c, cloud, tangent_mask, 0, s->pos, s->nrm, s->tgt);
-    if (rc) {
+    auto bail = [&](int rc) {
         tm_scene_destroy(s);
         return rc;
-    }
+    };
+    int rc = upload_cloud(c, cloud, tangent_mask, 0, s->pos, s->nrm, s->tgt);
+    if (rc) return bail(rc);
     s->dev = CloudDev{s->pos.as<float4>(), s->nrm.as<float4>(), s->tgt.as<float4>(), cloud->n};
     // bounding boxes of the BALL_SEG-point segments: lets the radius search (a8) skip whole
-    // segments; tight when the caller supplies the scene in a space-filling-curve order
-    const uint32_t n_seg = (cloud->n + BALL_SEG - 1) / BALL_SEG;
-    if (n_seg) {
-        if ((rc = s->seg_lo.ensure((size_t)n_seg * 16)) || (rc = s->seg_hi.ensure((size_t)n_seg * 16))) {
-            tm_scene_destroy(s);
-            return rc;
-        }
-        launch_seg_bbox(c->stream, s->dev.pos, cloud->n, s->seg_lo.as<float4>(), s->seg_hi.as<float4>());
-        cudaError_t e = cudaGetLastError();
+    // segments; tight when the scene is in a space-filling-curve order
+    if ((rc = scene_seg_boxes(c, s))) return bail(rc);
+    const uint32_t n = cloud->n;
+    if (sorted && n > 1) {
+        // cloud bounding box from the segment boxes (NaN / empty segments carry inverted boxes)
+        const uint32_t n_seg = (n + BALL_SEG - 1) / BALL_SEG;
+        std::vector<float4> lo(n_seg), hi(n_seg);
+        cudaError_t e = cudaMemcpyAsync(lo.data(), s->seg_lo.p, (size_t)n_seg * 16, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hi.data(), s->seg_hi.p, (size_t)n_seg * 16, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) {
-            tm_scene_destroy(s);
-            return fail(TM_ERR_CUDA, cudaGetErrorString(e));
+        if (e != cudaSuccess) return bail(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
+        float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (uint32_t g = 0; g < n_seg; ++g) {
+            if (!(lo[g].x <= hi[g].x)) continue;
+            blo[0] = std::min(blo[0], lo[g].x); bhi[0] = std::max(bhi[0], hi[g].x);
+            blo[1] = std::min(blo[1], lo[g].y); bhi[1] = std::max(bhi[1], hi[g].y);
+            blo[2] = std::min(blo[2], lo[g].z); bhi[2] = std::max(bhi[2], hi[g].z);
         }
-        s->dev.seg_lo = s->seg_lo.as<float4>();
-        s->dev.seg_hi = s->seg_hi.as<float4>();
+        float inv[3];
+        for (int k = 0; k < 3; ++k) {
+            const float d = bhi[k] - blo[k];
+            inv[k] = d > 0.f && std::isfinite(d) ? 1.f / d : 0.f;
+            if (!std::isfinite(blo[k])) blo[k] = 0.f;
+        }
+        const uint32_t nb = radix_blocks(n);
+        DevBuf ka, va, kb, vb, hist, offs, p2, n2, t2;
+        auto release = [&] { for (DevBuf* b : {&ka, &va, &kb, &vb, &hist, &offs, &p2, &n2, &t2}) b->release(); };
+        rc = ka.ensure((size_t)n * 4);
+        if (!rc) rc = va.ensure((size_t)n * 4);
+        if (!rc) rc = kb.ensure((size_t)n * 4);
+        if (!rc) rc = vb.ensure((size_t)n * 4);
+        if (!rc) rc = hist.ensure(((size_t)256 * nb + 1) * 4);
+        if (!rc) rc = offs.ensure(((size_t)256 * nb + 1) * 4);
+        if (!rc) rc = p2.ensure((size_t)n * 16);
+        if (!rc) rc = n2.ensure((size_t)n * 16);
+        if (!rc) rc = t2.ensure((size_t)n * 16);
+        if (rc) { release(); return bail(rc); }
+        launch_morton_codes(c->stream, s->dev.pos, n, blo, inv, ka.as<uint32_t>(), va.as<uint32_t>());
+        launch_radix_sort_pairs(c->stream, ka.as<uint32_t>(), va.as<uint32_t>(), kb.as<uint32_t>(), vb.as<uint32_t>(), n,
+                                hist.as<uint32_t>(), offs.as<uint32_t>());
+        launch_gather_cloud(c->stream, s->dev.pos, s->dev.nrm, s->dev.tgt, va.as<uint32_t>(), n, p2.as<float4>(),
+                            n2.as<float4>(), t2.as<float4>());
+        e = cudaGetLastError();
+        if (e == cudaSuccess && to_user)
+            e = cudaMemcpyAsync(to_user, va.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { release(); return bail(fail(TM_ERR_CUDA, cudaGetErrorString(e))); }
+        std::swap(s->pos, p2); std::swap(s->nrm, n2); std::swap(s->tgt, t2);  // the sorted copies become the scene
+        release();
+        s->dev = CloudDev{s->pos.as<float4>(), s->nrm.as<float4>(), s->tgt.as<float4>(), n};
+        if ((rc = scene_seg_boxes(c, s))) return bail(rc);
+    } else if (to_user) {
+        for (uint32_t i = 0; i < n; ++i) to_user[i] = i;
     }
     *out = s;
     return TM_OK;
+}
+int tm_scene_upload(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
+                    tm_scene** out) {
+    return scene_upload_impl(c, cloud, tangent_mask, false, nullptr, out);
+}
+int tm_scene_upload_sorted(tm_ctx* c, const tm_cloud_view* cloud, const uint8_t* tangent_mask,
+                           uint32_t* to_user, tm_scene** out) {
+    return scene_upload_impl(c, cloud, tangent_mask, true, to_user, out);
 }
 int tm_scene_set_mask(tm_scene* s, const uint8_t* mask) {
     REQUIRE(s, "null scene");

@@ -170,6 +170,15 @@ void launch_uvicp_correlation(cudaStream_t st, const float4* scene, const float4
                               const int* indices_model, int n, const float* centroid_scene,
                               const float* centroid_model, float* records, double* partials, double* cov9);
 
+// k_sort.cu (Z-curve ordering of a cloud)
+void launch_morton_codes(cudaStream_t st, const float4* pos, uint32_t n, const float lo[3], const float inv[3],
+                         uint32_t* codes, uint32_t* idx);
+uint32_t radix_blocks(uint32_t n);
+void launch_radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                             uint32_t n, uint32_t* hist, uint32_t* offsets);
+void launch_gather_cloud(cudaStream_t st, const float4* pos, const float4* nrm, const float4* tgt, const uint32_t* perm,
+                         uint32_t n, float4* opos, float4* onrm, float4* otgt);
+
 // k_model.cu (model::init pair enumeration)
 void launch_model_pair_bounds(cudaStream_t st, const float* pos3, const float* tgt3, uint32_t T, float lower, float upper,
                               uint32_t* bounds, unsigned long long* count, int grid);
