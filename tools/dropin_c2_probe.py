@@ -6,7 +6,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 import __graft_entry__ as ge
 ge.build()
-model, scene = bench.build_workload(1)
+if os.environ.get("C3"):
+    from triplet_match_b200 import synth
+    model = synth.freeform_model(seed=3, n_points=50000, radius=0.01 * np.sqrt(50000 / (4 * np.pi)), n_bumps=12, n_curves=8)
+    scene = synth.make_scene(seed=3, model=model, n_points=10_000_000, n_copies=8, extent=10.0 * np.sqrt(10.0), flat_copies=False)
+else:
+    model, scene = bench.build_workload(1)
 if os.environ.get("SHUFFLE"):
     from triplet_match_b200 import synth
     scene = scene.take(synth.shuffle_perm(9, 1, scene.n))
