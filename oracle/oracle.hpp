@@ -791,8 +791,8 @@ inline bool cylinder_project(const m4& g2l, float radius, float threshold, v3 xy
     if (fabsf(height) > threshold) return false;
     uvw[1] = loc[2];
     uvw[2] = height / radius;
-    // atan2(loc[1], loc[0]) over all four quadrants [parity unpinned: libm], built in
-    // double from the shared first-quadrant atan_pos and rounded once to float
+    // atan2(loc[1], loc[0]) on floats: the binary32 overload (PCL's <math.h> puts std::atan2 into the
+    // global namespace) = glibc atan2f.  PINNED against the reference's own header, oracle/_ref
     float ang = atan2f_full(loc[1], loc[0]);
     if (ang < 0.f) ang = (float)((double)ang + 2.0 * M_PI);  // :111 `+= 2.0*M_PI` in double
     uvw[0] = ang * radius;

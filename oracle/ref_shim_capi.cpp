@@ -26,6 +26,15 @@
 #include <impl/feature.hpp>
 #include <impl/model.hpp>
 #include <impl/scene.hpp>
+#include <numeric>
+#include <cylinder_traits>        // row a14: the traits' closed forms (project / unproject / tangent / normal /
+#include <plane_traits>           // intrinsic_distance); their init_* fits (PCL MSAC, SVD) are out of scope
+#include <plane2_traits>
+#include <identity_traits>
+#include <impl/cylinder_traits.hpp>
+#include <impl/plane_traits.hpp>
+#include <impl/plane2_traits.hpp>
+#include <impl/identity_traits.hpp>
 
 namespace Eigen {
 Matrix4f umeyama(const Matrix<float, 3, Dynamic>& src, const Matrix<float, 3, Dynamic>& dst, bool) {
@@ -85,6 +94,36 @@ struct ref_scene {
     cloud_t::Ptr cloud;
     std::unique_ptr<scene_access::impl_t> impl;
 };
+
+// ---- traits (a14): kind 0 cylinder, 1 plane, 2 plane2, 3 identity; g2l column-major -------------
+template <typename Tr>
+static std::shared_ptr<typename Tr::state_t> make_state(const float* g2l16, const float* l2g16, float radius, float threshold) {
+    auto h = std::make_shared<typename Tr::state_t>();
+    if constexpr (!std::is_same<Tr, tr::identity_traits<point_t>>::value) {
+        h->g2l = mat_from(g2l16);
+        h->l2g = mat_from(l2g16);  // given by the caller: Matrix4f::inverse() is a stand-in in the shim
+        h->threshold = threshold;
+        if constexpr (std::is_same<Tr, tr::cylinder_traits<point_t>>::value) h->radius = radius;
+    }
+    return h;
+}
+template <typename Tr>
+static int traits_ops(const float* g2l16, const float* l2g16, float radius, float threshold, const float* xyz, const float* pnt_n,
+                      const float* pnt_t, float* out15) {
+    typename Tr::const_handle_t h = make_state<Tr>(g2l16, l2g16, radius, threshold);
+    tr::vec3f_t p(xyz[0], xyz[1], xyz[2]);
+    auto uvw = Tr::project(h, p);
+    int ok = uvw ? 1 : 0;
+    tr::vec3f_t u = uvw ? *uvw : tr::vec3f_t(0.f, 0.f, 0.f);
+    tr::vec3f_t back = Tr::unproject(h, u);
+    point_t q = make_point(xyz, pnt_t);
+    q.normal_x = pnt_n[0]; q.normal_y = pnt_n[1]; q.normal_z = pnt_n[2];
+    tr::vec3f_t tg = Tr::tangent(h, q), nm = Tr::normal(h, q);
+    float dist = Tr::intrinsic_distance(h, u, tr::vec3f_t(pnt_t[0], pnt_t[1], pnt_t[2]));
+    for (int i = 0; i < 3; ++i) { out15[i] = u[i]; out15[3 + i] = back[i]; out15[6 + i] = tg[i]; out15[9 + i] = nm[i]; }
+    out15[12] = dist;
+    return ok;
+}
 
 extern "C" {
 
@@ -283,6 +322,16 @@ uint64_t ref_hypotheses_batch(void* sp, void* mp, const uint32_t* pair_i, const 
         }
     }
     return n;
+}
+// out15: uvw (3) | unproject(uvw) (3) | tangent(pnt) (3) | normal(pnt) (3) | intrinsic_distance(uvw, pnt_t) (1)
+int ref_traits(int kind, const float* g2l16, const float* l2g16, float radius, float threshold, const float* xyz, const float* pnt_n,
+               const float* pnt_t, float* out15) {
+    switch (kind) {
+        case 0: return traits_ops<tr::cylinder_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+        case 1: return traits_ops<tr::plane_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+        case 2: return traits_ops<tr::plane2_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+        default: return traits_ops<tr::identity_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+    }
 }
 // pointcloud::curvature(k, idx) = principal_curvatures(knn_inclusive(k, idx)) (pointcloud.hpp:200-204)
 void ref_curvature(const float* pos, const float* nrm, uint32_t n, const uint32_t* query, uint32_t n_query, uint32_t k,

@@ -3,6 +3,12 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+// PCL's pcl_macros.h (1.8 / 1.9, the releases of the reference's time) does `#define _USE_MATH_DEFINES`
+// + `#include <math.h>`; with libstdc++ that header pulls std::atan2 / std::fabs ... into the global
+// namespace, which is what makes the reference's unqualified `atan2(loc[1], loc[0])` on floats
+// (impl/cylinder_traits.hpp:109) resolve to the binary32 overload.  With <cmath> alone the call
+// would bind ::atan2(double, double) and round once more (<= 1 ulp apart).
+#include <math.h>
 #include <Eigen/Dense>
 namespace pcl {
 struct Vector3fMapConst : Eigen::Vector3f {

@@ -1,6 +1,8 @@
 // tests/cpp/test_dropin.cpp — exercises the drop-in C++ API (include/triplet_match/*).
 //   test_dropin cpu                      host-only checks (no GPU): feature / discretize / traits / octree
 //   test_dropin pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]   PCD reader / writer round trip
+//   test_dropin traits <in.bin> <out.bin>   project / unproject / tangent / normal / intrinsic_distance of
+//        the four traits for the states and points in <in.bin> (compared with the reference by the harness)
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
 //        the Python harness (n, then n x {pos3, nrm3, tgt3} floats); prints matches.
@@ -135,8 +137,60 @@ static int cpu_checks() {
     return 0;
 }
 
+// in: int32 kind | g2l[16] | l2g[16] | radius | threshold | uint32 n | n x {xyz, normal, tangent}
+// out: n x {ok, uvw3, unproject3, tangent3, normal3, intrinsic_distance(uvw, tangent)}  (14 floats)
+template <typename Tr>
+static void traits_rows(const float* g2l, const float* l2g, float radius, float threshold, const std::vector<float>& in,
+                        std::vector<float>& out) {
+    auto h = std::make_shared<typename Tr::state_t>();
+    if constexpr (!std::is_same<Tr, tr::identity_traits<point_t>>::value) {
+        for (int i = 0; i < 16; ++i) { h->g2l.data()[i] = g2l[i]; h->l2g.data()[i] = l2g[i]; }
+        h->threshold = threshold;
+        if constexpr (std::is_same<Tr, tr::cylinder_traits<point_t>>::value) h->radius = radius;
+    }
+    typename Tr::const_handle_t ch = h;
+    for (size_t i = 0; i < in.size() / 9; ++i) {
+        const float* v = &in[9 * i];
+        point_t q;
+        q.x = v[0]; q.y = v[1]; q.z = v[2];
+        q.normal_x = v[3]; q.normal_y = v[4]; q.normal_z = v[5];
+        tr::set_tangent(q, tr::vec3f_t(v[6], v[7], v[8]));
+        auto uvw = Tr::project(ch, q.getVector3f());
+        const tr::vec3f_t u = uvw ? *uvw : tr::vec3f_t(0.f, 0.f, 0.f);
+        const tr::vec3f_t back = Tr::unproject(ch, u), tg = Tr::tangent(ch, q), nm = Tr::normal(ch, q);
+        float* o = &out[14 * i];
+        o[0] = uvw ? 1.f : 0.f;
+        for (int k = 0; k < 3; ++k) { o[1 + k] = u[k]; o[4 + k] = back[k]; o[7 + k] = tg[k]; o[10 + k] = nm[k]; }
+        o[13] = Tr::intrinsic_distance(ch, u, tr::vec3f_t(v[6], v[7], v[8]));
+    }
+}
+static int traits_mode(const char* in_path, const char* out_path) {
+    std::ifstream f(in_path, std::ios::binary);
+    int32_t kind = 0;
+    float g2l[16], l2g[16], rt[2];
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&kind), 4);
+    f.read(reinterpret_cast<char*>(g2l), 64);
+    f.read(reinterpret_cast<char*>(l2g), 64);
+    f.read(reinterpret_cast<char*>(rt), 8);
+    f.read(reinterpret_cast<char*>(&n), 4);
+    std::vector<float> in(9 * (size_t)n), out(14 * (size_t)n);
+    f.read(reinterpret_cast<char*>(in.data()), in.size() * 4);
+    CHECK(f.good());
+    switch (kind) {
+        case 0: traits_rows<tr::cylinder_traits<point_t>>(g2l, l2g, rt[0], rt[1], in, out); break;
+        case 1: traits_rows<tr::plane_traits<point_t>>(g2l, l2g, rt[0], rt[1], in, out); break;
+        case 2: traits_rows<tr::plane2_traits<point_t>>(g2l, l2g, rt[0], rt[1], in, out); break;
+        default: traits_rows<tr::identity_traits<point_t>>(g2l, l2g, rt[0], rt[1], in, out); break;
+    }
+    std::ofstream o(out_path, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc >= 4 && std::string(argv[1]) == "traits") return traits_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "pcd") {  // pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]
         cloud_t::Ptr c;
         try {

@@ -293,3 +293,76 @@ def test_reference_resolution(ref):
     pos = _f32(c.pos)
     assert np.float32(ref.ref_resolution(_p(pos), C.c_uint32(c.n))) == np.float32(
         po.load().orc_resolution(_p(pos), C.c_uint32(c.n)))
+
+
+# ---- row a14: the traits' closed forms, compiled from the reference's impl/*_traits.hpp ----
+def _traits_cases():
+    rng = np.random.default_rng(8)
+    for kind in (0, 1, 2, 3):
+        for trial in range(4):
+            q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+            g = np.eye(4)
+            g[:3, :3] = q
+            g[:3, 3] = rng.standard_normal(3)
+            g16 = _f32(g.T.reshape(-1))  # column-major
+            l16 = _f32(np.linalg.inv(g).T.reshape(-1))
+            radius, thr = np.float32(0.4 + 0.2 * trial), np.float32(0.15)
+            pts = rng.standard_normal((400, 3)).astype(np.float32)
+            if kind == 0:  # points near the cylinder surface (some inside the threshold, some not), all four quadrants
+                loc = np.stack([np.cos(pts[:, 0] * 3) * (radius + 0.2 * pts[:, 1]), np.sin(pts[:, 0] * 3) * (radius + 0.2 * pts[:, 1]), pts[:, 2], np.ones(400)], 1)
+                pts = (loc @ np.linalg.inv(g).T)[:, :3].astype(np.float32)
+                pts[:4] = (np.array([[radius, 0, 0, 1], [-radius, 0, 0, 1], [0, radius, 0, 1], [0, -radius, 0, 1]]) @ np.linalg.inv(g).T)[:, :3].astype(np.float32)
+            elif kind == 1:
+                pts[:, :] = ((np.concatenate([pts[:, :2], 0.2 * pts[:, 2:3], np.ones((400, 1))], 1)) @ np.linalg.inv(g).T)[:, :3].astype(np.float32)
+            nrm = rng.standard_normal((400, 3))
+            nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+            tgt = np.cross(nrm, rng.standard_normal((400, 3)))
+            tgt /= np.linalg.norm(tgt, axis=1, keepdims=True)
+            yield kind, g16, l16, radius, thr, pts, _f32(nrm), _f32(tgt)
+
+
+def _ref_traits_rows(ref, kind, g16, l16, radius, thr, pts, nrm, tgt):
+    ref.ref_traits.restype = C.c_int
+    rows = np.zeros((pts.shape[0], 14), np.float32)
+    for i in range(pts.shape[0]):
+        out = np.zeros(15, np.float32)
+        ok = ref.ref_traits(C.c_int(kind), _p(g16), _p(l16), C.c_float(radius), C.c_float(thr), _p(pts[i]), _p(nrm[i]), _p(tgt[i]), _p(out))
+        rows[i, 0] = ok
+        rows[i, 1:] = out[:13]
+    return rows
+
+
+def test_reference_traits_project(ref):
+    """oracle restatement of the four `project` closed forms (what tm_traits_project is tested against)."""
+    for kind, g16, l16, radius, thr, pts, nrm, tgt in _traits_cases():
+        uvw_o, ok_o = po.traits_project(kind, g16, radius, thr, pts)
+        rows = _ref_traits_rows(ref, kind, g16, l16, radius, thr, pts, nrm, tgt)
+        assert np.array_equal(rows[:, 0] != 0, ok_o != 0), kind
+        sel = ok_o != 0
+        assert np.array_equal(rows[sel, 1:4].view(np.uint32), uvw_o[sel].view(np.uint32)), kind
+        assert sel.sum() > 50 and (kind >= 2 or sel.sum() < pts.shape[0])
+
+
+def test_reference_traits_dropin_headers(ref, tmp_path):
+    """include/triplet_match/*_traits (host code of the drop-in) against the reference's own
+    project / unproject / tangent / normal / intrinsic_distance, bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "triplet_match_b200")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_dropin.cpp"), "-o", exe, "-L" + libdir,
+                           "-ltriplet_match_b200", "-Wl,-rpath," + libdir])
+    names = ["ok", "u", "v", "w", "back_x", "back_y", "back_z", "tan_x", "tan_y", "tan_z", "nrm_x", "nrm_y", "nrm_z", "dist"]
+    for c, (kind, g16, l16, radius, thr, pts, nrm, tgt) in enumerate(_traits_cases()):
+        inp, outp = str(tmp_path / f"t{c}.in"), str(tmp_path / f"t{c}.out")
+        with open(inp, "wb") as f:
+            f.write(np.int32(kind).tobytes() + g16.tobytes() + l16.tobytes() + np.float32(radius).tobytes() + np.float32(thr).tobytes())
+            f.write(np.uint32(pts.shape[0]).tobytes())
+            f.write(np.ascontiguousarray(np.concatenate([pts, nrm, tgt], axis=1), dtype=np.float32).tobytes())
+        subprocess.check_call([exe, "traits", inp, outp])
+        got = np.fromfile(outp, dtype=np.float32).reshape(-1, 14)
+        want = _ref_traits_rows(ref, kind, g16, l16, radius, thr, pts, nrm, tgt)
+        for col in range(14):
+            bad = np.nonzero(got[:, col].view(np.uint32) != want[:, col].view(np.uint32))[0]
+            assert bad.size == 0, (kind, names[col], bad[:5], got[bad[:5], col], want[bad[:5], col])
