@@ -16,7 +16,7 @@
 #include "tm_kernels.cuh"
 
 namespace tmk {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }
 using namespace tmk;
 
@@ -189,11 +189,18 @@ int tm_ctx_create(int device, tm_ctx** out) {
     REQUIRE(device >= 0 && device < n, "tm_ctx_create: device out of range");
     tm_ctx* c = new tm_ctx();
     c->device = device;
-    CU(cudaSetDevice(device));
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&c->ev0));
-    CU(cudaEventCreate(&c->ev1));
-    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(TM_ERR_CUDA, std::string("tm_ctx_create: ") + cudaGetErrorString(e));
+    }
     *out = c;
     return TM_OK;
 }
@@ -240,7 +247,7 @@ int tm_ctx_flush_l2(tm_ctx* c) {
     CU(cudaGetLastError());
     return TM_OK;
 }
-uint64_t tm_ctx_kernel_launches(tm_ctx*) { return g_launch_count; }
+uint64_t tm_ctx_kernel_launches(tm_ctx*) { return g_launch_count.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------- cloud upload
 static int upload_cloud(tm_ctx* c, const tm_cloud_view* v, const uint8_t* flags, int model_mode,
@@ -316,6 +323,8 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
     REQUIRE(d->extents[0] > 0 && d->extents[1] > 0 && d->extents[2] > 0, "bad extents");
     const size_t cells = (size_t)d->extents[0] * d->extents[1] * d->extents[2];
     REQUIRE(cells < (1ull << 31), "voxel grid too large for 32-bit linear index");
+    REQUIRE(d->n_keys < (1u << 30), "too many hash keys");
+    REQUIRE(d->n_keys == 0 || (d->keys && d->offsets && d->pairs), "hash table arrays missing");
     float s[3], tr[3];
     TRY(check_to_voxel(d->to_voxel, s, tr));
     tm_model* m = new tm_model();
@@ -332,8 +341,11 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
     if ((rc = m->voxel.ensure(cells * sizeof(uint32_t)))) return bail(rc);
     for (size_t i = 0; i < cells; ++i)
         if (d->voxel[i] >= cloud->n) return bail(fail(TM_ERR_INVALID, "voxel entry out of range"));
-    CU(cudaMemcpyAsync(m->voxel.p, d->voxel, cells * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                       c->stream));
+    auto cuda_bail = [&](cudaError_t e, const char* what) {
+        return bail(fail(TM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)));
+    };
+    cudaError_t ce = cudaMemcpyAsync(m->voxel.p, d->voxel, cells * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (ce != cudaSuccess) return cuda_bail(ce, "voxel grid upload");
     // hash table: open addressing over the unique keys
     uint32_t cap = 16;
     while (cap < 2u * std::max(d->n_keys, 1u)) cap <<= 1;
@@ -350,15 +362,14 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
         slots[h].begin = d->offsets[k];
         slots[h].count = cnt;
     }
-    for (uint32_t i = 0; i < 2 * (size_t)n_hits; ++i)
+    for (size_t i = 0; i < 2 * (size_t)n_hits; ++i)
         if (d->pairs[i] >= cloud->n) return bail(fail(TM_ERR_INVALID, "hash pair out of range"));
     if ((rc = m->slots.ensure(sizeof(HashSlot) * cap))) return bail(rc);
     if ((rc = m->hits.ensure(sizeof(uint2) * (size_t)std::max(n_hits, 1u)))) return bail(rc);
-    CU(cudaMemcpyAsync(m->slots.p, slots.data(), sizeof(HashSlot) * cap, cudaMemcpyHostToDevice,
-                       c->stream));
-    if (n_hits)
-        CU(cudaMemcpyAsync(m->hits.p, d->pairs, sizeof(uint2) * (size_t)n_hits,
-                           cudaMemcpyHostToDevice, c->stream));
+    ce = cudaMemcpyAsync(m->slots.p, slots.data(), sizeof(HashSlot) * cap, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess && n_hits)
+        ce = cudaMemcpyAsync(m->hits.p, d->pairs, sizeof(uint2) * (size_t)n_hits, cudaMemcpyHostToDevice, c->stream);
+    if (ce != cudaSuccess) return cuda_bail(ce, "hash table upload");
     // fused grid (cell -> model point) when it stays L2-sized
     m->fused = cells * sizeof(float4) <= (96ull << 20);
     if (const char* e = getenv("TM_FUSED_GRID")) m->fused = atoi(e) != 0;
@@ -369,8 +380,9 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
     if ((rc = m->vref.ensure((size_t)cloud->n * sizeof(float4)))) return bail(rc);
     launch_model_ref(c->stream, m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n,
                      m->vref.as<float4>());
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);  // `slots` (host) is read by the copy above
+    if (ce != cudaSuccess) return cuda_bail(ce, "model upload");
     ModelDev& dv = m->dev;
     dv.cloud = CloudDev{m->pos.as<float4>(), m->nrm.as<float4>(), m->tgt.as<float4>(), cloud->n};
     dv.voxel = m->voxel.as<uint32_t>();
@@ -562,7 +574,7 @@ int tm_scene_set_mask(tm_scene* s, const uint8_t* mask) {
 void tm_scene_destroy(tm_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    for (DevBuf* b : {&s->pos, &s->nrm, &s->tgt, &s->mask_tmp}) b->release();
+    for (DevBuf* b : {&s->pos, &s->nrm, &s->tgt, &s->mask_tmp, &s->seg_lo, &s->seg_hi}) b->release();
     delete s;
 }
 
@@ -581,6 +593,8 @@ int tm_features(tm_scene* s, tm_model* m, const uint32_t* pi, const uint32_t* pj
     tm_ctx* c = s->ctx;
     TRY(bind(c));
     if (!n) return TM_OK;
+    for (uint64_t i = 0; i < n; ++i)
+        REQUIRE(pi[i] < s->dev.n && pj[i] < s->dev.n, "tm_features: scene index out of range");
     DevBuf &di = c->scratch[0], &dj = c->scratch[1], &df = c->scratch[2], &dk = c->scratch[3],
            &dv = c->scratch[4];
     TRY(di.ensure(n * 4)); TRY(dj.ensure(n * 4)); TRY(df.ensure(n * 16)); TRY(dk.ensure(n * 16));
@@ -1386,9 +1400,13 @@ int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query
     q->m = m;
     q->p = *p;
     memset(&q->host_out, 0, sizeof(QueryOut));
-    TRY(bind(s->ctx));
-    CU(cudaEventCreate(&q->ev_s0));
-    CU(cudaEventCreate(&q->ev_s1));
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s0);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s1);
+    if (e != cudaSuccess) {
+        tm_query_destroy(q);
+        return fail(TM_ERR_CUDA, std::string("tm_query_create: ") + cudaGetErrorString(e));
+    }
     *out = q;
     return TM_OK;
 }

@@ -1,11 +1,13 @@
 // tm_kernels.cuh — launch wrappers shared between the kernel files and capi.cu.
 #pragma once
+#include <atomic>
+
 #include "tm_device.cuh"
 
 namespace tmk {
 
 // kernels launched by this process (every launch_* wrapper launches exactly one)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;  // launches of this library's kernels (any host thread)
 
 // ---- tuning constants ------------------------------------------------------
 constexpr int SCORE_THREADS = 256;
