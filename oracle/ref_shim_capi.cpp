@@ -35,6 +35,8 @@
 #include <impl/plane_traits.hpp>
 #include <impl/plane2_traits.hpp>
 #include <impl/identity_traits.hpp>
+#include <octree>                 // row a16: octree build + the five traversals (octree.ipp)
+#include <impl/octree.hpp>
 
 namespace Eigen {
 Matrix4f umeyama(const Matrix<float, 3, Dynamic>& src, const Matrix<float, 3, Dynamic>& dst, bool) {
@@ -123,6 +125,31 @@ static int traits_ops(const float* g2l16, const float* l2g16, float radius, floa
     for (int i = 0; i < 3; ++i) { out15[i] = u[i]; out15[3 + i] = back[i]; out15[6 + i] = tg[i]; out15[9 + i] = nm[i]; }
     out15[12] = dist;
     return ok;
+}
+
+// ---- octree (a16): node rows {depth, is_leaf, n_points, bbox min3, bbox max3, sum idx, first idx, last idx} ----
+static void octree_row(const tr::node& nd, double* row) {
+    const tr::base_node* b = tr::as_base_node(nd);
+    row[0] = b->depth;
+    const tr::leaf_node* lf = std::get_if<tr::leaf_node>(&nd);
+    row[1] = lf ? 1.0 : 0.0;
+    row[2] = lf ? (double)lf->points.size() : 0.0;
+    for (int i = 0; i < 3; ++i) { row[3 + i] = b->bbox.min()[i]; row[6 + i] = b->bbox.max()[i]; }
+    double sum = 0.0;
+    if (lf) for (uint32_t i : lf->points) sum += (double)i;
+    row[9] = sum;
+    row[10] = lf && !lf->points.empty() ? (double)lf->points.front() : -1.0;
+    row[11] = lf && !lf->points.empty() ? (double)lf->points.back() : -1.0;
+}
+template <typename Trav>
+static uint32_t octree_walk(Trav t, double* rows, uint32_t cap) {
+    uint32_t n = 0;
+    while (!t.equal(ranges::default_sentinel{})) {
+        if (n < cap) octree_row(t.read(), rows + 12 * (size_t)n);
+        ++n;
+        t.next();
+    }
+    return n;
 }
 
 extern "C" {
@@ -331,6 +358,30 @@ int ref_traits(int kind, const float* g2l16, const float* l2g16, float radius, f
         case 1: return traits_ops<tr::plane_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
         case 2: return traits_ops<tr::plane2_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
         default: return traits_ops<tr::identity_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+    }
+}
+// crit_kind 0 min_voxel_size, 1 max_voxel_size, 2 max_point_count; traversal 0 depth, 1 breadth, 2 leaf,
+// 3 branch, 4 level(level); returns the number of visited nodes (rows beyond cap are counted, not written)
+uint32_t ref_octree(const float* pos, uint32_t n, const uint32_t* subset, uint32_t n_subset, uint32_t max_depth,
+                    int crit_kind, float crit_value, int traversal, uint32_t level, double* rows, uint32_t cap,
+                    uint32_t* depth_out) {
+    std::vector<float> z(3 * (size_t)n, 0.f);
+    cloud_t::Ptr c = make_cloud(pos, z.data(), z.data(), n);
+    tr::subdivision_criterion_t crit;
+    if (crit_kind == 0) crit = tr::min_voxel_size{crit_value};
+    else if (crit_kind == 1) crit = tr::max_voxel_size{crit_value};
+    else crit = tr::max_point_count{(uint32_t)crit_value};
+    std::optional<tr::subset_t> sub;
+    if (subset) sub = tr::subset_t(subset, subset + n_subset);
+    typedef tr::octree<point_t> tree_t;
+    auto tree = tree_t::from_pointcloud(c, max_depth, crit, sub);
+    if (depth_out) *depth_out = tree->depth();
+    switch (traversal) {
+        case 0: return octree_walk(tree_t::depth_traverse(tree->root()), rows, cap);
+        case 1: return octree_walk(tree_t::breadth_traverse(tree->root()), rows, cap);
+        case 2: return octree_walk(tree_t::leaf_traverse(tree->root()), rows, cap);
+        case 3: return octree_walk(tree_t::branch_traverse(tree->root()), rows, cap);
+        default: return octree_walk(tree_t::level_traverse(tree->root(), (uint8_t)level), rows, cap);
     }
 }
 // pointcloud::curvature(k, idx) = principal_curvatures(knn_inclusive(k, idx)) (pointcloud.hpp:200-204)

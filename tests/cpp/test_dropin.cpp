@@ -3,6 +3,7 @@
 //   test_dropin pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]   PCD reader / writer round trip
 //   test_dropin traits <in.bin> <out.bin>   project / unproject / tangent / normal / intrinsic_distance of
 //        the four traits for the states and points in <in.bin> (compared with the reference by the harness)
+//   test_dropin octree <in.bin> <out.bin>   octree build + the five traversals, one row per visited node
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
 //        the Python harness (n, then n x {pos3, nrm3, tgt3} floats); prints matches.
@@ -188,8 +189,73 @@ static int traits_mode(const char* in_path, const char* out_path) {
     return 0;
 }
 
+// in: uint32 n | n x xyz | uint32 n_subset (0xffffffff: none) | subset | uint32 max_depth | int32 crit_kind |
+//     float crit_value | int32 traversal | uint32 level
+// out: uint32 depth | uint32 rows | rows x 12 doubles {depth, is_leaf, n_points, bbox min3, max3, sum idx, first, last}
+static int octree_mode(const char* in_path, const char* out_path) {
+    std::ifstream f(in_path, std::ios::binary);
+    uint32_t n = 0, ns = 0, max_depth = 0, level = 0;
+    int32_t crit_kind = 0, traversal = 0;
+    float crit_value = 0.f;
+    f.read(reinterpret_cast<char*>(&n), 4);
+    cloud_t::Ptr c = cloud_t::empty();
+    for (uint32_t i = 0; i < n; ++i) {
+        float v[3];
+        f.read(reinterpret_cast<char*>(v), 12);
+        point_t p;
+        p.x = v[0]; p.y = v[1]; p.z = v[2];
+        c->push_back(p);
+    }
+    f.read(reinterpret_cast<char*>(&ns), 4);
+    std::optional<tr::subset_t> sub;
+    if (ns != 0xffffffffu) {
+        sub = tr::subset_t(ns);
+        f.read(reinterpret_cast<char*>(sub->data()), 4ull * ns);
+    }
+    f.read(reinterpret_cast<char*>(&max_depth), 4);
+    f.read(reinterpret_cast<char*>(&crit_kind), 4);
+    f.read(reinterpret_cast<char*>(&crit_value), 4);
+    f.read(reinterpret_cast<char*>(&traversal), 4);
+    f.read(reinterpret_cast<char*>(&level), 4);
+    CHECK(f.good());
+    tr::subdivision_criterion_t crit;
+    if (crit_kind == 0) crit = tr::min_voxel_size{crit_value};
+    else if (crit_kind == 1) crit = tr::max_voxel_size{crit_value};
+    else crit = tr::max_point_count{(uint32_t)crit_value};
+    auto tree = tr::octree<point_t>::from_pointcloud(c, max_depth, crit, sub);
+    std::vector<tr::node const*> nodes;
+    switch (traversal) {
+        case 0: nodes = tree->depth_traverse(); break;
+        case 1: nodes = tree->breadth_traverse(); break;
+        case 2: nodes = tree->leaf_traverse(); break;
+        case 3: nodes = tree->branch_traverse(); break;
+        default: nodes = tree->level_traverse((uint8_t)level); break;
+    }
+    std::vector<double> rows(12 * nodes.size());
+    for (size_t r = 0; r < nodes.size(); ++r) {
+        double* row = &rows[12 * r];
+        const tr::base_node* b = tr::as_base_node(*nodes[r]);
+        const tr::leaf_node* lf = std::get_if<tr::leaf_node>(nodes[r]);
+        row[0] = b->depth;
+        row[1] = lf ? 1.0 : 0.0;
+        row[2] = lf ? (double)lf->points.size() : 0.0;
+        for (int i = 0; i < 3; ++i) { row[3 + i] = b->bbox.min()[i]; row[6 + i] = b->bbox.max()[i]; }
+        double sum = 0.0;
+        if (lf) for (uint32_t i : lf->points) sum += (double)i;
+        row[9] = sum;
+        row[10] = lf && !lf->points.empty() ? (double)lf->points.front() : -1.0;
+        row[11] = lf && !lf->points.empty() ? (double)lf->points.back() : -1.0;
+    }
+    std::ofstream o(out_path, std::ios::binary);
+    const uint32_t hdr[2] = {tree->depth(), (uint32_t)nodes.size()};
+    o.write(reinterpret_cast<const char*>(hdr), 8);
+    o.write(reinterpret_cast<const char*>(rows.data()), rows.size() * 8);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc >= 4 && std::string(argv[1]) == "octree") return octree_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "traits") return traits_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "pcd") {  // pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]
         cloud_t::Ptr c;

@@ -366,3 +366,56 @@ def test_reference_traits_dropin_headers(ref, tmp_path):
         for col in range(14):
             bad = np.nonzero(got[:, col].view(np.uint32) != want[:, col].view(np.uint32))[0]
             assert bad.size == 0, (kind, names[col], bad[:5], got[bad[:5], col], want[bad[:5], col])
+
+
+# ---- row a16: octree build + traversals, compiled from include/octree(.ipp) + impl/octree.hpp ----
+def test_reference_octree_dropin_headers(ref, tmp_path):
+    """include/triplet_match/octree against the reference's own tree: same nodes (depth, kind, box bits,
+    leaf contents) in the same order for all five traversals, three criteria, with and without subset."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "triplet_match_b200")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_dropin.cpp"), "-o", exe, "-L" + libdir,
+                           "-ltriplet_match_b200", "-Wl,-rpath," + libdir])
+    ref.ref_octree.restype = C.c_uint32
+    rng = np.random.default_rng(16)
+    pts = rng.standard_normal((3000, 3)).astype(np.float32)
+    pts[:50] = pts[50:100]  # duplicates: a max_point_count tree bottoms out on the depth limit
+    pts[100:140, 0] = 0.25  # points on a splitting plane go to the low octant (strict '>')
+    one = pts[:1].copy()
+    cases = []
+    for crit_kind, crit_value, max_depth in ((2, 20.0, 6), (2, 1.0, 3), (1, 0.8, 8), (0, 0.3, 8), (2, 5000.0, 4)):
+        for subset in (None, rng.permutation(3000)[:700].astype(np.uint32)):
+            for trav, level in ((0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (4, 2), (4, 9)):
+                cases.append((pts, subset, max_depth, crit_kind, crit_value, trav, level))
+    cases.append((one, None, 4, 2, 8.0, 3, 0))  # a single leaf: branch_traverse yields the root leaf (reference quirk)
+    cases.append((one, None, 4, 2, 8.0, 2, 0))
+    n_nodes = 0
+    for c, (p, subset, max_depth, crit_kind, crit_value, trav, level) in enumerate(cases):
+        cap = 1 << 16
+        rows = np.zeros((cap, 12), np.float64)
+        depth = C.c_uint32()
+        sub_p = _p(subset) if subset is not None else None
+        n = ref.ref_octree(_p(p), C.c_uint32(p.shape[0]), sub_p, C.c_uint32(0 if subset is None else subset.size),
+                           C.c_uint32(max_depth), C.c_int(crit_kind), C.c_float(crit_value), C.c_int(trav),
+                           C.c_uint32(level), _p(rows), C.c_uint32(cap), C.byref(depth))
+        assert n <= cap
+        inp, outp = str(tmp_path / f"o{c}.in"), str(tmp_path / f"o{c}.out")
+        with open(inp, "wb") as f:
+            f.write(np.uint32(p.shape[0]).tobytes() + np.ascontiguousarray(p).tobytes())
+            if subset is None:
+                f.write(np.uint32(0xffffffff).tobytes())
+            else:
+                f.write(np.uint32(subset.size).tobytes() + subset.tobytes())
+            f.write(np.uint32(max_depth).tobytes() + np.int32(crit_kind).tobytes() + np.float32(crit_value).tobytes())
+            f.write(np.int32(trav).tobytes() + np.uint32(level).tobytes())
+        subprocess.check_call([exe, "octree", inp, outp])
+        raw = open(outp, "rb").read()
+        got_depth, got_n = np.frombuffer(raw[:8], dtype=np.uint32)
+        got = np.frombuffer(raw[8:], dtype=np.float64).reshape(-1, 12)
+        assert (got_depth, got_n) == (depth.value, n), (c, got_depth, got_n, depth.value, n)
+        assert np.array_equal(got.view(np.uint64), rows[:n].view(np.uint64)), c
+        n_nodes += n
+    assert n_nodes > 10000
