@@ -419,3 +419,49 @@ def test_reference_octree_dropin_headers(ref, tmp_path):
         assert np.array_equal(got.view(np.uint64), rows[:n].view(np.uint64)), c
         n_nodes += n
     assert n_nodes > 10000
+
+
+# ---- row a15: opencl/{util,cylinder,icp}.cl compiled as C++ (built-ins are stand-ins, see the shim) ----
+REF_CL = os.path.join(os.path.dirname(REF), "libtm_ref_cl.so")
+
+
+def test_reference_opencl_kernels(built):
+    """The oracle's restatement of icp_projection / icp_correlation against the reference's own kernel
+    source run one work-item at a time (with a padded range: the kernels' own guard stops the extras)."""
+    if not os.path.exists(REF_CL):
+        pytest.skip("oracle/_ref/libtm_ref_cl.so not built (no /root/reference in this environment)")
+    import test_uvicp as tu
+    L = C.CDLL(REF_CL)
+    L.ref_cl_icp_projection.restype = C.c_uint32
+    total_hits = 0
+    for seed, maxd in ((1, 0.02), (2, 0.05), (3, 1e9), (4, 0.0)):
+        pnts, image, sz, mg, ma, mu, mp, mn = tu._setup(seed, n=4000)
+        if seed == 3:  # a transform that throws many points out of the image, plus NaN / huge coordinates
+            pnts[:50, :3] *= 1e6
+            pnts[50:60, 0] = np.nan
+            pnts[60:70, 1] = np.inf
+        n = pnts.shape[0]
+        op_o, mi_o, si_o, c_o = po.cl_icp_projection(0, pnts, image, sz, mg, ma, mu, mp, mn, maxd)
+        op = np.full((n + 7, 4), 7.0, np.float32)
+        mi = np.full(n + 7, 12345, np.int32)
+        si = np.full(n + 7, 12345, np.int32)
+        c = L.ref_cl_icp_projection(_p(pnts), C.c_int(n), C.c_int(7), _p(image), _p(sz), _p(mg), _p(ma), _p(mu), _p(mp),
+                                    _p(mn), C.c_float(maxd), _p(op), _p(mi), _p(si))
+        assert c == c_o
+        assert np.array_equal(mi[:n], mi_o) and np.array_equal(si[:n], si_o)
+        assert np.array_equal(op[:n].view(np.uint32), op_o.view(np.uint32))
+        assert np.all(mi[n:] == 12345) and np.all(op[n:] == 7.0)  # `index >= n` guard
+        total_hits += c
+        # icp_correlation over the correspondences just found
+        sel = np.flatnonzero(mi_o >= 0)
+        if sel.size < 2:
+            continue
+        is_, im_ = si_o[sel].astype(np.int32), mi_o[sel].astype(np.int32)
+        cs = np.append(op_o[sel, :3].mean(0), 0).astype(np.float32)
+        cm = np.append(image[im_, :3].mean(0), 0).astype(np.float32)
+        rec_o, _ = po.cl_icp_correlation(op_o, image, is_, im_, cs, cm)
+        rec = np.full((sel.size + 3, 16), 7.0, np.float32)
+        L.ref_cl_icp_correlation(_p(op_o), _p(image), _p(is_), _p(im_), C.c_int(sel.size), C.c_int(3), _p(cs), _p(cm), _p(rec))
+        assert np.array_equal(rec[:sel.size].view(np.uint32), rec_o.view(np.uint32))
+        assert np.all(rec[sel.size:] == 7.0)
+    assert total_hits > 3000
