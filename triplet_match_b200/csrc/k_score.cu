@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     r0 = __ldg(&a.T[hb]); r1 = __ldg(&a.T[hb + 1]); r2 = __ldg(&a.T[hb + 2]);
                 }
                 // ---- exact path, stage 1: pos = t*pos, ijk = trunc(to_voxel*pos) (scene.hpp:444,
-                // model.hpp:182) for all P points; trunc-toward-zero bounds in the float domain
+                // model.hpp:182-189) for all P points
                 float x[P], y[P], z[P];
                 uint32_t lin[P];
                 uint32_t inb = 0;
@@ -215,11 +215,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     y[k] = row_apply(r1, px[k], py[k], pz[k]);
                     z[k] = row_apply(r2, px[k], py[k], pz[k]);
                     const float vx = m.sx * x[k] + m.tx, vy = m.sy * y[k] + m.ty, vz = m.sz * z[k] + m.tz;
-                    bool in = (vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) &
-                              (vz > -1.f) & (vz < m.ezf);
                     const int i = (int)vx, j = (int)vy, kk = (int)vz;
-                    if (OCC) {
-                        if (in) in = occ_test(m, i, j, kk);  // empty block: no inlier possible, skip the gathers
+                    // the reference's own test, on the truncated integers (model.hpp:186-189): cvt.rzi saturates, so
+                    // huge values stay out; a NaN converts to 0 and is rejected by the distance test (sq is NaN)
+                    bool in = ((uint32_t)i < (uint32_t)m.ex) & ((uint32_t)j < (uint32_t)m.ey) &
+                              ((uint32_t)kk < (uint32_t)m.ez);
+                    if (OCC) {  // branch-free: out-of-grid lanes look at block 0
+                        const uint32_t b = in ? (uint32_t)(((kk >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx +
+                                                           (i >> OCC_SHIFT))
+                                              : 0u;
+                        in = in & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
                     }
                     lin[k] = in ? (uint32_t)((kk * m.ey + j) * m.ex + i) : 0u;
                     inb |= in ? (1u << k) : 0u;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     const float dx = x[k] - mp[k].x, dy = y[k] - mp[k].y, dz = z[k] - mp[k].z;
                     const float sq = sum3(dx * dx, dy * dy, dz * dz);
                     const uint32_t pfl = (tflags >> k) & 1u;
-                    const bool inl = ((inb >> k) & 1u) && !(sq > a.sq_thres) &&
+                    const bool inl = ((inb >> k) & 1u) && (sq <= a.sq_thres) &&  // NaN: not an inlier
                                      (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
                     if (inl) {
                         ++c;
