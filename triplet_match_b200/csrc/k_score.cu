@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     __shared__ float4 s_rows[CULL ? (SCORE_THREADS / 32) * 32 * 3 : 1];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float4* my_ref = s_ref + (WITH_SCORE ? warp * 32 * P : 0);
+    // thread-private slots (each lane re-reads only what it staged): slot k of thread t at k * SCORE_THREADS + t,
+    // so the address is tid * 16 + a constant and no lane ever touches another lane's slot (no barrier needed)
+    float4* my_ref = s_ref + (WITH_SCORE ? threadIdx.x : 0);
     float4* my_rows = s_rows + (CULL ? warp * 32 * 3 : 0);
     const uint32_t n_items = *a.n_items;
     const ModelDev& m = a.model;
@@ -115,7 +117,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
         uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
         const float nanv = __int_as_float(0x7fc00000);
         float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
-        if (WITH_SCORE) __syncwarp();  // previous item's readers of my_ref are done
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const uint32_t q = k * 32 + lane;
@@ -132,11 +133,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     mny = fminf(mny, v.y); mxy = fmaxf(mxy, v.y);
                     mnz = fminf(mnz, v.z); mxz = fmaxf(mxz, v.z);
                     if (WITH_SCORE)  // ref = use_tangent ? tangent : normal (scene.hpp:441-442)
-                        my_ref[q] = (fl & FLAG_TANGENT) ? a.scene.tgt[idx] : a.scene.nrm[idx];
+                        my_ref[k * SCORE_THREADS] = (fl & FLAG_TANGENT) ? a.scene.tgt[idx] : a.scene.nrm[idx];
                 }
             }
         }
-        if (WITH_SCORE) __syncwarp();
         float cx = 0.f, cy = 0.f, cz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
         if (CULL) {
 #pragma unroll
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     if (inl) {
                         ++c;
                         if (WITH_SCORE) {
-                            const f3 ref = mk3(my_ref[k * 32 + lane]);
+                            const f3 ref = mk3(my_ref[k * SCORE_THREADS]);
                             f3 rn;
                             // the model point's ref vector (its class agrees with the scene point's)
                             const uint32_t mi = FUSED ? (__float_as_uint(mp[k].w) >> 1) : __ldg(&m.voxel[lin[k]]);
