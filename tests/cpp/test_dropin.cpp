@@ -307,6 +307,7 @@ int main(int argc, char** argv) {
     (void)m.query(*f);
     tr::scene<point_t> s(sc);
     s.set_curvature_test(curv);
+    if (const char* e = std::getenv("TM_DROPIN_EARLY_DROP")) s.set_early_drop(std::atoi(e) != 0);  // A/B: default off
     auto t3 = now();
     auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, 5);
     auto t4 = now();

@@ -1636,7 +1636,10 @@ int tm_query_run(tm_query* q) {
                   out->shard, &out->best, c->sm_count * 2);
     // (a12) ICP of the local top-k
     if (q->p.icp_top_k && q->p.max_icp_iterations) {
+        // a hypothesis the early drop gave up on never becomes a candidate (scene.hpp:330: a dropped
+        // project_ returns fewer correspondences than the acceptance bound), whatever its partial count
         launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
+                           q->p.early_out ? q->dropped.as<uint8_t>() : nullptr,
                            &out->n_local, q->cap_hyp, q->p.icp_top_k, q->topk_ids.as<uint32_t>(),
                            q->topk_keys.as<unsigned long long>());
         launch_gather_rows(c->stream, q->T.as<float4>(), q->topk_ids.as<uint32_t>(), q->p.icp_top_k,

@@ -91,7 +91,8 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
 }
 __global__ void __launch_bounds__(1024)
     topk_slice_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
-                      const uint32_t* __restrict__ n_local, uint32_t k, unsigned long long* __restrict__ cand) {
+                      const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local, uint32_t k,
+                      unsigned long long* __restrict__ cand) {
     __shared__ unsigned long long keys[TOPK_SLICE];
     __shared__ unsigned long long wbest[32];
     const uint32_t n = *n_local;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(1024)
     for (uint32_t t = threadIdx.x; t < TOPK_SLICE; t += blockDim.x) {
         const uint32_t i = base + t;
         unsigned long long key = 0;
-        if (i < n && (!valid || valid[i]) && counts[i])
+        if (i < n && (!valid || valid[i]) && (!excluded || !excluded[i]) && counts[i])
             key = ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
         keys[t] = key;
     }
@@ -146,13 +147,13 @@ __global__ void __launch_bounds__(1024)
 size_t topk_scratch_bytes(uint64_t capacity, uint32_t k) {
     return (size_t)((capacity + TOPK_SLICE - 1) / TOPK_SLICE) * k * 8 + 8;
 }
-void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                         const uint32_t* n_local, uint64_t capacity, uint32_t k, uint32_t* topk_ids,
                         unsigned long long* scratch_keys) {
     if (!k) return;
     const uint32_t slices = (uint32_t)std::max<uint64_t>(1, (capacity + TOPK_SLICE - 1) / TOPK_SLICE);
     g_launch_count += 2;
-    topk_slice_kernel<<<slices, 1024, 0, st>>>(counts, valid, n_local, k, scratch_keys);
+    topk_slice_kernel<<<slices, 1024, 0, st>>>(counts, valid, excluded, n_local, k, scratch_keys);
     topk_final_kernel<<<1, 1024, 0, st>>>(scratch_keys, slices * k, k, topk_ids);
 }
 

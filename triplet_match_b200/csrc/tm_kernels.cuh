@@ -208,7 +208,7 @@ void launch_group_hyp_ranges(cudaStream_t st, const unsigned long long* hyp_off,
 void launch_group_of_hyp(cudaStream_t st, const uint32_t* g_hyp, uint32_t n_groups,
                          uint32_t* g_of_hyp);
 size_t topk_scratch_bytes(uint64_t capacity, uint32_t k);
-void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                         const uint32_t* n_local, uint64_t capacity, uint32_t k, uint32_t* topk_ids,
                         unsigned long long* scratch_keys);
 void launch_gather_rows(cudaStream_t st, const float4* T, const uint32_t* ids, uint32_t k,
