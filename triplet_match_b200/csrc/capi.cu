@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -41,6 +42,25 @@ static int fail(int code, const std::string& msg) {
         int rc_ = (call);      \
         if (rc_) return rc_;   \
     } while (0)
+
+// development knobs (environment), read once per process; none of them changes results
+struct Knobs {
+    bool occ = true;               // TM_OCC=0: never use the block-occupancy mask
+    int fused_grid = -1;           // TM_FUSED_GRID=0/1: force the unfused / fused voxel grid
+    int score_grid = 0;            // TM_SCORE_GRID=n: CTAs of the scoring kernel
+    bool score_stats = false;      // TM_SCORE_STATS=1: cull / inlier statistics of the scoring kernel on stderr
+};
+static const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs v;
+        if (const char* e = getenv("TM_OCC")) v.occ = atoi(e) != 0;
+        if (const char* e = getenv("TM_FUSED_GRID")) v.fused_grid = atoi(e) != 0 ? 1 : 0;
+        if (const char* e = getenv("TM_SCORE_GRID")) v.score_grid = std::max(1, atoi(e));
+        v.score_stats = getenv("TM_SCORE_STATS") != nullptr;
+        return v;
+    }();
+    return k;
+}
 
 // grow-only device buffer
 struct DevBuf {
@@ -79,6 +99,7 @@ struct tm_ctx {
     DevBuf scratch[12];  // stage-call scratch, grow-only
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
 };
 
 struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
@@ -111,12 +132,7 @@ static int bind(tm_ctx* c) {
 // block-occupancy mask of that threshold (built on first use, cached per model).  TM_OCC=0 disables.
 static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
     *out = m->dev;
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("TM_OCC");
-        enabled = e ? (atoi(e) != 0) : 1;
-    }
-    if (!enabled || !(thres >= 0.f)) return TM_OK;
+    if (!knobs().occ || !(thres >= 0.f)) return TM_OK;
     OccMask* hit = nullptr;
     for (OccMask& o : m->occ)
         if (o.thres == thres) hit = &o;
@@ -372,7 +388,7 @@ int tm_model_upload(tm_ctx* c, const tm_cloud_view* cloud, const tm_model_desc* 
     if (ce != cudaSuccess) return cuda_bail(ce, "hash table upload");
     // fused grid (cell -> model point) when it stays L2-sized
     m->fused = cells * sizeof(float4) <= (96ull << 20);
-    if (const char* e = getenv("TM_FUSED_GRID")) m->fused = atoi(e) != 0;
+    if (knobs().fused_grid >= 0) m->fused = knobs().fused_grid != 0;
     if (m->fused) {
         if ((rc = m->vcell.ensure(cells * sizeof(float4)))) return bail(rc);
         launch_fuse_grid(c->stream, m->voxel.as<uint32_t>(), cells, m->pos.as<float4>(), m->vcell.as<float4>());
@@ -448,6 +464,7 @@ int tm_voxel_fill(tm_ctx* c, const tm_cloud_view* cloud, const int32_t extents[3
     int rc = upload_cloud(c, cloud, nullptr, 1, pos, nrm, tgt);
     if (!rc) rc = vox.ensure(cells * sizeof(uint32_t));
     // pruned two-pass fill unless TM_VOXEL_FILL_BRUTE=1 (the brute-force kernel is kept as its cross-check)
+    // read per call: the parity test fills the same grid both ways inside one process
     const char* brute_env = getenv("TM_VOXEL_FILL_BRUTE");
     const bool brute = brute_env && atoi(brute_env) != 0;
     if (!rc && !brute) rc = blk.ensure(voxel_fill_scratch_bytes(extents[0], extents[1], extents[2]));
@@ -778,11 +795,9 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
     a.scores = d_scores;
     a.sq_thres = sq_thres;
     a.stats = nullptr;
-    static int bps[2][2] = {{0, 0}, {0, 0}};
-    int& b = bps[m->fused ? 1 : 0][with_score ? 1 : 0];
+    int& b = c->score_bps[m->fused ? 1 : 0][with_score ? 1 : 0];
     if (!b) b = score_full_max_blocks_per_sm(m->fused, with_score);
-    int grid = c->sm_count * b;
-    if (const char* e = getenv("TM_SCORE_GRID")) grid = std::max(1, atoi(e));
+    const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
     launch_score_full(c->stream, a, grid, m->fused, with_score);
     CU(cudaGetLastError());
     return TM_OK;
@@ -1590,16 +1605,14 @@ int tm_query_run(tm_query* q) {
             a.scores = q->scores.as<unsigned long long>();
             a.sq_thres = sqt;
             a.stats = nullptr;
-            if (getenv("TM_SCORE_STATS")) {
+            if (knobs().score_stats) {
                 TRY(q->stats.ensure(64));
                 CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
                 a.stats = q->stats.as<unsigned long long>();
             }
-            static int bps[2] = {0, 0};
-            int& b = bps[m->fused ? 1 : 0];
+            int& b = c->score_bps[m->fused ? 1 : 0][1];
             if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
-            int grid = c->sm_count * b;
-            if (const char* e = getenv("TM_SCORE_GRID")) grid = std::max(1, atoi(e));
+            const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
             CU(cudaEventRecord(q->ev_s0, c->stream));
             launch_score_full(c->stream, a, grid, m->fused, true);
             CU(cudaEventRecord(q->ev_s1, c->stream));
@@ -1664,7 +1677,7 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
     CU(cudaStreamSynchronize(c->stream));
     memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
     const QueryOut& o = q->host_out;
-    if (q->stats.p && getenv("TM_SCORE_STATS")) {
+    if (q->stats.p && knobs().score_stats) {
         unsigned long long st[4] = {0, 0, 0, 0};
         CU(cudaMemcpy(st, q->stats.p, 32, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)\n",
@@ -1797,7 +1810,9 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;
 static int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.lib) return TM_OK;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     void* lib = nullptr;

@@ -305,13 +305,12 @@ static int occ_score_full_v() {
                 : ((c) ? FN<true, false, true>(__VA_ARGS__) : FN<true, false, false>(__VA_ARGS__)))  \
          : ((s) ? ((c) ? FN<false, true, true>(__VA_ARGS__) : FN<false, true, false>(__VA_ARGS__))   \
                 : ((c) ? FN<false, false, true>(__VA_ARGS__) : FN<false, false, false>(__VA_ARGS__))))
-static bool score_cull_enabled() {
-    static int v = -1;
-    if (v < 0) {
+static bool score_cull_enabled() {  // TM_SCORE_CULL=0: development knob, read once
+    static const bool v = [] {
         const char* e = getenv("TM_SCORE_CULL");
-        v = e ? (atoi(e) != 0) : 1;
-    }
-    return v != 0;
+        return e ? atoi(e) != 0 : true;
+    }();
+    return v;
 }
 void launch_score_full(cudaStream_t st, const ScoreArgs& a, int grid, bool fused, bool with_score) {
     TM_DISPATCH3(launch_score_full_v, fused, with_score, score_cull_enabled(), st, a, grid);
