@@ -475,6 +475,8 @@ def main():
             if it >= 3:
                 eo_ms.append(t_ms)
         r3 = q3.result()
+        d3 = q3.download()
+        alive3 = d3["dropped"] == 0
         q3.close()
         q3 = capi.Query(gs, gm, **QP, early_out=True, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
                         icp_top_k=64, max_icp_iterations=5)
@@ -489,9 +491,36 @@ def main():
         line["p50_query_early_drop_ms"] = float(np.median(lat3))
         line["early_drop_mode"] = {"value": r3.n_scored / (float(np.mean(eo_ms)) * 1e-3), "unit": UNIT,
                                    "ms_per_step": float(np.mean(eo_ms)), "tests_per_step": int(r3.n_tests),
+                                   "survivors": int(alive3.sum()),
+                                   "best_pose_survives": bool(alive3.any() and int(d3["counts"][alive3].max()) == int(r.best_inliers)),
                                    "note": "project_(early_out=true) semantics, bit-exact with the reference incl. drop points; "
                                            "not the headline (the headline scores every hypothesis over its whole subset)"}
         q3.close()
+        # the same drop test over an evenly sampling walk of each subset (early_out = 2, include/tm_b200.h): what the
+        # test presumes statistically; reports how many hypotheses survive it and whether the best pose does
+        q4 = capi.Query(gs, gm, **QP, early_out=2, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU)
+        q4.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        ev_ms = []
+        for it in range(1 + 2):  # ~0.4 s per pass: one warm-up, two timed
+            ctx.flush_l2()
+            ctx.timer_start()
+            q4.run()
+            t_ms = ctx.timer_stop()
+            if it >= 1:
+                ev_ms.append(t_ms)
+        r4 = q4.result()
+        d4 = q4.download()
+        alive = d4["dropped"] == 0
+        line["early_drop_even_walk_mode"] = {
+            "value": r4.n_scored / (float(np.mean(ev_ms)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ev_ms)),
+            "tests_per_step": int(r4.n_tests), "survivors": int(alive.sum()),
+            "best_inliers_among_survivors": int(d4["counts"][alive].max()) if alive.any() else 0,
+            "best_pose_survives": bool(alive.any() and int(d4["counts"][alive].max()) == int(r.best_inliers)),
+            "note": "early_out=2: the reference's drop test (bit-exact arithmetic) over the walk p -> (p*s) mod n of each "
+                    "subset; in the subset's own (Z-curve) order the test gives up on true poses.  One warp walks one "
+                    "hypothesis with scattered point loads and no tile culling, so on this workload (over half of the "
+                    "hypotheses pass the test) it is slower than scoring everything with the tiled kernel"}
+        q4.close()
         # p50 full-query latency incl. ICP of the top 64 (SURVEY §8d metric ii)
         q2 = capi.Query(gs, gm, **QP, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
                         icp_top_k=64, max_icp_iterations=5)

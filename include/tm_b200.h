@@ -135,6 +135,12 @@ int tm_ball_subsets(tm_scene* s, const uint32_t* centres, uint32_t n_centres, fl
  * (= scene_corrs.size()), score, and (early_out != 0) the reference's early-drop
  * outcome.  hyp_sub[h] selects subset CSR row; hyp_sub == NULL scores against all
  * scene points (finish_find, scene.hpp:100-106).  scores/dropped may be NULL.
+ * early_out: 0 = no drop; 1 = the drop test over the subset in the order given; 2 = the same test
+ * over an evenly sampling walk of the subset (position p visits element (p * s) mod n with
+ * s = tm_walk_stride(n)): the test extrapolates from the first 5 %, 10 %, ... of the walk
+ * (scene.hpp:486-504), which presumes that a prefix samples the subset evenly; the reference
+ * walks FLANN's unsorted radius-search order, ascending indices of a space-filling-curve-ordered
+ * scene are spatially compact prefixes.
  * Scores are accumulated as 2^-36 fixed point (order-independent, reproducible across tilings
  * and GPUs): exact for per-point terms |ref . ref_n| < 2^27, i.e. for every rigid transform
  * (terms <= 1); a matrix that scales vectors by more than that is outside the score's domain
@@ -143,6 +149,9 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
              const uint64_t* sub_offsets, const int32_t* sub_indices, uint32_t n_sub,
              float dist_thres, float accept_prob, int early_out, uint32_t* counts, double* scores,
              uint8_t* dropped);
+/* stride of the evenly sampling walk: the integer nearest n / golden ratio that is coprime with n
+ * (1 for n <= 2), so that p -> (p * s) mod n is a permutation whose prefixes spread over [0, n) */
+uint32_t tm_walk_stride(uint32_t n);
 /* correspondences of one transform over the whole scene (finish_find's
  * scene_corrs / model_corrs, ascending scene index).  Buffers sized scene n. */
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
@@ -218,7 +227,8 @@ typedef struct tm_query_params {
     uint32_t query_limit;      /* detail::query_limit = 200 (scene.hpp:19) */
     float dist_thres;
     float accept_prob;         /* model_match_factor */
-    int32_t early_out;         /* 0 = finish_find semantics, 1 = reference early-drop */
+    int32_t early_out;         /* 0 = finish_find semantics, 1 = reference early-drop in subset order,
+                                  2 = early-drop over the evenly sampling walk (see tm_score) */
     uint32_t icp_top_k;        /* 0 = no ICP stage */
     uint32_t max_icp_iterations;
     uint64_t max_hypotheses;   /* capacity; 0 = n_pairs * query_limit */

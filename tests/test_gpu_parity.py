@@ -107,6 +107,42 @@ def test_scoring_full_and_early_drop(setup):
         assert 0 < do.sum() < do.size  # both outcomes of the early-drop rule are exercised
 
 
+def test_early_drop_over_the_evenly_sampling_walk(setup):
+    """early_out = 2 == the reference's drop test on the subsets rewritten in walk order (the oracle gets the
+    permuted rows explicitly), and, on the resident query, dropped hypotheses are no ICP candidates."""
+    from triplet_match_b200 import capi
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    off, idx = _subsets(osc, om, rec)
+    hyp_sub = rec.pair_outer[hp]
+    walk = idx.copy()
+    for g in range(off.size - 1):
+        b, e = int(off[g]), int(off[g + 1])
+        walk[b:e] = idx[b:e][capi.walk_order(e - b)]
+    cg, sg, dg = gs.score(gm, T, hyp_sub, off, idx, early_out=2)
+    co, so, do = osc.score_batch(om, T, hyp_sub, off, walk, early_out=True, nthreads=4)
+    assert np.array_equal(cg, co) and np.array_equal(dg, do), name
+    assert np.allclose(sg, so, rtol=1e-9, atol=1e-9)
+    # whole scene as the subset (hyp_sub = None): identity rows in walk order
+    sel = np.linspace(0, T.shape[0] - 1, 24).astype(np.int64)
+    c2, s2, d2 = gs.score(gm, T[sel], early_out=2)
+    o_off = np.array([0, s.n], dtype=np.uint64)
+    c3, s3, d3 = osc.score_batch(om, T[sel], np.zeros(sel.size, np.uint32), o_off, capi.walk_order(s.n).astype(np.int32),
+                                 early_out=True, nthreads=4)
+    assert np.array_equal(c2, c3) and np.array_equal(d2, d3) and np.allclose(s2, s3, rtol=1e-9, atol=1e-9)
+    # resident query in the same mode: same outcomes, and the ICP candidates are the best non-dropped hypotheses
+    q = capi.Query(gs, gm, early_out=2, icp_top_k=4, max_icp_iterations=1)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    d = q.download()
+    assert np.array_equal(d["counts"], co) and np.array_equal(d["dropped"], do)
+    ids, *_ = q.icp_results()
+    keep = np.flatnonzero((do == 0) & (co > 0))
+    want = keep[np.argsort(-co[keep].astype(np.int64), kind="stable")][:4]
+    assert np.array_equal(ids[: want.size], want.astype(np.uint32)) and np.all(ids[want.size:] == 0xFFFFFFFF)
+    q.close()
+
+
 def test_scoring_with_mask_and_all_scene(setup):
     name, m, s, om, osc, rec, gm, gs = setup
     T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)

@@ -130,3 +130,25 @@ def test_model_blob_round_trip_and_corruption(built, tmp_path):
     with pytest.raises(capi.TmError):
         capi.HostModel.load(str(tmp_path / "missing.tmb"), m.pos, m.nrm, m.tgt)
     hm.close()
+
+
+def test_walk_stride_is_a_permutation_with_even_prefixes(built):
+    """tm_walk_stride (early_out = 2): coprime stride near n / golden ratio; every prefix of the walk spreads
+    over the whole index range."""
+    import math
+    from triplet_match_b200 import capi
+    for n in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 30, 64, 97, 100, 1000, 1024, 56789, 1 << 20, 999983, 2 ** 32 - 1):
+        st = capi.walk_stride(n)
+        if n <= 2:
+            assert st == 1
+            continue
+        assert 1 <= st < n and math.gcd(st, n) == 1, (n, st)
+        if n >= 30:
+            assert abs(st / n - 0.6180339887) < 0.2, (n, st)
+    for n in (1, 2, 5, 64, 1000, 56789):
+        w = capi.walk_order(n)
+        assert np.array_equal(np.sort(w), np.arange(n))
+    w = capi.walk_order(56789)
+    head = np.sort(w[: 56789 // 20])  # the first 5 %: no gap much larger than the mean spacing
+    gaps = np.diff(np.concatenate([[0], head, [56789]]))
+    assert gaps.max() < 6 * 20  # three-distance theorem: at most three gap lengths, the largest a few means

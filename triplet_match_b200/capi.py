@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_correspondences", "tm_icp",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -480,7 +480,7 @@ class Scene:
             n_sub = so.shape[0] - 1
         _chk(self.lib.tm_score(self.h, model.h, _p(T), C.c_uint64(n), _p(hs), _p(so), _p(si),
                                C.c_uint32(n_sub), C.c_float(dist_thres), C.c_float(accept_prob),
-                               C.c_int(1 if early_out else 0), _p(counts), _p(scores), _p(dropped)))
+                               C.c_int(int(early_out)), _p(counts), _p(scores), _p(dropped)))
         return counts, scores, dropped
 
     def correspondences(self, model: Model, T16, dist_thres: float):
@@ -552,7 +552,7 @@ class Query:
         self.lib = scene.lib
         self.scene, self.model = scene, model
         p = QueryParams(min_df, max_df, 1 if force_up else 0, query_limit, dist_thres, accept_prob,
-                        1 if early_out else 0, icp_top_k, max_icp_iterations, max_hypotheses,
+                        int(early_out), icp_top_k, max_icp_iterations, max_hypotheses,
                         hyp_limit)
         self.params = p
         self.h = C.c_void_p()
@@ -655,6 +655,20 @@ class Comm:
 
 
 # ---- host mirrors of the device-side sharding / key packing (k_query.cu, k_score.cu) ----
+def walk_stride(n: int) -> int:
+    """tm_walk_stride: stride s of the evenly sampling walk p -> (p * s) mod n (early_out = 2)."""
+    lib = load()
+    lib.tm_walk_stride.restype = C.c_uint32
+    return int(lib.tm_walk_stride(C.c_uint32(n)))
+
+
+def walk_order(n: int) -> np.ndarray:
+    """The walk as an index array: element visited at position p."""
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    return ((np.arange(n, dtype=np.uint64) * np.uint64(walk_stride(n))) % np.uint64(n)).astype(np.int64)
+
+
 def shard_range(n_hyp: int, rank: int, world: int, hyp_limit: int = 0):
     """[begin, end) of the global hypothesis list scored by `rank` (shard_range_kernel)."""
     H = min(n_hyp, hyp_limit) if hyp_limit else n_hyp

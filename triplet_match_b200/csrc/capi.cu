@@ -96,7 +96,7 @@ struct tm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     DevBuf flush;
-    DevBuf scratch[12];  // stage-call scratch, grow-only
+    DevBuf scratch[13];  // stage-call scratch, grow-only
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
@@ -810,6 +810,7 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
     REQUIRE(s && m, "null handle");
     REQUIRE(n_hyp == 0 || (T16s && counts), "tm_score: null buffer");
     REQUIRE(n_hyp < (1ull << 31), "tm_score: too many hypotheses for one call");
+    REQUIRE(early_out >= 0 && early_out <= 2, "tm_score: early_out must be 0, 1 or 2");
     tm_ctx* c = s->ctx;
     TRY(bind(c));
     if (!n_hyp) return TM_OK;
@@ -882,13 +883,23 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
         // boxes of every 32 subset positions: lets the walker skip steps that cannot reach the grid
         uint64_t max_sub = 0;
         for (uint32_t g = 0; g < n_groups; ++g) max_sub = std::max<uint64_t>(max_sub, soff[g + 1] - soff[g]);
-        const size_t n_tiles = (size_t)(soff[n_groups] / 32) + n_groups + 2;
-        TRY(w1.ensure(n_tiles * 16)); TRY(w2.ensure(n_tiles * 16));
-        launch_subset_tile_boxes(c->stream, s->dev, d_idx, dso.as<unsigned long long>(), n_groups,
-                                 (uint32_t)max_sub, w1.as<float4>(), w2.as<float4>());
         EarlyArgs a;
-        a.tile_lo = w1.as<float4>();
-        a.tile_hi = w2.as<float4>();
+        if (early_out == 2) {
+            // evenly sampling walk: the rows rewritten in walk order; consecutive positions are far apart,
+            // so there are no useful step boxes
+            DevBuf& walk = c->scratch[12];
+            TRY(walk.ensure(std::max<uint64_t>(soff[n_groups], 1) * 4));
+            launch_walk_order_rows(c->stream, d_idx, dso.as<unsigned long long>(), n_groups, (uint32_t)max_sub,
+                                   walk.as<int32_t>());
+            d_idx = walk.as<int32_t>();
+        } else {
+            const size_t n_tiles = (size_t)(soff[n_groups] / 32) + n_groups + 2;
+            TRY(w1.ensure(n_tiles * 16)); TRY(w2.ensure(n_tiles * 16));
+            launch_subset_tile_boxes(c->stream, s->dev, d_idx, dso.as<unsigned long long>(), n_groups,
+                                     (uint32_t)max_sub, w1.as<float4>(), w2.as<float4>());
+            a.tile_lo = w1.as<float4>();
+            a.tile_hi = w2.as<float4>();
+        }
         a.scene = s->dev;
         TRY(model_dev_for(c, m, thres, &a.model));
         a.sub_idx = d_idx;
@@ -926,6 +937,8 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
     }
     return TM_OK;
 }
+
+uint32_t tm_walk_stride(uint32_t n) { return walk_stride(n); }
 
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
                        uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,
@@ -1391,7 +1404,7 @@ struct tm_query {
     uint32_t items_cap = 0;
     uint64_t sub_total = 0;
     DevBuf outer, pair_outer, pair_j, outer_pair_off;
-    DevBuf ball_counts, ball_seg_off, sub_off, sub_idx;
+    DevBuf ball_counts, ball_seg_off, sub_off, sub_idx, sub_idx_walk;
     DevBuf valid, hit_begin, hit_count, hyp_off;
     DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
     DevBuf n_items_g, item_off, items, ctrl;
@@ -1410,6 +1423,7 @@ int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query
     REQUIRE(s && m && p && out, "tm_query_create: null argument");
     REQUIRE(s->ctx == m->ctx, "scene and model live in different contexts");
     REQUIRE(p->icp_top_k <= 4096, "icp_top_k too large");
+    REQUIRE(p->early_out >= 0 && p->early_out <= 2, "early_out must be 0, 1 or 2");
     tm_query* q = new tm_query();
     q->s = s;
     q->m = m;
@@ -1432,7 +1446,7 @@ void tm_query_destroy(tm_query* q) {
     if (q->ev_s1) cudaEventDestroy(q->ev_s1);
     for (DevBuf* b :
          {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
-          &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->valid, &q->hit_begin, &q->hit_count,
+          &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
           &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
@@ -1519,9 +1533,11 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
     TRY(q->item_off.ensure((n_outer + 1) * 4ull));
     TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
-    if (q->p.early_out) {
+    if (q->p.early_out == 1) {
         const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
         TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
+    } else if (q->p.early_out == 2) {
+        TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
     }
     if (q->p.icp_top_k) {
         TRY(q->icp.ensure(q->p.icp_top_k));
@@ -1619,14 +1635,20 @@ int tm_query_run(tm_query* q) {
         } else {
             launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
                                 q->g_of_hyp.as<uint32_t>());
-            launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
-                                     q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
             EarlyArgs a;
-            a.tile_lo = q->tile_lo.as<float4>();
-            a.tile_hi = q->tile_hi.as<float4>();
+            a.sub_idx = q->sub_idx.as<int32_t>();
+            if (q->p.early_out == 2) {  // evenly sampling walk order (see tm_score)
+                launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                                       q->n_outer, q->max_sub, q->sub_idx_walk.as<int32_t>());
+                a.sub_idx = q->sub_idx_walk.as<int32_t>();
+            } else {
+                launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                                         q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
+                a.tile_lo = q->tile_lo.as<float4>();
+                a.tile_hi = q->tile_hi.as<float4>();
+            }
             a.scene = sc;
             TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
-            a.sub_idx = q->sub_idx.as<int32_t>();
             a.sub_off = q->sub_off.as<unsigned long long>();
             a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
             a.T = q->T.as<float4>();

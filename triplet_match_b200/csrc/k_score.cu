@@ -17,6 +17,8 @@
 //                            of the best-pose all-reduce.
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "tm_kernels.cuh"
 
 namespace tmk {
@@ -430,6 +432,28 @@ void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int3
     ++g_launch_count;
     dim3 grid((tiles + 7) / 8, n_groups);
     subset_tile_boxes_kernel<<<grid, 256, 0, st>>>(scene, sub_idx, sub_off, tile_lo, tile_hi);
+}
+
+// rows of a subset CSR rewritten in the evenly sampling walk order: out[row + p] = in[row + (p * s) mod n]
+// (in == null: identity rows).  grid.y = group.
+__global__ void __launch_bounds__(256)
+    walk_order_rows_kernel(const int32_t* __restrict__ in, const unsigned long long* __restrict__ sub_off,
+                           int32_t* __restrict__ out) {
+    const uint32_t g = blockIdx.y;
+    const unsigned long long sb = sub_off[g];
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
+    const uint32_t s = walk_stride(n);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t e = (uint32_t)(((unsigned long long)p * s) % n);
+        out[sb + p] = in ? in[sb + e] : (int32_t)(sb + e);
+    }
+}
+void launch_walk_order_rows(cudaStream_t st, const int32_t* in, const unsigned long long* sub_off, uint32_t n_groups,
+                            uint32_t max_sub, int32_t* out) {
+    if (!n_groups || !max_sub) return;
+    ++g_launch_count;
+    const uint32_t bx = std::min<uint32_t>((max_sub + 255) / 256, 64u);
+    walk_order_rows_kernel<<<dim3(bx, n_groups), 256, 0, st>>>(in, sub_off, out);
 }
 
 template <bool FUSED>

@@ -68,6 +68,19 @@ __device__ __forceinline__ bool occ_test(const ModelDev& m, int i, int j, int k)
     return (__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u;
 }
 
+// stride of the evenly sampling walk (tm_walk_stride): floor(n * 0.6180339887) made coprime with n
+__host__ __device__ inline uint32_t walk_stride(uint32_t n) {
+    if (n <= 2u) return 1u;
+    uint32_t s = (uint32_t)(((unsigned long long)n * 2654435769ull) >> 32);  // n * (sqrt(5) - 1) / 2
+    if (s < 1u) s = 1u;
+    for (;; ++s) {
+        if (s >= n) s = 1u;
+        uint32_t a = n, b = s;
+        while (b) { const uint32_t t = a % b; a = b; b = t; }
+        if (a == 1u) return s;
+    }
+}
+
 // hypothesis transform: rows 0..2 of the 4x4 (row 3 is 0,0,0,1)
 struct Rows {
     float4 r0, r1, r2;

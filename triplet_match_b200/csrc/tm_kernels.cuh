@@ -139,6 +139,8 @@ void launch_work_count(cudaStream_t st, const unsigned long long* sub_off, const
                        uint32_t n_groups, uint32_t* n_items_g, unsigned long long* n_tests);
 void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
                       uint32_t n_groups, const uint32_t* item_off, WorkItem* items);
+void launch_walk_order_rows(cudaStream_t st, const int32_t* in, const unsigned long long* sub_off, uint32_t n_groups,
+                            uint32_t max_sub, int32_t* out);
 void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
 void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
                               const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
