@@ -152,6 +152,31 @@ static uint32_t octree_walk(Trav t, double* rows, uint32_t cap) {
     return n;
 }
 
+// ---- traits init_from_samples (cylinder impl:55-98, plane impl:46-62, plane2 impl:50-82) ----
+// samples: 3 x {pos3, normal3}; out21: ok | g2l (16, column-major) | radius | origin3
+template <typename Tr>
+static void traits_init_one(const float* samples, float threshold, float* out21) {
+    auto mh = std::make_shared<typename Tr::state_t>();
+    mh->threshold = threshold;
+    typename Tr::const_handle_t cmh = mh;
+    point_t pt[3];
+    const float z[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < 3; ++i) {
+        pt[i] = make_point(samples + 6 * i, z);
+        pt[i].normal_x = samples[6 * i + 3]; pt[i].normal_y = samples[6 * i + 4]; pt[i].normal_z = samples[6 * i + 5];
+    }
+    typename Tr::handle_t h;
+    if constexpr (Tr::sample_count == 1) h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0]));
+    else if constexpr (Tr::sample_count == 2) h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0], pt[1]));
+    else h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0], pt[1], pt[2]));
+    for (int i = 0; i < 21; ++i) out21[i] = 0.f;
+    if (!h) return;
+    out21[0] = 1.f;
+    for (int i = 0; i < 16; ++i) out21[1 + i] = h->g2l.data()[i];
+    if constexpr (std::is_same<Tr, tr::cylinder_traits<point_t>>::value) out21[17] = h->radius;
+    for (int i = 0; i < 3; ++i) out21[18 + i] = h->origin[i];
+}
+
 extern "C" {
 
 uint32_t ref_murmur4(const uint32_t* k) {
@@ -358,6 +383,15 @@ int ref_traits(int kind, const float* g2l16, const float* l2g16, float radius, f
         case 1: return traits_ops<tr::plane_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
         case 2: return traits_ops<tr::plane2_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
         default: return traits_ops<tr::identity_traits<point_t>>(g2l16, l2g16, radius, threshold, xyz, pnt_n, pnt_t, out15);
+    }
+}
+void ref_traits_init(int kind, const float* samples, uint32_t n_cases, float threshold, float* out21) {
+    for (uint32_t c = 0; c < n_cases; ++c) {
+        const float* sm = samples + 18 * (size_t)c;
+        float* o = out21 + 21 * (size_t)c;
+        if (kind == 0) traits_init_one<tr::cylinder_traits<point_t>>(sm, threshold, o);
+        else if (kind == 1) traits_init_one<tr::plane_traits<point_t>>(sm, threshold, o);
+        else traits_init_one<tr::plane2_traits<point_t>>(sm, threshold, o);
     }
 }
 // crit_kind 0 min_voxel_size, 1 max_voxel_size, 2 max_point_count; traversal 0 depth, 1 breadth, 2 leaf,

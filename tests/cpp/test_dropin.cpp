@@ -3,6 +3,7 @@
 //   test_dropin pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]   PCD reader / writer round trip
 //   test_dropin traits <in.bin> <out.bin>   project / unproject / tangent / normal / intrinsic_distance of
 //        the four traits for the states and points in <in.bin> (compared with the reference by the harness)
+//   test_dropin traits_init <in.bin> <out.bin>   init_from_samples of cylinder / plane / plane2 traits
 //   test_dropin octree <in.bin> <out.bin>   octree build + the five traversals, one row per visited node
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
@@ -253,8 +254,53 @@ static int octree_mode(const char* in_path, const char* out_path) {
     return 0;
 }
 
+// in: int32 kind | float threshold | uint32 n | n x 3 x {pos3, normal3};  out: n x {ok, g2l16, radius, origin3}
+template <typename Tr>
+static void traits_init_rows(float threshold, const std::vector<float>& in, std::vector<float>& out) {
+    auto mh = std::make_shared<typename Tr::state_t>();
+    mh->threshold = threshold;
+    typename Tr::const_handle_t cmh = mh;
+    for (size_t c = 0; c < in.size() / 18; ++c) {
+        point_t pt[3];
+        for (int i = 0; i < 3; ++i) {
+            const float* v = &in[18 * c + 6 * i];
+            pt[i].x = v[0]; pt[i].y = v[1]; pt[i].z = v[2];
+            pt[i].normal_x = v[3]; pt[i].normal_y = v[4]; pt[i].normal_z = v[5];
+        }
+        typename Tr::handle_t h;
+        if constexpr (Tr::sample_count == 1) h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0]));
+        else if constexpr (Tr::sample_count == 2) h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0], pt[1]));
+        else h = Tr::init_from_samples(cmh, typename Tr::samples_t(pt[0], pt[1], pt[2]));
+        float* o = &out[21 * c];
+        if (!h) continue;
+        o[0] = 1.f;
+        for (int i = 0; i < 16; ++i) o[1 + i] = h->g2l.data()[i];
+        if constexpr (std::is_same<Tr, tr::cylinder_traits<point_t>>::value) o[17] = h->radius;
+        for (int i = 0; i < 3; ++i) o[18 + i] = h->origin[i];
+    }
+}
+static int traits_init_mode(const char* in_path, const char* out_path) {
+    std::ifstream f(in_path, std::ios::binary);
+    int32_t kind = 0;
+    float threshold = 0.f;
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&kind), 4);
+    f.read(reinterpret_cast<char*>(&threshold), 4);
+    f.read(reinterpret_cast<char*>(&n), 4);
+    std::vector<float> in(18 * (size_t)n), out(21 * (size_t)n, 0.f);
+    f.read(reinterpret_cast<char*>(in.data()), in.size() * 4);
+    CHECK(f.good());
+    if (kind == 0) traits_init_rows<tr::cylinder_traits<point_t>>(threshold, in, out);
+    else if (kind == 1) traits_init_rows<tr::plane_traits<point_t>>(threshold, in, out);
+    else traits_init_rows<tr::plane2_traits<point_t>>(threshold, in, out);
+    std::ofstream o(out_path, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc >= 4 && std::string(argv[1]) == "traits_init") return traits_init_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "octree") return octree_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "traits") return traits_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "pcd") {  // pcd <in.pcd> <out.bin> [resave.pcd ascii|binary]

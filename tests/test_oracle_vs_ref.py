@@ -465,3 +465,54 @@ def test_reference_opencl_kernels(built):
         assert np.array_equal(rec[:sel.size].view(np.uint32), rec_o.view(np.uint32))
         assert np.all(rec[sel.size:] == 7.0)
     assert total_hits > 3000
+
+
+def test_reference_traits_init_from_samples(ref, tmp_path):
+    """init_from_samples of the cylinder / plane / plane2 traits (the frames `project` works in): drop-in
+    headers vs the reference's own code — frame, radius, origin bit for bit, and the same nullptr outcomes."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "triplet_match_b200")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_dropin.cpp"), "-o", exe, "-L" + libdir,
+                           "-ltriplet_match_b200", "-Wl,-rpath," + libdir])
+    rng = np.random.default_rng(21)
+    n = 600
+    for kind in (0, 1, 2):
+        pos = rng.standard_normal((n, 3, 3))
+        nrm = rng.standard_normal((n, 3, 3))
+        nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+        if kind == 0:  # samples on random cylinders (normals radial, + noise), plus parallel normals (denominator ~ 0)
+            for c in range(n):
+                q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+                rad, o = 0.2 + rng.random(), rng.standard_normal(3)
+                for k in range(2):
+                    th, z = rng.random() * 2 * np.pi, rng.standard_normal()
+                    loc = np.array([np.cos(th), np.sin(th), 0.0])
+                    pos[c, k] = o + q @ (rad * loc + np.array([0, 0, z]))
+                    nrm[c, k] = q @ loc + 0.02 * rng.standard_normal(3)
+            nrm[:20, 1] = nrm[:20, 0]
+        elif kind == 2:  # three points of a plane whose normals agree with it (or not: nullptr)
+            for c in range(n):
+                q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+                o = rng.standard_normal(3)
+                for k in range(3):
+                    pos[c, k] = o + q @ np.array([rng.standard_normal(), rng.standard_normal(), 0.0])
+                    nrm[c, k] = (q[:, 2] if c % 3 else rng.standard_normal(3)) + 0.05 * rng.standard_normal(3)
+            nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+        elif kind == 1:  # axis-aligned normals hit both unitOrthogonal branches
+            nrm[:6, 0] = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [1e-7, 0, 1], [0, 1e-7, 1]], dtype=np.float64)
+        samples = np.ascontiguousarray(np.concatenate([pos, nrm], axis=2).reshape(n, 18), dtype=np.float32)
+        want = np.zeros((n, 21), np.float32)
+        ref.ref_traits_init(C.c_int(kind), _p(samples), C.c_uint32(n), C.c_float(0.1), _p(want))
+        inp, outp = str(tmp_path / f"i{kind}.in"), str(tmp_path / f"i{kind}.out")
+        with open(inp, "wb") as f:
+            f.write(np.int32(kind).tobytes() + np.float32(0.1).tobytes() + np.uint32(n).tobytes() + samples.tobytes())
+        subprocess.check_call([exe, "traits_init", inp, outp])
+        got = np.fromfile(outp, dtype=np.float32).reshape(n, 21)
+        assert np.array_equal(got[:, 0], want[:, 0]), kind
+        if kind == 2:
+            assert 0 < want[:, 0].sum() < n  # both outcomes
+        bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
+        assert bad.size == 0, (kind, bad[:5], got[bad[:2]], want[bad[:2]])
