@@ -4,6 +4,7 @@
 //   test_dropin traits <in.bin> <out.bin>   project / unproject / tangent / normal / intrinsic_distance of
 //        the four traits for the states and points in <in.bin> (compared with the reference by the harness)
 //   test_dropin traits_init <in.bin> <out.bin>   init_from_samples of cylinder / plane / plane2 traits
+//   test_dropin free <in.bin> <out.bin>   feature / valid / valid_bounds / discretize_feature / murmur / std::hash
 //   test_dropin octree <in.bin> <out.bin>   octree build + the five traversals, one row per visited node
 //   test_dropin find <model.bin> <scene.bin> <out.txt>
 //        model<PointSurfel>::init + scene<PointSurfel>::find_all_parallel on clouds written by
@@ -11,6 +12,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -298,8 +300,50 @@ static int traits_init_mode(const char* in_path, const char* out_path) {
     return 0;
 }
 
+// in: float mn[4], mx[4], dist_steps, angle_step, min_rel, max_rel | uint32 n | n x {p0, t0, p1, t1} (12 floats)
+// out: n x 20 uint32 words {feature4 bits, valid, key4, murmur, hash lo, hash hi, valid_bounds min4 max4 bits (case 0 only)}
+static int free_mode(const char* in_path, const char* out_path) {
+    std::ifstream f(in_path, std::ios::binary);
+    float hdr[12];
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
+    f.read(reinterpret_cast<char*>(&n), 4);
+    std::vector<float> in(12 * (size_t)n);
+    f.read(reinterpret_cast<char*>(in.data()), in.size() * 4);
+    CHECK(f.good());
+    tr::feature_bounds_t b;
+    for (int i = 0; i < 4; ++i) { b.min()[i] = hdr[i]; b.max()[i] = hdr[4 + i]; }
+    const tr::discretization_params dp{hdr[8], hdr[9], 10.f};
+    const tr::feature_bounds_t vb = tr::valid_bounds(b, 0.f, 0.f, hdr[10], hdr[11]);
+    std::vector<uint32_t> out(20 * (size_t)n, 0u);
+    for (size_t c = 0; c < n; ++c) {
+        const float* v = &in[12 * c];
+        point_t a, q;
+        a.x = v[0]; a.y = v[1]; a.z = v[2];
+        tr::set_tangent(a, tr::vec3f_t(v[3], v[4], v[5]));
+        q.x = v[6]; q.y = v[7]; q.z = v[8];
+        tr::set_tangent(q, tr::vec3f_t(v[9], v[10], v[11]));
+        const tr::feature_t ft = *tr::feature<point_t>(a, q);
+        uint32_t* o = &out[20 * c];
+        for (int i = 0; i < 4; ++i) std::memcpy(&o[i], &ft[i], 4);
+        o[4] = tr::valid<point_t>(ft, vb) ? 1u : 0u;
+        const tr::discrete_feature_t key = tr::discretize_feature<point_t>(ft, b, dp);
+        for (int i = 0; i < 4; ++i) o[5 + i] = key[i];
+        o[9] = tr::detail::murmur<4>(key);
+        const uint64_t h = std::hash<tr::discrete_feature_t>()(key);
+        o[10] = (uint32_t)h;
+        o[11] = (uint32_t)(h >> 32);
+        if (c == 0)
+            for (int i = 0; i < 4; ++i) { std::memcpy(&o[12 + i], &vb.min()[i], 4); std::memcpy(&o[16 + i], &vb.max()[i], 4); }
+    }
+    std::ofstream o(out_path, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(out.data()), out.size() * 4);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return cpu_checks();
+    if (argc >= 4 && std::string(argv[1]) == "free") return free_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "traits_init") return traits_init_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "octree") return octree_mode(argv[2], argv[3]);
     if (argc >= 4 && std::string(argv[1]) == "traits") return traits_mode(argv[2], argv[3]);

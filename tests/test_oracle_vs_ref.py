@@ -516,3 +516,53 @@ def test_reference_traits_init_from_samples(ref, tmp_path):
             assert 0 < want[:, 0].sum() < n  # both outcomes
         bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
         assert bad.size == 0, (kind, bad[:5], got[bad[:2]], want[bad[:2]])
+
+
+def test_reference_free_functions_dropin_headers(ref, tmp_path):
+    """include/triplet_match/{feature,discretize} (the drop-in's host copies of rows a1-a4) against the
+    reference's own functions on random and degenerate pairs, bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "triplet_match_b200")
+    exe = str(tmp_path / "test_dropin")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_dropin.cpp"), "-o", exe, "-L" + libdir,
+                           "-ltriplet_match_b200", "-Wl,-rpath," + libdir])
+    rng = np.random.default_rng(31)
+    n = 4000
+    pairs = rng.standard_normal((n, 12)).astype(np.float32)
+    pairs[:, 3:6] /= np.linalg.norm(pairs[:, 3:6], axis=1, keepdims=True)
+    pairs[:, 9:12] /= np.linalg.norm(pairs[:, 9:12], axis=1, keepdims=True)
+    pairs[:50, 6:9] = pairs[:50, 0:3]            # coincident points: d = 0
+    pairs[50:100, 3:6] = 0                       # zero tangent
+    pairs[100:150, 6:9] = pairs[100:150, 0:3] + 0.3 * pairs[100:150, 3:6]  # d parallel to t0
+    pairs[150:200] *= 1e-3
+    mn = np.array([0.2, 0.0, 0.0, 0.2], np.float32)
+    mx = np.array([3.7, np.pi, np.pi, 3.7], np.float32)
+    dist_steps, angle_step, min_rel, max_rel = np.float32(20.0), np.float32(0.17453292), np.float32(0.2), np.float32(0.9)
+    inp, outp = str(tmp_path / "free.in"), str(tmp_path / "free.out")
+    with open(inp, "wb") as f:
+        f.write(mn.tobytes() + mx.tobytes() + dist_steps.tobytes() + angle_step.tobytes() + min_rel.tobytes() + max_rel.tobytes())
+        f.write(np.uint32(n).tobytes() + np.ascontiguousarray(pairs).tobytes())
+    subprocess.check_call([exe, "free", inp, outp])
+    got = np.fromfile(outp, dtype=np.uint32).reshape(n, 20)
+    ref.ref_valid.restype = C.c_int
+    vmn, vmx = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    ref.ref_valid_bounds(_p(mn), _p(mx), C.c_float(min_rel), C.c_float(max_rel), _p(vmn), _p(vmx))
+    assert np.array_equal(got[0, 12:16], vmn.view(np.uint32)) and np.array_equal(got[0, 16:20], vmx.view(np.uint32))
+    n_valid = 0
+    for c in range(n):
+        ft, key = np.zeros(4, np.float32), np.zeros(4, np.uint32)
+        ref.ref_feature(_p(pairs[c]), _p(ft))
+        same = (got[c, :4] == ft.view(np.uint32)) | (np.isnan(ft) & np.isnan(got[c, :4].view(np.float32)))
+        assert same.all(), (c, got[c, :4].view(np.float32), ft)
+        v = ref.ref_valid(_p(ft), _p(vmn), _p(vmx))
+        assert got[c, 4] == v, c
+        n_valid += v
+        if np.isnan(ft).any():
+            continue  # float -> uint32 of NaN is undefined in both
+        ref.ref_discretize_feature(_p(ft), _p(mn), _p(mx), C.c_float(dist_steps), C.c_float(angle_step), _p(key))
+        assert np.array_equal(got[c, 5:9], key), (c, got[c, 5:9], key)
+        assert got[c, 9] == ref.ref_murmur4(_p(key))
+        assert (int(got[c, 11]) << 32 | int(got[c, 10])) == ref.ref_std_hash4(_p(key))
+    assert 0 < n_valid < n
