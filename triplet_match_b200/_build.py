@@ -20,7 +20,6 @@ CSRC = os.path.join(ROOT, "csrc")
 _SUFFIX = os.environ.get("TM_LIB_SUFFIX", "")
 OBJ = os.path.join(ROOT, "_obj" + _SUFFIX)
 LIB = os.path.join(ROOT, "libtriplet_match_b200" + _SUFFIX + ".so")
-HOSTLIB = os.path.join(ROOT, "libtriplet_match_host.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
