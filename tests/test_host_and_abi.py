@@ -145,6 +145,10 @@ def test_walk_stride_is_a_permutation_with_even_prefixes(built):
         assert 1 <= st < n and math.gcd(st, n) == 1, (n, st)
         if n >= 30:
             assert abs(st / n - 0.6180339887) < 0.2, (n, st)
+    # known answers: the rule is part of the C-ABI contract (include/tm_b200.h), host and device share it
+    kat = {3: 1, 4: 3, 5: 3, 6: 5, 10: 7, 30: 19, 64: 39, 100: 61, 1000: 619, 1024: 633, 56789: 35097,
+           1 << 20: 648055, 999983: 618023, 2 ** 32 - 1: 2654435768}
+    assert {n: capi.walk_stride(n) for n in kat} == kat
     for n in (1, 2, 5, 64, 1000, 56789):
         w = capi.walk_order(n)
         assert np.array_equal(np.sort(w), np.arange(n))
