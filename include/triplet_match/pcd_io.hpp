@@ -3,9 +3,10 @@
 // pcl::io::loadPCDFile, apps/triplet_match.cpp:14-15,33-34 and include/impl/pointcloud.hpp:60-64).
 // Fields are matched by name: x y z | normal_x normal_y normal_z | rgba (or rgb) | radius
 // confidence curvature (the tangent overlays the last three, include/common:62-70);
-// tangent_x/y/z are accepted as aliases.  Missing fields stay zero.  DATA ascii and binary are
-// supported; binary_compressed (LZF) is reported as an error.  SIZE 4 / 8 floats, 1 / 2 / 4 byte
-// integers.
+// tangent_x/y/z are accepted as aliases.  Missing fields stay zero.  DATA ascii, binary and
+// binary_compressed (PCL's layout: u32 compressed size, u32 raw size, LZF stream of the records
+// transposed field by field) are read; the writer emits ascii or binary.  SIZE 4 / 8 floats,
+// 1 / 2 / 4 byte integers.
 #ifndef TRIPLET_MATCH_PCD_IO_HPP_
 #define TRIPLET_MATCH_PCD_IO_HPP_
 
@@ -60,6 +61,36 @@ inline double read_scalar(const char* p, const field_t& f) {
             break;
     }
     throw std::runtime_error("pcd: unsupported field type/size for '" + f.name + "'");
+}
+
+// LZF (liblzf) stream -> exactly out.size() bytes.  Control byte c: c < 32 copies c + 1 literal bytes;
+// otherwise a back-reference of length (c >> 5) + 2 (length field 7: + the next byte) at distance
+// ((c & 31) << 8 | next byte) + 1, which may overlap its own output.
+inline bool lzf_decompress(const unsigned char* in, size_t n_in, std::vector<char>& out) {
+    size_t ip = 0, op = 0;
+    const size_t n_out = out.size();
+    while (ip < n_in) {
+        const unsigned c = in[ip++];
+        if (c < 32u) {
+            const size_t run = c + 1u;
+            if (ip + run > n_in || op + run > n_out) return false;
+            std::memcpy(&out[op], in + ip, run);
+            ip += run;
+            op += run;
+        } else {
+            size_t len = c >> 5;
+            if (len == 7u) {
+                if (ip >= n_in) return false;
+                len += in[ip++];
+            }
+            if (ip >= n_in) return false;
+            const size_t dist = (static_cast<size_t>(c & 31u) << 8 | in[ip++]) + 1u;
+            len += 2u;
+            if (dist > op || op + len > n_out) return false;
+            for (size_t k = 0; k < len; ++k, ++op) out[op] = out[op - dist];
+        }
+    }
+    return op == n_out;
 }
 
 inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out) {
@@ -143,8 +174,33 @@ inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out
                 store(out[i], slot, f, slot == 8 && f.size == 4 ? 0.0 : read_scalar(p, f), p);
             }
         }
+    } else if (data_kind == "binary_compressed") {
+        uint32_t sizes[2] = {0u, 0u};  // compressed, raw
+        in.read(reinterpret_cast<char*>(sizes), 8);
+        if (in.gcount() != 8) throw std::runtime_error("pcd: truncated binary_compressed header in '" + filename + "'");
+        if (static_cast<uint64_t>(sizes[1]) != static_cast<uint64_t>(rec) * points)
+            throw std::runtime_error("pcd: binary_compressed size does not match FIELDS x POINTS in '" + filename + "'");
+        std::vector<unsigned char> packed(sizes[0]);
+        in.read(reinterpret_cast<char*>(packed.data()), static_cast<std::streamsize>(packed.size()));
+        if (static_cast<size_t>(in.gcount()) != packed.size())
+            throw std::runtime_error("pcd: truncated binary_compressed data in '" + filename + "'");
+        std::vector<char> buf(sizes[1]);
+        if (!lzf_decompress(packed.data(), packed.size(), buf))
+            throw std::runtime_error("pcd: corrupt LZF stream in '" + filename + "'");
+        // field-major: all values of field 0, then field 1, ... (each value f.size * f.count bytes)
+        size_t column = 0;
+        for (const auto& f : fields) {
+            const int slot = surfel_slot(f.name);
+            const size_t stride = static_cast<size_t>(f.size) * f.count;
+            if (slot >= 0)
+                for (uint64_t i = 0; i < points; ++i) {
+                    const char* p = buf.data() + column + stride * i;
+                    store(out[i], slot, f, slot == 8 && f.size == 4 ? 0.0 : read_scalar(p, f), p);
+                }
+            column += stride * points;
+        }
     } else {
-        throw std::runtime_error("pcd: DATA '" + data_kind + "' is not supported (ascii and binary are)");
+        throw std::runtime_error("pcd: DATA '" + data_kind + "' is not supported (ascii, binary, binary_compressed are)");
     }
     for (auto& p : out) p.data[3] = 1.f;
 }

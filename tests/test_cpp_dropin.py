@@ -117,6 +117,92 @@ def _surfels(path, n):
     return raw
 
 
+def _lzf_compress(data: bytes, literal_only=False) -> bytes:
+    """A small LZF encoder for the tests (format of liblzf / PCL's binary_compressed): greedy matches found
+    through a 3-byte hash of the last position, literal runs of at most 32 bytes."""
+    out = bytearray()
+    lit = bytearray()
+
+    def flush():
+        for k in range(0, len(lit), 32):
+            chunk = lit[k:k + 32]
+            out.append(len(chunk) - 1)
+            out.extend(chunk)
+        lit.clear()
+
+    last = {}
+    i, n = 0, len(data)
+    while i < n:
+        best_len = 0
+        if not literal_only and i + 3 <= n:
+            key = data[i:i + 3]
+            j = last.get(key)
+            last[key] = i
+            if j is not None and 0 < i - j <= 8192:
+                m = 0
+                while i + m < n and m < 264 and data[j + m] == data[i + m]:  # overlapping matches are legal
+                    m += 1
+                if m >= 3:
+                    best_len, dist = m, i - j - 1
+        if best_len:
+            flush()
+            ln = best_len - 2
+            if ln < 7:
+                out.append((ln << 5) | (dist >> 8))
+            else:
+                out.append((7 << 5) | (dist >> 8))
+                out.append(ln - 7)
+            out.append(dist & 0xFF)
+            i += best_len
+        else:
+            lit.append(data[i])
+            i += 1
+    flush()
+    return bytes(out)
+
+
+def test_pcd_binary_compressed(exe, tmp_path):
+    """PCL's DATA binary_compressed: u32 compressed size, u32 raw size, LZF stream of the field-major records."""
+    m, *_ = common.config("plane_small")
+    src_b, out_b = str(tmp_path / "plain.pcd"), str(tmp_path / "plain.bin")
+    rec = write_pcd(m, src_b, binary=True)
+    assert subprocess.run([exe, "pcd", src_b, out_b], capture_output=True).returncode == 0
+    fields = ["x", "y", "z", "normal_x", "normal_y", "normal_z", "rgba", "radius", "confidence", "curvature"]
+    raw = np.ascontiguousarray(rec.T).tobytes()  # field-major
+    for literal_only in (False, True):
+        packed = _lzf_compress(raw, literal_only)
+        if not literal_only:
+            assert len(packed) < len(raw)  # the plane's constant normals compress: back-references are exercised
+        p = str(tmp_path / "c.pcd")
+        with open(p, "wb") as f:
+            f.write(_pcd_header(fields, [4] * 10, ["F"] * 6 + ["U"] + ["F"] * 3, m.n, "binary_compressed"))
+            f.write(np.uint32(len(packed)).tobytes() + np.uint32(len(raw)).tobytes() + packed)
+        out = str(tmp_path / "c.bin")
+        r = subprocess.run([exe, "pcd", p, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert np.array_equal(np.fromfile(out, np.uint32), np.fromfile(out_b, np.uint32))
+    # a run of one byte: the back-reference overlaps its own output
+    ones = np.full((64, 3), 1.0, np.float32)
+    raw = np.ascontiguousarray(ones.T).tobytes()
+    packed = _lzf_compress(raw)
+    assert len(packed) < 40
+    p = str(tmp_path / "o.pcd")
+    with open(p, "wb") as f:
+        f.write(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, 64, "binary_compressed"))
+        f.write(np.uint32(len(packed)).tobytes() + np.uint32(len(raw)).tobytes() + packed)
+    out = str(tmp_path / "o.bin")
+    assert subprocess.run([exe, "pcd", p, out], capture_output=True).returncode == 0
+    assert np.array_equal(_surfels(out, 64)[:, 0:3], ones)
+    # corrupt streams and inconsistent sizes are errors, not crashes
+    for blob in (np.uint32(len(packed)).tobytes() + np.uint32(len(raw)).tobytes() + packed[:-3],          # truncated
+                 np.uint32(len(packed)).tobytes() + np.uint32(len(raw) + 4).tobytes() + packed,            # wrong raw size
+                 np.uint32(4).tobytes() + np.uint32(len(raw)).tobytes() + bytes([0xE0, 0xFF, 0xFF, 0x00]),  # reference before start
+                 np.uint32(len(packed) - 1).tobytes() + np.uint32(len(raw)).tobytes() + packed[:-1]):      # short output
+        with open(p, "wb") as f:
+            f.write(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, 64, "binary_compressed") + blob)
+        assert subprocess.run([exe, "pcd", p, out], capture_output=True).returncode == 3
+
+
 def test_pcd_reader_and_writer(exe, tmp_path):
     m, *_ = common.config("plane_small")
     for binary in (True, False):
