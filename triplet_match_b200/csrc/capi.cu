@@ -49,6 +49,8 @@ struct Knobs {
     int fused_grid = -1;           // TM_FUSED_GRID=0/1: force the unfused / fused voxel grid
     int score_grid = 0;            // TM_SCORE_GRID=n: CTAs of the scoring kernel
     bool score_stats = false;      // TM_SCORE_STATS=1: cull / inlier statistics of the scoring kernel on stderr
+    int scorer = 8;                // TM_SCORER=7: the fused count+score kernel everywhere (A/B against the count-only
+                                   // packed-FP32 kernel + lazy score, which is the default where scores are not asked for)
 };
 static const Knobs& knobs() {
     static const Knobs k = [] {
@@ -57,6 +59,7 @@ static const Knobs& knobs() {
         if (const char* e = getenv("TM_FUSED_GRID")) v.fused_grid = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("TM_SCORE_GRID")) v.score_grid = std::max(1, atoi(e));
         v.score_stats = getenv("TM_SCORE_STATS") != nullptr;
+        if (const char* e = getenv("TM_SCORER")) v.scorer = atoi(e);
         return v;
     }();
     return k;
@@ -100,6 +103,7 @@ struct tm_ctx {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
+    int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
 };
 
 struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
@@ -795,10 +799,17 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
     a.scores = d_scores;
     a.sq_thres = sq_thres;
     a.stats = nullptr;
-    int& b = c->score_bps[m->fused ? 1 : 0][with_score ? 1 : 0];
-    if (!b) b = score_full_max_blocks_per_sm(m->fused, with_score);
-    const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
-    launch_score_full(c->stream, a, grid, m->fused, with_score);
+    if (!with_score && knobs().scorer >= 8) {
+        int& b = c->count_bps[m->fused ? 1 : 0];
+        if (!b) b = score_count_x2_max_blocks_per_sm(m->fused);
+        const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+        launch_score_count_x2(c->stream, a, grid, m->fused);
+    } else {
+        int& b = c->score_bps[m->fused ? 1 : 0][with_score ? 1 : 0];
+        if (!b) b = score_full_max_blocks_per_sm(m->fused, with_score);
+        const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+        launch_score_full(c->stream, a, grid, m->fused, with_score);
+    }
     CU(cudaGetLastError());
     return TM_OK;
 }
@@ -1391,6 +1402,7 @@ struct QueryOut {  // one contiguous device block, read back in one copy
     uint32_t err;
     uint32_t work_counter;
     uint32_t pad;
+    unsigned long long best_acc[2];  // lazy score of the selected pose: fixed-point sum, inlier count
 };
 
 struct tm_query {
@@ -1414,6 +1426,9 @@ struct tm_query {
     IcpBufs icp;
     QueryOut host_out;
     bool ran = false;
+    bool lazy = false;          // last run used the count-only scorer: scores[] is filled on demand
+    bool scores_valid = false;  // scores[] holds every hypothesis' score
+    float run_thres = 0.f, run_sqt = 0.f;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the scoring kernel
 };
 
@@ -1549,6 +1564,57 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     return TM_OK;
 }
 
+// export the pose and score of the hypothesis named by out->best (if this shard owns it).  After the count-only
+// scorer the score of that one pose is summed here (score_best_kernel); scores[] stays empty until asked for.
+static int finalize_best(tm_query* q) {
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    const unsigned long long* lazy_acc = nullptr;
+    if (q->lazy && !q->scores_valid) {
+        ModelDev md;
+        TRY(model_dev_for(c, q->m, q->run_thres, &md));
+        CU(cudaMemsetAsync(out->best_acc, 0, 16, c->stream));
+        launch_score_best(c->stream, q->s->dev, md, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                          q->g_hyp.as<uint32_t>(), q->n_outer, q->T.as<float4>(), &out->best, out->shard, q->run_sqt,
+                          out->best_acc, q->m->fused);
+        lazy_acc = out->best_acc;
+    }
+    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(), q->scores.as<unsigned long long>(),
+                         lazy_acc, q->m->dev.cloud.n, out->best_T16, &out->best_score);
+    return TM_OK;
+}
+
+// scores[] of every hypothesis on request (tm_query_download): re-run the scoring pass with the fused
+// count+score kernel over the resident work list.  Counts go to a scratch array and must come out the same.
+static int ensure_scores(tm_query* q) {
+    if (q->scores_valid || !q->lazy || !q->n_outer) return TM_OK;
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    DevBuf& cnt2 = c->scratch[5];
+    TRY(cnt2.ensure(q->cap_hyp * 4));
+    CU(cudaMemsetAsync(cnt2.p, 0, q->cap_hyp * 4, c->stream));
+    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
+    CU(cudaMemsetAsync(&out->work_counter, 0, 4, c->stream));
+    ScoreArgs a;
+    a.scene = q->s->dev;
+    TRY(model_dev_for(c, q->m, q->run_thres, &a.model));
+    a.sub_idx = q->sub_idx.as<int32_t>();
+    a.items = q->items.as<WorkItem>();
+    a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
+    a.work_counter = &out->work_counter;
+    a.T = q->T.as<float4>();
+    a.counts = cnt2.as<uint32_t>();
+    a.scores = q->scores.as<unsigned long long>();
+    a.sq_thres = q->run_sqt;
+    a.stats = nullptr;
+    int& b = c->score_bps[q->m->fused ? 1 : 0][1];
+    if (!b) b = score_full_max_blocks_per_sm(q->m->fused, true);
+    launch_score_full(c->stream, a, c->sm_count * b, q->m->fused, true);
+    CU(cudaGetLastError());
+    q->scores_valid = true;
+    return TM_OK;
+}
+
 int tm_query_run(tm_query* q) {
     REQUIRE(q, "null query");
     tm_ctx* c = q->s->ctx;
@@ -1600,6 +1666,9 @@ int tm_query_run(tm_query* q) {
     // (a10) scoring
     const float thres = q->p.dist_thres * m->dev.resolution;
     const float sqt = sq_threshold(thres);
+    q->lazy = false;
+    q->run_thres = thres;
+    q->run_sqt = sqt;
     if (q->n_outer) {
         if (!q->p.early_out) {
             launch_work_count(c->stream, q->sub_off.as<unsigned long long>(),
@@ -1626,12 +1695,22 @@ int tm_query_run(tm_query* q) {
                 CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
                 a.stats = q->stats.as<unsigned long long>();
             }
-            int& b = c->score_bps[m->fused ? 1 : 0][1];
-            if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
-            const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
-            CU(cudaEventRecord(q->ev_s0, c->stream));
-            launch_score_full(c->stream, a, grid, m->fused, true);
-            CU(cudaEventRecord(q->ev_s1, c->stream));
+            q->lazy = knobs().scorer >= 8;
+            if (q->lazy) {
+                int& b = c->count_bps[m->fused ? 1 : 0];
+                if (!b) b = score_count_x2_max_blocks_per_sm(m->fused);
+                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+                CU(cudaEventRecord(q->ev_s0, c->stream));
+                launch_score_count_x2(c->stream, a, grid, m->fused);
+                CU(cudaEventRecord(q->ev_s1, c->stream));
+            } else {
+                int& b = c->score_bps[m->fused ? 1 : 0][1];
+                if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
+                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+                CU(cudaEventRecord(q->ev_s0, c->stream));
+                launch_score_full(c->stream, a, grid, m->fused, true);
+                CU(cudaEventRecord(q->ev_s1, c->stream));
+            }
         } else {
             launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
                                 q->g_of_hyp.as<uint32_t>());
@@ -1681,11 +1760,10 @@ int tm_query_run(tm_query* q) {
                            q->icp.Tcur.as<float4>(), q->icp.active.as<uint32_t>());
         TRY(icp_enqueue(c, sc, m, q->icp, q->p.icp_top_k, q->p.max_icp_iterations, q->p.dist_thres));
     }
-    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
-                         q->scores.as<unsigned long long>(), m->dev.cloud.n, out->best_T16,
-                         &out->best_score);
+    TRY(finalize_best(q));
     CU(cudaGetLastError());
     q->ran = true;
+    q->scores_valid = !q->lazy;
     return TM_OK;
 }
 
@@ -1740,9 +1818,7 @@ int tm_query_set_global_best(tm_query* q, uint64_t key) {
     CU(cudaMemcpyAsync(&out->best, &key, 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
     CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
-                         q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
-                         &out->best_score);
+    TRY(finalize_best(q));
     CU(cudaGetLastError());
     return TM_OK;
 }
@@ -1771,6 +1847,7 @@ int tm_query_download(tm_query* q, uint64_t capacity, uint32_t* counts, double* 
         CU(cudaMemcpyAsync(dr.data(), q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
     }
     if (scores) {
+        TRY(ensure_scores(q));
         fx.resize(n);
         CU(cudaMemcpyAsync(fx.data(), q->scores.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -1920,9 +1997,7 @@ int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* cm) {
         CU(cudaMemcpyAsync(&out->best, keys + i, 8, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
         CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-        launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
-                             q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
-                             &out->best_score);
+        TRY(finalize_best(q));
         CU(cudaMemcpyAsync(recs + 72 * (size_t)i, &out->best_score, 72, cudaMemcpyDeviceToDevice, c->stream));
     }
     CU(cudaGetLastError());
@@ -1962,9 +2037,7 @@ int tm_query_allreduce_best(tm_query* q, tm_comm* cm) {
     // the owner re-exports the winning pose; everybody else contributes zeros
     CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
     CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(),
-                         q->scores.as<unsigned long long>(), q->m->dev.cloud.n, out->best_T16,
-                         &out->best_score);
+    TRY(finalize_best(q));
     CU(cudaGetLastError());
     // best_score (8 B) and best_T16 (64 B) are adjacent in QueryOut
     NC(g_nccl.AllReduce(&out->best_score, &out->best_score, 72, ncclUint8_, ncclSum_, cm->comm,

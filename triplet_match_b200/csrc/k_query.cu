@@ -187,6 +187,7 @@ __global__ void finalize_best_kernel(const unsigned long long* __restrict__ best
                                      const unsigned long long* __restrict__ shard,
                                      const float4* __restrict__ T,
                                      const unsigned long long* __restrict__ scores,
+                                     const unsigned long long* __restrict__ lazy_acc,
                                      uint32_t model_n, float* __restrict__ best_T16,
                                      double* __restrict__ best_score) {
     unsigned long long key = *best;
@@ -203,14 +204,16 @@ __global__ void finalize_best_kernel(const unsigned long long* __restrict__ best
     }
     best_T16[3] = best_T16[7] = best_T16[11] = 0.f;
     best_T16[15] = 1.f;
-    if (scores) *best_score = (double)scores[l] / SCORE_SCALE / (double)model_n;
+    // lazy_acc: the selected pose's score summed by score_best_kernel (count-only bulk scorer)
+    if (lazy_acc) *best_score = (double)lazy_acc[0] / SCORE_SCALE / (double)model_n;
+    else if (scores) *best_score = (double)scores[l] / SCORE_SCALE / (double)model_n;
 }
 void launch_finalize_best(cudaStream_t st, const unsigned long long* best,
                           const unsigned long long* shard, const float4* T,
-                          const unsigned long long* scores, uint32_t model_n, float* best_T16,
-                          double* best_score) {
+                          const unsigned long long* scores, const unsigned long long* lazy_acc, uint32_t model_n,
+                          float* best_T16, double* best_score) {
     ++g_launch_count;
-    finalize_best_kernel<<<1, 1, 0, st>>>(best, shard, T, scores, model_n, best_T16, best_score);
+    finalize_best_kernel<<<1, 1, 0, st>>>(best, shard, T, scores, lazy_acc, model_n, best_T16, best_score);
 }
 
 }  // namespace tmk

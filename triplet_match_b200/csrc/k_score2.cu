@@ -1,0 +1,333 @@
+// k_score2.cu — the count-only bulk scorer (v8) and the lazy score pass.
+//
+//   score_count_x2_kernel   project_ with early_out = false (include/impl/scene.hpp:411-510 through
+//                           finish_find semantics), inlier COUNTS only.  Same work decomposition as
+//                           score_full_kernel (k_score.cu): warp-granular (tile, hypothesis chunk)
+//                           items, box cull per 32 hypotheses, exact test for the survivors.  What is
+//                           new is the arithmetic unit: the reference's no-FMA sequence is evaluated
+//                           two points at a time on the packed FP32 pipe (FFMA2) WITHOUT giving up a
+//                           single rounding:
+//                               a * b  ==  fma(a, b, -0)      (one rounding of the exact product;
+//                                                              (+0) + (-0) = +0, (-0) + (-0) = -0)
+//                               a + b  ==  fma(a,  1,  b)     (one rounding of the exact sum)
+//                               a - b  ==  fma(b, -1,  a)
+//                           The constants -0, 1, -1 arrive as kernel arguments, so ptxas cannot fold
+//                           fma(a, b, -0) back into a multiply and contract it with the add that
+//                           follows (which it does for mul.rn.f32x2 + add.rn.f32x2 even under
+//                           -fmad=false).  One FFMA2 issue slot then does the work of two FMUL or two
+//                           FADD; the scorer is issue-bound, not FP32-pipe-bound.
+//   score_best_kernel       Σ|ref·ref_n| (scene.hpp:461,479-483) of the selected pose only: the
+//                           per-hypothesis score is not part of the selection (argmax / top-k use
+//                           counts), so the bulk pass does not pay an LDS.128 + LDG.128 + ~30
+//                           instructions per inlier for it.
+#include <cstring>
+
+#include "tm_kernels.cuh"
+
+namespace tmk {
+
+// ---- exact packed FP32 -----------------------------------------------------------------------------
+// A pair of floats lives in one 64-bit register (p2) from load to last use, so ptxas allocates it an aligned
+// register pair once instead of re-assembling it from two scalars for every FFMA2.
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 pack2(float lo, float hi) {
+    p2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(p2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(p2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ p2 ffma2(p2 a, p2 b, p2 c) {
+    p2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ p2 splat(float v) { return pack2(v, v); }
+struct X2 {  // the three opaque constants
+    p2 nz, one, mone;
+    __device__ __forceinline__ p2 mul(p2 a, p2 b) const { return ffma2(a, b, nz); }
+    __device__ __forceinline__ p2 mul(float a, p2 b) const { return ffma2(splat(a), b, nz); }
+    __device__ __forceinline__ p2 add(p2 a, p2 b) const { return ffma2(a, one, b); }
+    __device__ __forceinline__ p2 add(p2 a, float b) const { return ffma2(a, one, splat(b)); }
+    // row of Matrix4f * (x,y,z,1) for two points: ((r.x*x + r.y*y) + r.z*z) + r.w  (tm_device.cuh row_apply)
+    __device__ __forceinline__ p2 row_apply(float4 r, p2 x, p2 y, p2 z) const {
+        return add(add(add(mul(r.x, x), mul(r.y, y)), mul(r.z, z)), r.w);
+    }
+    // a0 + (a1 + a2) (tm_device.cuh sum3) of the squares
+    __device__ __forceinline__ p2 sqnorm(p2 dx, p2 dy, p2 dz) const {
+        return add(mul(dx, dx), add(mul(dy, dy), mul(dz, dz)));
+    }
+};
+
+template <bool FUSED, bool OCC, bool STATS>
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
+    score_count_x2_kernel(ScoreArgs a, p2 k_nz, p2 k_one, p2 k_mone) {
+    static_assert(SCORE_P == 4, "two point pairs per lane");
+    __shared__ float4 s_rows[(SCORE_THREADS / 32) * 32 * 3];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float4* my_rows = s_rows + warp * 32 * 3;
+    const uint32_t n_items = *a.n_items;
+    const ModelDev& m = a.model;
+    X2 e;
+    e.nz = k_nz; e.one = k_one; e.mone = k_mone;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const WorkItem w = a.items[item];
+        // points k = 0..3 of this lane: pairs A = (0, 1), B = (2, 3)
+        float px[4], py[4], pz[4];
+        uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
+        const float nanv = __int_as_float(0x7fc00000);
+        float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t q = k * 32 + lane;
+            px[k] = py[k] = pz[k] = nanv;  // a NaN point fails every test
+            if (q < w.npts) {
+                const uint32_t idx = a.sub_idx ? (uint32_t)a.sub_idx[w.sub_begin + q] : (uint32_t)(w.sub_begin + q);
+                const float4 v = a.scene.pos[idx];
+                const uint32_t fl = __float_as_uint(v.w);
+                if (!(fl & FLAG_MASKED)) {  // mask_ (scene.hpp:434)
+                    px[k] = v.x; py[k] = v.y; pz[k] = v.z;
+                    if (fl & FLAG_TANGENT) tflags |= 1u << k;
+                    mnx = fminf(mnx, v.x); mxx = fmaxf(mxx, v.x);
+                    mny = fminf(mny, v.y); mxy = fmaxf(mxy, v.y);
+                    mnz = fminf(mnz, v.z); mxz = fmaxf(mxz, v.z);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+            mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+        }
+        if (!(mnx <= mxx)) continue;  // no live (finite, unmasked) point in this tile
+        const float cx = 0.5f * (mnx + mxx), hx = 0.5f * (mxx - mnx);
+        const float cy = 0.5f * (mny + mxy), hy = 0.5f * (mxy - mny);
+        const float cz = 0.5f * (mnz + mxz), hz = 0.5f * (mxz - mnz);
+        // v * 1 + (-0) == v for every v (signed zeros and NaN included): the pairs become results of an FFMA2, which
+        // pins them to aligned register pairs for the whole hypothesis loop (ptxas otherwise re-packs per use)
+        const p2 pxA = e.add(pack2(px[0], px[1]), e.nz), pyA = e.add(pack2(py[0], py[1]), e.nz),
+                 pzA = e.add(pack2(pz[0], pz[1]), e.nz);
+        const p2 pxB = e.add(pack2(px[2], px[3]), e.nz), pyB = e.add(pack2(py[2], py[3]), e.nz),
+                 pzB = e.add(pack2(pz[2], pz[3]), e.nz);
+        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {
+            const uint32_t h = h0 + lane;
+            bool survive = false;
+            __syncwarp();  // readers of the previous batch's rows are done
+            if (h < w.hyp_end) {  // cull: identical to score_full_kernel (interval test, NaN never culls)
+                const float4 r0 = __ldg(&a.T[3 * (size_t)h]), r1 = __ldg(&a.T[3 * (size_t)h + 1]),
+                             r2 = __ldg(&a.T[3 * (size_t)h + 2]);
+                my_rows[lane] = r0;
+                my_rows[32 + lane] = r1;
+                my_rows[64 + lane] = r2;
+                const float acx = fabsf(cx) + hx, acy = fabsf(cy) + hy, acz = fabsf(cz) + hz;
+                bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                  \
+    {                                                                                           \
+        float cc = r.x * cx + r.y * cy + r.z * cz + r.w;                                        \
+        float ee = fabsf(r.x) * hx + fabsf(r.y) * hy + fabsf(r.z) * hz;                         \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
+        ee += 1e-5f * mag + 1e-30f;                                                             \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
+        float lo = S * (cc - ee) + TV - sl, hi = S * (cc + ee) + TV + sl;                       \
+        out = out || (lo >= EXF) || (hi <= -1.0f);                                              \
+    }
+                TM_AXIS(r0, m.sx, m.tx, m.exf)
+                TM_AXIS(r1, m.sy, m.ty, m.eyf)
+                TM_AXIS(r2, m.sz, m.tz, m.ezf)
+#undef TM_AXIS
+                survive = !out;
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, survive);  // also orders the smem stores
+            if (STATS && lane == 0) {
+                atomicAdd(&a.stats[0], (unsigned long long)min(32u, w.hyp_end - h0));
+                atomicAdd(&a.stats[1], (unsigned long long)__popc(mask));
+            }
+            uint32_t mycnt = 0;
+            while (mask) {
+                const int hh = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const float4 r0 = my_rows[hh], r1 = my_rows[32 + hh], r2 = my_rows[64 + hh];
+                // ---- pos = t*pos (scene.hpp:444) and to_voxel*pos (model.hpp:182), two points per FFMA2
+                const p2 xA = e.row_apply(r0, pxA, pyA, pzA), xB = e.row_apply(r0, pxB, pyB, pzB);
+                const p2 yA = e.row_apply(r1, pxA, pyA, pzA), yB = e.row_apply(r1, pxB, pyB, pzB);
+                const p2 zA = e.row_apply(r2, pxA, pyA, pzA), zB = e.row_apply(r2, pxB, pyB, pzB);
+                const p2 vxA = e.add(e.mul(m.sx, xA), m.tx), vxB = e.add(e.mul(m.sx, xB), m.tx);
+                const p2 vyA = e.add(e.mul(m.sy, yA), m.ty), vyB = e.add(e.mul(m.sy, yB), m.ty);
+                const p2 vzA = e.add(e.mul(m.sz, zA), m.tz), vzB = e.add(e.mul(m.sz, zB), m.tz);
+                const float x[4] = {lo2(xA), hi2(xA), lo2(xB), hi2(xB)}, y[4] = {lo2(yA), hi2(yA), lo2(yB), hi2(yB)},
+                            z[4] = {lo2(zA), hi2(zA), lo2(zB), hi2(zB)};
+                const float vx[4] = {lo2(vxA), hi2(vxA), lo2(vxB), hi2(vxB)},
+                            vy[4] = {lo2(vyA), hi2(vyA), lo2(vyB), hi2(vyB)},
+                            vz[4] = {lo2(vzA), hi2(vzA), lo2(vzB), hi2(vzB)};
+                uint32_t lin[4];
+                bool in[4];
+                bool any_in = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // ijk = trunc(v); the reference's own test on the truncated integers (model.hpp:186-189):
+                    // cvt.rzi saturates, a NaN converts to 0 and is rejected by the distance test (sq is NaN)
+                    const int i = (int)vx[k], j = (int)vy[k], kk = (int)vz[k];
+                    bool ok = ((uint32_t)i < (uint32_t)m.ex) & ((uint32_t)j < (uint32_t)m.ey) &
+                              ((uint32_t)kk < (uint32_t)m.ez);
+                    if (OCC) {  // branch-free: out-of-grid lanes look at block 0
+                        const uint32_t b = ok ? (uint32_t)(((kk >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx +
+                                                           (i >> OCC_SHIFT))
+                                              : 0u;
+                        ok = ok & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
+                    }
+                    lin[k] = ok ? (uint32_t)((kk * m.ey + j) * m.ex + i) : 0u;
+                    in[k] = ok;
+                    any_in |= ok;
+                }
+                if (!__any_sync(0xffffffffu, any_in)) continue;  // nothing reaches the grid
+                // ---- the 4 cell gathers in flight (out-of-grid lanes read cell 0, unused)
+                float4 mp[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
+                    else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+                }
+                // ---- dist > thres (scene.hpp:464-467), class agreement (:469-478)
+                const p2 dxA = pack2(x[0] - mp[0].x, x[1] - mp[1].x), dxB = pack2(x[2] - mp[2].x, x[3] - mp[3].x);
+                const p2 dyA = pack2(y[0] - mp[0].y, y[1] - mp[1].y), dyB = pack2(y[2] - mp[2].y, y[3] - mp[3].y);
+                const p2 dzA = pack2(z[0] - mp[0].z, z[1] - mp[1].z), dzB = pack2(z[2] - mp[2].z, z[3] - mp[3].z);
+                const p2 sqA = e.sqnorm(dxA, dyA, dzA), sqB = e.sqnorm(dxB, dyB, dzB);
+                const float sq[4] = {lo2(sqA), hi2(sqA), lo2(sqB), hi2(sqB)};
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t pfl = (tflags >> k) & 1u;
+                    const bool inl = in[k] && (sq[k] <= a.sq_thres) &&  // NaN: not an inlier
+                                     (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
+                    c += inl ? 1u : 0u;
+                }
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+                if (STATS && tot && lane == 0) atomicAdd(&a.stats[2], 1ull);
+                if (lane == hh) mycnt = tot;
+            }
+            if (mycnt) atomicAdd(&a.counts[h], mycnt);
+        }
+    }
+}
+
+// ---- lazy score of the selected pose ----------------------------------------------------------------
+// score = Σ|ref·ref_n| over the inliers of ONE hypothesis (scene.hpp:461,479-483), the hypothesis named by the
+// packed best key; same fixed-point sum as the bulk scorer's WITH_SCORE path, so the value is identical.
+// acc[0] += score (2^-36 quanta), acc[1] += inliers (cross-check against the key).  The caller zeroes acc.
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+    score_best_kernel(CloudDev scene, ModelDev m, const int32_t* __restrict__ sub_idx,
+                      const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
+                      uint32_t n_groups, const float4* __restrict__ T, const unsigned long long* __restrict__ best_key,
+                      const unsigned long long* __restrict__ shard, float sq_thres, unsigned long long* acc) {
+    const unsigned long long key = *best_key;
+    if (!key) return;
+    const unsigned long long gid = 0xFFFFFFFFull - (key & 0xFFFFFFFFull);
+    if (gid < shard[0] || gid >= shard[1]) return;  // another rank owns the winner
+    const uint32_t l = (uint32_t)(gid - shard[0]);
+    // subset row: the last g with g_hyp[g] <= l (rows without hypotheses have g_hyp[g] == g_hyp[g+1])
+    uint32_t lo = 0, hi = n_groups;  // invariant: g_hyp[lo] <= l < g_hyp[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (g_hyp[mid] <= l) lo = mid; else hi = mid;
+    }
+    const unsigned long long sb = sub_off[lo];
+    const uint32_t nsub = (uint32_t)(sub_off[lo + 1] - sb);
+    const float4 r0 = T[3 * (size_t)l], r1 = T[3 * (size_t)l + 1], r2 = T[3 * (size_t)l + 2];
+    unsigned long long sc = 0;
+    uint32_t cnt = 0;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nsub; q += gridDim.x * blockDim.x) {
+        const uint32_t idx = sub_idx ? (uint32_t)sub_idx[sb + q] : (uint32_t)(sb + q);
+        const float4 v = scene.pos[idx];
+        const uint32_t fl = __float_as_uint(v.w);
+        if (fl & FLAG_MASKED) continue;
+        const float x = row_apply(r0, v.x, v.y, v.z), y = row_apply(r1, v.x, v.y, v.z), z = row_apply(r2, v.x, v.y, v.z);
+        const float vx = m.sx * x + m.tx, vy = m.sy * y + m.ty, vz = m.sz * z + m.tz;
+        if (!((vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) & (vz > -1.f) & (vz < m.ezf))) continue;
+        const uint32_t lin = (uint32_t)(((int)vz * m.ey + (int)vy) * m.ex + (int)vx);
+        const uint32_t mi = __ldg(&m.voxel[lin]);
+        const float4 mp = FUSED ? __ldg(&m.vcell[lin]) : __ldg(&m.cloud.pos[mi]);
+        const float dx = x - mp.x, dy = y - mp.y, dz = z - mp.z;
+        const float sq = sum3(dx * dx, dy * dy, dz * dz);
+        if (!(sq <= sq_thres)) continue;
+        if (((fl ^ __float_as_uint(mp.w)) & FLAG_TANGENT) != 0u) continue;
+        const f3 ref = mk3((fl & FLAG_TANGENT) ? scene.tgt[idx] : scene.nrm[idx]);
+        const f3 rn = mk3(__ldg(&m.mref[mi]));
+        const f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
+        sc += score_fixed(fabsf(dot3(rr, rn)));
+        ++cnt;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, d);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&acc[0], sc);
+        atomicAdd(&acc[1], (unsigned long long)cnt);
+    }
+}
+void launch_score_best(cudaStream_t st, const CloudDev& scene, const ModelDev& m, const int32_t* sub_idx,
+                       const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups, const float4* T,
+                       const unsigned long long* best_key, const unsigned long long* shard, float sq_thres,
+                       unsigned long long* acc, bool fused) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    if (fused) score_best_kernel<true><<<64, 256, 0, st>>>(scene, m, sub_idx, sub_off, g_hyp, n_groups, T, best_key,
+                                                           shard, sq_thres, acc);
+    else score_best_kernel<false><<<64, 256, 0, st>>>(scene, m, sub_idx, sub_off, g_hyp, n_groups, T, best_key, shard,
+                                                      sq_thres, acc);
+}
+
+static p2 host_pair(float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return ((p2)b << 32) | b;
+}
+template <bool FUSED, bool OCC>
+static void launch_x2_v(cudaStream_t st, const ScoreArgs& a, int grid) {
+    const p2 nz = host_pair(-0.0f), one = host_pair(1.0f), mone = host_pair(-1.0f);
+    if (a.stats) score_count_x2_kernel<FUSED, OCC, true><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one, mone);
+    else score_count_x2_kernel<FUSED, OCC, false><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one, mone);
+}
+void launch_score_count_x2(cudaStream_t st, const ScoreArgs& a, int grid, bool fused) {
+    ++g_launch_count;
+    if (fused) {
+        if (a.model.occ) launch_x2_v<true, true>(st, a, grid);
+        else launch_x2_v<true, false>(st, a, grid);
+    } else {
+        if (a.model.occ) launch_x2_v<false, true>(st, a, grid);
+        else launch_x2_v<false, false>(st, a, grid);
+    }
+}
+int score_count_x2_max_blocks_per_sm(bool fused) {
+    int nb = 0, nb2 = 0;
+    if (fused) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_count_x2_kernel<true, false, false>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_count_x2_kernel<true, true, false>, SCORE_THREADS, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_count_x2_kernel<false, false, false>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_count_x2_kernel<false, true, false>, SCORE_THREADS, 0);
+    }
+    nb = nb < nb2 ? nb : nb2;
+    return nb > 0 ? nb : 1;
+}
+
+}  // namespace tmk

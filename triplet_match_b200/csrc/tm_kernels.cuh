@@ -135,6 +135,13 @@ void launch_colmajor_from_rows(cudaStream_t st, const float4* rows, uint64_t n, 
 // k_score.cu
 void launch_score_full(cudaStream_t st, const ScoreArgs& a, int grid, bool fused, bool with_score);
 int score_full_max_blocks_per_sm(bool fused, bool with_score);
+// k_score2.cu: count-only bulk scorer on the packed FP32 pipe (exact), lazy score of the selected pose
+void launch_score_count_x2(cudaStream_t st, const ScoreArgs& a, int grid, bool fused);
+int score_count_x2_max_blocks_per_sm(bool fused);
+void launch_score_best(cudaStream_t st, const CloudDev& scene, const ModelDev& m, const int32_t* sub_idx,
+                       const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups, const float4* T,
+                       const unsigned long long* best_key, const unsigned long long* shard, float sq_thres,
+                       unsigned long long* acc, bool fused);
 void launch_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
                        uint32_t n_groups, uint32_t* n_items_g, unsigned long long* n_tests);
 void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp,
@@ -217,7 +224,7 @@ void launch_gather_rows(cudaStream_t st, const float4* T, const uint32_t* ids, u
                         float4* out, uint32_t* active);
 void launch_finalize_best(cudaStream_t st, const unsigned long long* best,
                           const unsigned long long* shard, const float4* T,
-                          const unsigned long long* scores, uint32_t model_n, float* best_T16,
-                          double* best_score);
+                          const unsigned long long* scores, const unsigned long long* lazy_acc, uint32_t model_n,
+                          float* best_T16, double* best_score);
 
 }  // namespace tmk
