@@ -348,6 +348,19 @@ struct sample_parameters {  // include/common:72-82 (only the read fields)
     bool force_up;
 };
 
+// include/impl/model.hpp:63 — to_voxel_.inverse() for to_voxel_ = diag(scale) + trans, as Eigen's SSE
+// Matrix4f::inverse() (2x2-block cofactor routine, Intel AP-928) leaves it once the products with the
+// structural zeros are dropped; see model::init below.  ia = inverse diagonal, ib = inverse translation.
+inline void voxel_centre_map(const float scale[3], const float trans[3], float ia[3], float ib[3]) {
+    const float sxy = scale[0] * scale[1], rd = 1.0f / (sxy * scale[2]);
+    ia[0] = rd * (scale[1] * scale[2]);
+    ia[1] = rd * (scale[0] * scale[2]);
+    ia[2] = rd * sxy;
+    ib[0] = (-rd) * (0.0f - (0.0f - scale[1] * (scale[2] * trans[0])));
+    ib[1] = rd * (0.0f - scale[0] * (scale[2] * trans[1]));
+    ib[2] = (-rd) * (trans[2] * sxy);
+}
+
 struct model {
     cloud c;
     discretization_params dp;
@@ -377,8 +390,28 @@ struct model {
     // curvature criterion pc_min/pc_max < 0.2 (:98) — the synthetic generators
     // supply the mask; nullptr = all true.  resolution < 0 =>
     // computed by brute force.
+    // model.hpp:87-88: nearest model point of the centre of cell (i, j, k)
+    uint32_t cell_nearest(int i, int j, int k) const {
+        float ia[3], ib[3];
+        voxel_centre_map(scale, trans, ia, ib);
+        v3 q = {ia[0] * (float)i + ib[0], ia[1] * (float)j + ib[1], ia[2] * (float)k + ib[2]};
+        float best = std::numeric_limits<float>::max();
+        uint32_t bi = 0;
+        for (uint32_t p = 0; p < c.n; ++p) {
+            float d = sqdist_seq(ld3(c.pos, p), q);
+            if (d < best) {
+                best = d;
+                bi = p;
+            }
+        }
+        return bi;
+    }
+
+    // voxel_in != nullptr: the grid is supplied instead of filled (checks at sizes where the brute-force
+    // fill below, O(cells x points), does not finish: the supplied grid is then spot-checked cell by cell
+    // with cell_nearest()).
     void init(const cloud& cl, const discretization_params& params, const sample_parameters& sp,
-              const uint8_t* curv_ok, float given_resolution) {
+              const uint8_t* curv_ok, float given_resolution, const uint32_t* voxel_in = nullptr) {
         c = cl;
         dp = params;
         std::vector<uint32_t> all;
@@ -413,27 +446,24 @@ struct model {
             // :58-61  diag(scale)*(-min) via Matrix3f*Vector3f redux s*(-m) + (0 + 0)
             trans[k] = (scale[k] * (-lo[k]) + static_cast<float>(margin)) - 0.5f;
         }
-        // :81-94 grid fill.  World centre of voxel (i,j,k): the reference applies
-        // Eigen's SSE Matrix4f::inverse() [parity unpinned]; the oracle fixes
-        // centre = (index - trans) / scale.  1-NN [parity unpinned: FLANN] is exact
-        // brute force, squared distance (dx*dx + dy*dy) + dz*dz, lowest index wins ties.
+        // :63, :81-94 grid fill.  World centre of voxel (i,j,k) = (to_voxel_.inverse() * (i,j,k,1)).head(3).
+        // Matrix4f::inverse() is Eigen's SSE 2x2-block cofactor routine (Intel AP-928); for to_voxel_ =
+        // diag(scale) + trans all its products with structural zeros vanish and it leaves
+        //   rd = 1 / ((sx*sy)*sz),  inv_aa = rd * (product of the other two scales),
+        //   inv_03 = -rd*(sy*(sz*tx)), inv_13 = -rd*(sx*(sz*ty)), inv_23 = -rd*(tz*(sx*sy))
+        // (checked against the lane-by-lane restatement in oracle/shim/Eigen/inverse_size4_sse.h), and
+        // inv * (i,j,k,1) in Eigen's packet order is inv_aa * index + inv_a3 per axis.
+        // 1-NN [parity unpinned: FLANN] is exact brute force, squared distance (dx*dx + dy*dy) + dz*dz,
+        // lowest index wins ties.
         voxel.assign((size_t)extents[0] * extents[1] * extents[2], 0u);
-        for (int k = 0; k < extents[2]; ++k)
-            for (int j = 0; j < extents[1]; ++j)
-                for (int i = 0; i < extents[0]; ++i) {
-                    v3 q = {((float)i - trans[0]) / scale[0], ((float)j - trans[1]) / scale[1],
-                            ((float)k - trans[2]) / scale[2]};
-                    float best = std::numeric_limits<float>::max();
-                    uint32_t bi = 0;
-                    for (uint32_t p = 0; p < c.n; ++p) {
-                        float d = sqdist_seq(ld3(c.pos, p), q);
-                        if (d < best) {
-                            best = d;
-                            bi = p;
-                        }
-                    }
-                    voxel[(size_t)k * extents[0] * extents[1] + (size_t)j * extents[0] + i] = bi;
-                }
+        if (voxel_in) {
+            std::copy(voxel_in, voxel_in + voxel.size(), voxel.begin());
+        } else {
+            for (int k = 0; k < extents[2]; ++k)
+                for (int j = 0; j < extents[1]; ++j)
+                    for (int i = 0; i < extents[0]; ++i)
+                        voxel[(size_t)k * extents[0] * extents[1] + (size_t)j * extents[0] + i] = cell_nearest(i, j, k);
+        }
         // :96-99 tangent subset
         subset.clear();
         for (uint32_t i : all)

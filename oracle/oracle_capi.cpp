@@ -86,6 +86,9 @@ void orc_early_drop_tests(uint64_t nsub, uint32_t* out18) {
     auto t = early_drop_tests(nsub);
     for (size_t i = 0; i < t.size(); ++i) out18[i] = t[i];
 }
+void orc_voxel_centre_map(const float* scale3, const float* trans3, float* ia3, float* ib3) {
+    voxel_centre_map(scale3, trans3, ia3, ib3);
+}
 float orc_resolution(const float* pos, uint32_t n) {
     cloud c{pos, nullptr, nullptr, n};
     return resolution(c);
@@ -183,6 +186,26 @@ void* orc_model_create(const float* pos, const float* nrm, const float* tgt, uin
     sample_parameters sp{min_diameter_factor, max_diameter_factor, false};
     h->m.init(c, dp, sp, curv_ok, resolution_);
     return h;
+}
+// the same with the voxel grid supplied (extents product entries, reference linearisation) instead of filled
+void* orc_model_create_with_grid(const float* pos, const float* nrm, const float* tgt, uint32_t n,
+                                 const uint8_t* curv_ok, float distance_step_count, float angle_step,
+                                 float min_diameter_factor, float max_diameter_factor, float resolution_,
+                                 const uint32_t* voxel_in) {
+    auto* h = new model_h();
+    h->pos.assign(pos, pos + 3 * (size_t)n);
+    h->nrm.assign(nrm, nrm + 3 * (size_t)n);
+    h->tgt.assign(tgt, tgt + 3 * (size_t)n);
+    cloud c{h->pos.data(), h->nrm.data(), h->tgt.data(), n};
+    discretization_params dp{distance_step_count, angle_step, 10.f};
+    sample_parameters sp{min_diameter_factor, max_diameter_factor, false};
+    h->m.init(c, dp, sp, curv_ok, resolution_, voxel_in);
+    return h;
+}
+// model.hpp:87-88 for n cells given as (i, j, k) triples: the exact brute-force nearest point
+void orc_model_cell_nearest(void* p, const int32_t* ijk, uint64_t n, uint32_t* out) {
+    const model& m = static_cast<model_h*>(p)->m;
+    for (uint64_t q = 0; q < n; ++q) out[q] = m.cell_nearest(ijk[3 * q], ijk[3 * q + 1], ijk[3 * q + 2]);
 }
 void orc_model_destroy(void* p) { delete static_cast<model_h*>(p); }
 // floats: resolution, diameter, scale[3], trans[3], fb.mn[4], fb.mx[4]  (16)

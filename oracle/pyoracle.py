@@ -195,17 +195,28 @@ def cl_icp_correlation(scene4, model4, indices_scene, indices_model, centroid_sc
 
 class OModel:
     def __init__(self, cloud, distance_step_count=20.0, angle_step=0.17453292, min_df=0.2,
-                 max_df=1.0, resolution=-1.0, curv_ok=None):
+                 max_df=1.0, resolution=-1.0, curv_ok=None, voxel=None):
+        """voxel: a grid supplied instead of filled (the brute-force fill is O(cells x points)); spot-check it
+        with cell_nearest()."""
         L = load()
         self.pos, self.nrm, self.tgt = _f32(cloud.pos), _f32(cloud.nrm), _f32(cloud.tgt)
         self.n = self.pos.shape[0]
         co = cloud.tangent_mask if curv_ok is None else curv_ok
         co = None if co is None else np.ascontiguousarray(co, dtype=np.uint8)
-        self.h = C.c_void_p(L.orc_model_create(_p(self.pos), _p(self.nrm), _p(self.tgt),
-                                               C.c_uint32(self.n), _p(co),
-                                               C.c_float(distance_step_count), C.c_float(angle_step),
-                                               C.c_float(min_df), C.c_float(max_df),
-                                               C.c_float(resolution)))
+        if voxel is None:
+            self.h = C.c_void_p(L.orc_model_create(_p(self.pos), _p(self.nrm), _p(self.tgt),
+                                                   C.c_uint32(self.n), _p(co),
+                                                   C.c_float(distance_step_count), C.c_float(angle_step),
+                                                   C.c_float(min_df), C.c_float(max_df),
+                                                   C.c_float(resolution)))
+        else:
+            vin = np.ascontiguousarray(voxel, dtype=np.uint32)
+            L.orc_model_create_with_grid.restype = C.c_void_p
+            self.h = C.c_void_p(L.orc_model_create_with_grid(_p(self.pos), _p(self.nrm), _p(self.tgt),
+                                                             C.c_uint32(self.n), _p(co),
+                                                             C.c_float(distance_step_count), C.c_float(angle_step),
+                                                             C.c_float(min_df), C.c_float(max_df),
+                                                             C.c_float(resolution), _p(vin)))
         f16 = np.zeros(16, dtype=np.float32)
         i4 = np.zeros(4, dtype=np.int32)
         c3 = np.zeros(3, dtype=np.uint64)
@@ -245,6 +256,13 @@ class OModel:
         out = np.zeros((max(limit, 1) if limit else self.n_entries, 2), dtype=np.uint32)
         n = load().orc_model_query(self.h, _p(f), C.c_uint32(limit), _p(out))
         return out[:n]
+
+    def cell_nearest(self, ijk) -> np.ndarray:
+        """model.hpp:87-88 for the given cells (n x 3 int32): exact brute-force nearest model point."""
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros(ijk.shape[0], dtype=np.uint32)
+        load().orc_model_cell_nearest(self.h, _p(ijk), C.c_uint64(ijk.shape[0]), _p(out))
+        return out
 
     def voxel_query(self, pos4):
         p = _f32(pos4, (4,))

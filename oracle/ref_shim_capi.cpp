@@ -241,6 +241,35 @@ void ref_model_info(void* p, float* f10, float* to_voxel16, int* i5) {
     i5[3] = h->m->margin();
     i5[4] = (int)h->m->point_count();
 }
+// Matrix4f::inverse() as the reference build evaluates it (model.hpp:63), column-major in and out
+void ref_matrix4f_inverse(const float* m16, float* out16) {
+    tr::mat4f_t m;
+    for (int k = 0; k < 16; ++k) m.data()[k] = m16[k];
+    tr::mat4f_t inv = m.inverse();
+    for (int k = 0; k < 16; ++k) out16[k] = inv.data()[k];
+}
+// the whole voxel grid of the reference-built model (voxel_data_ is private: every cell is read back through
+// the public voxel_query at a position a quarter cell inside it).  out: extents product entries, reference
+// linearisation k*ex*ey + j*ex + i.  Returns the number of cells whose query did not land in the cell (0).
+uint64_t ref_model_voxels(void* p, uint32_t* out) {
+    auto* h = static_cast<ref_model*>(p);
+    const auto ext = h->m->extents();
+    const float* tv = h->m->voxel_transform().data();
+    uint64_t bad = 0;
+    for (int k = 0; k < ext[2]; ++k)
+        for (int j = 0; j < ext[1]; ++j)
+            for (int i = 0; i < ext[0]; ++i) {
+                const float x = ((float)i + 0.25f - tv[12]) / tv[0], y = ((float)j + 0.25f - tv[13]) / tv[5],
+                            z = ((float)k + 0.25f - tv[14]) / tv[10];
+                const tr::vec4f_t pos(x, y, z, 1.f);
+                const tr::vec4f_t v = h->m->voxel_transform() * pos;
+                if ((int)v[0] != i || (int)v[1] != j || (int)v[2] != k) ++bad;
+                auto r = h->m->voxel_query(pos);
+                const size_t lin = ((size_t)k * ext[1] + j) * ext[0] + i;
+                out[lin] = r ? (*r)[0] : 0xffffffffu;
+            }
+    return bad;
+}
 int ref_model_voxel_query(void* p, const float* pos4, uint32_t* out) {
     auto* h = static_cast<ref_model*>(p);
     auto r = h->m->voxel_query(tr::vec4f_t(pos4[0], pos4[1], pos4[2], pos4[3]));

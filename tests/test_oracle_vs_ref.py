@@ -170,25 +170,20 @@ def test_reference_model_init(refcfg):
     assert np.array_equal(rm.feat_min.view(np.uint32), om.feat_min.view(np.uint32))
     assert np.array_equal(rm.feat_max.view(np.uint32), om.feat_max.view(np.uint32))
     assert rm.point_count == om.n_subset
-    # voxel grid through the reference's voxel_query at every cell (+ outside positions).
-    # The reference places voxel centres with Matrix4f::inverse() (stand-in: Gauss-Jordan), the
-    # oracle with (index - t)/s: centres differ by rounding, so only exact near-ties may differ.
+    # voxel grid through the reference's voxel_query at sampled cells (+ outside positions).  The
+    # reference places voxel centres with Matrix4f::inverse() (model.hpp:63,87; the shim restates Eigen's
+    # SSE cofactor routine lane by lane), the oracle with that routine's closed form for diag + translation:
+    # the grids must be identical, near-ties included.
     ex = om.extents.astype(np.int64)
     rng = np.random.default_rng(0)
     cells = rng.choice(int(ex.prod()), size=min(4000, int(ex.prod())), replace=False)
-    diff = 0
     for lin in cells:
         k, r = divmod(int(lin), int(ex[0] * ex[1]))
         j, i = divmod(r, int(ex[0]))
         centre = (np.array([i, j, k], np.float32) + np.float32(0.25) - om.trans) / om.scale
         got = rm.voxel_query([centre[0], centre[1], centre[2], 1.0])
         exp = om.voxel_query([centre[0], centre[1], centre[2], 1.0])
-        assert (got is None) == (exp is None)
-        if got != exp:
-            d = np.linalg.norm(m.pos[[got, exp]].astype(np.float64) - ((np.array([i, j, k]) - om.trans) / om.scale), axis=1)
-            assert abs(d[0] - d[1]) < 1e-5
-            diff += 1
-    assert diff <= len(cells) // 500
+        assert got == exp
     for p in ([1e3, 0, 0, 1], [-1e3, 0, 0, 1], [np.nan, 0, 0, 1]):
         assert rm.voxel_query(p) is None and om.voxel_query(p) is None
 

@@ -39,11 +39,9 @@ def test_oracle_model_equals_reference(cfg):
     assert np.array_equal(_bits(om.feat_max), _bits(g["feat_max"]))
     assert om.n_subset == int(g["point_count"])
     got = np.array([-1 if (r := om.voxel_query(p)) is None else r for p in g["vq_pos"]], dtype=np.int64)
-    diff = got != g["vq"]
-    # voxel centres: the reference inverts to_voxel_ with Matrix4f::inverse() (stand-in), the oracle
-    # uses (index - t)/s; only exact nearest-neighbour near-ties may pick another point
-    assert diff.sum() <= g["vq"].size // 500
-    assert not ((got < 0) ^ (g["vq"] < 0)).any()
+    # voxel centres: Matrix4f::inverse() in the reference build (Eigen's SSE routine restated in the shim),
+    # its closed form for diag + translation in the oracle: identical grids, near-ties included
+    assert np.array_equal(got, g["vq"])
 
 
 def test_oracle_features_keys_hits_equal_reference(cfg):

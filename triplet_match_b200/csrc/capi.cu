@@ -1778,10 +1778,12 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
     memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
     const QueryOut& o = q->host_out;
     if (q->stats.p && knobs().score_stats) {
-        unsigned long long st[4] = {0, 0, 0, 0};
-        CU(cudaMemcpy(st, q->stats.p, 32, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)\n",
-                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0);
+        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CU(cudaMemcpy(st, q->stats.p, 64, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)"
+                "  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
+                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4],
+                st[5]);
     }
     if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
     memset(r, 0, sizeof(*r));

@@ -16,6 +16,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../../include/triplet_match/tm_voxel_centre.h"
+
 #include "../../include/tm_b200.h"
 #include "../../include/tm_b200_host.h"
 #include "../../include/triplet_match/tm_atan2f.h"
@@ -276,12 +278,13 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
     } else {
         NNGrid g;
         g.build(c->pos, c->stride, c->n, 2.f * m->resolution);
+        const tm_centre_map cm = tm_voxel_centre_map(scale, trans);  // model.hpp:63 inverse(), :87 centre
 #pragma omp parallel for schedule(dynamic, 1)
         for (int k = 0; k < m->extents[2]; ++k)
             for (int j = 0; j < m->extents[1]; ++j)
                 for (int i = 0; i < m->extents[0]; ++i) {
-                    v3 q = {((float)i - trans[0]) / scale[0], ((float)j - trans[1]) / scale[1],
-                            ((float)k - trans[2]) / scale[2]};
+                    v3 q = {tm_voxel_centre(cm.a[0], cm.b[0], i), tm_voxel_centre(cm.a[1], cm.b[1], j),
+                            tm_voxel_centre(cm.a[2], cm.b[2], k)};
                     float best;
                     uint32_t bi;
                     g.nearest(q, 0xffffffffu, best, bi);

@@ -117,6 +117,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
             mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
         }
         if (!(mnx <= mxx)) continue;  // no live (finite, unmasked) point in this tile
+        uint32_t n_live = 0;  // STATS only
+        if (STATS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n_live += (px[k] == px[k]) ? 1u : 0u;
+            n_live = __reduce_add_sync(0xffffffffu, n_live);
+        }
         const float cx = 0.5f * (mnx + mxx), hx = 0.5f * (mxx - mnx);
         const float cy = 0.5f * (mny + mxy), hy = 0.5f * (mxy - mny);
         const float cz = 0.5f * (mnz + mxz), hz = 0.5f * (mxz - mnz);
@@ -192,17 +198,20 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                                               : 0u;
                         ok = ok & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
                     }
-                    lin[k] = ok ? (uint32_t)((kk * m.ey + j) * m.ex + i) : 0u;
+                    lin[k] = (uint32_t)((kk * m.ey + j) * m.ex + i);  // only dereferenced when in[k]
                     in[k] = ok;
                     any_in |= ok;
                 }
                 if (!__any_sync(0xffffffffu, any_in)) continue;  // nothing reaches the grid
-                // ---- the 4 cell gathers in flight (out-of-grid lanes read cell 0, unused)
+                // ---- the 4 cell gathers in flight; out-of-grid lanes issue no request (predicated loads)
                 float4 mp[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
-                    else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+                    mp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (in[k]) {
+                        if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
+                        else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+                    }
                 }
                 // ---- dist > thres (scene.hpp:464-467), class agreement (:469-478)
                 const p2 dxA = pack2(x[0] - mp[0].x, x[1] - mp[1].x), dxB = pack2(x[2] - mp[2].x, x[3] - mp[3].x);
@@ -219,7 +228,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     c += inl ? 1u : 0u;
                 }
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
-                if (STATS && tot && lane == 0) atomicAdd(&a.stats[2], 1ull);
+                if (STATS && tot && lane == 0) {
+                    atomicAdd(&a.stats[2], 1ull);
+                    if (tot == n_live) atomicAdd(&a.stats[3], 1ull);           // every live point of the tile is an inlier
+                    else if (tot * 10u >= n_live * 9u) atomicAdd(&a.stats[4], 1ull);  // >= 90 %
+                    atomicAdd(&a.stats[5], (unsigned long long)tot);
+                }
                 if (lane == hh) mycnt = tot;
             }
             if (mycnt) atomicAdd(&a.counts[h], mycnt);

@@ -6,6 +6,7 @@
 //   voxel_fill      exact 1-NN grid fill (include/impl/model.hpp:81-94)
 //   traits_project  per-point closed forms (cylinder/plane/plane2/identity _traits::project)
 #include "tm_kernels.cuh"
+#include "../../include/triplet_match/tm_voxel_centre.h"
 
 namespace tmk {
 
@@ -298,12 +299,12 @@ void launch_ball_seg_scan(cudaStream_t st, uint32_t* counts, uint32_t n_centres,
 
 // ---------------------------------------------------------------- voxel_fill
 // One thread per voxel; model points streamed through shared memory in tiles.
-// centre = (index - t) / s; squared distance (dx*dx + dy*dy) + dz*dz; the
+// centre = inverse(to_voxel_) * (i,j,k,1) as the reference's Matrix4f::inverse() leaves it
+// (tm_voxel_centre.h: a*index + b per axis); squared distance (dx*dx + dy*dy) + dz*dz; the
 // lowest point index wins ties (strict '<' while scanning ascending).
 constexpr int VF_TILE = 1024;
 __global__ void __launch_bounds__(256)
-    voxel_fill_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, float sx,
-                      float sy, float sz, float tx, float ty, float tz,
+    voxel_fill_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, tm_centre_map cm,
                       uint32_t* __restrict__ voxel) {
     __shared__ float4 tile[VF_TILE];
     const size_t total = (size_t)ex * ey * ez;
@@ -315,7 +316,8 @@ __global__ void __launch_bounds__(256)
         j = (int)((lin / ex) % ey);
         k = (int)(lin / ((size_t)ex * ey));
     }
-    float qx = ((float)i - tx) / sx, qy = ((float)j - ty) / sy, qz = ((float)k - tz) / sz;
+    float qx = tm_voxel_centre(cm.a[0], cm.b[0], i), qy = tm_voxel_centre(cm.a[1], cm.b[1], j),
+          qz = tm_voxel_centre(cm.a[2], cm.b[2], k);
     float best = 3.402823466e+38f;
     uint32_t bi = 0;
     for (uint32_t base = 0; base < n; base += VF_TILE) {
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(256)
 constexpr int VF2_TILE = 1024;
 __global__ void __launch_bounds__(256)
     voxel_fill_pruned_kernel(const float4* __restrict__ mpos, uint32_t n, int ex, int ey, int ez, float sx, float sy,
-                             float sz, float tx, float ty, float tz, int bx, int by,
+                             float sz, float tx, float ty, float tz, tm_centre_map cm, int bx, int by,
                              const float* __restrict__ radius2, uint32_t* __restrict__ voxel) {
     __shared__ float4 cand[VF2_TILE];  // xyz + index bits in w
     __shared__ uint32_t warp_cnt[8];
@@ -403,9 +405,9 @@ __global__ void __launch_bounds__(256)
         const int i = bi * VB + (l & 7), j = bj * VB + ((l >> 3) & 7), k = bk * VB + (l >> 6);
         live[c] = i < ex && j < ey && k < ez;
         lin[c] = ((size_t)k * ey + j) * ex + i;
-        qx[c] = ((float)i - tx) / sx;
-        qy[c] = ((float)j - ty) / sy;
-        qz[c] = ((float)k - tz) / sz;
+        qx[c] = tm_voxel_centre(cm.a[0], cm.b[0], i);  // exact reference centres (the block ball above is a guarded bound)
+        qy[c] = tm_voxel_centre(cm.a[1], cm.b[1], j);
+        qz[c] = tm_voxel_centre(cm.a[2], cm.b[2], k);
         best[c] = 3.402823466e+38f;
         bidx[c] = 0;
     }
@@ -460,10 +462,11 @@ void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, 
                        uint32_t* voxel, float* block_scratch) {
     size_t total = (size_t)ex * ey * ez;
     if (!total) return;
+    const float s3[3] = {sx, sy, sz}, t3[3] = {tx, ty, tz};
+    const tm_centre_map cm = tm_voxel_centre_map(s3, t3);  // model.hpp:63
     if (!block_scratch) {  // brute force (small grids, and the cross-check of the pruned kernel)
         ++g_launch_count;
-        voxel_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy,
-                                                                          sz, tx, ty, tz, voxel);
+        voxel_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mpos, n, ex, ey, ez, cm, voxel);
         return;
     }
     const int bx = (ex + VB - 1) / VB, by = (ey + VB - 1) / VB, bz = (ez + VB - 1) / VB;
@@ -471,7 +474,7 @@ void launch_voxel_fill(cudaStream_t st, const float4* mpos, uint32_t n, int ex, 
     g_launch_count += 2;
     voxel_block_radius_kernel<<<(nb + 7) / 8, 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy, sz, tx, ty, tz, bx, by, bz,
                                                            block_scratch);
-    voxel_fill_pruned_kernel<<<nb, 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy, sz, tx, ty, tz, bx, by,
+    voxel_fill_pruned_kernel<<<nb, 256, 0, st>>>(mpos, n, ex, ey, ez, sx, sy, sz, tx, ty, tz, cm, bx, by,
                                                  block_scratch, voxel);
 }
 size_t voxel_fill_scratch_bytes(int ex, int ey, int ez) {
