@@ -1,58 +1,18 @@
-// capi.cu — implementation of include/tm_b200.h: resident model/scene state,
-// the stage calls with host buffers, and the resident query pipeline.  Host
-// logic only; every data-parallel step is one of the kernels in k_*.cu.
-#include "../../include/tm_b200.h"
-
-#include <dlfcn.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <limits>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "tm_kernels.cuh"
+// capi_core.cu — contexts, resident clouds / models / scenes and the stage calls with host buffers
+// (include/tm_b200.h up to the resident query).
+#include "capi_internal.cuh"
 
 namespace tmk {
 std::atomic<unsigned long long> g_launch_count{0};
 }
-using namespace tmk;
 
-// ------------------------------------------------------------------- errors
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) {
+int tm_fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-#define CU(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(TM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
-    } while (0)
-#define REQUIRE(cond, msg)                          \
-    do {                                            \
-        if (!(cond)) return fail(TM_ERR_INVALID, msg); \
-    } while (0)
-#define TRY(call)              \
-    do {                       \
-        int rc_ = (call);      \
-        if (rc_) return rc_;   \
-    } while (0)
 
-// development knobs (environment), read once per process; none of them changes results
-struct Knobs {
-    bool occ = true;               // TM_OCC=0: never use the block-occupancy mask
-    int fused_grid = -1;           // TM_FUSED_GRID=0/1: force the unfused / fused voxel grid
-    int score_grid = 0;            // TM_SCORE_GRID=n: CTAs of the scoring kernel
-    bool score_stats = false;      // TM_SCORE_STATS=1: cull / inlier statistics of the scoring kernel on stderr
-    int scorer = 8;                // TM_SCORER=7: the fused count+score kernel everywhere (A/B against the count-only
-                                   // packed-FP32 kernel + lazy score, which is the default where scores are not asked for)
-};
-static const Knobs& knobs() {
+const Knobs& knobs() {
     static const Knobs k = [] {
         Knobs v;
         if (const char* e = getenv("TM_OCC")) v.occ = atoi(e) != 0;
@@ -65,76 +25,13 @@ static const Knobs& knobs() {
     return k;
 }
 
-// grow-only device buffer
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return TM_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = std::max<size_t>(bytes, 256);
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess)
-            return fail(TM_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) +
-                                         "): " + cudaGetErrorString(e));
-        cap = want;
-        return TM_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <typename T>
-    T* as() const {
-        return static_cast<T*>(p);
-    }
-};
-
-struct tm_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int sm_count = 0;
-    DevBuf flush;
-    DevBuf scratch[13];  // stage-call scratch, grow-only
-    void* pinned = nullptr;
-    size_t pinned_cap = 0;
-    int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
-    int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
-};
-
-struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
-    float thres = -1.f;
-    DevBuf bits;
-    bool useful = false;  // enough empty blocks to pay for the extra look-up
-};
-struct tm_model {
-    tm_ctx* ctx;
-    DevBuf pos, nrm, tgt, voxel, vcell, vref, slots, hits;
-    ModelDev dev;
-    float centre[3];
-    float half_diag;
-    bool fused;
-    OccMask occ[2];  // scoring threshold and the ICP one (2 x dist_thres); replaced round-robin
-    int occ_next = 0;
-};
-
-struct tm_scene {
-    tm_ctx* ctx;
-    DevBuf pos, nrm, tgt, mask_tmp, seg_lo, seg_hi;
-    CloudDev dev;
-};
-
-static int bind(tm_ctx* c) {
+int bind(tm_ctx* c) {
     CU(cudaSetDevice(c->device));
     return TM_OK;
 }
 // ModelDev for kernels that test against `thres`: the resident description plus, when it pays, the
 // block-occupancy mask of that threshold (built on first use, cached per model).  TM_OCC=0 disables.
-static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
+int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
     *out = m->dev;
     if (!knobs().occ || !(thres >= 0.f)) return TM_OK;
     OccMask* hit = nullptr;
@@ -169,7 +66,7 @@ static int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out) {
     }
     return TM_OK;
 }
-static int pinned_ensure(tm_ctx* c, size_t bytes) {
+int pinned_ensure(tm_ctx* c, size_t bytes) {
     if (bytes <= c->pinned_cap) return TM_OK;
     if (c->pinned) cudaFreeHost(c->pinned);
     c->pinned = nullptr;
@@ -181,7 +78,7 @@ static int pinned_ensure(tm_ctx* c, size_t bytes) {
 
 // `dist > thres` with dist = sqrtf(sq) (scene.hpp:464-465) <=> sq > S, where S is the
 // largest float whose correctly rounded square root is <= thres.
-static float sq_threshold(float thres) {
+float sq_threshold(float thres) {
     if (!(thres >= 0.f)) return -1.f;
     float c = thres * thres;
     while (sqrtf(c) > thres) c = nextafterf(c, 0.f);
@@ -600,7 +497,7 @@ void tm_scene_destroy(tm_scene* s) {
 }
 
 // ------------------------------------------------------------- stage calls
-static void pair_window(const tm_model* m, float min_df, float max_df, float& lower, float& upper) {
+void pair_window(const tm_model* m, float min_df, float max_df, float& lower, float& upper) {
     lower = m->dev.diameter * min_df;  // scene.hpp:117-120
     upper = m->dev.diameter * max_df;
     lower *= lower;
@@ -709,7 +606,7 @@ int tm_hypotheses(tm_scene* s, tm_model* m, const uint32_t* pi, const uint32_t* 
 // counts: [centre][segment] u32 (becomes in-row offsets), row_tot: per-centre totals,
 // row_off: CSR offsets.  active_ranges (device, n_centres + 1, or null): centre c is searched
 // only when active_ranges[c + 1] > active_ranges[c]; skipped centres get an empty row.
-static int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t* d_centres,
+int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t* d_centres,
                             uint32_t n_centres, const uint32_t* active_ranges, float radius, DevBuf& counts,
                             DevBuf& row_tot, DevBuf& row_off, DevBuf* indices, uint64_t* total_out) {
     const uint32_t n_seg = (scene.n + BALL_SEG - 1) / BALL_SEG;
@@ -992,132 +889,6 @@ int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_th
     return TM_OK;
 }
 
-// --------------------------------------------------------------------- ICP
-struct IcpBufs {
-    DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
-    void release() {
-        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
-    }
-    int ensure(uint32_t k) {
-        size_t kk = std::max(k, 1u);
-        TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
-        TRY(sums_cur.ensure(kk * ICP_NSUM * 8)); TRY(sums_best.ensure(kk * ICP_NSUM * 8));
-        TRY(iters.ensure(kk * 4)); TRY(active.ensure(kk * 4));
-        return TM_OK;
-    }
-    IcpState state() {
-        return IcpState{Tcur.as<float4>(), Tbest.as<float4>(), sums_cur.as<long long>(),
-                        sums_best.as<long long>(), iters.as<uint32_t>(), active.as<uint32_t>()};
-    }
-};
-static double icp_fix_scale(const tm_model* m, uint32_t n_scene, float thres) {
-    // |s'|,|m'| <= r = half bbox diagonal + thres; n * r^2 * 2^bits < 2^62
-    double r = (double)m->half_diag + (double)thres + 1e-6;
-    double bound = std::max(1.0, (double)std::max(n_scene, 1u) * std::max(r * r, r));
-    int bits = (int)std::floor(62.0 - std::log2(bound));
-    bits = std::max(8, std::min(40, bits));
-    return std::ldexp(1.0, bits);
-}
-struct tm_comm;
-static int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st);  // NCCL section
-// how the scene points of one ICP pass are split: this process accumulates [pt_begin, pt_end)
-// (as `emulate` consecutive sub-ranges when emulate > 1) and, with a communicator, the 64-bit
-// fixed-point sums are all-reduced — integer sums, so any split gives the same bits.
-struct IcpSplit {
-    uint32_t pt_begin = 0, pt_end = 0;
-    uint64_t n_total = 0;  // scene points over all ranks (fixes the fixed-point scale)
-    tm_comm* comm = nullptr;
-    uint32_t emulate = 1;
-};
-// enqueue the ICP loop for k transforms already in b.Tcur with b.active set
-static int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpBufs& b, uint32_t k,
-                       uint32_t max_iterations, float dist_thres, const IcpSplit* split = nullptr) {
-    const float thres = (2 * dist_thres) * m->dev.resolution;  // scene.hpp:373 + :413
-    const float sqt = sq_threshold(thres);
-    IcpSplit sp;
-    if (split) sp = *split;
-    else { sp.pt_end = scene.n; sp.n_total = scene.n; }
-    const double fs = icp_fix_scale(m, (uint32_t)std::min<uint64_t>(sp.n_total, 0xffffffffull), thres);
-    ModelDev mdev;
-    TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &mdev));
-    CU(cudaMemsetAsync(b.sums_cur.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
-    CU(cudaMemsetAsync(b.sums_best.p, 0, (size_t)k * ICP_NSUM * 8, c->stream));
-    CU(cudaMemsetAsync(b.iters.p, 0, (size_t)k * 4, c->stream));
-    const int grid = c->sm_count * 4;
-    IcpState st = b.state();
-    const uint32_t parts = std::max(1u, sp.emulate);
-    const uint64_t span = sp.pt_end - sp.pt_begin;
-    for (uint32_t it = 0; it <= max_iterations; ++it) {
-        for (uint32_t w = 0; w < parts; ++w) {
-            const uint32_t b0 = sp.pt_begin + (uint32_t)(span * w / parts);
-            const uint32_t b1 = sp.pt_begin + (uint32_t)(span * (w + 1) / parts);
-            if (b1 > b0)
-                launch_icp_accumulate(c->stream, scene, mdev, st.Tcur, st.active, k, b0, b1, sqt,
-                                      m->centre[0], m->centre[1], m->centre[2], fs, st.sums_cur, grid,
-                                      m->fused);
-        }
-        if (sp.comm) TRY(comm_allreduce_sum_i64(sp.comm, st.sums_cur, (size_t)k * ICP_NSUM, c->stream));
-        launch_icp_step(c->stream, st, k, it == 0 ? 1 : 0, max_iterations, 1.0 / fs, m->centre[0],
-                        m->centre[1], m->centre[2]);
-    }
-    CU(cudaGetLastError());
-    return TM_OK;
-}
-
-static int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
-                   float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters,
-                   const IcpSplit* split) {
-    REQUIRE(s && m, "null handle");
-    REQUIRE(n == 0 || (T16s && T16s_out && counts), "tm_icp: null buffer");
-    tm_ctx* c = s->ctx;
-    TRY(bind(c));
-    if (!n) return TM_OK;
-    if (max_iterations == 0 && !split) {  // scene.hpp:371: the match is returned unchanged
-        memcpy(T16s_out, T16s, (size_t)n * 64);
-        if (iters) memset(iters, 0, (size_t)n * 4);
-        return tm_score(s, m, T16s, n, nullptr, nullptr, nullptr, 0, dist_thres, 0.f, 0, counts,
-                        scores, nullptr);
-    }
-    IcpBufs b;
-    int rc = b.ensure(n);
-    DevBuf d16;
-    if (!rc) rc = d16.ensure((size_t)n * 64);
-    auto done = [&](int code) {
-        b.release();
-        d16.release();
-        return code;
-    };
-    if (rc) return done(rc);
-    std::vector<uint32_t> ones(n, 1u);
-    cudaError_t e = cudaMemcpyAsync(d16.p, T16s, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(b.active.p, ones.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) return done(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
-    launch_rows_from_colmajor(c->stream, d16.as<float>(), n, b.Tcur.as<float4>());
-    if ((rc = icp_enqueue(c, s->dev, m, b, n, max_iterations, dist_thres, split))) return done(rc);
-    launch_colmajor_from_rows(c->stream, b.Tbest.as<float4>(), n, d16.as<float>());
-    std::vector<long long> sums((size_t)n * ICP_NSUM);
-    e = cudaMemcpyAsync(T16s_out, d16.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(sums.data(), b.sums_best.p, sums.size() * 8, cudaMemcpyDeviceToHost,
-                            c->stream);
-    if (e == cudaSuccess && iters)
-        e = cudaMemcpyAsync(iters, b.iters.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) return done(fail(TM_ERR_CUDA, cudaGetErrorString(e)));
-    for (uint32_t h = 0; h < n; ++h) {
-        counts[h] = (uint32_t)sums[(size_t)h * ICP_NSUM];
-        if (scores)
-            scores[h] = (double)sums[(size_t)h * ICP_NSUM + 16] / SCORE_SCALE / (double)m->dev.cloud.n;
-    }
-    return done(TM_OK);
-}
-
-int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,
-           float dist_thres, float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters) {
-    return icp_run(s, m, T16s, n, max_iterations, dist_thres, T16s_out, counts, scores, iters, nullptr);
-}
-
 int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, float threshold,
                       const float* xyz, uint64_t n, float* uvw, uint8_t* ok) {
     REQUIRE(c && g2l, "tm_traits_project: null argument");
@@ -1387,663 +1158,6 @@ int tm_uvicp_correlation(tm_ctx* c, const float* scene4, uint32_t n_scene, const
     if (records16 && n) CU(cudaMemcpyAsync(records16, drec.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(cov9, dcov.p, 72, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return TM_OK;
-}
-
-// ------------------------------------------------------------ resident query
-struct QueryOut {  // one contiguous device block, read back in one copy
-    unsigned long long shard[3];  // h_begin, h_end, H
-    unsigned long long best;
-    unsigned long long n_tests;
-    unsigned long long n_valid;
-    double best_score;
-    float best_T16[16];
-    uint32_t n_local;
-    uint32_t err;
-    uint32_t work_counter;
-    uint32_t pad;
-    unsigned long long best_acc[2];  // lazy score of the selected pose: fixed-point sum, inlier count
-};
-
-struct tm_query {
-    tm_scene* s;
-    tm_model* m;
-    tm_query_params p;
-    uint32_t rank = 0, world = 1;
-    uint32_t n_outer = 0;
-    uint64_t n_pairs = 0;
-    uint64_t cap_hyp = 0;
-    uint32_t items_cap = 0;
-    uint64_t sub_total = 0;
-    DevBuf outer, pair_outer, pair_j, outer_pair_off;
-    DevBuf ball_counts, ball_seg_off, sub_off, sub_idx, sub_idx_walk;
-    DevBuf valid, hit_begin, hit_count, hyp_off;
-    DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
-    DevBuf n_items_g, item_off, items, ctrl;
-    DevBuf out;  // QueryOut
-    DevBuf topk_ids, topk_keys, icp_T16, stats, tile_lo, tile_hi;
-    uint32_t max_sub = 0;
-    IcpBufs icp;
-    QueryOut host_out;
-    bool ran = false;
-    bool lazy = false;          // last run used the count-only scorer: scores[] is filled on demand
-    bool scores_valid = false;  // scores[] holds every hypothesis' score
-    float run_thres = 0.f, run_sqt = 0.f;
-    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the scoring kernel
-};
-
-static int count_valid_pairs_dev(tm_query* q);
-
-int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query** out) {
-    REQUIRE(s && m && p && out, "tm_query_create: null argument");
-    REQUIRE(s->ctx == m->ctx, "scene and model live in different contexts");
-    REQUIRE(p->icp_top_k <= 4096, "icp_top_k too large");
-    REQUIRE(p->early_out >= 0 && p->early_out <= 2, "early_out must be 0, 1 or 2");
-    tm_query* q = new tm_query();
-    q->s = s;
-    q->m = m;
-    q->p = *p;
-    memset(&q->host_out, 0, sizeof(QueryOut));
-    cudaError_t e = cudaSetDevice(s->ctx->device);
-    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s0);
-    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s1);
-    if (e != cudaSuccess) {
-        tm_query_destroy(q);
-        return fail(TM_ERR_CUDA, std::string("tm_query_create: ") + cudaGetErrorString(e));
-    }
-    *out = q;
-    return TM_OK;
-}
-void tm_query_destroy(tm_query* q) {
-    if (!q) return;
-    cudaSetDevice(q->s->ctx->device);
-    if (q->ev_s0) cudaEventDestroy(q->ev_s0);
-    if (q->ev_s1) cudaEventDestroy(q->ev_s1);
-    for (DevBuf* b :
-         {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
-          &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
-          &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
-          &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
-        b->release();
-    q->icp.release();
-    delete q;
-}
-
-int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world) {
-    REQUIRE(q && world > 0 && rank < world, "tm_query_set_shard: bad rank/world");
-    q->rank = rank;
-    q->world = world;
-    return TM_OK;
-}
-
-int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
-                       const uint32_t* pair_outer, const uint32_t* pair_j, uint64_t n_pairs) {
-    REQUIRE(q, "null query");
-    REQUIRE(n_outer == 0 || outer, "null outer");
-    REQUIRE(n_pairs == 0 || (pair_outer && pair_j), "null pairs");
-    REQUIRE(n_pairs < (1ull << 31), "too many pairs");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    const uint32_t ns = q->s->dev.n;
-    for (uint32_t o = 0; o < n_outer; ++o) REQUIRE(outer[o] < ns, "outer index out of range");
-    std::vector<uint32_t> opo(n_outer + 1, 0);
-    for (uint64_t k = 0; k < n_pairs; ++k) {
-        REQUIRE(pair_outer[k] < n_outer && pair_j[k] < ns, "pair index out of range");
-        REQUIRE(k == 0 || pair_outer[k] >= pair_outer[k - 1], "pairs must be sorted by outer");
-        ++opo[pair_outer[k] + 1];
-    }
-    for (uint32_t o = 0; o < n_outer; ++o) opo[o + 1] += opo[o];
-    q->n_outer = n_outer;
-    q->n_pairs = n_pairs;
-    TRY(q->outer.ensure(std::max(n_outer, 1u) * 4ull));
-    TRY(q->pair_outer.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
-    TRY(q->pair_j.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
-    TRY(q->outer_pair_off.ensure((n_outer + 1) * 4ull));
-    if (n_outer) CU(cudaMemcpyAsync(q->outer.p, outer, n_outer * 4ull, cudaMemcpyHostToDevice, c->stream));
-    if (n_pairs) {
-        CU(cudaMemcpyAsync(q->pair_outer.p, pair_outer, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(q->pair_j.p, pair_j, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
-    }
-    CU(cudaMemcpyAsync(q->outer_pair_off.p, opo.data(), (n_outer + 1) * 4ull, cudaMemcpyHostToDevice,
-                       c->stream));
-    // capacities: hypotheses, subset indices (one sizing pass), work items
-    uint64_t limit = q->p.query_limit ? q->p.query_limit : 200;
-    uint64_t cap = q->p.max_hypotheses ? q->p.max_hypotheses
-                                       : std::min<uint64_t>(n_pairs * limit, 1ull << 24);
-    if (q->p.hyp_limit) cap = std::min<uint64_t>(cap, q->p.hyp_limit);
-    cap = std::max<uint64_t>(cap, 1);
-    q->cap_hyp = cap;
-    TRY(q->T.ensure(cap * 48)); TRY(q->hyp_valid.ensure(cap)); TRY(q->hyp_pair.ensure(cap * 4));
-    TRY(q->counts.ensure(cap * 4)); TRY(q->scores.ensure(cap * 8)); TRY(q->dropped.ensure(cap));
-    TRY(q->g_of_hyp.ensure(cap * 4));
-    TRY(q->valid.ensure(std::max<uint64_t>(n_pairs, 1))); TRY(q->hit_begin.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
-    TRY(q->hit_count.ensure(std::max<uint64_t>(n_pairs, 1) * 4)); TRY(q->hyp_off.ensure((n_pairs + 1) * 8));
-    TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
-    TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
-    uint64_t total = 0;
-    std::vector<unsigned long long> so(n_outer + 1, 0);
-    if (n_outer) {
-        // sizing pass over ALL outer samples (a rank's shard is only known per run)
-        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, nullptr, q->m->dev.diameter,
-                             q->ball_counts, q->ball_seg_off, q->sub_off, &q->sub_idx, &total));
-        CU(cudaMemcpyAsync(so.data(), q->sub_off.p, (n_outer + 1) * 8ull, cudaMemcpyDeviceToHost,
-                           c->stream));
-    } else {
-        TRY(q->sub_off.ensure(8));
-        CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    q->sub_total = total;
-    uint64_t items = 0;
-    q->max_sub = 0;
-    for (uint32_t o = 0; o < n_outer; ++o) {
-        uint64_t np = so[o + 1] - so[o];
-        q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
-        uint64_t nh = std::min<uint64_t>((uint64_t)(opo[o + 1] - opo[o]) * limit, cap);
-        items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
-    }
-    REQUIRE(items < (1ull << 31), "too many work items");
-    q->items_cap = (uint32_t)std::max<uint64_t>(items, 1);
-    TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
-    TRY(q->item_off.ensure((n_outer + 1) * 4ull));
-    TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
-    if (q->p.early_out == 1) {
-        const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
-        TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
-    } else if (q->p.early_out == 2) {
-        TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
-    }
-    if (q->p.icp_top_k) {
-        TRY(q->icp.ensure(q->p.icp_top_k));
-        TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
-        TRY(q->topk_keys.ensure(topk_scratch_bytes(q->cap_hyp, q->p.icp_top_k)));
-        TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
-    }
-    q->ran = false;
-    return TM_OK;
-}
-
-// export the pose and score of the hypothesis named by out->best (if this shard owns it).  After the count-only
-// scorer the score of that one pose is summed here (score_best_kernel); scores[] stays empty until asked for.
-static int finalize_best(tm_query* q) {
-    tm_ctx* c = q->s->ctx;
-    QueryOut* out = q->out.as<QueryOut>();
-    const unsigned long long* lazy_acc = nullptr;
-    if (q->lazy && !q->scores_valid) {
-        ModelDev md;
-        TRY(model_dev_for(c, q->m, q->run_thres, &md));
-        CU(cudaMemsetAsync(out->best_acc, 0, 16, c->stream));
-        launch_score_best(c->stream, q->s->dev, md, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
-                          q->g_hyp.as<uint32_t>(), q->n_outer, q->T.as<float4>(), &out->best, out->shard, q->run_sqt,
-                          out->best_acc, q->m->fused);
-        lazy_acc = out->best_acc;
-    }
-    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(), q->scores.as<unsigned long long>(),
-                         lazy_acc, q->m->dev.cloud.n, out->best_T16, &out->best_score);
-    return TM_OK;
-}
-
-// scores[] of every hypothesis on request (tm_query_download): re-run the scoring pass with the fused
-// count+score kernel over the resident work list.  Counts go to a scratch array and must come out the same.
-static int ensure_scores(tm_query* q) {
-    if (q->scores_valid || !q->lazy || !q->n_outer) return TM_OK;
-    tm_ctx* c = q->s->ctx;
-    QueryOut* out = q->out.as<QueryOut>();
-    DevBuf& cnt2 = c->scratch[5];
-    TRY(cnt2.ensure(q->cap_hyp * 4));
-    CU(cudaMemsetAsync(cnt2.p, 0, q->cap_hyp * 4, c->stream));
-    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
-    CU(cudaMemsetAsync(&out->work_counter, 0, 4, c->stream));
-    ScoreArgs a;
-    a.scene = q->s->dev;
-    TRY(model_dev_for(c, q->m, q->run_thres, &a.model));
-    a.sub_idx = q->sub_idx.as<int32_t>();
-    a.items = q->items.as<WorkItem>();
-    a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
-    a.work_counter = &out->work_counter;
-    a.T = q->T.as<float4>();
-    a.counts = cnt2.as<uint32_t>();
-    a.scores = q->scores.as<unsigned long long>();
-    a.sq_thres = q->run_sqt;
-    a.stats = nullptr;
-    int& b = c->score_bps[q->m->fused ? 1 : 0][1];
-    if (!b) b = score_full_max_blocks_per_sm(q->m->fused, true);
-    launch_score_full(c->stream, a, c->sm_count * b, q->m->fused, true);
-    CU(cudaGetLastError());
-    q->scores_valid = true;
-    return TM_OK;
-}
-
-int tm_query_run(tm_query* q) {
-    REQUIRE(q, "null query");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    const tm_model* m = q->m;
-    const CloudDev& sc = q->s->dev;
-    QueryOut* out = q->out.as<QueryOut>();
-    CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
-    CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
-    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
-    // (a1-a5) pair filter, feature, key, probe
-    float lower, upper;
-    pair_window(m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
-    const uint32_t limit = q->p.query_limit ? q->p.query_limit : 200;
-    launch_pair_features_probe(c->stream, sc, m->dev, q->outer.as<uint32_t>(),
-                               q->pair_outer.as<uint32_t>(), q->pair_j.as<uint32_t>(), q->n_pairs,
-                               lower, upper, limit, nullptr, nullptr, q->valid.as<uint8_t>(),
-                               q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(),
-                               &out->n_valid);
-    if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
-    else
-        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(),
-                                  q->hyp_off.as<unsigned long long>(), q->n_pairs);
-    launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
-                       q->rank, q->world, q->cap_hyp, out->shard, &out->n_local, &out->err);
-    launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
-                            q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
-                            q->g_hyp.as<uint32_t>());
-    // (a8) radius subsets, only of the outer samples that own hypotheses of this rank's shard
-    // (g_hyp); the others get empty rows, so N ranks do not repeat each other's searches
-    if (q->n_outer) {
-        const float r2 = m->dev.diameter * m->dev.diameter;
-        const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
-        launch_ball_count(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
-                          q->ball_counts.as<uint32_t>());
-        launch_ball_seg_scan(c->stream, q->ball_counts.as<uint32_t>(), q->n_outer, n_seg,
-                             q->ball_seg_off.as<uint32_t>());
-        launch_exclusive_scan_u64(c->stream, q->ball_seg_off.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
-                                  q->n_outer);
-        launch_ball_fill(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
-                         q->ball_counts.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
-                         q->sub_idx.as<int32_t>());
-    }
-    // (a6, a7) hypotheses
-    launch_hypotheses(c->stream, sc, m->dev, q->outer.as<uint32_t>(), q->pair_outer.as<uint32_t>(),
-                      q->pair_j.as<uint32_t>(), q->n_pairs, q->hyp_off.as<unsigned long long>(),
-                      q->hit_begin.as<uint32_t>(), m->dev.hits, q->p.force_up, out->shard,
-                      q->T.as<float4>(), q->hyp_valid.as<uint8_t>(), q->hyp_pair.as<uint32_t>());
-    // (a10) scoring
-    const float thres = q->p.dist_thres * m->dev.resolution;
-    const float sqt = sq_threshold(thres);
-    q->lazy = false;
-    q->run_thres = thres;
-    q->run_sqt = sqt;
-    if (q->n_outer) {
-        if (!q->p.early_out) {
-            launch_work_count(c->stream, q->sub_off.as<unsigned long long>(),
-                              q->g_hyp.as<uint32_t>(), q->n_outer, q->n_items_g.as<uint32_t>(),
-                              &out->n_tests);
-            launch_exclusive_scan_u32(c->stream, q->n_items_g.as<uint32_t>(),
-                                      q->item_off.as<uint32_t>(), q->n_outer);
-            launch_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(),
-                             q->n_outer, q->item_off.as<uint32_t>(), q->items.as<WorkItem>());
-            ScoreArgs a;
-            a.scene = sc;
-            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
-            a.sub_idx = q->sub_idx.as<int32_t>();
-            a.items = q->items.as<WorkItem>();
-            a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
-            a.work_counter = &out->work_counter;
-            a.T = q->T.as<float4>();
-            a.counts = q->counts.as<uint32_t>();
-            a.scores = q->scores.as<unsigned long long>();
-            a.sq_thres = sqt;
-            a.stats = nullptr;
-            if (knobs().score_stats) {
-                TRY(q->stats.ensure(64));
-                CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
-                a.stats = q->stats.as<unsigned long long>();
-            }
-            q->lazy = knobs().scorer >= 8;
-            if (q->lazy) {
-                int& b = c->count_bps[m->fused ? 1 : 0];
-                if (!b) b = score_count_x2_max_blocks_per_sm(m->fused);
-                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
-                CU(cudaEventRecord(q->ev_s0, c->stream));
-                launch_score_count_x2(c->stream, a, grid, m->fused);
-                CU(cudaEventRecord(q->ev_s1, c->stream));
-            } else {
-                int& b = c->score_bps[m->fused ? 1 : 0][1];
-                if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
-                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
-                CU(cudaEventRecord(q->ev_s0, c->stream));
-                launch_score_full(c->stream, a, grid, m->fused, true);
-                CU(cudaEventRecord(q->ev_s1, c->stream));
-            }
-        } else {
-            launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
-                                q->g_of_hyp.as<uint32_t>());
-            EarlyArgs a;
-            a.sub_idx = q->sub_idx.as<int32_t>();
-            if (q->p.early_out == 2) {  // evenly sampling walk order (see tm_score)
-                launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
-                                       q->n_outer, q->max_sub, q->sub_idx_walk.as<int32_t>());
-                a.sub_idx = q->sub_idx_walk.as<int32_t>();
-            } else {
-                launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
-                                         q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
-                a.tile_lo = q->tile_lo.as<float4>();
-                a.tile_hi = q->tile_hi.as<float4>();
-            }
-            a.scene = sc;
-            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
-            a.sub_off = q->sub_off.as<unsigned long long>();
-            a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
-            a.T = q->T.as<float4>();
-            a.n_hyp = (uint32_t)q->cap_hyp;  // grid bound; the kernel clips to n_local
-            a.n_hyp_dev = &out->n_local;
-            a.n_tests = &out->n_tests;
-            a.sq_thres = sqt;
-            a.accept_prob = q->p.accept_prob;
-            a.early_out = 1;
-            a.counts = q->counts.as<uint32_t>();
-            a.scores = q->scores.as<unsigned long long>();
-            a.dropped = q->dropped.as<uint8_t>();
-            a.tested = nullptr;
-            CU(cudaEventRecord(q->ev_s0, c->stream));
-            launch_score_early_drop(c->stream, a, m->fused);
-            CU(cudaEventRecord(q->ev_s1, c->stream));
-        }
-    }
-    launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(), &out->n_local,
-                  out->shard, &out->best, c->sm_count * 2);
-    // (a12) ICP of the local top-k
-    if (q->p.icp_top_k && q->p.max_icp_iterations) {
-        // a hypothesis the early drop gave up on never becomes a candidate (scene.hpp:330: a dropped
-        // project_ returns fewer correspondences than the acceptance bound), whatever its partial count
-        launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
-                           q->p.early_out ? q->dropped.as<uint8_t>() : nullptr,
-                           &out->n_local, q->cap_hyp, q->p.icp_top_k, q->topk_ids.as<uint32_t>(),
-                           q->topk_keys.as<unsigned long long>());
-        launch_gather_rows(c->stream, q->T.as<float4>(), q->topk_ids.as<uint32_t>(), q->p.icp_top_k,
-                           q->icp.Tcur.as<float4>(), q->icp.active.as<uint32_t>());
-        TRY(icp_enqueue(c, sc, m, q->icp, q->p.icp_top_k, q->p.max_icp_iterations, q->p.dist_thres));
-    }
-    TRY(finalize_best(q));
-    CU(cudaGetLastError());
-    q->ran = true;
-    q->scores_valid = !q->lazy;
-    return TM_OK;
-}
-
-int tm_query_result_get(tm_query* q, tm_query_result* r) {
-    REQUIRE(q && r, "null argument");
-    REQUIRE(q->ran, "tm_query_result_get before tm_query_run");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    TRY(pinned_ensure(c, sizeof(QueryOut) + 16));
-    CU(cudaMemcpyAsync(c->pinned, q->out.p, sizeof(QueryOut), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
-    const QueryOut& o = q->host_out;
-    if (q->stats.p && knobs().score_stats) {
-        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        CU(cudaMemcpy(st, q->stats.p, 64, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)"
-                "  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
-                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4],
-                st[5]);
-    }
-    if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
-    memset(r, 0, sizeof(*r));
-    r->n_pairs_valid = o.n_valid;
-    r->n_hypotheses = o.shard[2];
-    r->n_scored = o.n_local;
-    r->n_tests = o.n_tests;
-    r->best_key = o.best;
-    if (o.best) {
-        r->best_inliers = (uint32_t)(o.best >> 32);
-        r->best_hypothesis = 0xFFFFFFFFu - (uint32_t)(o.best & 0xFFFFFFFFull);
-        r->best_score = o.best_score;
-        memcpy(r->best_T, o.best_T16, 64);
-    }
-    return TM_OK;
-}
-int tm_query_score_kernel_ms(tm_query* q, float* ms) {
-    REQUIRE(q && ms && q->ran, "tm_query_score_kernel_ms: null/unrun query");
-    TRY(bind(q->s->ctx));
-    *ms = 0.f;
-    if (!q->n_outer) return TM_OK;
-    CU(cudaEventSynchronize(q->ev_s1));
-    CU(cudaEventElapsedTime(ms, q->ev_s0, q->ev_s1));
-    return TM_OK;
-}
-void* tm_query_best_key_device(tm_query* q) {
-    return q ? (void*)&q->out.as<QueryOut>()->best : nullptr;
-}
-int tm_query_set_global_best(tm_query* q, uint64_t key) {
-    REQUIRE(q && q->ran, "null/unrun query");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    QueryOut* out = q->out.as<QueryOut>();
-    CU(cudaMemcpyAsync(&out->best, &key, 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
-    CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-    TRY(finalize_best(q));
-    CU(cudaGetLastError());
-    return TM_OK;
-}
-
-int tm_query_download(tm_query* q, uint64_t capacity, uint32_t* counts, double* scores,
-                      float* T16s, uint8_t* valid, uint32_t* hyp_pair, uint8_t* dropped) {
-    REQUIRE(q && q->ran, "null/unrun query");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    tm_query_result r;
-    TRY(tm_query_result_get(q, &r));
-    const uint64_t n = r.n_scored;
-    if (n > capacity) return fail(TM_ERR_CAPACITY, "tm_query_download: capacity too small");
-    if (!n) return TM_OK;
-    if (counts) CU(cudaMemcpyAsync(counts, q->counts.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (valid) CU(cudaMemcpyAsync(valid, q->hyp_valid.p, n, cudaMemcpyDeviceToHost, c->stream));
-    if (hyp_pair) CU(cudaMemcpyAsync(hyp_pair, q->hyp_pair.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (dropped) {
-        if (q->p.early_out) CU(cudaMemcpyAsync(dropped, q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
-        else memset(dropped, 0, n);
-    }
-    std::vector<unsigned long long> fx;
-    std::vector<uint8_t> dr;
-    if (scores && q->p.early_out) {
-        dr.resize(n);
-        CU(cudaMemcpyAsync(dr.data(), q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (scores) {
-        TRY(ensure_scores(q));
-        fx.resize(n);
-        CU(cudaMemcpyAsync(fx.data(), q->scores.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (T16s) {
-        DevBuf& d16 = c->scratch[0];
-        TRY(d16.ensure(n * 64));
-        launch_colmajor_from_rows(c->stream, q->T.as<float4>(), n, d16.as<float>());
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(T16s, d16.p, n * 64, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    if (scores)
-        for (uint64_t i = 0; i < n; ++i) {
-            double v = (double)fx[i] / SCORE_SCALE;
-            scores[i] = (!dr.empty() && dr[i]) ? v : v / (double)q->m->dev.cloud.n;
-        }
-    return TM_OK;
-}
-
-int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* counts,
-                         double* scores, uint32_t* iters) {
-    REQUIRE(q && q->ran, "null/unrun query");
-    const uint32_t k = q->p.icp_top_k;
-    REQUIRE(k && q->p.max_icp_iterations, "query has no ICP stage");
-    tm_ctx* c = q->s->ctx;
-    TRY(bind(c));
-    std::vector<long long> sums((size_t)k * ICP_NSUM);
-    std::vector<uint32_t> ids(k);
-    launch_colmajor_from_rows(c->stream, q->icp.Tbest.as<float4>(), k, q->icp_T16.as<float>());
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(sums.data(), q->icp.sums_best.p, sums.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(ids.data(), q->topk_ids.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
-    if (T16s) CU(cudaMemcpyAsync(T16s, q->icp_T16.p, k * 64ull, cudaMemcpyDeviceToHost, c->stream));
-    if (iters) CU(cudaMemcpyAsync(iters, q->icp.iters.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    for (uint32_t r = 0; r < k; ++r) {
-        if (hyp_ids) hyp_ids[r] = ids[r];
-        if (counts) counts[r] = (uint32_t)sums[(size_t)r * ICP_NSUM];
-        if (scores)
-            scores[r] = (double)sums[(size_t)r * ICP_NSUM + 16] / SCORE_SCALE / (double)q->m->dev.cloud.n;
-    }
-    return TM_OK;
-}
-
-// ------------------------------------------------------------------- NCCL
-// The one collective of the path.  NCCL is resolved at run time
-// with dlopen so the library loads in processes that never go multi-GPU.
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSuccess_ = 0 };
-enum { ncclUint8_ = 1, ncclInt64_ = 4, ncclUint64_ = 5 };  // ncclDataType_t
-enum { ncclSum_ = 0, ncclMax_ = 2 };       // ncclRedOp_t
-struct NcclApi {
-    void* lib = nullptr;
-    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    int (*CommDestroy)(ncclComm_t) = nullptr;
-    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
-};
-static NcclApi g_nccl;
-static std::mutex g_nccl_mutex;
-static int nccl_load() {
-    std::lock_guard<std::mutex> lock(g_nccl_mutex);
-    if (g_nccl.lib) return TM_OK;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    void* lib = nullptr;
-    for (const char* n : names)
-        if ((lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-    if (!lib) return fail(TM_ERR_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
-    g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
-    g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
-    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
-    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
-        lib, "ncclAllReduce");
-    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
-        return fail(TM_ERR_NCCL, "libnccl is missing required symbols");
-    g_nccl.lib = lib;
-    return TM_OK;
-}
-#define NC(call)                                                                             \
-    do {                                                                                     \
-        int r_ = (call);                                                                     \
-        if (r_ != 0)                                                                         \
-            return fail(TM_ERR_NCCL, std::string(#call) + ": " +                            \
-                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
-    } while (0)
-
-struct tm_comm {
-    tm_ctx* ctx;
-    ncclComm_t comm;
-    int rank, world;
-    DevBuf stage;  // batched best-pose reduce: n keys, then n x (score, pose)
-};
-
-int tm_nccl_unique_id(uint8_t out[128]) {
-    REQUIRE(out, "null out");
-    TRY(nccl_load());
-    ncclUniqueId id;
-    NC(g_nccl.GetUniqueId(&id));
-    memcpy(out, id.internal, 128);
-    return TM_OK;
-}
-int tm_comm_create(tm_ctx* c, const uint8_t idb[128], int rank, int world, tm_comm** out) {
-    REQUIRE(c && idb && out && world > 0 && rank >= 0 && rank < world, "tm_comm_create: bad argument");
-    TRY(nccl_load());
-    TRY(bind(c));
-    ncclUniqueId id;
-    memcpy(id.internal, idb, 128);
-    tm_comm* cm = new tm_comm{c, nullptr, rank, world, DevBuf()};
-    int r = g_nccl.CommInitRank(&cm->comm, world, id, rank);
-    if (r != 0) {
-        delete cm;
-        return fail(TM_ERR_NCCL, std::string("ncclCommInitRank: ") +
-                                     (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-    }
-    *out = cm;
-    return TM_OK;
-}
-void tm_comm_destroy(tm_comm* cm) {
-    if (!cm) return;
-    cudaSetDevice(cm->ctx->device);
-    if (cm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm->comm);
-    cm->stage.release();
-    delete cm;
-}
-// batched form for several queries over the same scene (BASELINE configs[3]: 16 models x one
-// scene): ONE max all-reduce over the n packed keys and ONE sum all-reduce over the n x 72-byte
-// (score, pose) records instead of 2n collectives
-int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* cm) {
-    REQUIRE(cm && (n == 0 || qs), "tm_queries_allreduce_best: null argument");
-    if (!n) return TM_OK;
-    tm_ctx* c = cm->ctx;
-    for (uint32_t i = 0; i < n; ++i)
-        REQUIRE(qs[i] && qs[i]->ran && qs[i]->s->ctx == c, "tm_queries_allreduce_best: bad query");
-    TRY(bind(c));
-    TRY(cm->stage.ensure((size_t)n * 8 + (size_t)n * 72));
-    unsigned long long* keys = cm->stage.as<unsigned long long>();
-    uint8_t* recs = reinterpret_cast<uint8_t*>(keys + n);
-    for (uint32_t i = 0; i < n; ++i)
-        CU(cudaMemcpyAsync(keys + i, &qs[i]->out.as<QueryOut>()->best, 8, cudaMemcpyDeviceToDevice, c->stream));
-    NC(g_nccl.AllReduce(keys, keys, n, ncclUint64_, ncclMax_, cm->comm, c->stream));
-    for (uint32_t i = 0; i < n; ++i) {
-        tm_query* q = qs[i];
-        QueryOut* out = q->out.as<QueryOut>();
-        CU(cudaMemcpyAsync(&out->best, keys + i, 8, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
-        CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-        TRY(finalize_best(q));
-        CU(cudaMemcpyAsync(recs + 72 * (size_t)i, &out->best_score, 72, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    CU(cudaGetLastError());
-    NC(g_nccl.AllReduce(recs, recs, (size_t)n * 72, ncclUint8_, ncclSum_, cm->comm, c->stream));
-    for (uint32_t i = 0; i < n; ++i)
-        CU(cudaMemcpyAsync(&qs[i]->out.as<QueryOut>()->best_score, recs + 72 * (size_t)i, 72,
-                           cudaMemcpyDeviceToDevice, c->stream));
-    return TM_OK;
-}
-static int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st) {
-    NC(g_nccl.AllReduce(buf, buf, count, ncclInt64_, ncclSum_, cm->comm, st));
-    return TM_OK;
-}
-int tm_icp_sharded(tm_scene* s, tm_model* m, tm_comm* cm, const float* T16s, uint32_t n,
-                   uint32_t max_iterations, float dist_thres, uint32_t pt_begin, uint32_t pt_end,
-                   uint64_t n_scene_total, uint32_t emulate_parts, float* T16s_out, uint32_t* counts,
-                   double* scores, uint32_t* iters) {
-    REQUIRE(s && m, "null handle");
-    REQUIRE(pt_begin <= pt_end && pt_end <= s->dev.n, "tm_icp_sharded: bad point range");
-    REQUIRE(n_scene_total >= (uint64_t)(pt_end - pt_begin), "tm_icp_sharded: n_scene_total too small");
-    REQUIRE(!cm || cm->ctx == s->ctx, "communicator belongs to another context");
-    REQUIRE(!(cm && emulate_parts > 1), "tm_icp_sharded: emulate_parts is for single-process runs");
-    REQUIRE(max_iterations > 0, "tm_icp_sharded: max_iterations must be > 0");
-    IcpSplit sp;
-    sp.pt_begin = pt_begin; sp.pt_end = pt_end; sp.n_total = n_scene_total; sp.comm = cm;
-    sp.emulate = std::max(1u, emulate_parts);
-    return icp_run(s, m, T16s, n, max_iterations, dist_thres, T16s_out, counts, scores, iters, &sp);
-}
-int tm_query_allreduce_best(tm_query* q, tm_comm* cm) {
-    REQUIRE(q && cm && q->ran, "tm_query_allreduce_best: bad argument");
-    tm_ctx* c = q->s->ctx;
-    REQUIRE(c == cm->ctx, "communicator belongs to another context");
-    TRY(bind(c));
-    QueryOut* out = q->out.as<QueryOut>();
-    // max over ranks of (inliers << 32 | ~global id): 8 bytes, latency-bound
-    NC(g_nccl.AllReduce(&out->best, &out->best, 1, ncclUint64_, ncclMax_, cm->comm, c->stream));
-    // the owner re-exports the winning pose; everybody else contributes zeros
-    CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
-    CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
-    TRY(finalize_best(q));
-    CU(cudaGetLastError());
-    // best_score (8 B) and best_T16 (64 B) are adjacent in QueryOut
-    NC(g_nccl.AllReduce(&out->best_score, &out->best_score, 72, ncclUint8_, ncclSum_, cm->comm,
-                        c->stream));
     return TM_OK;
 }
 

@@ -1,0 +1,213 @@
+// capi_internal.cuh — state and helpers shared by the capi_*.cu translation units (the implementation of
+// include/tm_b200.h).  Host logic only; every data-parallel step is one of the kernels in k_*.cu.
+//   capi_core.cu    contexts, cloud / model / scene upload, the stage calls with host buffers
+//   capi_icp.cu     icp_ (tm_icp, tm_icp_sharded, tm_icp_poses) and its enqueue used by the resident query
+//   capi_query.cu   the resident query pipeline (tm_query_*)
+//   capi_nccl.cu    the NCCL loader, communicators and the best-pose all-reduce
+#pragma once
+#include "../../include/tm_b200.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "tm_kernels.cuh"
+
+using namespace tmk;
+
+// ------------------------------------------------------------------- errors
+int tm_fail(int code, const std::string& msg);  // records the thread's last error, returns code
+#define fail tm_fail
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(TM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+#define REQUIRE(cond, msg)                          \
+    do {                                            \
+        if (!(cond)) return fail(TM_ERR_INVALID, msg); \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+// development knobs (environment), read once per process; none of them changes results
+struct Knobs {
+    bool occ = true;               // TM_OCC=0: never use the block-occupancy mask
+    int fused_grid = -1;           // TM_FUSED_GRID=0/1: force the unfused / fused voxel grid
+    int score_grid = 0;            // TM_SCORE_GRID=n: CTAs of the scoring kernel
+    bool score_stats = false;      // TM_SCORE_STATS=1: cull / inlier statistics of the scoring kernel on stderr
+    int scorer = 8;                // TM_SCORER=7: the fused count+score kernel everywhere (A/B against the count-only
+                                   // packed-FP32 kernel + lazy score, which is the default where scores are not asked for)
+};
+const Knobs& knobs();
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return TM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess)
+            return fail(TM_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) +
+                                         "): " + cudaGetErrorString(e));
+        cap = want;
+        return TM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+struct tm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    DevBuf flush;
+    DevBuf scratch[13];  // stage-call scratch, grow-only
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+    int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
+    int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
+};
+
+struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
+    float thres = -1.f;
+    DevBuf bits;
+    bool useful = false;  // enough empty blocks to pay for the extra look-up
+};
+struct tm_model {
+    tm_ctx* ctx;
+    DevBuf pos, nrm, tgt, voxel, vcell, vref, slots, hits;
+    ModelDev dev;
+    float centre[3];
+    float half_diag;
+    bool fused;
+    OccMask occ[2];  // scoring threshold and the ICP one (2 x dist_thres); replaced round-robin
+    int occ_next = 0;
+};
+
+struct tm_scene {
+    tm_ctx* ctx;
+    DevBuf pos, nrm, tgt, mask_tmp, seg_lo, seg_hi;
+    CloudDev dev;
+};
+
+int bind(tm_ctx* c);
+// ModelDev for kernels that test against `thres`: the resident description plus, when it pays, the
+// block-occupancy mask of that threshold (built on first use, cached per model).  TM_OCC=0 disables.
+int model_dev_for(tm_ctx* c, tm_model* m, float thres, ModelDev* out);
+int pinned_ensure(tm_ctx* c, size_t bytes);
+// `dist > thres` with dist = sqrtf(sq) (scene.hpp:464-465) <=> sq > S, where S is the
+// largest float whose correctly rounded square root is <= thres.
+float sq_threshold(float thres);
+extern "C" void pair_window(const tm_model* m, float min_df, float max_df, float& lower, float& upper);
+extern "C" int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t* d_centres, uint32_t n_centres,
+                     const uint32_t* active_ranges, float radius, DevBuf& counts, DevBuf& row_tot, DevBuf& row_off,
+                     DevBuf* indices, uint64_t* total_out);
+
+// --------------------------------------------------------------------- ICP
+struct IcpBufs {
+    DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
+    void release() {
+        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
+    }
+    int ensure(uint32_t k) {
+        size_t kk = std::max(k, 1u);
+        TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
+        TRY(sums_cur.ensure(kk * ICP_NSUM * 8)); TRY(sums_best.ensure(kk * ICP_NSUM * 8));
+        TRY(iters.ensure(kk * 4)); TRY(active.ensure(kk * 4));
+        return TM_OK;
+    }
+    IcpState state() {
+        return IcpState{Tcur.as<float4>(), Tbest.as<float4>(), sums_cur.as<long long>(),
+                        sums_best.as<long long>(), iters.as<uint32_t>(), active.as<uint32_t>()};
+    }
+};
+typedef struct ncclComm* ncclComm_t;
+struct tm_comm {
+    tm_ctx* ctx;
+    ncclComm_t comm;
+    int rank, world;
+    DevBuf stage;  // batched best-pose reduce: n keys, then n x (score, pose)
+};
+int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st);  // capi_nccl.cu
+// how the scene points of one ICP pass are split: this process accumulates [pt_begin, pt_end)
+// (as `emulate` consecutive sub-ranges when emulate > 1) and, with a communicator, the 64-bit
+// fixed-point sums are all-reduced — integer sums, so any split gives the same bits.
+struct IcpSplit {
+    uint32_t pt_begin = 0, pt_end = 0;
+    uint64_t n_total = 0;  // scene points over all ranks (fixes the fixed-point scale)
+    tm_comm* comm = nullptr;
+    uint32_t emulate = 1;
+};
+// enqueue the ICP loop for k transforms already in b.Tcur with b.active set
+int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpBufs& b, uint32_t k, uint32_t max_iterations,
+                float dist_thres, const IcpSplit* split = nullptr);
+int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations, float dist_thres,
+            float* T16s_out, uint32_t* counts, double* scores, uint32_t* iters, const IcpSplit* split);
+
+// ------------------------------------------------------------ resident query
+struct QueryOut {  // one contiguous device block, read back in one copy
+    unsigned long long shard[3];  // h_begin, h_end, H
+    unsigned long long best;
+    unsigned long long n_tests;
+    unsigned long long n_valid;
+    double best_score;
+    float best_T16[16];
+    uint32_t n_local;
+    uint32_t err;
+    uint32_t work_counter;
+    uint32_t pad;
+    unsigned long long best_acc[2];  // lazy score of the selected pose: fixed-point sum, inlier count
+};
+
+struct tm_query {
+    tm_scene* s;
+    tm_model* m;
+    tm_query_params p;
+    uint32_t rank = 0, world = 1;
+    uint32_t n_outer = 0;
+    uint64_t n_pairs = 0;
+    uint64_t cap_hyp = 0;
+    uint32_t items_cap = 0;
+    uint64_t sub_total = 0;
+    DevBuf outer, pair_outer, pair_j, outer_pair_off;
+    DevBuf ball_counts, ball_seg_off, sub_off, sub_idx, sub_idx_walk;
+    DevBuf valid, hit_begin, hit_count, hyp_off;
+    DevBuf g_hyp, g_of_hyp, T, hyp_valid, hyp_pair, counts, scores, dropped;
+    DevBuf n_items_g, item_off, items, ctrl;
+    DevBuf out;  // QueryOut
+    DevBuf topk_ids, topk_keys, icp_T16, stats, tile_lo, tile_hi;
+    uint32_t max_sub = 0;
+    IcpBufs icp;
+    QueryOut host_out;
+    bool ran = false;
+    bool lazy = false;          // last run used the count-only scorer: scores[] is filled on demand
+    bool scores_valid = false;  // scores[] holds every hypothesis' score
+    float run_thres = 0.f, run_sqt = 0.f;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the scoring kernel
+};
+int finalize_best(tm_query* q);  // capi_query.cu

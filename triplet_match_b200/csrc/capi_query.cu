@@ -1,0 +1,473 @@
+// capi_query.cu — the resident query (tm_query_*): the whole recorded-list search enqueued on one stream with
+// no host round trip: features + probe -> scan -> shard -> subsets -> hypotheses -> work list -> scoring ->
+// argmax (-> top-k -> ICP) -> best-pose export.
+#include "capi_internal.cuh"
+
+
+extern "C" {
+
+int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query** out) {
+    REQUIRE(s && m && p && out, "tm_query_create: null argument");
+    REQUIRE(s->ctx == m->ctx, "scene and model live in different contexts");
+    REQUIRE(p->icp_top_k <= 4096, "icp_top_k too large");
+    REQUIRE(p->early_out >= 0 && p->early_out <= 2, "early_out must be 0, 1 or 2");
+    tm_query* q = new tm_query();
+    q->s = s;
+    q->m = m;
+    q->p = *p;
+    memset(&q->host_out, 0, sizeof(QueryOut));
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s0);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s1);
+    if (e != cudaSuccess) {
+        tm_query_destroy(q);
+        return fail(TM_ERR_CUDA, std::string("tm_query_create: ") + cudaGetErrorString(e));
+    }
+    *out = q;
+    return TM_OK;
+}
+void tm_query_destroy(tm_query* q) {
+    if (!q) return;
+    cudaSetDevice(q->s->ctx->device);
+    if (q->ev_s0) cudaEventDestroy(q->ev_s0);
+    if (q->ev_s1) cudaEventDestroy(q->ev_s1);
+    for (DevBuf* b :
+         {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
+          &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
+          &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
+          &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
+          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
+        b->release();
+    q->icp.release();
+    delete q;
+}
+
+int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world) {
+    REQUIRE(q && world > 0 && rank < world, "tm_query_set_shard: bad rank/world");
+    q->rank = rank;
+    q->world = world;
+    return TM_OK;
+}
+
+int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
+                       const uint32_t* pair_outer, const uint32_t* pair_j, uint64_t n_pairs) {
+    REQUIRE(q, "null query");
+    REQUIRE(n_outer == 0 || outer, "null outer");
+    REQUIRE(n_pairs == 0 || (pair_outer && pair_j), "null pairs");
+    REQUIRE(n_pairs < (1ull << 31), "too many pairs");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    const uint32_t ns = q->s->dev.n;
+    for (uint32_t o = 0; o < n_outer; ++o) REQUIRE(outer[o] < ns, "outer index out of range");
+    std::vector<uint32_t> opo(n_outer + 1, 0);
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        REQUIRE(pair_outer[k] < n_outer && pair_j[k] < ns, "pair index out of range");
+        REQUIRE(k == 0 || pair_outer[k] >= pair_outer[k - 1], "pairs must be sorted by outer");
+        ++opo[pair_outer[k] + 1];
+    }
+    for (uint32_t o = 0; o < n_outer; ++o) opo[o + 1] += opo[o];
+    q->n_outer = n_outer;
+    q->n_pairs = n_pairs;
+    TRY(q->outer.ensure(std::max(n_outer, 1u) * 4ull));
+    TRY(q->pair_outer.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->pair_j.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->outer_pair_off.ensure((n_outer + 1) * 4ull));
+    if (n_outer) CU(cudaMemcpyAsync(q->outer.p, outer, n_outer * 4ull, cudaMemcpyHostToDevice, c->stream));
+    if (n_pairs) {
+        CU(cudaMemcpyAsync(q->pair_outer.p, pair_outer, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(q->pair_j.p, pair_j, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(q->outer_pair_off.p, opo.data(), (n_outer + 1) * 4ull, cudaMemcpyHostToDevice,
+                       c->stream));
+    // capacities: hypotheses, subset indices (one sizing pass), work items
+    uint64_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    uint64_t cap = q->p.max_hypotheses ? q->p.max_hypotheses
+                                       : std::min<uint64_t>(n_pairs * limit, 1ull << 24);
+    if (q->p.hyp_limit) cap = std::min<uint64_t>(cap, q->p.hyp_limit);
+    cap = std::max<uint64_t>(cap, 1);
+    q->cap_hyp = cap;
+    TRY(q->T.ensure(cap * 48)); TRY(q->hyp_valid.ensure(cap)); TRY(q->hyp_pair.ensure(cap * 4));
+    TRY(q->counts.ensure(cap * 4)); TRY(q->scores.ensure(cap * 8)); TRY(q->dropped.ensure(cap));
+    TRY(q->g_of_hyp.ensure(cap * 4));
+    TRY(q->valid.ensure(std::max<uint64_t>(n_pairs, 1))); TRY(q->hit_begin.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->hit_count.ensure(std::max<uint64_t>(n_pairs, 1) * 4)); TRY(q->hyp_off.ensure((n_pairs + 1) * 8));
+    TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
+    TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
+    uint64_t total = 0;
+    std::vector<unsigned long long> so(n_outer + 1, 0);
+    if (n_outer) {
+        // sizing pass over ALL outer samples (a rank's shard is only known per run)
+        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, nullptr, q->m->dev.diameter,
+                             q->ball_counts, q->ball_seg_off, q->sub_off, &q->sub_idx, &total));
+        CU(cudaMemcpyAsync(so.data(), q->sub_off.p, (n_outer + 1) * 8ull, cudaMemcpyDeviceToHost,
+                           c->stream));
+    } else {
+        TRY(q->sub_off.ensure(8));
+        CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    q->sub_total = total;
+    uint64_t items = 0;
+    q->max_sub = 0;
+    for (uint32_t o = 0; o < n_outer; ++o) {
+        uint64_t np = so[o + 1] - so[o];
+        q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
+        uint64_t nh = std::min<uint64_t>((uint64_t)(opo[o + 1] - opo[o]) * limit, cap);
+        items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
+    }
+    REQUIRE(items < (1ull << 31), "too many work items");
+    q->items_cap = (uint32_t)std::max<uint64_t>(items, 1);
+    TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
+    TRY(q->item_off.ensure((n_outer + 1) * 4ull));
+    TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
+    if (q->p.early_out == 1) {
+        const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
+        TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
+    } else if (q->p.early_out == 2) {
+        TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
+    }
+    if (q->p.icp_top_k) {
+        TRY(q->icp.ensure(q->p.icp_top_k));
+        TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
+        TRY(q->topk_keys.ensure(topk_scratch_bytes(q->cap_hyp, q->p.icp_top_k)));
+        TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
+    }
+    q->ran = false;
+    return TM_OK;
+}
+
+}  // extern "C"
+
+// export the pose and score of the hypothesis named by out->best (if this shard owns it).  After the count-only
+// scorer the score of that one pose is summed here (score_best_kernel); scores[] stays empty until asked for.
+int finalize_best(tm_query* q) {
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    const unsigned long long* lazy_acc = nullptr;
+    if (q->lazy && !q->scores_valid) {
+        ModelDev md;
+        TRY(model_dev_for(c, q->m, q->run_thres, &md));
+        CU(cudaMemsetAsync(out->best_acc, 0, 16, c->stream));
+        launch_score_best(c->stream, q->s->dev, md, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                          q->g_hyp.as<uint32_t>(), q->n_outer, q->T.as<float4>(), &out->best, out->shard, q->run_sqt,
+                          out->best_acc, q->m->fused);
+        lazy_acc = out->best_acc;
+    }
+    launch_finalize_best(c->stream, &out->best, out->shard, q->T.as<float4>(), q->scores.as<unsigned long long>(),
+                         lazy_acc, q->m->dev.cloud.n, out->best_T16, &out->best_score);
+    return TM_OK;
+}
+
+// scores[] of every hypothesis on request (tm_query_download): re-run the scoring pass with the fused
+// count+score kernel over the resident work list.  Counts go to a scratch array and must come out the same.
+static int ensure_scores(tm_query* q) {
+    if (q->scores_valid || !q->lazy || !q->n_outer) return TM_OK;
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    DevBuf& cnt2 = c->scratch[5];
+    TRY(cnt2.ensure(q->cap_hyp * 4));
+    CU(cudaMemsetAsync(cnt2.p, 0, q->cap_hyp * 4, c->stream));
+    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
+    CU(cudaMemsetAsync(&out->work_counter, 0, 4, c->stream));
+    ScoreArgs a;
+    a.scene = q->s->dev;
+    TRY(model_dev_for(c, q->m, q->run_thres, &a.model));
+    a.sub_idx = q->sub_idx.as<int32_t>();
+    a.items = q->items.as<WorkItem>();
+    a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
+    a.work_counter = &out->work_counter;
+    a.T = q->T.as<float4>();
+    a.counts = cnt2.as<uint32_t>();
+    a.scores = q->scores.as<unsigned long long>();
+    a.sq_thres = q->run_sqt;
+    a.stats = nullptr;
+    int& b = c->score_bps[q->m->fused ? 1 : 0][1];
+    if (!b) b = score_full_max_blocks_per_sm(q->m->fused, true);
+    launch_score_full(c->stream, a, c->sm_count * b, q->m->fused, true);
+    CU(cudaGetLastError());
+    q->scores_valid = true;
+    return TM_OK;
+}
+
+extern "C" {
+
+int tm_query_run(tm_query* q) {
+    REQUIRE(q, "null query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    const tm_model* m = q->m;
+    const CloudDev& sc = q->s->dev;
+    QueryOut* out = q->out.as<QueryOut>();
+    CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
+    CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
+    CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
+    // (a1-a5) pair filter, feature, key, probe
+    float lower, upper;
+    pair_window(m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
+    const uint32_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    launch_pair_features_probe(c->stream, sc, m->dev, q->outer.as<uint32_t>(),
+                               q->pair_outer.as<uint32_t>(), q->pair_j.as<uint32_t>(), q->n_pairs,
+                               lower, upper, limit, nullptr, nullptr, q->valid.as<uint8_t>(),
+                               q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(),
+                               &out->n_valid);
+    if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
+    else
+        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(),
+                                  q->hyp_off.as<unsigned long long>(), q->n_pairs);
+    launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
+                       q->rank, q->world, q->cap_hyp, out->shard, &out->n_local, &out->err);
+    launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
+                            q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
+                            q->g_hyp.as<uint32_t>());
+    // (a8) radius subsets, only of the outer samples that own hypotheses of this rank's shard
+    // (g_hyp); the others get empty rows, so N ranks do not repeat each other's searches
+    if (q->n_outer) {
+        const float r2 = m->dev.diameter * m->dev.diameter;
+        const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
+        launch_ball_count(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
+                          q->ball_counts.as<uint32_t>());
+        launch_ball_seg_scan(c->stream, q->ball_counts.as<uint32_t>(), q->n_outer, n_seg,
+                             q->ball_seg_off.as<uint32_t>());
+        launch_exclusive_scan_u64(c->stream, q->ball_seg_off.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
+                                  q->n_outer);
+        launch_ball_fill(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
+                         q->ball_counts.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
+                         q->sub_idx.as<int32_t>());
+    }
+    // (a6, a7) hypotheses
+    launch_hypotheses(c->stream, sc, m->dev, q->outer.as<uint32_t>(), q->pair_outer.as<uint32_t>(),
+                      q->pair_j.as<uint32_t>(), q->n_pairs, q->hyp_off.as<unsigned long long>(),
+                      q->hit_begin.as<uint32_t>(), m->dev.hits, q->p.force_up, out->shard,
+                      q->T.as<float4>(), q->hyp_valid.as<uint8_t>(), q->hyp_pair.as<uint32_t>());
+    // (a10) scoring
+    const float thres = q->p.dist_thres * m->dev.resolution;
+    const float sqt = sq_threshold(thres);
+    q->lazy = false;
+    q->run_thres = thres;
+    q->run_sqt = sqt;
+    if (q->n_outer) {
+        if (!q->p.early_out) {
+            launch_work_count(c->stream, q->sub_off.as<unsigned long long>(),
+                              q->g_hyp.as<uint32_t>(), q->n_outer, q->n_items_g.as<uint32_t>(),
+                              &out->n_tests);
+            launch_exclusive_scan_u32(c->stream, q->n_items_g.as<uint32_t>(),
+                                      q->item_off.as<uint32_t>(), q->n_outer);
+            launch_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(),
+                             q->n_outer, q->item_off.as<uint32_t>(), q->items.as<WorkItem>());
+            ScoreArgs a;
+            a.scene = sc;
+            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
+            a.sub_idx = q->sub_idx.as<int32_t>();
+            a.items = q->items.as<WorkItem>();
+            a.n_items = q->item_off.as<uint32_t>() + q->n_outer;
+            a.work_counter = &out->work_counter;
+            a.T = q->T.as<float4>();
+            a.counts = q->counts.as<uint32_t>();
+            a.scores = q->scores.as<unsigned long long>();
+            a.sq_thres = sqt;
+            a.stats = nullptr;
+            if (knobs().score_stats) {
+                TRY(q->stats.ensure(64));
+                CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
+                a.stats = q->stats.as<unsigned long long>();
+            }
+            q->lazy = knobs().scorer >= 8;
+            if (q->lazy) {
+                int& b = c->count_bps[m->fused ? 1 : 0];
+                if (!b) b = score_count_x2_max_blocks_per_sm(m->fused);
+                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+                CU(cudaEventRecord(q->ev_s0, c->stream));
+                launch_score_count_x2(c->stream, a, grid, m->fused);
+                CU(cudaEventRecord(q->ev_s1, c->stream));
+            } else {
+                int& b = c->score_bps[m->fused ? 1 : 0][1];
+                if (!b) b = score_full_max_blocks_per_sm(m->fused, true);
+                const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+                CU(cudaEventRecord(q->ev_s0, c->stream));
+                launch_score_full(c->stream, a, grid, m->fused, true);
+                CU(cudaEventRecord(q->ev_s1, c->stream));
+            }
+        } else {
+            launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
+                                q->g_of_hyp.as<uint32_t>());
+            EarlyArgs a;
+            a.sub_idx = q->sub_idx.as<int32_t>();
+            if (q->p.early_out == 2) {  // evenly sampling walk order (see tm_score)
+                launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                                       q->n_outer, q->max_sub, q->sub_idx_walk.as<int32_t>());
+                a.sub_idx = q->sub_idx_walk.as<int32_t>();
+            } else {
+                launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
+                                         q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
+                a.tile_lo = q->tile_lo.as<float4>();
+                a.tile_hi = q->tile_hi.as<float4>();
+            }
+            a.scene = sc;
+            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
+            a.sub_off = q->sub_off.as<unsigned long long>();
+            a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
+            a.T = q->T.as<float4>();
+            a.n_hyp = (uint32_t)q->cap_hyp;  // grid bound; the kernel clips to n_local
+            a.n_hyp_dev = &out->n_local;
+            a.n_tests = &out->n_tests;
+            a.sq_thres = sqt;
+            a.accept_prob = q->p.accept_prob;
+            a.early_out = 1;
+            a.counts = q->counts.as<uint32_t>();
+            a.scores = q->scores.as<unsigned long long>();
+            a.dropped = q->dropped.as<uint8_t>();
+            a.tested = nullptr;
+            CU(cudaEventRecord(q->ev_s0, c->stream));
+            launch_score_early_drop(c->stream, a, m->fused);
+            CU(cudaEventRecord(q->ev_s1, c->stream));
+        }
+    }
+    launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(), &out->n_local,
+                  out->shard, &out->best, c->sm_count * 2);
+    // (a12) ICP of the local top-k
+    if (q->p.icp_top_k && q->p.max_icp_iterations) {
+        // a hypothesis the early drop gave up on never becomes a candidate (scene.hpp:330: a dropped
+        // project_ returns fewer correspondences than the acceptance bound), whatever its partial count
+        launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
+                           q->p.early_out ? q->dropped.as<uint8_t>() : nullptr,
+                           &out->n_local, q->cap_hyp, q->p.icp_top_k, q->topk_ids.as<uint32_t>(),
+                           q->topk_keys.as<unsigned long long>());
+        launch_gather_rows(c->stream, q->T.as<float4>(), q->topk_ids.as<uint32_t>(), q->p.icp_top_k,
+                           q->icp.Tcur.as<float4>(), q->icp.active.as<uint32_t>());
+        TRY(icp_enqueue(c, sc, m, q->icp, q->p.icp_top_k, q->p.max_icp_iterations, q->p.dist_thres));
+    }
+    TRY(finalize_best(q));
+    CU(cudaGetLastError());
+    q->ran = true;
+    q->scores_valid = !q->lazy;
+    return TM_OK;
+}
+
+int tm_query_result_get(tm_query* q, tm_query_result* r) {
+    REQUIRE(q && r, "null argument");
+    REQUIRE(q->ran, "tm_query_result_get before tm_query_run");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    TRY(pinned_ensure(c, sizeof(QueryOut) + 16));
+    CU(cudaMemcpyAsync(c->pinned, q->out.p, sizeof(QueryOut), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(&q->host_out, c->pinned, sizeof(QueryOut));
+    const QueryOut& o = q->host_out;
+    if (q->stats.p && knobs().score_stats) {
+        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CU(cudaMemcpy(st, q->stats.p, 64, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)"
+                "  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
+                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4],
+                st[5]);
+    }
+    if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
+    memset(r, 0, sizeof(*r));
+    r->n_pairs_valid = o.n_valid;
+    r->n_hypotheses = o.shard[2];
+    r->n_scored = o.n_local;
+    r->n_tests = o.n_tests;
+    r->best_key = o.best;
+    if (o.best) {
+        r->best_inliers = (uint32_t)(o.best >> 32);
+        r->best_hypothesis = 0xFFFFFFFFu - (uint32_t)(o.best & 0xFFFFFFFFull);
+        r->best_score = o.best_score;
+        memcpy(r->best_T, o.best_T16, 64);
+    }
+    return TM_OK;
+}
+int tm_query_score_kernel_ms(tm_query* q, float* ms) {
+    REQUIRE(q && ms && q->ran, "tm_query_score_kernel_ms: null/unrun query");
+    TRY(bind(q->s->ctx));
+    *ms = 0.f;
+    if (!q->n_outer) return TM_OK;
+    CU(cudaEventSynchronize(q->ev_s1));
+    CU(cudaEventElapsedTime(ms, q->ev_s0, q->ev_s1));
+    return TM_OK;
+}
+void* tm_query_best_key_device(tm_query* q) {
+    return q ? (void*)&q->out.as<QueryOut>()->best : nullptr;
+}
+int tm_query_set_global_best(tm_query* q, uint64_t key) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    QueryOut* out = q->out.as<QueryOut>();
+    CU(cudaMemcpyAsync(&out->best, &key, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(out->best_T16, 0, 64, c->stream));
+    CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
+    TRY(finalize_best(q));
+    CU(cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_query_download(tm_query* q, uint64_t capacity, uint32_t* counts, double* scores,
+                      float* T16s, uint8_t* valid, uint32_t* hyp_pair, uint8_t* dropped) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    tm_query_result r;
+    TRY(tm_query_result_get(q, &r));
+    const uint64_t n = r.n_scored;
+    if (n > capacity) return fail(TM_ERR_CAPACITY, "tm_query_download: capacity too small");
+    if (!n) return TM_OK;
+    if (counts) CU(cudaMemcpyAsync(counts, q->counts.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (valid) CU(cudaMemcpyAsync(valid, q->hyp_valid.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (hyp_pair) CU(cudaMemcpyAsync(hyp_pair, q->hyp_pair.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (dropped) {
+        if (q->p.early_out) CU(cudaMemcpyAsync(dropped, q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
+        else memset(dropped, 0, n);
+    }
+    std::vector<unsigned long long> fx;
+    std::vector<uint8_t> dr;
+    if (scores && q->p.early_out) {
+        dr.resize(n);
+        CU(cudaMemcpyAsync(dr.data(), q->dropped.p, n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (scores) {
+        TRY(ensure_scores(q));
+        fx.resize(n);
+        CU(cudaMemcpyAsync(fx.data(), q->scores.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (T16s) {
+        DevBuf& d16 = c->scratch[0];
+        TRY(d16.ensure(n * 64));
+        launch_colmajor_from_rows(c->stream, q->T.as<float4>(), n, d16.as<float>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(T16s, d16.p, n * 64, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (scores)
+        for (uint64_t i = 0; i < n; ++i) {
+            double v = (double)fx[i] / SCORE_SCALE;
+            scores[i] = (!dr.empty() && dr[i]) ? v : v / (double)q->m->dev.cloud.n;
+        }
+    return TM_OK;
+}
+
+int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* counts,
+                         double* scores, uint32_t* iters) {
+    REQUIRE(q && q->ran, "null/unrun query");
+    const uint32_t k = q->p.icp_top_k;
+    REQUIRE(k && q->p.max_icp_iterations, "query has no ICP stage");
+    tm_ctx* c = q->s->ctx;
+    TRY(bind(c));
+    std::vector<long long> sums((size_t)k * ICP_NSUM);
+    std::vector<uint32_t> ids(k);
+    launch_colmajor_from_rows(c->stream, q->icp.Tbest.as<float4>(), k, q->icp_T16.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sums.data(), q->icp.sums_best.p, sums.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ids.data(), q->topk_ids.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    if (T16s) CU(cudaMemcpyAsync(T16s, q->icp_T16.p, k * 64ull, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, q->icp.iters.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t r = 0; r < k; ++r) {
+        if (hyp_ids) hyp_ids[r] = ids[r];
+        if (counts) counts[r] = (uint32_t)sums[(size_t)r * ICP_NSUM];
+        if (scores)
+            scores[r] = (double)sums[(size_t)r * ICP_NSUM + 16] / SCORE_SCALE / (double)q->m->dev.cloud.n;
+    }
+    return TM_OK;
+}
+
+}  // extern "C"

@@ -1,4 +1,4 @@
-// tm_kernels.cuh — launch wrappers shared between the kernel files and capi.cu.
+// tm_kernels.cuh — launch wrappers shared between the kernel files and capi_*.cu.
 #pragma once
 #include <atomic>
 
