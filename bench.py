@@ -2,15 +2,18 @@
 """bench.py — hypotheses scored / s of the triplet_match search path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref)
 
-Workload "C2" (BASELINE.json configs[1]): plane_traits-style model (1 m x 1 m plane patch,
-10 201 points, 12 line-segment feature curves) in a 1 M-point synthetic scene, 2^20 pose
-hypotheses per GPU generated from a recorded, seed-fixed sample list.  One step = one pass
-of the hot path over that batch: radius subsets -> pair features + keys -> hash probe ->
-base_transform_ -> inlier scoring of every hypothesis against its subset (finish_find
-semantics, i.e. no early drop) -> best-pose argmax (+ one NCCL max all-reduce when N > 1).
-Hypotheses are sharded across ranks (weak scaling: 2^20 per GPU), scene + model replicated.
+Headline workload "C2" (BASELINE.json configs[1]): plane_traits-style model (1 m x 1 m plane patch,
+10 201 points, 12 line-segment feature curves) in a 1 M-point synthetic scene, 2^20 pose hypotheses per
+GPU generated from a recorded, seed-fixed sample list.  One step = one pass of the hot path over that
+batch: radius subsets -> pair features + keys -> hash probe -> base_transform_ -> inlier scoring of every
+hypothesis against its subset (finish_find semantics, i.e. no early drop) -> best-pose argmax (+ one NCCL
+max all-reduce when N > 1).  Hypotheses are sharded across ranks (weak scaling: 2^20 per GPU, shards of
+equal hypothesis-point tests), scene + model replicated.
+
+The same line carries, at the same N: `strong` (ONE 2^20-hypothesis C2 query split N ways), `configs`
+(C3, C4, C5 of BASELINE.json, timed the same way) and `per_rank` (kernel time / tests min..max over ranks).
 
 Prints ONE JSON line (see DESIGN.md "Measurement").
 """
@@ -32,27 +35,13 @@ sys.path.insert(0, ROOT)
 METRIC = "pose hypotheses scored/sec"
 UNIT = "hypotheses/s"
 BYTES_PER_TEST = 36  # 16 B scene float4 + 4 B voxel cell + 16 B model float4
-HYP_PER_GPU = 1 << 20
-
-DP = dict(distance_step_count=20.0, angle_step=0.17453292)
-QP = dict(min_df=0.2, max_df=1.0, query_limit=200, dist_thres=1.0, accept_prob=0.5)
+SM_COUNT = 148
+L1_WAVEFRONT_BYTES = 128  # one L1 data-stage wavefront moves at most one 128-byte line
 
 
-def build_workload(n_gpus: int, scale: float = 1.0):
-    """Seed-fixed C2 clouds + recorded pair list sized for n_gpus * 2^20 hypotheses."""
-    from triplet_match_b200 import synth
-    n_scene = int(1_000_000 * scale)
-    model = synth.plane_model(seed=2, size=1.0, res=0.01, n_curves=12)
-    scene = synth.make_scene(seed=2, model=model, n_points=n_scene, n_copies=8, extent=10.0 * np.sqrt(scale))
-    scene = scene.take(synth.morton_order(scene.pos))
-    return model, scene
-
-
-def record_list(scene, diameter: float, n_gpus: int):
-    from triplet_match_b200 import synth
-    # ~ 9 k hypotheses per outer sample on this workload; oversample, the query clips
-    # the global list to exactly n_gpus * 2^20 hypotheses (hyp_limit)
-    return synth.record_pairs(2, scene, diameter, n_outer=256 * n_gpus, pairs_per_outer=128)
+def host_threads() -> int:
+    """Worker threads of both CPU legs: hardware_concurrency() - 1, as find_parallel does (scene.hpp:146)."""
+    return max(1, (os.cpu_count() or 2) - 1)
 
 
 class ClockSampler:
@@ -119,21 +108,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the scoring kernel from the committed ncu summary, or None."""
-    p = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+def kernel_profile():
+    """Per-launch counters of the scoring kernel on the C2 step, from the committed ncu capture."""
     try:
-        with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
+# ------------------------------------------------------------------------------------------- CPU legs
 def cpu_reference_run(model, scene, rec, n_hyp_sample: int, steps: int, warmup: int, threads: int):
     """The reference's CPU path (oracle port) on a bounded sample: pair features -> query ->
     base_transform_ -> project_ (early_out = false) with `threads` std::threads.
     Returns (hyps/s, tests/s, ms/step, sample description)."""
     from oracle import pyoracle as po
+    from triplet_match_b200.workloads import DP, QP
     om = po.OModel(model, **DP, min_df=QP["min_df"], max_df=QP["max_df"])
     osc = po.OScene(scene)
     # bounded sample: the first pairs of the recorded list until n_hyp_sample hypotheses
@@ -167,7 +157,7 @@ def cpu_reference_run(model, scene, rec, n_hyp_sample: int, steps: int, warmup: 
     sec = float(np.mean(times))
     sample = (f"first {T.shape[0]} hypotheses of the recorded C2 list ({npairs} pairs, "
               f"{len(subs)} outer samples, {tests:.3e} hypothesis-point tests per step), "
-              f"project_ early_out=false, {threads} std::threads")
+              f"project_ early_out=false, {threads} std::threads (hardware_concurrency - 1)")
     return T.shape[0] / sec, tests / sec, sec * 1e3, sample
 
 
@@ -185,6 +175,7 @@ def cpu_reference_run_ref(model, scene, rec, n_hyp_sample: int, steps: int, warm
     if not os.path.exists(REF_LIB):
         return None
     from oracle import pyoracle as po
+    from triplet_match_b200.workloads import DP, QP
     L = C.CDLL(REF_LIB)
     L.ref_model_create.restype = C.c_void_p
     L.ref_model_create.argtypes = [C.c_void_p] * 3 + [C.c_uint32] + [C.c_float] * 4
@@ -242,16 +233,120 @@ def cpu_reference_run_ref(model, scene, rec, n_hyp_sample: int, steps: int, warm
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    # the reference's counts on this sample must equal the oracle's (cheap cross-check of the arm)
+    # the reference's counts on this sample against the oracle's (cross-check of the arm; the GPU is held to
+    # both at this size by tests/test_parity_at_size.py)
     co, _, _ = osc.score_batch(om, T, hyp_sub, off, idx, accept_prob=QP["accept_prob"], dist_thres=QP["dist_thres"],
                                early_out=False, nthreads=threads)
-    agree = f"{int((co == counts).sum())} of {n} (differences: voxel-grid nearest-neighbour near-ties at model::init, DESIGN.md section 2)"
+    n_equal = int((co == counts).sum())
     sec = float(np.mean(times))
     sample = (f"first {n} hypotheses of the recorded C2 list ({int(pi.size)} valid pairs, {len(subs)} outer "
               f"samples, {tests:.3e} hypothesis-point tests per step): reference feature/valid/query/"
               f"base_transform_/project_(early_out=false) compiled from /root/reference against header stand-ins, "
-              f"{threads} std::threads; counts equal the oracle's: {agree}; reference model::init took {t_init:.1f} s (untimed)")
-    return n / sec, tests / sec, sec * 1e3, sample
+              f"{threads} std::threads (hardware_concurrency - 1); counts equal the oracle's: {n_equal} of {n}; "
+              f"reference model::init took {t_init:.1f} s (untimed)")
+    return n / sec, tests / sec, sec * 1e3, sample, n_equal, n
+
+
+# ------------------------------------------------------------------------------------------- GPU legs
+class Dist:
+    """torch.distributed plumbing (NCCL): barrier and max / sum / gather over ranks."""
+
+    def __init__(self, world, local_rank):
+        self.on = world > 1
+        self.torch = None
+        if self.on:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        if self.on:
+            self.dist.barrier()
+
+    def _red(self, v, op):
+        if not self.on:
+            return float(v)
+        t = self.torch.tensor([float(v)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, v):
+        return self._red(v, self.dist.ReduceOp.MAX) if self.on else float(v)
+
+    def min(self, v):
+        return self._red(v, self.dist.ReduceOp.MIN) if self.on else float(v)
+
+    def sum(self, v):
+        return self._red(v, self.dist.ReduceOp.SUM) if self.on else float(v)
+
+    def close(self):
+        if self.on:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_steps(ctx, D, step, steps, warmup, queries=None):
+    """W warm-ups, then K steps, each between CUDA events on the context stream with L2 flushed before it
+    (outside the events).  Returns (per-rank total ms, [scoring-kernel ms per step], kernel launches inside
+    the timed steps)."""
+    for _ in range(warmup):
+        step()
+    ctx.sync()
+    D.barrier()
+    ms, kms = [], []
+    l0 = ctx.kernel_launches()
+    for _ in range(steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        step()
+        ms.append(ctx.timer_stop())
+        if queries:
+            kms.append(float(sum(q.score_kernel_ms() for q in queries)))
+    ctx.sync()
+    launches = ctx.kernel_launches() - l0 - steps  # minus the untimed L2-flush launches
+    D.barrier()
+    return float(np.sum(ms)), kms, int(launches)
+
+
+def run_query_config(ctx, D, comm, gs, gm_list, recs, hyp_per_query, steps, warmup, world, rank, balance=True):
+    """One resident query per model over the same scene, shards of equal tests; one (batched) best-pose
+    all-reduce per step.  Returns a dict of whole-job numbers."""
+    from triplet_match_b200 import capi
+    from triplet_match_b200.workloads import QP
+    queries = []
+    for gm, rec in zip(gm_list, recs):
+        q = capi.Query(gs, gm, **QP, hyp_limit=hyp_per_query * world,
+                       max_hypotheses=int(hyp_per_query * (1.25 if world > 1 else 1.0)) + 4096)
+        q.set_shard(rank, world)
+        if balance and world > 1:
+            q.set_balance(True, comm)
+        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        queries.append(q)
+
+    def step():
+        for q in queries:
+            q.run()
+        if comm is not None:
+            if len(queries) == 1:
+                comm.allreduce_best(queries[0])
+            else:
+                comm.allreduce_best_many(queries)
+
+    total_ms, kms, launches = timed_steps(ctx, D, step, steps, warmup, queries)
+    rs = [q.result() for q in queries]
+    scored = float(sum(int(r.n_scored) for r in rs))
+    tests = float(sum(int(r.n_tests) for r in rs))
+    sec = D.max(total_ms) * 1e-3
+    k_ms = float(np.mean(kms)) if kms else 0.0
+    out = {"value": D.sum(scored) * steps / sec, "unit": UNIT, "ms_per_step": sec * 1e3 / steps,
+           "tests_per_sec": D.sum(tests) * steps / sec, "hypotheses_per_step": D.sum(scored),
+           "tests_per_step": D.sum(tests),
+           "per_rank": {"score_kernel_ms": [D.min(k_ms), D.max(k_ms)], "tests": [D.min(tests), D.max(tests)],
+                        "hypotheses": [D.min(scored), D.max(scored)], "step_ms": [D.min(total_ms / steps), D.max(total_ms / steps)]},
+           "best_inliers": [int(r.best_inliers) for r in rs][:4], "gpu_launches": launches}
+    return out, queries, step
 
 
 def main():
@@ -264,6 +359,7 @@ def main():
                     help="scene size scale (dev only; 1.0 = the named configuration)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TM_CPU_SAMPLE", 16384)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 legs (dev)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -271,30 +367,33 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     n_gpus = max(args.gpus, world)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
 
-    import __graft_entry__ as ge
+    from triplet_match_b200 import workloads as wl
+    DP, QP, HYP_PER_GPU = wl.DP, wl.QP, wl.HYP_PER_GPU
     config = {"workload": "C2: plane model 10201 pts / 1M-point synthetic scene / 2^20 hypotheses "
                           "per GPU from a recorded seed-fixed sample list (BASELINE.json configs[1])",
               "scene_points": int(1_000_000 * args.scale), "hypotheses_per_gpu": HYP_PER_GPU,
               "scoring": "finish_find semantics (project_ early_out=false)",
-              "parallelism": f"hypotheses sharded x{n_gpus}, scene+model replicated",
+              "parallelism": f"hypotheses sharded x{n_gpus} (shards of equal hypothesis-point tests), scene+model replicated",
               "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        ge.build()
-        model, scene = build_workload(n_gpus, args.scale)
+        # test infrastructure only: the oracle and the shim-compiled reference; this arm never loads the CUDA library
+        from oracle import build as oracle_build
+        oracle_build.build_oracle()
+        model, scene = wl.c2_clouds(args.scale)
         # recorded list needs the model diameter only (no GPU): bbox diagonal in float32
         lo, hi = model.pos.min(axis=0), model.pos.max(axis=0)
         d = (hi - lo).astype(np.float32)
         diam = float(np.sqrt(np.float32(d[0] * d[0]) + (np.float32(d[1] * d[1]) + np.float32(d[2] * d[2]))))
-        rec = record_list(scene, diam, n_gpus)
+        rec = wl.c2_record(scene, diam, n_gpus)
         port = cpu_reference_run(model, scene, rec, args.cpu_sample, max(1, min(args.steps, 3)), 1, threads)
         ref = cpu_reference_run_ref(model, scene, rec, args.cpu_sample, args.steps, args.warmup, threads)
         kind = "reference" if ref is not None else "port"
-        hps, tps, ms, sample = ref if ref is not None else port
+        hps, tps, ms, sample = (ref if ref is not None else port)[:4]
         line = {"impl": "reference", "metric": METRIC, "value": hps, "unit": UNIT, "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -307,220 +406,134 @@ def main():
                                 "cores": threads},
                 "note": "the reference's own build (cmake + PCL/FLANN/Eigen/range-v3/boost/fmt) is impossible here; "
                         "kind=reference runs its sources compiled against header stand-ins (oracle/_ref), "
-                        "kind=port the dependency-free oracle restatement; the faster of the two is oracle_port"}
+                        "kind=port the dependency-free oracle restatement"}
+        if ref is not None:
+            line["counts_equal_oracle"] = {"equal": ref[4], "of": ref[5]}
         print(json.dumps(line), flush=True)
         return
 
     # ------------------------------------------------------------------ ours
+    import __graft_entry__ as ge
     ge.build()
     import torch
     from triplet_match_b200 import capi
 
-    dist_on = world > 1
-    if dist_on:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = Dist(world, local_rank)
     ctx = capi.Context(local_rank)
-    model, scene = build_workload(n_gpus, args.scale)
+    comm = None
+    if D.on:
+        ids = [capi.Comm.unique_id() if rank == 0 else None]
+        D.dist.broadcast_object_list(ids, src=0)
+        comm = capi.Comm(ctx, ids[0], rank, world)
+
+    model, scene = wl.c2_clouds(args.scale)
     hm = capi.HostModel(ctx, model.pos, model.nrm, model.tgt, curv_ok=model.tangent_mask, **DP,
                         min_df=QP["min_df"], max_df=QP["max_df"], cap=QP["query_limit"])
     gm = hm.upload(ctx)
     gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
-    rec = record_list(scene, hm.diameter, n_gpus)
-    total_limit = HYP_PER_GPU * n_gpus
-    q = capi.Query(gs, gm, **QP, hyp_limit=total_limit, max_hypotheses=HYP_PER_GPU)
-    q.set_shard(rank, world)
-    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
-    comm = None
-    if dist_on:
-        ids = [capi.Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        comm = capi.Comm(ctx, ids[0], rank, world)
+    rec = wl.c2_record(scene, hm.diameter, n_gpus)
 
-    def step():
-        q.run()
-        if comm is not None:
-            comm.allreduce_best(q)
-
-    def barrier():
-        ctx.sync()
-        if dist_on:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
-    r0 = q.result()
+    # ---- headline: weak scaling, 2^20 hypotheses per GPU ------------------------------------------
     sampler = ClockSampler(local_rank)
-    launches0 = ctx.kernel_launches()
-    barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    step_ms, kern_ms = [], []
-    for _ in range(args.steps):
-        ctx.flush_l2()
-        ctx.timer_start()
-        step()
-        step_ms.append(ctx.timer_stop())
-        kern_ms.append(q.score_kernel_ms())
-    barrier()
+    head, queries, step = run_query_config(ctx, D, comm, gs, [gm], [rec], HYP_PER_GPU, args.steps, args.warmup, world, rank)
+    torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    launches = ctx.kernel_launches() - launches0 - args.steps  # minus the untimed L2-flush launches
+    q = queries[0]
+    launches = head["gpu_launches"]
     r = q.result()
-    total_ms = float(np.sum(step_ms))
-    n_scored = int(r.n_scored)
-    n_tests = int(r.n_tests)
-    if dist_on:
-        t = torch.tensor([total_ms, float(n_scored), float(n_tests)], device="cuda", dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms = float(tmax[0].item())
-        all_scored = int(tsum[1].item())
-        all_tests = int(tsum[2].item())
-    else:
-        all_scored, all_tests = n_scored, n_tests
-    sec = total_ms * 1e-3
-    value = all_scored * args.steps / sec
-    tests_per_sec = all_tests * args.steps / sec
+    n_scored, n_tests = int(r.n_scored), int(r.n_tests)
+    front_ms = q.frontend_ms()
 
     # ---- e2e: host buffers in, host results out, through the C-ABI ----------
     e2e_ms = []
     for it in range(2 + args.steps):
-        if dist_on:
-            dist.barrier()
+        D.barrier()
         t0 = time.perf_counter()
-        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # H2D: recorded list (+ sizing pass)
+        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # H2D: recorded list; front end + sizing of this rank's shard
         q.run()
         if comm is not None:
             comm.allreduce_best(q)
-        d = q.download_counts()                              # D2H: result + per-hypothesis counts
+        q.download_counts()                                  # D2H: result + per-hypothesis counts
         dt = (time.perf_counter() - t0) * 1e3
         if it >= 2:
             e2e_ms.append(dt)
-    e2e_sec = float(np.mean(e2e_ms)) * 1e-3
-    if dist_on:
-        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
+    e2e_sec = D.max(float(np.mean(e2e_ms))) * 1e-3
     h2d = 4 * (rec.outer.size + 2 * rec.pair_j.size)
-    d2h = 4 * n_scored + 152
-    e2e = {"value": all_scored / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+    d2h = 4 * n_scored + 152 + 8 * (rec.outer.size + 1)
+    e2e = {"value": head["hypotheses_per_step"] / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3,
            "call": "tm_query_set_pairs + tm_query_run + tm_query_result_get + tm_query_download "
                    "(scene + model resident, as in the reference where they are built before find)"}
 
-    # ---- roofline of the dominant kernel (score_full_kernel) ----------------
-    peak, peak_src = measured_peak_gbs()
-    k_ms = float(np.mean(kern_ms))
-    achieved = n_tests * BYTES_PER_TEST / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "kernel": "score_full_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / float(np.sum(step_ms)),
-                "algorithmic_bytes_per_launch": n_tests * BYTES_PER_TEST,
-                "note": "36 B/test is the no-reuse algorithmic figure (SURVEY §8d); the kernel keeps scene "
-                        "points in registers and the grid in L2, so frac > 1 is expected and DRAM traffic "
-                        "is far below it"}
+    # ---- roofline of the dominant kernel (score_count_x2_kernel) ------------
+    # What binds it is on-chip: the L1 data stage (ncu l1tex__data_pipe_lsu_wavefronts 96 % of peak), fed by the
+    # scattered 16-byte cell gathers.  achieved = data-stage wavefronts of one launch (from the committed ncu
+    # capture of this exact workload: they depend on the data, not on the run) x 128 B / this run's kernel time;
+    # peak = one wavefront per SM per cycle at the SM clock sampled during the timed region.
+    prof = kernel_profile()
+    peak_hbm, peak_src = measured_peak_gbs()
+    k_ms = head["per_rank"]["score_kernel_ms"][1]
+    sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
+    wavefronts = float(prof.get("l1_data_pipe_wavefronts_per_launch") or 0.0)
+    l1_peak = SM_COUNT * L1_WAVEFRONT_BYTES * sm_mhz * 1e6 / 1e9
+    l1_ach = wavefronts * L1_WAVEFRONT_BYTES / (k_ms * 1e-3) / 1e9 if (k_ms > 0 and args.scale == 1.0) else 0.0
+    hbm_ach = n_tests * BYTES_PER_TEST / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    executed = prof.get("executed_tests_per_launch")
+    roofline = {"bound": "l1tex", "achieved": l1_ach, "peak": l1_peak, "unit": "GB/s", "frac": l1_ach / l1_peak if l1_peak else None,
+                "traffic": prof.get("dram_bytes_per_launch"),
+                "kernel": prof.get("kernel", "score_count_x2_kernel"), "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms / head["ms_per_step"] if head["ms_per_step"] else None,
+                "definition": "L1 data-stage wavefronts per launch (ncu l1tex__data_pipe_lsu_wavefronts.sum, committed "
+                              "capture of this workload) x 128 B / live kernel time, against 148 SMs x 1 wavefront/clk x "
+                              "the SM clock sampled in this run; ncu read 96 % for the same quantity",
+                "ncu": {k: prof.get(k) for k in ("l1tex_data_pipe_pct", "lsu_writeback_pct", "issue_active_pct", "lts_throughput_pct",
+                                                  "dram_throughput_pct", "l2_hit_pct", "warp_instructions_per_launch", "source")},
+                "nominal_tests_per_step": n_tests, "executed_tests_per_step": executed,
+                "executed_tests_note": "tests that survive the exact box cull (TM_SCORE_STATS); the rest are proven misses",
+                "warp_instructions_per_32_executed_tests": (prof["warp_instructions_per_launch"] * 32.0 / executed)
+                if executed and prof.get("warp_instructions_per_launch") else None,
+                "hbm_form": {"achieved": hbm_ach, "peak": peak_hbm, "unit": "GB/s", "frac": hbm_ach / peak_hbm, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": n_tests * BYTES_PER_TEST,
+                             "note": "SURVEY §8d's 36 B per nominal test against measured HBM copy bandwidth: far above 1 because "
+                                     "78 % of the nominal tests are culled and the rest is served from registers and L2 "
+                                     "(DRAM moves ~0.1 GB per launch) — kept for the contract, it is not what bounds the kernel"}}
 
-    # the limit that actually binds (ncu, profiles/r1_score_full_v4_ncu_summary.txt): L2 -> L1 gather
-    # sectors.  Bytes per launch come from the committed ncu capture of this exact workload (they
-    # depend on the data, not on the run); time is this run's live kernel time.
-    try:
-        with open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")) as f:
-            tj = json.load(f)
-        l2_bytes = float(tj["l2_to_l1_bytes_per_launch"])
-        sm_mhz = float(clocks.get("sm_mhz") or 1965.0)
-        l2_peak = 6300.0 * sm_mhz * 1e6 / 1e9  # ~6300 B/cycle full-chip LTS cap (B300_MICROARCH.md) at the sampled SM clock
-        l2_measured = ctx.measure_l2_gather(32 << 20)  # random 16-B cell gathers over 32 MiB, measured now
-        if args.scale == 1.0 and k_ms > 0:
-            roofline["l2_gather"] = {"achieved": l2_bytes / (k_ms * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
-                                     "frac": l2_bytes / (k_ms * 1e-3) / 1e9 / l2_peak,
-                                     "l1_sector_requests_per_launch": tj.get("l1_sector_requests_per_launch"),
-                                     "peak_source": "guide: LTS throughput cap ~6300 B/cycle x sampled SM clock",
-                                     "measured_random_gather_gbs": l2_measured,
-                                     "frac_of_measured_random_gather": l2_bytes / (k_ms * 1e-3) / 1e9 / l2_measured if l2_measured > 0 else None,
-                                     "measured_note": "tm_ctx_measure_l2_gather: independent random 16-byte cell reads (32-B sectors) "
-                                                      "over a 32 MiB working set, 8 in flight per lane, timed in this run",
-                                     "bytes_source": tj.get("source")}
-    except Exception:
-        pass
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+    line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config, "tests_per_sec": tests_per_sec,
-            "hypotheses_per_step": all_scored, "tests_per_step": all_tests,
+            "config": config, "tests_per_sec": head["tests_per_sec"],
+            "hypotheses_per_step": head["hypotheses_per_step"], "tests_per_step": head["tests_per_step"],
             "best_inliers": int(r.best_inliers), "best_hypothesis": int(r.best_hypothesis),
-            "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+            "wall_ms_per_step_incl_flush": wall * 1e3 / (args.steps + args.warmup),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "per_rank": head["per_rank"],
+            "front_end_ms": {"value": D.max(front_ms), "note": "replicated on every rank: pair features + probe + scan over the "
+                             f"whole {rec.pair_j.size}-pair list, shard and per-outer ranges (CUDA events, last step)"}}
+
+    # ---- strong scaling: ONE 2^20-hypothesis C2 query split N ways ----------------------------------
+    if world > 1:
+        try:
+            sq, squeries, _ = run_query_config(ctx, D, comm, gs, [gm], [rec], HYP_PER_GPU // world, args.steps, args.warmup,
+                                               world, rank)
+            line["strong"] = {"value": sq["value"], "unit": UNIT, "ms_per_step": sq["ms_per_step"],
+                              "hypotheses_per_step": sq["hypotheses_per_step"], "per_rank": sq["per_rank"],
+                              "workload": f"one 2^20-hypothesis C2 query split over {world} GPUs"}
+            for x in squeries:
+                x.close()
+        except Exception as e:  # noqa: BLE001
+            line["strong"] = {"error": repr(e)}
+    else:
+        line["strong"] = {"value": head["value"], "unit": UNIT, "ms_per_step": head["ms_per_step"],
+                          "hypotheses_per_step": head["hypotheses_per_step"],
+                          "workload": "one 2^20-hypothesis C2 query on 1 GPU (= the headline)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         hps, tps, ms, sample = cpu_reference_run(model, scene, rec, args.cpu_sample, 3, 1, threads)
         line["cpu_baseline"] = {"value": hps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": sample, "tests_per_sec": tps, "ms_per_step": ms}
-        # the reference's own operating mode: project_(early_out = true) with the 18-checkpoint early drop
-        # (scene.hpp:326, 492-506).  Reported beside the headline, which scores every hypothesis in full.
-        q3 = capi.Query(gs, gm, **QP, early_out=True, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU)
-        q3.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
-        eo_ms = []
-        for it in range(3 + 5):
-            ctx.flush_l2()
-            ctx.timer_start()
-            q3.run()
-            t_ms = ctx.timer_stop()
-            if it >= 3:
-                eo_ms.append(t_ms)
-        r3 = q3.result()
-        d3 = q3.download()
-        alive3 = d3["dropped"] == 0
-        q3.close()
-        q3 = capi.Query(gs, gm, **QP, early_out=True, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
-                        icp_top_k=64, max_icp_iterations=5)
-        q3.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
-        lat3 = []
-        for it in range(3 + 20):
-            t0 = time.perf_counter()
-            q3.run()
-            q3.result()
-            if it >= 3:
-                lat3.append((time.perf_counter() - t0) * 1e3)
-        line["p50_query_early_drop_ms"] = float(np.median(lat3))
-        line["early_drop_mode"] = {"value": r3.n_scored / (float(np.mean(eo_ms)) * 1e-3), "unit": UNIT,
-                                   "ms_per_step": float(np.mean(eo_ms)), "tests_per_step": int(r3.n_tests),
-                                   "survivors": int(alive3.sum()),
-                                   "best_pose_survives": bool(alive3.any() and int(d3["counts"][alive3].max()) == int(r.best_inliers)),
-                                   "note": "project_(early_out=true) semantics, bit-exact with the reference incl. drop points; "
-                                           "not the headline (the headline scores every hypothesis over its whole subset)"}
-        q3.close()
-        # the same drop test over an evenly sampling walk of each subset (early_out = 2, include/tm_b200.h): what the
-        # test presumes statistically; reports how many hypotheses survive it and whether the best pose does
-        q4 = capi.Query(gs, gm, **QP, early_out=2, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU)
-        q4.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
-        ev_ms = []
-        for it in range(1 + 2):  # ~0.4 s per pass: one warm-up, two timed
-            ctx.flush_l2()
-            ctx.timer_start()
-            q4.run()
-            t_ms = ctx.timer_stop()
-            if it >= 1:
-                ev_ms.append(t_ms)
-        r4 = q4.result()
-        d4 = q4.download()
-        alive = d4["dropped"] == 0
-        line["early_drop_even_walk_mode"] = {
-            "value": r4.n_scored / (float(np.mean(ev_ms)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ev_ms)),
-            "tests_per_step": int(r4.n_tests), "survivors": int(alive.sum()),
-            "best_inliers_among_survivors": int(d4["counts"][alive].max()) if alive.any() else 0,
-            "best_pose_survives": bool(alive.any() and int(d4["counts"][alive].max()) == int(r.best_inliers)),
-            "note": "early_out=2: the reference's drop test (bit-exact arithmetic) over the walk p -> (p*s) mod n of each "
-                    "subset; in the subset's own (Z-curve) order the test gives up on true poses.  One warp walks one "
-                    "hypothesis with scattered point loads and no tile culling, so on this workload (over half of the "
-                    "hypotheses pass the test) it is slower than scoring everything with the tiled kernel"}
-        q4.close()
         # p50 full-query latency incl. ICP of the top 64 (SURVEY §8d metric ii)
         q2 = capi.Query(gs, gm, **QP, hyp_limit=HYP_PER_GPU, max_hypotheses=HYP_PER_GPU,
                         icp_top_k=64, max_icp_iterations=5)
@@ -536,13 +549,121 @@ def main():
         line["p50_query_def"] = ("resident scene+model; subsets->features->probe->hypotheses(2^20)->"
                                  "score->argmax->ICP(top 64, 5 iterations); 20 repeats after 3 warm-ups")
         q2.close()
+        # the reference's own operating mode, project_(early_out = true) (scene.hpp:326, 492-506), beside the headline
+        try:
+            line["early_drop_modes"] = early_drop_legs(ctx, capi, gs, gm, rec, r, QP, HYP_PER_GPU)
+        except Exception as e:  # noqa: BLE001
+            line["early_drop_modes"] = {"error": repr(e)}
+    q.close()
+    gm.close(); gs.close(); hm.close()
+
+    # ---- the other named configurations at the same N -------------------------------------------------
+    if not args.no_configs and args.scale == 1.0:
+        cfgs = {}
+        for name, fn in (("C3", bench_c3_c5), ("C4", bench_c4)):
+            try:
+                cfgs.update(fn(ctx, D, comm, capi, wl, args.steps, args.warmup, world, rank))
+            except Exception as e:  # noqa: BLE001
+                cfgs[name] = {"error": repr(e)}
+        line["configs"] = cfgs
     if comm is not None:
         comm.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if dist_on:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
+
+
+def early_drop_legs(ctx, capi, gs, gm, rec, r_full, QP, hyp):
+    out = {}
+    for mode, key in ((1, "subset_order"), (2, "even_walk")):
+        qe = capi.Query(gs, gm, **QP, early_out=mode, hyp_limit=hyp, max_hypotheses=hyp)
+        qe.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        ms = []
+        for it in range(2 + 3):
+            ctx.flush_l2()
+            ctx.timer_start()
+            qe.run()
+            t = ctx.timer_stop()
+            if it >= 2:
+                ms.append(t)
+        re_ = qe.result()
+        d = qe.download()
+        alive = d["dropped"] == 0
+        out[key] = {"value": re_.n_scored / (float(np.mean(ms)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)),
+                    "tests_per_step": int(re_.n_tests), "survivors": int(alive.sum()),
+                    "best_pose_survives": bool(alive.any() and int(d["counts"][alive].max()) == int(r_full.best_inliers))}
+        qe.close()
+    out["note"] = ("project_(early_out=true) semantics, bit-exact with the reference incl. drop points: in the subset's own order "
+                   "(early_out=1) and over the evenly sampling walk p -> (p*s) mod n (early_out=2); not the headline, which scores "
+                   "every hypothesis over its whole subset")
+    return out
+
+
+def bench_c3_c5(ctx, D, comm, capi, wl, steps, warmup, world, rank):
+    """C3 (free-form 50 k model vs 10 M scene, 2^20 hypotheses per GPU) and C5 (ICP of 64 poses on that scene,
+    poses sharded over the ranks: strong scaling)."""
+    model, scene, poses = wl.c3_clouds()
+    hm = capi.HostModel(ctx, model.pos, model.nrm, model.tgt, curv_ok=model.tangent_mask, **wl.DP,
+                        min_df=wl.QP["min_df"], max_df=wl.QP["max_df"], cap=wl.QP["query_limit"])
+    gm = hm.upload(ctx)
+    gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
+    rec = wl.c3_record(scene, hm.diameter, world)
+    c3, queries, _ = run_query_config(ctx, D, comm, gs, [gm], [rec], wl.HYP_PER_GPU, max(2, steps // 2), 3, world, rank)
+    c3["scaling"] = "weak"
+    c3["workload"] = (f"free-form {model.n}-point model vs {scene.n}-point scene, 2^20 hypotheses per GPU, grid "
+                      f"{hm.extents.tolist()}")
+    for q in queries:
+        q.close()
+    # C5
+    Ts = wl.c5_start_poses(poses)
+    n_top, iters = Ts.shape[0], wl.C5_ITERS
+
+    def icp_step():
+        return gs.icp_pose_sharded(gm, Ts, iters, wl.QP["dist_thres"], rank=rank, world=world, comm=comm)
+    for _ in range(3):
+        res = icp_step()
+    ctx.sync()
+    D.barrier()
+    reps = max(5, steps)
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        res = icp_step()
+    ctx.sync()
+    sec = D.max(time.perf_counter() - t1)
+    To, co, so, io = res
+    c5 = {"value": n_top * reps / sec, "unit": "poses/s", "ms_per_step": sec * 1e3 / reps, "scaling": "strong",
+          "metric": "ICP refinements/sec (64 poses, whole scene per pass)",
+          "timing": "host wall clock around tm_icp_pose_sharded incl. pose H2D, result D2H and the all-gather; max over ranks",
+          "workload": f"ICP (max {iters} iterations, 2 x dist_thres) of {n_top} perturbed poses against a {scene.n}-point scene; "
+                      f"poses sharded x{world}, whole scene on every GPU, one all-gather of 80-byte records at the end",
+          "counts_min_max": [int(co.min()), int(co.max())]}
+    gm.close(); gs.close(); hm.close()
+    return {"C3": c3, "C5": c5}
+
+
+def bench_c4(ctx, D, comm, capi, wl, steps, warmup, world, rank):
+    """C4: 16 models x one 5 M-point scene, 2^18 hypotheses per model per GPU, one batched best-pose all-reduce."""
+    models, scene = wl.c4_clouds()
+    gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
+    hms, gms, recs = [], [], []
+    for k, mdl in enumerate(models):
+        hmk = capi.HostModel(ctx, mdl.pos, mdl.nrm, mdl.tgt, curv_ok=mdl.tangent_mask, **wl.DP, min_df=wl.QP["min_df"],
+                             max_df=wl.QP["max_df"], cap=wl.QP["query_limit"])
+        hms.append(hmk)
+        gms.append(hmk.upload(ctx))
+        recs.append(wl.c4_record(scene, k, hmk.diameter, world))
+    c4, queries, _ = run_query_config(ctx, D, comm, gs, gms, recs, wl.C4_HYP_PER_MODEL, max(2, steps // 2), 3, world, rank)
+    c4["scaling"] = "weak"
+    c4["workload"] = (f"16 models (plane / cylinder / free-form) x one {scene.n}-point scene, 2^18 hypotheses per model per GPU, "
+                      "one batched best-pose all-reduce")
+    for q in queries:
+        q.close()
+    for g in gms:
+        g.close()
+    for h in hms:
+        h.close()
+    gs.close()
+    return {"C4": c4}
 
 
 if __name__ == "__main__":

@@ -255,6 +255,17 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
                        const uint32_t* pair_outer, const uint32_t* pair_j, uint64_t n_pairs);
 /* this rank scores hypotheses [rank*ceil(H/world), ...) of the global list */
 int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world);
+/* How the global hypothesis list is cut into `world` contiguous shards.  by_tests == 0 (default): equal
+ * hypothesis counts, [rank*ceil(H/world), ...).  by_tests != 0: equal hypothesis-point tests — a shard's work is
+ * sum(|subset(outer)| x hypotheses(outer)), and a step takes as long as the slowest rank.  The split needs the
+ * subset size of every outer sample: each rank measures the outer samples of its count-based share and one
+ * ncclAllReduce(max) of n_outer x 4 bytes over `comm` completes the table (comm == NULL: every rank sizes all
+ * outer samples itself).  All ranks must use the same setting; concatenating the shards in rank order still
+ * gives the global list.  Leave headroom in max_hypotheses: shards no longer have equal counts. */
+int tm_query_set_balance(tm_query* q, int by_tests, tm_comm* comm);
+/* device time of the replicated front end of the last tm_query_run (pair features + probe over the whole list,
+ * scan, shard and per-outer ranges) */
+int tm_query_frontend_ms(tm_query* q, float* ms);
 /* enqueue subsets -> features -> probe -> hypotheses -> score -> argmax (-> ICP) on the
  * context stream; inputs and outputs stay resident */
 int tm_query_run(tm_query* q);
@@ -293,6 +304,16 @@ int tm_icp_sharded(tm_scene* s, tm_model* m, tm_comm* comm, const float* T16s, u
                    uint32_t max_iterations, float dist_thres, uint32_t pt_begin, uint32_t pt_end,
                    uint64_t n_scene_total, uint32_t emulate_parts, float* T16s_out, uint32_t* counts,
                    double* scores, uint32_t* iters);
+
+/* icp_ with the POSES sharded across ranks (the first option for BASELINE configs[4]): every rank
+ * holds the whole scene and refines poses [n*rank/world, n*(rank+1)/world) exactly as tm_icp does — no
+ * collective inside the iteration loop — and ONE ncclAllGather of 80-byte records {pose, count, iterations,
+ * score} publishes all n results on every rank, bit-identical to tm_icp of the whole list.  comm == NULL
+ * runs the given (rank, world) slice in this process and writes only that slice of the outputs (how the
+ * split is tested on one GPU and with a CPU-side gather); with a communicator rank / world come from it. */
+int tm_icp_pose_sharded(tm_scene* s, tm_model* m, tm_comm* comm, uint32_t rank, uint32_t world, const float* T16s,
+                        uint32_t n, uint32_t max_iterations, float dist_thres, float* T16s_out, uint32_t* counts,
+                        double* scores, uint32_t* iters);
 
 #ifdef __cplusplus
 }

@@ -205,6 +205,30 @@ def test_scene_sharded_icp_is_split_invariant(setup):
     assert (ch <= co).all() and ch.sum() < co.sum()
 
 
+def test_pose_sharded_icp_equals_icp(setup):
+    """tm_icp_pose_sharded (SURVEY 8e first option): the slices of any pose split, refined rank by rank with no
+    collective, concatenate to tm_icp's result bit for bit; repeated calls replay the cached CUDA graph."""
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    cnt, _, _ = osc.score_batch(om, T, nthreads=4)
+    top = np.argsort(-cnt.astype(np.int64), kind="stable")[:7]
+    To, co, so, io = gs.icp(gm, T[top], 4, 1.0)
+    for world in (1, 2, 3):
+        Tc, cc = np.zeros_like(To), np.zeros_like(co)
+        sc, ic = np.zeros_like(so), np.zeros_like(io)
+        for rank in range(world):
+            Tr, cr, sr, ir = gs.icp_pose_sharded(gm, T[top], 4, 1.0, rank=rank, world=world)
+            b, e = (7 * rank) // world, (7 * (rank + 1)) // world
+            Tc[b:e], cc[b:e], sc[b:e], ic[b:e] = Tr[b:e], cr[b:e], sr[b:e], ir[b:e]
+            assert not Tr[:b].any() and not Tr[e:].any()  # only the slice is written
+        assert np.array_equal(_bits(Tc), _bits(To)) and np.array_equal(cc, co) and np.array_equal(ic, io)
+        assert np.array_equal(sc, so)
+    # graph replay: same inputs, same bits, again and again
+    for _ in range(3):
+        T2, c2, s2, i2 = gs.icp(gm, T[top], 4, 1.0)
+        assert np.array_equal(_bits(T2), _bits(To)) and np.array_equal(c2, co) and np.array_equal(s2, so)
+
+
 def test_resident_query_and_golden(setup, ctx):
     from triplet_match_b200 import capi
     name, m, s, om, osc, rec, gm, gs = setup
@@ -423,10 +447,9 @@ def test_empty_inputs(ctx):
 def test_full_size_properties(ctx):
     """C2-sized run (1M-point scene): properties that do not need the CPU oracle at full
     size, plus an oracle spot check on a sample of hypotheses."""
-    import bench
     from oracle import pyoracle as po
-    from triplet_match_b200 import capi, synth
-    model, scene = bench.build_workload(1, 1.0)
+    from triplet_match_b200 import capi, synth, workloads
+    model, scene = workloads.c2_clouds()
     hm = capi.HostModel(ctx, model.pos, model.nrm, model.tgt, curv_ok=model.tangent_mask, **common.DP, **common.SP)
     gm = hm.upload(ctx)
     gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
@@ -456,6 +479,32 @@ def test_full_size_properties(ctx):
         parts.append(q2.download_counts()[0])
         q2.close()
     assert np.array_equal(np.concatenate(parts), d["counts"])
+    # (3b) shards of equal TESTS (tm_query_set_balance): still a partition of the list in rank order, and the
+    # per-rank test counts are within 2 % of each other (the count-based split is not); changing the shard
+    # after set_pairs re-sizes on the next run
+    for world in (2, 3, 8):
+        parts, tests, tests_cnt = [], [], []
+        for rank in range(world):
+            q2 = capi.Query(gs, gm)
+            q2.set_shard(rank, world)
+            q2.set_balance(True)
+            q2.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+            q2.run()
+            parts.append(q2.download_counts()[0])
+            tests.append(int(q2.result().n_tests))
+            q2.set_balance(False)  # re-sized lazily by the next run
+            q2.run()
+            tests_cnt.append(int(q2.result().n_tests))
+            q2.close()
+        assert np.array_equal(np.concatenate(parts), d["counts"])
+        assert sum(tests) == sum(tests_cnt) == int(q.result().n_tests)
+        assert max(tests) <= 1.02 * (sum(tests) / world)
+    q2 = capi.Query(gs, gm)
+    q2.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # sized for (0, 1)
+    q2.set_shard(1, 2)                                    # then re-sharded
+    q2.run()
+    assert np.array_equal(q2.download_counts()[0], d["counts"][(n + 1) // 2:])
+    q2.close()
     # (4) every hypothesis sees its own pair: p1 -> m_i exactly => at least one inlier
     assert (d["counts"][d["valid"].astype(bool)] >= 1).all()
     # (5) oracle spot check at full size

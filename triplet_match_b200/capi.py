@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -527,6 +527,22 @@ class Scene:
                                             C.byref(cnt)))
         return mask[:self.n], int(cnt.value)
 
+    def icp_pose_sharded(self, model: Model, T16s, max_iterations: int, dist_thres: float, rank: int = 0,
+                         world: int = 1, comm=None):
+        """tm_icp_pose_sharded: this rank refines its slice of the poses against the whole resident scene; with a
+        communicator all n results come back on every rank, without one only the slice [n*rank/world, ...)."""
+        T = _f32(T16s, (-1, 16))
+        n = T.shape[0]
+        out = np.zeros_like(T)
+        counts = np.zeros(n, dtype=np.uint32)
+        scores = np.zeros(n, dtype=np.float64)
+        iters = np.zeros(n, dtype=np.uint32)
+        _chk(self.lib.tm_icp_pose_sharded(self.h, model.h, comm.h if comm is not None else None,
+                                          C.c_uint32(rank), C.c_uint32(world), _p(T), C.c_uint32(n),
+                                          C.c_uint32(max_iterations), C.c_float(dist_thres), _p(out), _p(counts),
+                                          _p(scores), _p(iters)))
+        return out, counts, scores, iters
+
     def icp_sharded(self, model: Model, T16s, max_iterations: int, dist_thres: float, pt_begin: int,
                     pt_end: int, n_scene_total: int, comm=None, emulate_parts: int = 1):
         """tm_icp_sharded: this process accumulates scene points [pt_begin, pt_end)."""
@@ -573,8 +589,17 @@ class Query:
     def set_shard(self, rank: int, world: int):
         _chk(self.lib.tm_query_set_shard(self.h, C.c_uint32(rank), C.c_uint32(world)))
 
+    def set_balance(self, by_tests: bool, comm=None):
+        """Shards of equal hypothesis-point tests instead of equal hypothesis counts (tm_query_set_balance)."""
+        _chk(self.lib.tm_query_set_balance(self.h, C.c_int(1 if by_tests else 0), comm.h if comm is not None else None))
+
     def run(self):
         _chk(self.lib.tm_query_run(self.h))
+
+    def frontend_ms(self) -> float:
+        ms = C.c_float()
+        _chk(self.lib.tm_query_frontend_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def result(self) -> QueryResult:
         r = QueryResult()

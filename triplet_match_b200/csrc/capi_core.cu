@@ -127,6 +127,10 @@ void tm_ctx_destroy(tm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->flush.release();
     for (auto& s : c->scratch) s.release();
+    c->icp.release();
+    c->icp_d16.release();
+    c->icp_pack.release();
+    c->icp_graph.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

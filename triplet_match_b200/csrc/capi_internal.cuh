@@ -80,6 +80,49 @@ struct DevBuf {
     }
 };
 
+struct IcpBufs {
+    DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
+    void release() {
+        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
+    }
+    int ensure(uint32_t k) {
+        size_t kk = std::max(k, 1u);
+        TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
+        TRY(sums_cur.ensure(kk * ICP_NSUM * 8)); TRY(sums_best.ensure(kk * ICP_NSUM * 8));
+        TRY(iters.ensure(kk * 4)); TRY(active.ensure(kk * 4));
+        return TM_OK;
+    }
+    IcpState state() {
+        return IcpState{Tcur.as<float4>(), Tbest.as<float4>(), sums_cur.as<long long>(),
+                        sums_best.as<long long>(), iters.as<uint32_t>(), active.as<uint32_t>()};
+    }
+};
+// one cached CUDA graph of a whole refinement (tm_icp and friends): H2D of the poses, layout change, the
+// 2 * (1 + max_iterations) accumulate / step launches, layout change, D2H of the results.  Replayed while the
+// key (every pointer and scalar baked into the captured launches) is unchanged.
+struct IcpGraphKey {
+    const void* scene_pos = nullptr; const void* model_vox = nullptr; const void* occ = nullptr;
+    const void* bufs = nullptr; const void* pinned = nullptr; const void* d16 = nullptr;
+    uint32_t scene_n = 0, k = 0, max_iterations = 0, pt_begin = 0, pt_end = 0, emulate = 0;
+    uint64_t n_total = 0;
+    float thres = 0.f;
+    bool operator==(const IcpGraphKey& o) const {
+        return scene_pos == o.scene_pos && model_vox == o.model_vox && occ == o.occ && bufs == o.bufs &&
+               pinned == o.pinned && d16 == o.d16 && scene_n == o.scene_n && k == o.k &&
+               max_iterations == o.max_iterations && pt_begin == o.pt_begin && pt_end == o.pt_end &&
+               emulate == o.emulate && n_total == o.n_total && thres == o.thres;
+    }
+};
+struct IcpGraph {
+    IcpGraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t kernels = 0;  // launches one replay stands for (tm_ctx_kernel_launches)
+    void release() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+};
+
 struct tm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -91,6 +134,9 @@ struct tm_ctx {
     size_t pinned_cap = 0;
     int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
     int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
+    IcpBufs icp;                             // refinement state of tm_icp*, grow-only (no allocation per call)
+    DevBuf icp_d16, icp_pack;                // poses in / out (column-major), packed records of the pose-sharded gather
+    IcpGraph icp_graph;
 };
 
 struct OccMask {  // block-occupancy mask of one distance threshold (k_util.cu occupancy_kernel)
@@ -129,23 +175,6 @@ extern "C" int ball_subsets_dev(tm_ctx* c, const CloudDev& scene, const uint32_t
                      DevBuf* indices, uint64_t* total_out);
 
 // --------------------------------------------------------------------- ICP
-struct IcpBufs {
-    DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
-    void release() {
-        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
-    }
-    int ensure(uint32_t k) {
-        size_t kk = std::max(k, 1u);
-        TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
-        TRY(sums_cur.ensure(kk * ICP_NSUM * 8)); TRY(sums_best.ensure(kk * ICP_NSUM * 8));
-        TRY(iters.ensure(kk * 4)); TRY(active.ensure(kk * 4));
-        return TM_OK;
-    }
-    IcpState state() {
-        return IcpState{Tcur.as<float4>(), Tbest.as<float4>(), sums_cur.as<long long>(),
-                        sums_best.as<long long>(), iters.as<uint32_t>(), active.as<uint32_t>()};
-    }
-};
 typedef struct ncclComm* ncclComm_t;
 struct tm_comm {
     tm_ctx* ctx;
@@ -154,6 +183,8 @@ struct tm_comm {
     DevBuf stage;  // batched best-pose reduce: n keys, then n x (score, pose)
 };
 int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st);  // capi_nccl.cu
+int comm_allreduce_max_u32(tm_comm* cm, void* buf, size_t count, cudaStream_t st);
+int comm_allgather_bytes(tm_comm* cm, const void* send, void* recv, size_t bytes, cudaStream_t st);
 // how the scene points of one ICP pass are split: this process accumulates [pt_begin, pt_end)
 // (as `emulate` consecutive sub-ranges when emulate > 1) and, with a communicator, the 64-bit
 // fixed-point sums are all-reduced — integer sums, so any split gives the same bits.
@@ -209,5 +240,14 @@ struct tm_query {
     bool scores_valid = false;  // scores[] holds every hypothesis' score
     float run_thres = 0.f, run_sqt = 0.f;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the scoring kernel
+    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;  // around the replicated front end (features, probe, scan, shard)
+    // sharding
+    bool by_tests = false;       // tm_query_set_balance: equal hypothesis-point tests instead of equal counts
+    bool balanced = false;       // bounds[] holds the by-tests split of the current list
+    tm_comm* comm = nullptr;     // completes the per-outer subset sizes of the by-tests split (one all-reduce)
+    DevBuf bounds, bal_cum;
+    bool pairs_set = false, need_size = false;
+    uint32_t sized_rank = 0, sized_world = 1;
+    std::vector<uint32_t> opo_host;  // pairs per outer sample (prefix), kept for re-sizing
 };
 int finalize_best(tm_query* q);  // capi_query.cu

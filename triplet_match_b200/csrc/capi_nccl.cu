@@ -5,7 +5,7 @@
 
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess_ = 0 };
-enum { ncclUint8_ = 1, ncclInt64_ = 4, ncclUint64_ = 5 };  // ncclDataType_t
+enum { ncclUint8_ = 1, ncclUint32_ = 3, ncclInt64_ = 4, ncclUint64_ = 5 };  // ncclDataType_t
 enum { ncclSum_ = 0, ncclMax_ = 2 };       // ncclRedOp_t
 struct NcclApi {
     void* lib = nullptr;
@@ -13,6 +13,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -30,8 +31,9 @@ static int nccl_load() {
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
         lib, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather)
         return fail(TM_ERR_NCCL, "libnccl is missing required symbols");
     g_nccl.lib = lib;
     return TM_OK;
@@ -112,6 +114,15 @@ int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* cm) {
 }
 }  // extern "C"
 
+// every rank contributes `bytes` bytes; recv holds world x bytes in rank order
+int comm_allgather_bytes(tm_comm* cm, const void* send, void* recv, size_t bytes, cudaStream_t st) {
+    NC(g_nccl.AllGather(send, recv, bytes, ncclUint8_, cm->comm, st));
+    return TM_OK;
+}
+int comm_allreduce_max_u32(tm_comm* cm, void* buf, size_t count, cudaStream_t st) {
+    NC(g_nccl.AllReduce(buf, buf, count, ncclUint32_, ncclMax_, cm->comm, st));
+    return TM_OK;
+}
 int comm_allreduce_sum_i64(tm_comm* cm, void* buf, size_t count, cudaStream_t st) {
     NC(g_nccl.AllReduce(buf, buf, count, ncclInt64_, ncclSum_, cm->comm, st));
     return TM_OK;

@@ -4,6 +4,119 @@
 #include "capi_internal.cuh"
 
 
+// (a1-a5) on the device for the whole recorded list: pair filter, feature, key, probe, and the exclusive scan of
+// the hit counts (hyp_off).  Replicated on every rank: one thread per pair and one scan, a few tens of
+// microseconds for the 2.6e5 pairs of an 8-GPU C2 list (tm_query_frontend_ms reports it).
+static int enqueue_front_end(tm_query* q, unsigned long long* n_valid) {
+    tm_ctx* c = q->s->ctx;
+    float lower, upper;
+    pair_window(q->m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
+    const uint32_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    launch_pair_features_probe(c->stream, q->s->dev, q->m->dev, q->outer.as<uint32_t>(), q->pair_outer.as<uint32_t>(),
+                               q->pair_j.as<uint32_t>(), q->n_pairs, lower, upper, limit, nullptr, nullptr,
+                               q->valid.as<uint8_t>(), q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(), n_valid);
+    if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
+    else
+        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(), q->hyp_off.as<unsigned long long>(), q->n_pairs);
+    return TM_OK;
+}
+
+// Decide this rank's shard and size everything that depends on it.  The shard is a contiguous range of the
+// global hypothesis list: equal hypothesis counts (default) or, with tm_query_set_balance(by_tests), equal
+// hypothesis-point tests (balance_bounds_kernel).  Only the outer samples that own hypotheses of the shard are
+// sized (radius-search counting pass), so N ranks do not repeat each other's sizing; the by-tests split needs
+// the subset size of EVERY outer sample, which each rank measures for its count-based share and one
+// ncclAllReduce(max) of n_outer x 4 bytes completes (without a communicator every rank sizes all of them).
+static int size_for_shard(tm_query* q) {
+    tm_ctx* c = q->s->ctx;
+    const uint32_t n_outer = q->n_outer;
+    const uint64_t n_pairs = q->n_pairs;
+    const std::vector<uint32_t>& opo = q->opo_host;
+    // capacities: hypotheses, subset indices (one sizing pass), work items
+    uint64_t limit = q->p.query_limit ? q->p.query_limit : 200;
+    uint64_t cap = q->p.max_hypotheses ? q->p.max_hypotheses
+                                       : std::min<uint64_t>(n_pairs * limit, 1ull << 24);
+    if (q->p.hyp_limit) cap = std::min<uint64_t>(cap, q->p.hyp_limit);
+    cap = std::max<uint64_t>(cap, 1);
+    q->cap_hyp = cap;
+    TRY(q->T.ensure(cap * 48)); TRY(q->hyp_valid.ensure(cap)); TRY(q->hyp_pair.ensure(cap * 4));
+    TRY(q->counts.ensure(cap * 4)); TRY(q->scores.ensure(cap * 8)); TRY(q->dropped.ensure(cap));
+    TRY(q->g_of_hyp.ensure(cap * 4));
+    TRY(q->valid.ensure(std::max<uint64_t>(n_pairs, 1))); TRY(q->hit_begin.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
+    TRY(q->hit_count.ensure(std::max<uint64_t>(n_pairs, 1) * 4)); TRY(q->hyp_off.ensure((n_pairs + 1) * 8));
+    TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
+    TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
+    TRY(q->bounds.ensure(((size_t)q->world + 1) * 8)); TRY(q->bal_cum.ensure(((size_t)n_outer + 1) * 8));
+    QueryOut* out = q->out.as<QueryOut>();
+    q->balanced = false;
+    std::vector<uint32_t> gh(n_outer + 1, 0), sizes(n_outer + 1, 0);
+    if (n_outer) {
+        CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
+        TRY(enqueue_front_end(q, &out->n_valid));
+        // count-based shard and the outer samples it touches
+        launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit, q->rank, q->world,
+                           ~0ull, nullptr, out->shard, &out->n_local, &out->err);
+        launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(), q->outer_pair_off.as<uint32_t>(), n_outer,
+                                out->shard, q->g_hyp.as<uint32_t>());
+        const bool by_tests = q->by_tests && q->world > 1;
+        const uint32_t* active = (by_tests && !q->comm) ? nullptr : q->g_hyp.as<uint32_t>();
+        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, active, q->m->dev.diameter, q->ball_counts,
+                             q->ball_seg_off, q->sub_off, nullptr, nullptr));
+        if (by_tests) {
+            if (q->comm) TRY(comm_allreduce_max_u32(q->comm, q->ball_seg_off.p, n_outer, c->stream));
+            launch_balance_bounds(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit,
+                                  q->outer_pair_off.as<uint32_t>(), q->ball_seg_off.as<uint32_t>(), n_outer, q->world,
+                                  q->bal_cum.as<unsigned long long>(), q->bounds.as<unsigned long long>());
+            launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit, q->rank, q->world,
+                               ~0ull, q->bounds.as<unsigned long long>(), out->shard, &out->n_local, &out->err);
+            launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(), q->outer_pair_off.as<uint32_t>(),
+                                    n_outer, out->shard, q->g_hyp.as<uint32_t>());
+            q->balanced = true;
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(gh.data(), q->g_hyp.p, (n_outer + 1) * 4ull, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(sizes.data(), q->ball_seg_off.p, n_outer * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        TRY(q->sub_off.ensure(8));
+        CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t total = 0, items = 0;
+    q->max_sub = 0;
+    for (uint32_t o = 0; o < n_outer; ++o) {
+        const uint64_t nh = gh[o + 1] - gh[o];
+        if (!nh) continue;  // not in this rank's shard: its subset row stays empty
+        const uint64_t np = sizes[o];
+        total += np;
+        q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
+        items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
+    }
+    (void)opo;
+    q->sub_total = total;
+    TRY(q->sub_idx.ensure(std::max<uint64_t>(total, 1) * 4));
+    REQUIRE(items < (1ull << 31), "too many work items");
+    q->items_cap = (uint32_t)std::max<uint64_t>(items, 1);
+    TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
+    TRY(q->item_off.ensure((n_outer + 1) * 4ull));
+    TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
+    if (q->p.early_out == 1) {
+        const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
+        TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
+    } else if (q->p.early_out == 2) {
+        TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
+    }
+    if (q->p.icp_top_k) {
+        TRY(q->icp.ensure(q->p.icp_top_k));
+        TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
+        TRY(q->topk_keys.ensure(topk_scratch_bytes(q->cap_hyp, q->p.icp_top_k)));
+        TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
+    }
+    q->sized_rank = q->rank;
+    q->sized_world = q->world;
+    q->need_size = false;
+    return TM_OK;
+}
+
 extern "C" {
 
 int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query** out) {
@@ -19,6 +132,8 @@ int tm_query_create(tm_scene* s, tm_model* m, const tm_query_params* p, tm_query
     cudaError_t e = cudaSetDevice(s->ctx->device);
     if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s0);
     if (e == cudaSuccess) e = cudaEventCreate(&q->ev_s1);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_f0);
+    if (e == cudaSuccess) e = cudaEventCreate(&q->ev_f1);
     if (e != cudaSuccess) {
         tm_query_destroy(q);
         return fail(TM_ERR_CUDA, std::string("tm_query_create: ") + cudaGetErrorString(e));
@@ -31,12 +146,14 @@ void tm_query_destroy(tm_query* q) {
     cudaSetDevice(q->s->ctx->device);
     if (q->ev_s0) cudaEventDestroy(q->ev_s0);
     if (q->ev_s1) cudaEventDestroy(q->ev_s1);
+    if (q->ev_f0) cudaEventDestroy(q->ev_f0);
+    if (q->ev_f1) cudaEventDestroy(q->ev_f1);
     for (DevBuf* b :
          {&q->outer, &q->pair_outer, &q->pair_j, &q->outer_pair_off, &q->ball_counts,
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi})
+          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum})
         b->release();
     q->icp.release();
     delete q;
@@ -44,8 +161,18 @@ void tm_query_destroy(tm_query* q) {
 
 int tm_query_set_shard(tm_query* q, uint32_t rank, uint32_t world) {
     REQUIRE(q && world > 0 && rank < world, "tm_query_set_shard: bad rank/world");
+    if (q->pairs_set && (rank != q->sized_rank || world != q->sized_world)) q->need_size = true;
     q->rank = rank;
     q->world = world;
+    return TM_OK;
+}
+
+int tm_query_set_balance(tm_query* q, int by_tests, tm_comm* comm) {
+    REQUIRE(q, "tm_query_set_balance: null query");
+    REQUIRE(!comm || comm->ctx == q->s->ctx, "communicator belongs to another context");
+    if (q->pairs_set && ((by_tests != 0) != q->by_tests || comm != q->comm)) q->need_size = true;
+    q->by_tests = by_tests != 0;
+    q->comm = comm;
     return TM_OK;
 }
 
@@ -79,59 +206,9 @@ int tm_query_set_pairs(tm_query* q, const uint32_t* outer, uint32_t n_outer,
     }
     CU(cudaMemcpyAsync(q->outer_pair_off.p, opo.data(), (n_outer + 1) * 4ull, cudaMemcpyHostToDevice,
                        c->stream));
-    // capacities: hypotheses, subset indices (one sizing pass), work items
-    uint64_t limit = q->p.query_limit ? q->p.query_limit : 200;
-    uint64_t cap = q->p.max_hypotheses ? q->p.max_hypotheses
-                                       : std::min<uint64_t>(n_pairs * limit, 1ull << 24);
-    if (q->p.hyp_limit) cap = std::min<uint64_t>(cap, q->p.hyp_limit);
-    cap = std::max<uint64_t>(cap, 1);
-    q->cap_hyp = cap;
-    TRY(q->T.ensure(cap * 48)); TRY(q->hyp_valid.ensure(cap)); TRY(q->hyp_pair.ensure(cap * 4));
-    TRY(q->counts.ensure(cap * 4)); TRY(q->scores.ensure(cap * 8)); TRY(q->dropped.ensure(cap));
-    TRY(q->g_of_hyp.ensure(cap * 4));
-    TRY(q->valid.ensure(std::max<uint64_t>(n_pairs, 1))); TRY(q->hit_begin.ensure(std::max<uint64_t>(n_pairs, 1) * 4));
-    TRY(q->hit_count.ensure(std::max<uint64_t>(n_pairs, 1) * 4)); TRY(q->hyp_off.ensure((n_pairs + 1) * 8));
-    TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
-    TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
-    uint64_t total = 0;
-    std::vector<unsigned long long> so(n_outer + 1, 0);
-    if (n_outer) {
-        // sizing pass over ALL outer samples (a rank's shard is only known per run)
-        TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, nullptr, q->m->dev.diameter,
-                             q->ball_counts, q->ball_seg_off, q->sub_off, &q->sub_idx, &total));
-        CU(cudaMemcpyAsync(so.data(), q->sub_off.p, (n_outer + 1) * 8ull, cudaMemcpyDeviceToHost,
-                           c->stream));
-    } else {
-        TRY(q->sub_off.ensure(8));
-        CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    q->sub_total = total;
-    uint64_t items = 0;
-    q->max_sub = 0;
-    for (uint32_t o = 0; o < n_outer; ++o) {
-        uint64_t np = so[o + 1] - so[o];
-        q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
-        uint64_t nh = std::min<uint64_t>((uint64_t)(opo[o + 1] - opo[o]) * limit, cap);
-        items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
-    }
-    REQUIRE(items < (1ull << 31), "too many work items");
-    q->items_cap = (uint32_t)std::max<uint64_t>(items, 1);
-    TRY(q->n_items_g.ensure(std::max(n_outer, 1u) * 4ull));
-    TRY(q->item_off.ensure((n_outer + 1) * 4ull));
-    TRY(q->items.ensure((size_t)q->items_cap * sizeof(WorkItem)));
-    if (q->p.early_out == 1) {
-        const size_t n_tiles = (size_t)(total / 32) + n_outer + 2;
-        TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
-    } else if (q->p.early_out == 2) {
-        TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
-    }
-    if (q->p.icp_top_k) {
-        TRY(q->icp.ensure(q->p.icp_top_k));
-        TRY(q->topk_ids.ensure(q->p.icp_top_k * 4ull));
-        TRY(q->topk_keys.ensure(topk_scratch_bytes(q->cap_hyp, q->p.icp_top_k)));
-        TRY(q->icp_T16.ensure(q->p.icp_top_k * 64ull));
-    }
+    q->opo_host = opo;
+    q->pairs_set = true;
+    TRY(size_for_shard(q));
     q->ran = false;
     return TM_OK;
 }
@@ -197,28 +274,21 @@ int tm_query_run(tm_query* q) {
     TRY(bind(c));
     const tm_model* m = q->m;
     const CloudDev& sc = q->s->dev;
+    if (q->need_size) TRY(size_for_shard(q));  // rank / world / balance changed after tm_query_set_pairs
     QueryOut* out = q->out.as<QueryOut>();
     CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
     CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
     CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
     // (a1-a5) pair filter, feature, key, probe
-    float lower, upper;
-    pair_window(m, q->p.min_diameter_factor, q->p.max_diameter_factor, lower, upper);
-    const uint32_t limit = q->p.query_limit ? q->p.query_limit : 200;
-    launch_pair_features_probe(c->stream, sc, m->dev, q->outer.as<uint32_t>(),
-                               q->pair_outer.as<uint32_t>(), q->pair_j.as<uint32_t>(), q->n_pairs,
-                               lower, upper, limit, nullptr, nullptr, q->valid.as<uint8_t>(),
-                               q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(),
-                               &out->n_valid);
-    if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
-    else
-        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(),
-                                  q->hyp_off.as<unsigned long long>(), q->n_pairs);
+    CU(cudaEventRecord(q->ev_f0, c->stream));
+    TRY(enqueue_front_end(q, &out->n_valid));
     launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
-                       q->rank, q->world, q->cap_hyp, out->shard, &out->n_local, &out->err);
+                       q->rank, q->world, q->cap_hyp, q->balanced ? q->bounds.as<unsigned long long>() : nullptr,
+                       out->shard, &out->n_local, &out->err);
     launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
                             q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
                             q->g_hyp.as<uint32_t>());
+    CU(cudaEventRecord(q->ev_f1, c->stream));
     // (a8) radius subsets, only of the outer samples that own hypotheses of this rank's shard
     // (g_hyp); the others get empty rows, so N ranks do not repeat each other's searches
     if (q->n_outer) {
@@ -383,6 +453,13 @@ int tm_query_score_kernel_ms(tm_query* q, float* ms) {
     if (!q->n_outer) return TM_OK;
     CU(cudaEventSynchronize(q->ev_s1));
     CU(cudaEventElapsedTime(ms, q->ev_s0, q->ev_s1));
+    return TM_OK;
+}
+int tm_query_frontend_ms(tm_query* q, float* ms) {
+    REQUIRE(q && ms && q->ran, "tm_query_frontend_ms: null/unrun query");
+    TRY(bind(q->s->ctx));
+    CU(cudaEventSynchronize(q->ev_f1));
+    CU(cudaEventElapsedTime(ms, q->ev_f0, q->ev_f1));
     return TM_OK;
 }
 void* tm_query_best_key_device(tm_query* q) {

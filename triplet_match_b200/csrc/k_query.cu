@@ -9,15 +9,20 @@
 namespace tmk {
 
 // shard = [h_begin, h_end) of the global hypothesis list owned by this rank
+// bounds != null: the test-balanced split of balance_bounds_kernel ([bounds[rank], bounds[rank+1]))
 __global__ void shard_range_kernel(const unsigned long long* __restrict__ hyp_off, uint64_t n_pairs,
                                    unsigned long long hyp_limit, uint32_t rank, uint32_t world,
-                                   unsigned long long capacity, unsigned long long* shard,
-                                   uint32_t* n_local, uint32_t* err) {
+                                   unsigned long long capacity, const unsigned long long* __restrict__ bounds,
+                                   unsigned long long* shard, uint32_t* n_local, uint32_t* err) {
     unsigned long long H = hyp_off[n_pairs];
     if (hyp_limit && H > hyp_limit) H = hyp_limit;
     unsigned long long per = (H + world - 1) / world;
     unsigned long long hb = min((unsigned long long)rank * per, H);
     unsigned long long he = min(hb + per, H);
+    if (bounds) {
+        hb = min(bounds[rank], H);
+        he = min(bounds[rank + 1], H);
+    }
     if (he - hb > capacity) {
         *err = 1u;
         he = hb + capacity;
@@ -29,11 +34,85 @@ __global__ void shard_range_kernel(const unsigned long long* __restrict__ hyp_of
 }
 void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
                         unsigned long long hyp_limit, uint32_t rank, uint32_t world,
-                        unsigned long long capacity, unsigned long long* shard, uint32_t* n_local,
-                        uint32_t* err) {
+                        unsigned long long capacity, const unsigned long long* bounds, unsigned long long* shard,
+                        uint32_t* n_local, uint32_t* err) {
     ++g_launch_count;
-    shard_range_kernel<<<1, 1, 0, st>>>(hyp_off, n_pairs, hyp_limit, rank, world, capacity, shard,
+    shard_range_kernel<<<1, 1, 0, st>>>(hyp_off, n_pairs, hyp_limit, rank, world, capacity, bounds, shard,
                                         n_local, err);
+}
+
+// ---- test-balanced shards -------------------------------------------------------------------------
+// A shard's work is the number of hypothesis-point tests, |subset(outer)| x hypotheses(outer) summed over
+// its outer samples, not its number of hypotheses.  balance_bounds_kernel cuts the global hypothesis list
+// into `world` contiguous ranges of (nearly) equal tests: cum[o] = tests before outer sample o (block scan),
+// rank r starts at the hypothesis where the running test count reaches total * r / world.  One CTA; every
+// rank computes the same bounds from the same inputs.
+__global__ void __launch_bounds__(1024)
+    balance_bounds_kernel(const unsigned long long* __restrict__ hyp_off, uint64_t n_pairs,
+                          unsigned long long hyp_limit, const uint32_t* __restrict__ outer_pair_off,
+                          const uint32_t* __restrict__ sizes, uint32_t n_outer, uint32_t world,
+                          unsigned long long* __restrict__ cum, unsigned long long* __restrict__ bounds) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    unsigned long long H = hyp_off[n_pairs];
+    if (hyp_limit && H > hyp_limit) H = hyp_limit;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0ull;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_outer; base += blockDim.x) {
+        const uint32_t o = base + threadIdx.x;
+        unsigned long long t = 0ull;
+        if (o < n_outer) {
+            const unsigned long long hb = min(hyp_off[outer_pair_off[o]], H), he = min(hyp_off[outer_pair_off[o + 1]], H);
+            t = (he - hb) * (unsigned long long)sizes[o];
+        }
+        unsigned long long incl = t;  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long woff = 0ull;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        const unsigned long long carry = carry_s;
+        if (o < n_outer) cum[o] = carry + woff + incl - t;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    const unsigned long long total = carry_s;
+    if (threadIdx.x == 0) cum[n_outer] = total;
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r <= world; r += blockDim.x) {
+        unsigned long long b;
+        if (r == 0) b = 0ull;
+        else if (r == world || total == 0ull) b = (r == world) ? H : min(H, (H + world - 1) / world * r);
+        else {
+            // total * r / world without overflow: total < 2^63 / world for any realistic list; use 128-bit
+            const unsigned long long hi = __umul64hi(total, (unsigned long long)r);
+            const unsigned long long lo = total * (unsigned long long)r;
+            unsigned long long target = hi ? ~0ull : lo / world;
+            // the last outer sample o with cum[o] <= target
+            uint32_t a = 0, e = n_outer;  // cum[a] <= target < cum[e] (cum[n_outer] = total > target)
+            while (e - a > 1) {
+                const uint32_t mid = (a + e) >> 1;
+                if (cum[mid] <= target) a = mid; else e = mid;
+            }
+            const unsigned long long hb = min(hyp_off[outer_pair_off[a]], H), he = min(hyp_off[outer_pair_off[a + 1]], H);
+            const unsigned long long sz = sizes[a];
+            b = sz ? min(he, hb + (target - cum[a]) / sz) : hb;
+        }
+        bounds[r] = b;
+    }
+}
+void launch_balance_bounds(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
+                           unsigned long long hyp_limit, const uint32_t* outer_pair_off, const uint32_t* sizes,
+                           uint32_t n_outer, uint32_t world, unsigned long long* cum, unsigned long long* bounds) {
+    ++g_launch_count;
+    balance_bounds_kernel<<<1, 1024, 0, st>>>(hyp_off, n_pairs, hyp_limit, outer_pair_off, sizes, n_outer, world, cum,
+                                              bounds);
 }
 
 // g_hyp[g] = local index of the first hypothesis of outer sample g (n_outer+1 entries)

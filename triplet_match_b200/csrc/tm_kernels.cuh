@@ -209,8 +209,11 @@ void launch_tangent_mask(cudaStream_t st, float4* pos, uint32_t n, const uint32_
 // k_query.cu (device-side glue of the resident query)
 void launch_shard_range(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
                         unsigned long long hyp_limit, uint32_t rank, uint32_t world,
-                        unsigned long long capacity, unsigned long long* shard, uint32_t* n_local,
-                        uint32_t* err);
+                        unsigned long long capacity, const unsigned long long* bounds, unsigned long long* shard,
+                        uint32_t* n_local, uint32_t* err);
+void launch_balance_bounds(cudaStream_t st, const unsigned long long* hyp_off, uint64_t n_pairs,
+                           unsigned long long hyp_limit, const uint32_t* outer_pair_off, const uint32_t* sizes,
+                           uint32_t n_outer, uint32_t world, unsigned long long* cum, unsigned long long* bounds);
 void launch_group_hyp_ranges(cudaStream_t st, const unsigned long long* hyp_off,
                              const uint32_t* outer_pair_off, uint32_t n_outer,
                              const unsigned long long* shard, uint32_t* g_hyp);
