@@ -3,7 +3,11 @@
        --master-port 29511 tools/mgpu_check.py
 1. hypothesis-sharded query + tm_query_allreduce_best == the unsharded query's best pose;
 2. scene-sharded ICP (tm_icp_sharded over NCCL) == tm_icp on the whole scene, bit for bit,
-   and identical on every rank."""
+   and identical on every rank;
+3. pose-sharded ICP (tm_icp_pose_sharded + one ncclAllGather) == tm_icp on every rank;
+4. test-balanced shards (tm_query_set_balance with the communicator's max all-reduce of the subset
+   sizes): the shards still partition the list (counts gathered in rank order == the unsharded
+   counts) and the best pose is the unsharded one."""
 import os
 import sys
 
@@ -55,14 +59,34 @@ def main():
         Ts, cs, ss, is_ = gs.icp_sharded(gm, d["T"][top], 5, 1.0, b, e, s.n, comm=comm)
         same_icp = (np.array_equal(Ts.view(np.uint32), To.view(np.uint32)) and np.array_equal(cs, co) and
                     np.array_equal(ss, so) and np.array_equal(is_, io))
-        flag = torch.tensor([int(same), int(same_icp)], device="cuda")
+        # 3. pose-sharded ICP
+        Tp, cp, sp_, ip = gs.icp_pose_sharded(gm, d["T"][top], 5, 1.0, comm=comm)
+        same_pose = (np.array_equal(Tp.view(np.uint32), To.view(np.uint32)) and np.array_equal(cp, co) and
+                     np.array_equal(sp_, so) and np.array_equal(ip, io))
+        # 4. test-balanced shards
+        qb = capi.Query(gs, gm)
+        qb.set_shard(rank, world)
+        qb.set_balance(True, comm)
+        qb.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        qb.run()
+        comm.allreduce_best(qb)
+        rb = qb.result()
+        mine = qb.download_counts()[0]
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        same_bal = (np.array_equal(np.concatenate(parts), d["counts"]) and rb.best_inliers == r1.best_inliers and
+                    rb.best_hypothesis == r1.best_hypothesis)
+        tests = [None] * world
+        dist.all_gather_object(tests, int(rb.n_tests))
+        flag = torch.tensor([int(same), int(same_icp), int(same_pose), int(same_bal)], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(f"{name}: world {world}: sharded best == unsharded: {bool(flag[0])} (inliers {r.best_inliers} @ "
-                  f"{r.best_hypothesis}); scene-sharded ICP == tm_icp on all ranks: {bool(flag[1])} (counts {cs.tolist()})",
-                  flush=True)
-        ok = ok and bool(flag[0]) and bool(flag[1])
-        q.close(); q1.close(); gm.close(); gs.close()
+                  f"{r.best_hypothesis}); scene-sharded ICP == tm_icp on all ranks: {bool(flag[1])} (counts {cs.tolist()}); "
+                  f"pose-sharded ICP == tm_icp on all ranks: {bool(flag[2])}; test-balanced shards partition the list and find "
+                  f"the same best: {bool(flag[3])} (tests per rank {tests})", flush=True)
+        ok = ok and all(bool(x) for x in flag)
+        q.close(); q1.close(); qb.close(); gm.close(); gs.close()
     comm.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -37,8 +37,9 @@ static int icp_enqueue_with(tm_ctx* c, const CloudDev& scene, const tm_model* m,
             const uint32_t b1 = sp.pt_begin + (uint32_t)(span * (w + 1) / parts);
             if (b1 > b0) {
                 launch_icp_accumulate(c->stream, scene, mdev, st.Tcur, st.active, k, b0, b1, sqt, m->centre[0],
-                                      m->centre[1], m->centre[2], fs, st.sums_cur, grid, m->fused);
-                ++nk;
+                                      m->centre[1], m->centre[2], fs, st.sums_cur, b.pair_list(), b.pair_count(), grid,
+                                      m->fused);
+                nk += 2;
             }
         }
         if (sp.comm) TRY(comm_allreduce_sum_i64(sp.comm, st.sums_cur, (size_t)k * ICP_NSUM, c->stream));
@@ -58,6 +59,7 @@ int icp_enqueue(tm_ctx* c, const CloudDev& scene, const tm_model* m, IcpBufs& b,
     else { sp.pt_end = scene.n; sp.n_total = scene.n; }
     ModelDev mdev;
     TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &mdev));
+    TRY(b.pairs.ensure(icp_pairs_bytes(sp.pt_begin, sp.pt_end, k)));
     TRY(icp_enqueue_with(c, scene, m, mdev, b, k, max_iterations, thres, sp, nullptr));
     CU(cudaGetLastError());
     return TM_OK;
@@ -113,6 +115,7 @@ int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t ma
     if (split) sp = *split;
     else { sp.pt_end = s->dev.n; sp.n_total = s->dev.n; }
     TRY(c->icp.ensure(n));
+    TRY(c->icp.pairs.ensure(icp_pairs_bytes(sp.pt_begin, sp.pt_end, n)));
     TRY(c->icp_d16.ensure((size_t)n * 64));
     TRY(pinned_ensure(c, IcpStage::bytes(n)));
     ModelDev mdev;
@@ -129,7 +132,7 @@ int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t ma
     } else {
         IcpGraphKey key;
         key.scene_pos = s->dev.pos; key.model_vox = m->dev.voxel; key.occ = mdev.occ; key.bufs = c->icp.Tcur.p;
-        key.pinned = c->pinned; key.d16 = c->icp_d16.p; key.scene_n = s->dev.n; key.k = n;
+        key.pinned = c->pinned; key.d16 = c->icp_d16.p; key.pairs = c->icp.pairs.p; key.pairs_cap = c->icp.pairs.cap; key.scene_n = s->dev.n; key.k = n;
         key.max_iterations = max_iterations; key.pt_begin = sp.pt_begin; key.pt_end = sp.pt_end; key.emulate = sp.emulate;
         key.n_total = sp.n_total; key.thres = thres;
         IcpGraph& g = c->icp_graph;

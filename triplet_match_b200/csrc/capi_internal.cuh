@@ -82,9 +82,12 @@ struct DevBuf {
 
 struct IcpBufs {
     DevBuf Tcur, Tbest, sums_cur, sums_best, iters, active;
+    DevBuf pairs;  // surviving (segment, transform) pairs of one pass + their counter (last 8 bytes)
     void release() {
-        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active}) b->release();
+        for (DevBuf* b : {&Tcur, &Tbest, &sums_cur, &sums_best, &iters, &active, &pairs}) b->release();
     }
+    uint2* pair_list() const { return pairs.as<uint2>(); }
+    uint32_t* pair_count() const { return reinterpret_cast<uint32_t*>(pairs.as<uint8_t>() + pairs.cap - 8); }
     int ensure(uint32_t k) {
         size_t kk = std::max(k, 1u);
         TRY(Tcur.ensure(kk * 48)); TRY(Tbest.ensure(kk * 48));
@@ -102,13 +105,14 @@ struct IcpBufs {
 // key (every pointer and scalar baked into the captured launches) is unchanged.
 struct IcpGraphKey {
     const void* scene_pos = nullptr; const void* model_vox = nullptr; const void* occ = nullptr;
-    const void* bufs = nullptr; const void* pinned = nullptr; const void* d16 = nullptr;
+    const void* bufs = nullptr; const void* pinned = nullptr; const void* d16 = nullptr; const void* pairs = nullptr;
+    size_t pairs_cap = 0;
     uint32_t scene_n = 0, k = 0, max_iterations = 0, pt_begin = 0, pt_end = 0, emulate = 0;
     uint64_t n_total = 0;
     float thres = 0.f;
     bool operator==(const IcpGraphKey& o) const {
         return scene_pos == o.scene_pos && model_vox == o.model_vox && occ == o.occ && bufs == o.bufs &&
-               pinned == o.pinned && d16 == o.d16 && scene_n == o.scene_n && k == o.k &&
+               pinned == o.pinned && d16 == o.d16 && pairs == o.pairs && pairs_cap == o.pairs_cap && scene_n == o.scene_n && k == o.k &&
                max_iterations == o.max_iterations && pt_begin == o.pt_begin && pt_end == o.pt_end &&
                emulate == o.emulate && n_total == o.n_total && thres == o.thres;
     }

@@ -14,6 +14,8 @@
 //                          sums (3x3 one-sided Jacobi SVD in double).
 //   corr_count/fill        scene_corrs / model_corrs lists of one transform in
 //                          ascending scene order (finish_find, scene.hpp:100-106).
+#include <algorithm>
+
 #include "tm_kernels.cuh"
 
 namespace tmk {
@@ -52,49 +54,40 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
 
 // sums[h][ICP_NSUM]: 0 count, 1..3 sum s', 4..6 sum m', 7..15 sum s'_a m'_b, 16 score.
 // s' = (T s) - c, m' = m - c with c the model bbox centre; quantum 2^-fix_bits.
-template <bool FUSED>
+//
+// Two launches per pass.
+//   icp_cull_kernel        one warp per BALL_SEG-point segment of the scene: its bounding box is tested against every
+//                          transform (lane l screens transform h0 + l with the scorer's interval test; NaN never
+//                          culls) and the surviving (segment, transform) pairs go to a compact list.  A refinement
+//                          touches the few dozen segments around each instance, so a pass over a 10 M-point scene
+//                          reads 20 k boxes instead of 10 M points.
+//   icp_accumulate_kernel  one warp per (pair, 128-point chunk): exact test of 4 points per lane, the 17 fixed-point
+//                          sums reduced in the warp and added with at most 17 atomics.  Integer sums: any order,
+//                          same bits (the list order is not deterministic, the result is).
 __global__ void __launch_bounds__(256)
-    icp_accumulate_kernel(CloudDev scene, ModelDev model, const float4* __restrict__ T,
-                          const uint32_t* __restrict__ active, uint32_t n_hyp, uint32_t pt_begin,
-                          uint32_t pt_end, float sq_thres, float cx, float cy, float cz,
-                          double fix_scale, long long* __restrict__ sums) {
+    icp_cull_kernel(CloudDev scene, ModelDev model, const float4* __restrict__ T, const uint32_t* __restrict__ active,
+                    uint32_t h_begin, uint32_t h_end, uint32_t pt_begin, uint32_t pt_end, uint2* __restrict__ pairs,
+                    uint32_t* __restrict__ n_pairs) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // each warp owns chunks of 32*ICP_P consecutive points, strided over the grid
-    for (uint64_t base = pt_begin + (uint64_t)warp_id * 32 * ICP_P; base < pt_end;
-         base += (uint64_t)warps_total * 32 * ICP_P) {
-        float4 v[ICP_P];
-        uint32_t idx[ICP_P];
-#pragma unroll
-        for (int k = 0; k < ICP_P; ++k) {
-            uint64_t i = base + k * 32 + lane;
-            idx[k] = (uint32_t)i;
-            const float nanv = __int_as_float(0x7fc00000);
-            v[k] = i < pt_end ? scene.pos[i] : make_float4(nanv, nanv, nanv, 0.f);
-        }
-        // the chunk's points lie in at most two BALL_SEG segments: their boxes (scenes only) bound it
-        float blx = -3.0e38f, bly = -3.0e38f, blz = -3.0e38f, bhx = 3.0e38f, bhy = 3.0e38f, bhz = 3.0e38f;
-        const bool have_box = scene.seg_lo != nullptr;
+    const bool have_box = scene.seg_lo != nullptr;
+    const uint32_t seg_first = pt_begin / BALL_SEG, seg_last = (pt_end - 1u) / BALL_SEG;  // pt_end > pt_begin
+    for (uint32_t seg = seg_first + warp_id; seg <= seg_last; seg += warps_total) {
+        float cx_ = 0.f, cy_ = 0.f, cz_ = 0.f, hx_ = 0.f, hy_ = 0.f, hz_ = 0.f;
         if (have_box) {
-            const uint64_t end_ = base + 32ull * ICP_P < (uint64_t)pt_end ? base + 32ull * ICP_P : (uint64_t)pt_end;
-            const uint64_t last = end_ - 1;
-            const uint32_t sa = (uint32_t)(base / BALL_SEG), sb = (uint32_t)(last / BALL_SEG);
-            const float4 la = scene.seg_lo[sa], ha = scene.seg_hi[sa], lb = scene.seg_lo[sb], hb = scene.seg_hi[sb];
-            blx = fminf(la.x, lb.x); bly = fminf(la.y, lb.y); blz = fminf(la.z, lb.z);
-            bhx = fmaxf(ha.x, hb.x); bhy = fmaxf(ha.y, hb.y); bhz = fmaxf(ha.z, hb.z);
+            const float4 lo = scene.seg_lo[seg], hi = scene.seg_hi[seg];
+            if (!(lo.x <= hi.x)) continue;  // no finite point in the segment
+            cx_ = 0.5f * (lo.x + hi.x); hx_ = 0.5f * (hi.x - lo.x);
+            cy_ = 0.5f * (lo.y + hi.y); hy_ = 0.5f * (hi.y - lo.y);
+            cz_ = 0.5f * (lo.z + hi.z); hz_ = 0.5f * (hi.z - lo.z);
         }
-        const float cx_ = 0.5f * (blx + bhx), hx_ = 0.5f * (bhx - blx);
-        const float cy_ = 0.5f * (bly + bhy), hy_ = 0.5f * (bhy - bly);
-        const float cz_ = 0.5f * (blz + bhz), hz_ = 0.5f * (bhz - blz);
-        for (uint32_t h0 = 0; h0 < n_hyp; h0 += 32) {
-          // lane l screens transform h0 + l: skip (chunk, transform) pairs whose box misses the grid
-          bool live = false;
-          {
+        for (uint32_t h0 = h_begin; h0 < h_end; h0 += 32) {
+            bool live = false;
             const uint32_t hl = h0 + lane;
-            if (hl < n_hyp && (!active || active[hl])) {
+            if (hl < h_end && (!active || active[hl])) {
                 live = true;
-                if (have_box && blx <= bhx) {
+                if (have_box) {
                     const float4 q0 = __ldg(&T[3 * hl]), q1 = __ldg(&T[3 * hl + 1]), q2 = __ldg(&T[3 * hl + 2]);
                     const float acx = fabsf(cx_) + hx_, acy = fabsf(cy_) + hy_, acz = fabsf(cz_) + hz_;
                     bool out = false;
@@ -113,76 +106,109 @@ __global__ void __launch_bounds__(256)
                     TM_AXIS(q2, model.sz, model.tz, model.ezf)
 #undef TM_AXIS
                     live = !out;
-                } else if (have_box) {
-                    live = false;  // no finite point in either segment
                 }
             }
-          }
-          uint32_t todo = __ballot_sync(0xffffffffu, live);
-          while (todo) {
-            const uint32_t h = h0 + (uint32_t)(__ffs(todo) - 1);
-            todo &= todo - 1u;
-            const float4 r0 = __ldg(&T[3 * h]), r1 = __ldg(&T[3 * h + 1]), r2 = __ldg(&T[3 * h + 2]);
-            long long acc[ICP_NSUM];
-#pragma unroll
-            for (int s = 0; s < ICP_NSUM; ++s) acc[s] = 0;
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < ICP_P; ++k) {
-                float x, y, z;
-                float4 mp;
-                uint32_t lin;
-                if (icp_point_test<FUSED>(model, r0, r1, r2, v[k], sq_thres, x, y, z, mp, lin)) {
-                    any = true;
-                    double s[3] = {(double)x - (double)cx, (double)y - (double)cy, (double)z - (double)cz};
-                    double m[3] = {(double)mp.x - (double)cx, (double)mp.y - (double)cy,
-                                   (double)mp.z - (double)cz};
-                    acc[0] += 1;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        acc[1 + a] += __double2ll_rn(s[a] * fix_scale);
-                        acc[4 + a] += __double2ll_rn(m[a] * fix_scale);
-#pragma unroll
-                        for (int b = 0; b < 3; ++b)
-                            acc[7 + 3 * a + b] += __double2ll_rn(s[a] * m[b] * fix_scale);
-                    }
-                    // score term |ref . ref_n|
-                    uint32_t fl = __float_as_uint(v[k].w);
-                    bool use_t = (fl & FLAG_TANGENT) != 0u;
-                    f3 ref = mk3(use_t ? scene.tgt[idx[k]] : scene.nrm[idx[k]]);
-                    uint32_t mi = model.voxel[lin];
-                    f3 rn = mk3(use_t ? model.cloud.tgt[mi] : model.cloud.nrm[mi]);
-                    f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
-                    acc[16] += (long long)score_fixed(fabsf(dot3(rr, rn)));
-                }
-            }
-            if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-                for (int s = 0; s < ICP_NSUM; ++s) {
-                    long long t = warp_sum_i64(acc[s]);
-                    if (lane == 0 && t)
-                        atomicAdd((unsigned long long*)&sums[(size_t)h * ICP_NSUM + s],
-                                  (unsigned long long)t);
-                }
-            }
-          }
+            const uint32_t todo = __ballot_sync(0xffffffffu, live);
+            if (!todo) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(n_pairs, (uint32_t)__popc(todo));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) pairs[base + __popc(todo & ((1u << lane) - 1u))] = make_uint2(seg, hl);
         }
     }
 }
+
+constexpr uint32_t ICP_CHUNK = 32u * ICP_P;                  // points per (pair, chunk) item
+constexpr uint32_t ICP_CHUNKS_PER_SEG = BALL_SEG / ICP_CHUNK;
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+    icp_accumulate_kernel(CloudDev scene, ModelDev model, const float4* __restrict__ T, const uint2* __restrict__ pairs,
+                          const uint32_t* __restrict__ n_pairs, uint32_t pt_begin, uint32_t pt_end, float sq_thres,
+                          float cx, float cy, float cz, double fix_scale, long long* __restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long n_items = (unsigned long long)(*n_pairs) * ICP_CHUNKS_PER_SEG;
+    for (unsigned long long item = warp_id; item < n_items; item += warps_total) {
+        const uint2 pr = pairs[item / ICP_CHUNKS_PER_SEG];
+        const uint32_t chunk = (uint32_t)(item % ICP_CHUNKS_PER_SEG);
+        const uint32_t base = pr.x * BALL_SEG + chunk * ICP_CHUNK;
+        const uint32_t p1 = (uint32_t)min((unsigned long long)pt_end, (unsigned long long)(pr.x + 1u) * BALL_SEG);
+        if (base >= p1 || base + ICP_CHUNK <= pt_begin) continue;
+        const uint32_t h = pr.y;
+        const float4 r0 = __ldg(&T[3 * h]), r1 = __ldg(&T[3 * h + 1]), r2 = __ldg(&T[3 * h + 2]);
+        float4 v[ICP_P];
+        uint32_t idx[ICP_P];
+#pragma unroll
+        for (int k = 0; k < ICP_P; ++k) {
+            const uint32_t i = base + k * 32 + lane;
+            idx[k] = i;
+            const float nanv = __int_as_float(0x7fc00000);
+            v[k] = (i >= pt_begin && i < p1) ? scene.pos[i] : make_float4(nanv, nanv, nanv, 0.f);
+        }
+        long long acc[ICP_NSUM];
+#pragma unroll
+        for (int s = 0; s < ICP_NSUM; ++s) acc[s] = 0;
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < ICP_P; ++k) {
+            float x, y, z;
+            float4 mp;
+            uint32_t lin;
+            if (icp_point_test<FUSED>(model, r0, r1, r2, v[k], sq_thres, x, y, z, mp, lin)) {
+                any = true;
+                double s[3] = {(double)x - (double)cx, (double)y - (double)cy, (double)z - (double)cz};
+                double m[3] = {(double)mp.x - (double)cx, (double)mp.y - (double)cy, (double)mp.z - (double)cz};
+                acc[0] += 1;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    acc[1 + a] += __double2ll_rn(s[a] * fix_scale);
+                    acc[4 + a] += __double2ll_rn(m[a] * fix_scale);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        acc[7 + 3 * a + b] += __double2ll_rn(s[a] * m[b] * fix_scale);
+                }
+                // score term |ref . ref_n|
+                uint32_t fl = __float_as_uint(v[k].w);
+                bool use_t = (fl & FLAG_TANGENT) != 0u;
+                f3 ref = mk3(use_t ? scene.tgt[idx[k]] : scene.nrm[idx[k]]);
+                uint32_t mi = model.voxel[lin];
+                f3 rn = mk3(use_t ? model.cloud.tgt[mi] : model.cloud.nrm[mi]);
+                f3 rr = {row_rot(r0, ref), row_rot(r1, ref), row_rot(r2, ref)};
+                acc[16] += (long long)score_fixed(fabsf(dot3(rr, rn)));
+            }
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int s = 0; s < ICP_NSUM; ++s) {
+                long long t = warp_sum_i64(acc[s]);
+                if (lane == 0 && t)
+                    atomicAdd((unsigned long long*)&sums[(size_t)h * ICP_NSUM + s], (unsigned long long)t);
+            }
+        }
+    }
+}
+// pairs: room for (segments of [pt_begin, pt_end)) x n_hyp entries; n_pairs: one device counter (zeroed here)
 void launch_icp_accumulate(cudaStream_t st, const CloudDev& scene, const ModelDev& model,
                            const float4* T, const uint32_t* active, uint32_t n_hyp,
                            uint32_t pt_begin, uint32_t pt_end, float sq_thres, float cx, float cy,
-                           float cz, double fix_scale, long long* sums, int grid, bool fused) {
+                           float cz, double fix_scale, long long* sums, uint2* pairs, uint32_t* n_pairs, int grid,
+                           bool fused) {
     if (!n_hyp || pt_end <= pt_begin) return;
-    ++g_launch_count;
+    g_launch_count += 2;
+    cudaMemsetAsync(n_pairs, 0, 4, st);
+    icp_cull_kernel<<<grid, 256, 0, st>>>(scene, model, T, active, 0u, n_hyp, pt_begin, pt_end, pairs, n_pairs);
     if (fused)
-        icp_accumulate_kernel<true><<<grid, 256, 0, st>>>(scene, model, T, active, n_hyp, pt_begin,
-                                                          pt_end, sq_thres, cx, cy, cz, fix_scale,
-                                                          sums);
+        icp_accumulate_kernel<true><<<grid, 256, 0, st>>>(scene, model, T, pairs, n_pairs, pt_begin, pt_end, sq_thres,
+                                                          cx, cy, cz, fix_scale, sums);
     else
-        icp_accumulate_kernel<false><<<grid, 256, 0, st>>>(scene, model, T, active, n_hyp, pt_begin,
-                                                           pt_end, sq_thres, cx, cy, cz, fix_scale,
-                                                           sums);
+        icp_accumulate_kernel<false><<<grid, 256, 0, st>>>(scene, model, T, pairs, n_pairs, pt_begin, pt_end, sq_thres,
+                                                           cx, cy, cz, fix_scale, sums);
+}
+size_t icp_pairs_bytes(uint32_t pt_begin, uint32_t pt_end, uint32_t n_hyp) {
+    if (pt_end <= pt_begin) return 8;
+    const size_t segs = (size_t)((pt_end - 1u) / BALL_SEG) - (size_t)(pt_begin / BALL_SEG) + 1;
+    return segs * (size_t)std::max(n_hyp, 1u) * sizeof(uint2) + 8;
 }
 
 // ------------------------------------------------------------- rigid solve
@@ -193,8 +219,11 @@ __device__ void svd3_jacobi(const double A[3][3], double U[3][3], double S[3], d
             B[i][j] = A[i][j];
             V[i][j] = i == j ? 1.0 : 0.0;
         }
+    // long-latency FP64 operations are what this single-thread routine spends its time on (it sits on the
+    // dependent chain of every ICP iteration): the convergence test compares squares (no sqrt, no division) and
+    // the rotation uses one rsqrt.
     for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0;
+        bool converged = true;  // every pair: |g| <= 1e-15 * sqrt(a * b)
         for (int p = 0; p < 2; ++p)
             for (int q = p + 1; q < 3; ++q) {
                 double a = 0, b = 0, g = 0;
@@ -203,12 +232,11 @@ __device__ void svd3_jacobi(const double A[3][3], double U[3][3], double S[3], d
                     b += B[i][q] * B[i][q];
                     g += B[i][p] * B[i][q];
                 }
-                double rel = fabs(g) / (sqrt(a * b) + 1e-300);
-                off = rel > off ? rel : off;
+                if (g * g > 1e-30 * (a * b)) converged = false;
                 if (fabs(g) < 1e-300) continue;
                 double zeta = (b - a) / (2.0 * g);
                 double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                double cs = rsqrt(1.0 + tt * tt), sn = cs * tt;
                 for (int i = 0; i < 3; ++i) {
                     double bp = B[i][p], bq = B[i][q];
                     B[i][p] = cs * bp - sn * bq;
@@ -218,7 +246,7 @@ __device__ void svd3_jacobi(const double A[3][3], double U[3][3], double S[3], d
                     V[i][q] = sn * vp + cs * vq;
                 }
             }
-        if (off < 1e-15) break;
+        if (converged) break;
     }
     double Sn[3];
     for (int j = 0; j < 3; ++j)

@@ -160,7 +160,9 @@ void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid
 void launch_icp_accumulate(cudaStream_t st, const CloudDev& scene, const ModelDev& model,
                            const float4* T, const uint32_t* active, uint32_t n_hyp,
                            uint32_t pt_begin, uint32_t pt_end, float sq_thres, float cx, float cy,
-                           float cz, double fix_scale, long long* sums, int grid, bool fused);
+                           float cz, double fix_scale, long long* sums, uint2* pairs, uint32_t* n_pairs, int grid,
+                           bool fused);
+size_t icp_pairs_bytes(uint32_t pt_begin, uint32_t pt_end, uint32_t n_hyp);
 void launch_icp_step(cudaStream_t stream, const IcpState& st, uint32_t n_hyp, int first,
                      uint32_t max_iterations, double inv_scale, float cx, float cy, float cz);
 void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
