@@ -39,6 +39,12 @@ SM_COUNT = 148
 L1_WAVEFRONT_BYTES = 128  # one L1 data-stage wavefront moves at most one 128-byte line
 
 
+def log(msg: str) -> None:
+    """progress on stderr (the JSON line is the only thing on stdout)"""
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
 def host_threads() -> int:
     """Worker threads of both CPU legs: hardware_concurrency() - 1, as find_parallel does (scene.hpp:146)."""
     return max(1, (os.cpu_count() or 2) - 1)
@@ -447,6 +453,7 @@ def main():
     n_scored, n_tests = int(r.n_scored), int(r.n_tests)
     front_ms = q.frontend_ms()
 
+    log(f"headline done: {head['ms_per_step']:.2f} ms/step")
     # ---- e2e: host buffers in, host results out, through the C-ABI ----------
     e2e_ms = []
     for it in range(2 + args.steps):
@@ -468,6 +475,7 @@ def main():
            "call": "tm_query_set_pairs + tm_query_run + tm_query_result_get + tm_query_download "
                    "(scene + model resident, as in the reference where they are built before find)"}
 
+    log(f"e2e done: {e2e_sec * 1e3:.2f} ms/step")
     # ---- roofline of the dominant kernel (score_count_x2_kernel) ------------
     # What binds it is on-chip: the L1 data stage (ncu l1tex__data_pipe_lsu_wavefronts 96 % of peak), fed by the
     # scattered 16-byte cell gathers.  achieved = data-stage wavefronts of one launch (from the committed ncu
@@ -524,7 +532,9 @@ def main():
             for x in squeries:
                 x.close()
         except Exception as e:  # noqa: BLE001
+            log("strong leg failed: " + repr(e))
             line["strong"] = {"error": repr(e)}
+        log("strong done")
     else:
         line["strong"] = {"value": head["value"], "unit": UNIT, "ms_per_step": head["ms_per_step"],
                           "hypotheses_per_step": head["hypotheses_per_step"],
@@ -563,7 +573,9 @@ def main():
         for name, fn in (("C3", bench_c3_c5), ("C4", bench_c4)):
             try:
                 cfgs.update(fn(ctx, D, comm, capi, wl, args.steps, args.warmup, world, rank))
+                log(f"{name} leg done")
             except Exception as e:  # noqa: BLE001
+                log(f"{name} leg failed: " + repr(e))
                 cfgs[name] = {"error": repr(e)}
         line["configs"] = cfgs
     if comm is not None:

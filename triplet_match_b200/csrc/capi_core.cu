@@ -73,6 +73,7 @@ int pinned_ensure(tm_ctx* c, size_t bytes) {
     c->pinned_cap = 0;
     CU(cudaMallocHost(&c->pinned, bytes));
     c->pinned_cap = bytes;
+    ++c->pinned_gen;
     return TM_OK;
 }
 
@@ -132,6 +133,7 @@ void tm_ctx_destroy(tm_ctx* c) {
     c->icp_pack.release();
     c->icp_graph.release();
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pinned_gather) cudaFreeHost(c->pinned_gather);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);

@@ -132,7 +132,7 @@ int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t ma
     } else {
         IcpGraphKey key;
         key.scene_pos = s->dev.pos; key.model_vox = m->dev.voxel; key.occ = mdev.occ; key.bufs = c->icp.Tcur.p;
-        key.pinned = c->pinned; key.d16 = c->icp_d16.p; key.pairs = c->icp.pairs.p; key.pairs_cap = c->icp.pairs.cap; key.scene_n = s->dev.n; key.k = n;
+        key.pinned = c->pinned; key.d16 = c->icp_d16.p; key.pairs = c->icp.pairs.p; key.pairs_cap = c->icp.pairs.cap; key.pinned_gen = c->pinned_gen; key.scene_n = s->dev.n; key.k = n;
         key.max_iterations = max_iterations; key.pt_begin = sp.pt_begin; key.pt_end = sp.pt_end; key.emulate = sp.emulate;
         key.n_total = sp.n_total; key.thres = thres;
         IcpGraph& g = c->icp_graph;
@@ -220,11 +220,18 @@ int tm_icp_pose_sharded(tm_scene* s, tm_model* m, tm_comm* cm, uint32_t rank, ui
     const uint32_t per = (n + world - 1) / world;
     constexpr size_t REC = 64 + 4 + 4 + 8;
     const size_t slot = (size_t)per * REC;
-    // the staging area sits behind the refinement's own pinned block (the cached graph points into that)
-    const size_t stage_off = (IcpStage::bytes(per) + 255) & ~(size_t)255;
-    TRY(pinned_ensure(c, stage_off + (size_t)(world + 1) * slot));
-    TRY(c->icp_pack.ensure((size_t)(world + 1) * slot));
-    uint8_t* hsend = static_cast<uint8_t*>(c->pinned) + stage_off;
+    // own pinned block: the refinement's cached graph copies to / from c->pinned, which must not be re-allocated
+    // between replays
+    const size_t need = (size_t)(world + 1) * slot;
+    if (need > c->pinned_gather_cap) {
+        if (c->pinned_gather) cudaFreeHost(c->pinned_gather);
+        c->pinned_gather = nullptr;
+        c->pinned_gather_cap = 0;
+        CU(cudaMallocHost(&c->pinned_gather, need));
+        c->pinned_gather_cap = need;
+    }
+    TRY(c->icp_pack.ensure(need));
+    uint8_t* hsend = static_cast<uint8_t*>(c->pinned_gather);
     memset(hsend, 0, slot);
     for (uint32_t h = b; h < e; ++h) {
         uint8_t* r = hsend + (size_t)(h - b) * REC;

@@ -107,12 +107,13 @@ struct IcpGraphKey {
     const void* scene_pos = nullptr; const void* model_vox = nullptr; const void* occ = nullptr;
     const void* bufs = nullptr; const void* pinned = nullptr; const void* d16 = nullptr; const void* pairs = nullptr;
     size_t pairs_cap = 0;
+    uint64_t pinned_gen = 0;
     uint32_t scene_n = 0, k = 0, max_iterations = 0, pt_begin = 0, pt_end = 0, emulate = 0;
     uint64_t n_total = 0;
     float thres = 0.f;
     bool operator==(const IcpGraphKey& o) const {
         return scene_pos == o.scene_pos && model_vox == o.model_vox && occ == o.occ && bufs == o.bufs &&
-               pinned == o.pinned && d16 == o.d16 && pairs == o.pairs && pairs_cap == o.pairs_cap && scene_n == o.scene_n && k == o.k &&
+               pinned == o.pinned && d16 == o.d16 && pairs == o.pairs && pairs_cap == o.pairs_cap && pinned_gen == o.pinned_gen && scene_n == o.scene_n && k == o.k &&
                max_iterations == o.max_iterations && pt_begin == o.pt_begin && pt_end == o.pt_end &&
                emulate == o.emulate && n_total == o.n_total && thres == o.thres;
     }
@@ -136,6 +137,10 @@ struct tm_ctx {
     DevBuf scratch[13];  // stage-call scratch, grow-only
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    uint64_t pinned_gen = 0;                 // bumped whenever the pinned block is re-allocated (a cached graph that
+                                             // copies to / from it must be re-captured even if the address repeats)
+    void* pinned_gather = nullptr;           // staging of the pose-sharded all-gather (kept apart from `pinned`)
+    size_t pinned_gather_cap = 0;
     int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
     int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
     IcpBufs icp;                             // refinement state of tm_icp*, grow-only (no allocation per call)
