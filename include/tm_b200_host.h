@@ -28,6 +28,12 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* c
                        float distance_step_count, float angle_step, float min_diameter_factor,
                        float max_diameter_factor, float resolution, uint32_t cap,
                        tm_hostmodel** out);
+/* model::init(subset, params) (model.hpp:16-39): in_subset[i] != 0 marks the caller's subset (NULL = every point).
+ * As in the reference the bounding box, diameter, voxel-grid geometry and the tangent subset come from the
+ * finite points OF THE SUBSET, while the nearest-neighbour grid is filled from the whole cloud. */
+int tm_hostmodel_build_subset(tm_ctx* ctx, const tm_cloud_view* cloud, const uint8_t* in_subset, const uint8_t* curv_ok,
+                              float distance_step_count, float angle_step, float min_diameter_factor,
+                              float max_diameter_factor, float resolution, uint32_t cap, tm_hostmodel** out);
 void tm_hostmodel_destroy(tm_hostmodel* m);
 /* Model blob: serialises what model::init produced (grid, hash table in insertion and in
  * equal_range order, bounds) so a model is built once and reloaded — the reference rebuilds both

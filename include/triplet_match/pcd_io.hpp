@@ -116,9 +116,9 @@ inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out
             }
         };
         if (key == "FIELDS") fill([](field_t& f, const std::string& t) { f.name = t; });
-        else if (key == "SIZE") fill([](field_t& f, const std::string& t) { f.size = std::stoi(t); });
-        else if (key == "TYPE") fill([](field_t& f, const std::string& t) { f.type = t[0]; });
-        else if (key == "COUNT") fill([](field_t& f, const std::string& t) { f.count = std::stoi(t); });
+        else if (key == "SIZE") fill([](field_t& f, const std::string& t) { f.size = static_cast<int>(std::strtol(t.c_str(), nullptr, 10)); });
+        else if (key == "TYPE") fill([](field_t& f, const std::string& t) { f.type = t.empty() ? '?' : t[0]; });
+        else if (key == "COUNT") fill([](field_t& f, const std::string& t) { f.count = static_cast<int>(std::strtol(t.c_str(), nullptr, 10)); });
         else if (key == "WIDTH") ls >> width;
         else if (key == "HEIGHT") ls >> height;
         else if (key == "POINTS") { ls >> points; have_points = true; }
@@ -127,10 +127,30 @@ inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out
     }
     if (fields.empty()) throw std::runtime_error("pcd: no FIELDS line in '" + filename + "'");
     if (!have_points) points = width * height;
-    int rec = 0;
+    // the header comes from an untrusted file: validate everything a buffer size or an offset is derived from
+    int64_t rec64 = 0;
     for (auto& f : fields) {
-        f.offset = rec;
-        rec += f.size * f.count;
+        if (!(f.size == 1 || f.size == 2 || f.size == 4 || f.size == 8) || f.count < 1 || f.count > (1 << 20))
+            throw std::runtime_error("pcd: bad SIZE / COUNT in '" + filename + "'");
+        if (!(f.type == 'F' || f.type == 'I' || f.type == 'U'))
+            throw std::runtime_error("pcd: bad TYPE in '" + filename + "'");
+        f.offset = static_cast<int>(rec64);
+        rec64 += static_cast<int64_t>(f.size) * f.count;
+        if (rec64 > (1 << 24)) throw std::runtime_error("pcd: record too large in '" + filename + "'");
+    }
+    const int rec = static_cast<int>(rec64);
+    {  // POINTS cannot exceed what the rest of the file can hold: >= 2 bytes per ascii point, a record per binary
+       // point; an LZF token of 3 bytes expands to at most 264 bytes
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        in.seekg(here);
+        const uint64_t remaining = (here >= 0 && end >= here) ? static_cast<uint64_t>(end - here) : 0;
+        const uint64_t need = data_kind == "binary" ? points * static_cast<uint64_t>(rec)
+                              : data_kind == "ascii" ? points * 2ull
+                                                     : (points * static_cast<uint64_t>(rec)) / 128ull;
+        if (points > (1ull << 40) || need > remaining)
+            throw std::runtime_error("pcd: POINTS exceeds the file size in '" + filename + "'");
     }
     out.assign(points, pcl::PointSurfel());
     auto store = [](pcl::PointSurfel& p, int slot, const field_t& f, double v, const char* raw) {
@@ -152,11 +172,18 @@ inline void load(const std::string& filename, std::vector<pcl::PointSurfel>& out
                     std::string tok;
                     if (!(ls >> tok)) throw std::runtime_error("pcd: short ascii record in '" + filename + "'");
                     if (slot < 0 || c > 0) continue;
+                    // strtof / strtod: a packed rgb with alpha 0 is a denormal literal (std::stof throws on those),
+                    // and "nan" / "inf" are legal PCD values; out-of-range values clamp instead of throwing
+                    const char* cs = tok.c_str();
+                    char* endp = nullptr;
                     if (slot == 8 && f.type == 'F') {  // PCL writes packed rgb as a float literal
-                        float fv = std::stof(tok);
+                        float fv = std::strtof(cs, &endp);
+                        if (endp == cs) throw std::runtime_error("pcd: bad number '" + tok + "' in '" + filename + "'");
                         std::memcpy(&out[i].rgba, &fv, 4);
                     } else {
-                        store(out[i], slot, f, f.type == 'F' ? std::stod(tok) : static_cast<double>(std::stoll(tok)), nullptr);
+                        const double dv = f.type == 'F' ? std::strtod(cs, &endp) : static_cast<double>(std::strtoll(cs, &endp, 10));
+                        if (endp == cs) throw std::runtime_error("pcd: bad number '" + tok + "' in '" + filename + "'");
+                        store(out[i], slot, f, dv, nullptr);
                     }
                 }
             }

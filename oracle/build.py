@@ -29,6 +29,7 @@ def _make(target: str) -> None:
 
 def build_oracle(force: bool = False) -> str:
     deps = [os.path.join(ORACLE_DIR, f) for f in ("oracle.hpp", "oracle_capi.cpp", "Makefile")]
+    deps.append(os.path.join(os.path.dirname(ORACLE_DIR), "include", "triplet_match", "tm_sincosf.h"))
     if force or not _newer(ORACLE_LIB, deps):
         _make(ORACLE_DIR + "/liboracle.so")
     if os.path.isdir("/root/reference/include"):

@@ -41,6 +41,9 @@
 #include <utility>
 #include <vector>
 
+// the one definition shared with the product (device + host): sinf / cosf on [0, pi/3] for pcl::eigen33
+#include "../include/triplet_match/tm_sincosf.h"
+
 namespace orc {
 
 // ---------------------------------------------------------------- small math
@@ -411,11 +414,13 @@ struct model {
     // fill below, O(cells x points), does not finish: the supplied grid is then spot-checked cell by cell
     // with cell_nearest()).
     void init(const cloud& cl, const discretization_params& params, const sample_parameters& sp,
-              const uint8_t* curv_ok, float given_resolution, const uint32_t* voxel_in = nullptr) {
+              const uint8_t* curv_ok, float given_resolution, const uint32_t* voxel_in = nullptr,
+              const uint8_t* in_subset = nullptr) {
         c = cl;
         dp = params;
         std::vector<uint32_t> all;
-        for (uint32_t i = 0; i < c.n; ++i) {  // :24-30 allFinite filter
+        for (uint32_t i = 0; i < c.n; ++i) {  // :17-22 subset_ (every point when the caller's is empty), :24-30 allFinite
+            if (in_subset && !in_subset[i]) continue;
             bool fin = true;
             for (int k = 0; k < 3; ++k)
                 fin = fin && std::isfinite(c.pos[3 * i + k]) && std::isfinite(c.nrm[3 * i + k]) &&
@@ -870,7 +875,7 @@ inline void knn_inclusive(const cloud& c, uint32_t q, uint32_t k, std::vector<in
     }
 }
 // pcl::eigen33 (pcl/common/impl/eigen.hpp; third-party, restated from the published algorithm):
-// closed-form eigenvalues of a symmetric 3x3, ascending.  [parity unpinned: PCL version, libm cos/sin]
+// closed-form eigenvalues of a symmetric 3x3, ascending.  [parity unpinned: PCL version; cos / sin: tm_sincosf.h]
 inline void pcl_roots2(float b, float c, float r[3]) {
     r[0] = 0.f;
     float d = (float)((double)(b * b) - 4.0 * (double)c);
@@ -906,8 +911,12 @@ inline void pcl_eigen33(const float cov[3][3], float evals[3]) {
         if (q > 0.f) q = 0.f;
         float rho = std::sqrt(-a_over_3);
         float theta = atan2f_full(std::sqrt(-q), half_b) * s_inv3;
-        float cos_theta = std::cos(theta);
-        float sin_theta = std::sin(theta);
+        // theta in [0, pi/3].  The reference takes cos / sin from its libm; glibc's binary32 routines are not
+        // correctly rounded and no device routine reproduces them bit for bit, so oracle and device share
+        // tm_sincosf.h (binary64 Taylor series, rounded once: equal to (float)cos((double)theta) for every
+        // binary32 theta in [0, 1.6], within 1 ulp of glibc's cosf / sinf).
+        float cos_theta = tm_math::cosf_small(theta);
+        float sin_theta = tm_math::sinf_small(theta);
         r[0] = c2_over_3 + 2.f * rho * cos_theta;
         r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
         r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);

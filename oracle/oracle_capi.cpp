@@ -68,6 +68,15 @@ void orc_atan2f_q1_batch(const float* y, const float* x, uint64_t n, float* out,
     }
 }
 // in: p0,t0,p1,t1 (12 floats) -> f[4]
+// tm_sincosf.h (pcl::eigen33's cos / sin) next to the host libm's binary32 routines
+void orc_sincosf_small_batch(const float* x, uint64_t n, float* s, float* c, float* s_libm, float* c_libm) {
+    for (uint64_t i = 0; i < n; ++i) {
+        s[i] = tm_math::sinf_small(x[i]);
+        c[i] = tm_math::cosf_small(x[i]);
+        s_libm[i] = ::sinf(x[i]);
+        c_libm[i] = ::cosf(x[i]);
+    }
+}
 void orc_feature(const float* in, int use_libm, float* f) {
     feature({in[0], in[1], in[2]}, {in[3], in[4], in[5]}, {in[6], in[7], in[8]},
             {in[9], in[10], in[11]}, f, use_libm != 0);
@@ -200,6 +209,20 @@ void* orc_model_create_with_grid(const float* pos, const float* nrm, const float
     discretization_params dp{distance_step_count, angle_step, 10.f};
     sample_parameters sp{min_diameter_factor, max_diameter_factor, false};
     h->m.init(c, dp, sp, curv_ok, resolution_, voxel_in);
+    return h;
+}
+// model::init(subset, params): in_subset[i] != 0 marks the caller's subset
+void* orc_model_create_subset(const float* pos, const float* nrm, const float* tgt, uint32_t n,
+                              const uint8_t* in_subset, const uint8_t* curv_ok, float distance_step_count,
+                              float angle_step, float min_diameter_factor, float max_diameter_factor, float resolution_) {
+    auto* h = new model_h();
+    h->pos.assign(pos, pos + 3 * (size_t)n);
+    h->nrm.assign(nrm, nrm + 3 * (size_t)n);
+    h->tgt.assign(tgt, tgt + 3 * (size_t)n);
+    cloud c{h->pos.data(), h->nrm.data(), h->tgt.data(), n};
+    discretization_params dp{distance_step_count, angle_step, 10.f};
+    sample_parameters sp{min_diameter_factor, max_diameter_factor, false};
+    h->m.init(c, dp, sp, curv_ok, resolution_, nullptr, in_subset);
     return h;
 }
 // model.hpp:87-88 for n cells given as (i, j, k) triples: the exact brute-force nearest point

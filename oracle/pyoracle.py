@@ -195,7 +195,7 @@ def cl_icp_correlation(scene4, model4, indices_scene, indices_model, centroid_sc
 
 class OModel:
     def __init__(self, cloud, distance_step_count=20.0, angle_step=0.17453292, min_df=0.2,
-                 max_df=1.0, resolution=-1.0, curv_ok=None, voxel=None):
+                 max_df=1.0, resolution=-1.0, curv_ok=None, voxel=None, subset=None):
         """voxel: a grid supplied instead of filled (the brute-force fill is O(cells x points)); spot-check it
         with cell_nearest()."""
         L = load()
@@ -203,7 +203,15 @@ class OModel:
         self.n = self.pos.shape[0]
         co = cloud.tangent_mask if curv_ok is None else curv_ok
         co = None if co is None else np.ascontiguousarray(co, dtype=np.uint8)
-        if voxel is None:
+        if subset is not None:  # model::init(subset, params)
+            ins = np.zeros(self.n, dtype=np.uint8)
+            ins[np.asarray(subset, dtype=np.int64)] = 1
+            L.orc_model_create_subset.restype = C.c_void_p
+            self.h = C.c_void_p(L.orc_model_create_subset(_p(self.pos), _p(self.nrm), _p(self.tgt), C.c_uint32(self.n),
+                                                          _p(ins), _p(co), C.c_float(distance_step_count),
+                                                          C.c_float(angle_step), C.c_float(min_df), C.c_float(max_df),
+                                                          C.c_float(resolution)))
+        elif voxel is None:
             self.h = C.c_void_p(L.orc_model_create(_p(self.pos), _p(self.nrm), _p(self.tgt),
                                                    C.c_uint32(self.n), _p(co),
                                                    C.c_float(distance_step_count), C.c_float(angle_step),

@@ -226,6 +226,18 @@ void* ref_model_create(const float* pos, const float* nrm, const float* tgt, uin
     h->m->init(sp);
     return h;
 }
+// model::init(subset, params) (model.hpp:16-22)
+void* ref_model_create_subset(const float* pos, const float* nrm, const float* tgt, uint32_t n, const uint32_t* subset,
+                              uint32_t n_subset, float dist_steps, float angle_step, float min_df, float max_df) {
+    auto* h = new ref_model();
+    h->cloud = make_cloud(pos, nrm, tgt, n);
+    tr::discretization_params dp{dist_steps, angle_step, 10.f};
+    h->m.reset(new tr::model<point_t>(h->cloud, dp));
+    tr::sample_parameters sp{0.f, 0.f, 1.f, 1.f, min_df, max_df, 0.f, 1.f, false};
+    tr::subset_t sub(subset, subset + n_subset);
+    h->m->init(sub, sp);
+    return h;
+}
 void ref_model_destroy(void* p) { delete static_cast<ref_model*>(p); }
 // f: resolution, diameter, feat_min[4], feat_max[4] (10); to_voxel16 column-major; ints: extents[3], margin, point_count
 void ref_model_info(void* p, float* f10, float* to_voxel16, int* i5) {

@@ -61,8 +61,12 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
     _write(m, mp)
     _write(s, sp)
     extra = ["curv" if curv else "nocurv"] + ([str(tmp_path / "model.tmb")] if not curv and not shuffled else [])
-    r = subprocess.run([exe, "find", mp, sp, op] + extra, capture_output=True, text=True)
+    dump = str(tmp_path / "rounds.txt")
+    r = subprocess.run([exe, "find", mp, sp, op] + extra, capture_output=True, text=True,
+                       env=dict(os.environ, TM_DROPIN_DUMP=dump))
     assert r.returncode == 0, r.stderr + r.stdout
+    if not curv:
+        _check_rounds_against_oracle(dump, s if not shuffled else s, om)
     lines = open(op).read().strip().split("\n")
     n = int(lines[0])
     assert n >= 1, r.stdout
@@ -83,6 +87,42 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
             dmin = np.abs(s.pos[corr].astype(np.float64)[:, None, :] - placed[None, ::7, :]).sum(-1).min(1)
             assert np.median(dmin) < 6 * res
     assert len(found) == n  # no instance is reported twice (overlap-free acceptance)
+
+
+def _check_rounds_against_oracle(dump, s, om):
+    """Every find_parallel round of the drop-in dumps its recorded (p1, p2) list in the caller's indices and the number
+    of hypotheses the device generated from it; the oracle must generate as many from the same list, and the list must
+    honour the reference's inner budget (scene.hpp:277-305, 350-352): only pairs that pass window / collinearity /
+    valid are recorded, and per outer sample at most inner_bound + 1 of them."""
+    from oracle import pyoracle as po
+    osc = po.OScene(s)
+    rounds, cur = [], None
+    for ln in open(dump).read().strip().split("\n"):
+        t = ln.split()
+        if t[0] == "round":
+            cur = dict(n_outer=int(t[1]), n_pairs=int(t[2]), n_hyp=int(t[3]), pairs=[])
+            rounds.append(cur)
+        else:
+            cur["pairs"].append((int(t[0]), int(t[1])))
+    assert rounds and any(r["n_hyp"] > 0 for r in rounds)
+    for r in rounds:
+        assert len(r["pairs"]) == r["n_pairs"]
+        if not r["pairs"]:
+            assert r["n_hyp"] == 0
+            continue
+        pi = np.array([p[0] for p in r["pairs"]], dtype=np.uint32)
+        pj = np.array([p[1] for p in r["pairs"]], dtype=np.uint32)
+        f, k, v = osc.pair_features(om, pi, pj)
+        assert v.all()  # the host-side filters of the drop-in are the oracle's: every recorded pair is a valid sample
+        T, hp, *_ = osc.hypotheses(om, pi, pj)
+        assert T.shape[0] == r["n_hyp"]
+        # inner budget: <= inner_bound + 1 valid samples per outer sample
+        n_model_all = om.n
+        for o in np.unique(pi):
+            nn = osc.ball_subset(int(o), om.diameter).size
+            bound = int(-np.log(1.0 - 0.999) / (n_model_all / nn))
+            bound = min(max(bound, 10), nn)
+            assert int((pi == o).sum()) <= bound + 1
 
 
 # ---- PCD I/O + the CLI (SURVEY 8f rank 3) ------------------------------------------------------
@@ -242,6 +282,23 @@ def test_pcd_reader_and_writer(exe, tmp_path):
         f.write(_pcd_header(["x", "y", "z"], [4] * 3, ["F"] * 3, 4, "binary") + b"\0" * 20)
     assert subprocess.run([exe, "pcd", bad, out], capture_output=True).returncode == 3
     assert subprocess.run([exe, "pcd", str(tmp_path / "nope.pcd"), out], capture_output=True).returncode == 3
+    # hostile headers: zero / negative SIZE, zero COUNT, POINTS larger than the file — an error, never a crash
+    def hdr(sizes, counts, npts, data="binary"):
+        return ("VERSION 0.7\nFIELDS x y z\nSIZE " + " ".join(map(str, sizes)) + "\nTYPE F F F\nCOUNT " +
+                " ".join(map(str, counts)) + f"\nWIDTH {npts}\nHEIGHT 1\nPOINTS {npts}\nDATA {data}\n").encode()
+    for h in (hdr([0, 4, 4], [1, 1, 1], 4), hdr([4, -4, 4], [1, 1, 1], 4), hdr([4, 4, 4], [1, 0, 1], 4),
+              hdr([4, 4, 4], [1, 1, 1], 10**12), hdr([4, 4, 3], [1, 1, 1], 2), hdr([4, 4, 4], [1, 1, 1], 10**12, "ascii")):
+        with open(bad, "wb") as f:
+            f.write(h + b"\0" * 64)
+        assert subprocess.run([exe, "pcd", bad, out], capture_output=True).returncode == 3
+    # legacy ascii 'rgb F' with a denormal literal (alpha 0, R < 128), nan and inf coordinates
+    with open(bad, "wb") as f:
+        f.write(("VERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\n"
+                 "DATA ascii\n1 2 3 4.2e-39\nnan inf -1 5.9e-39\n").encode())
+    assert subprocess.run([exe, "pcd", bad, out], capture_output=True).returncode == 0
+    s2 = _surfels(out, 2)
+    assert np.array_equal(s2[0, 0:3], np.float32([1, 2, 3])) and np.isnan(s2[1, 0]) and np.isinf(s2[1, 1])
+    assert s2[:, 8].view(np.uint32)[0] == np.float32(4.2e-39).view(np.uint32)
 
 
 @pytest.fixture(scope="module")

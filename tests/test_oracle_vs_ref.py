@@ -188,6 +188,40 @@ def test_reference_model_init(refcfg):
         assert rm.voxel_query(p) is None and om.voxel_query(p) is None
 
 
+def test_reference_model_init_with_subset(ref):
+    """model::init(subset, params) (model.hpp:16-61): bounding box, diameter, grid geometry and the tangent subset come
+    from the caller's subset, the nearest-neighbour grid from the whole cloud.  Reference == oracle == the product's host
+    build (CPU path, no device), incl. the grid and the hash table."""
+    import common
+    from triplet_match_b200 import capi
+    m, s, om_full, osc, rec = common.config("cylinder_small")
+    sub = np.flatnonzero(m.pos[:, 2] > np.median(m.pos[:, 2])).astype(np.uint32)  # the upper half of the cylinder
+    ref.ref_model_create_subset.restype = C.c_void_p
+    ref.ref_model_create_subset.argtypes = [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_uint32] + [C.c_float] * 4
+    pos, nrm, tgt = _f32(m.pos), _f32(m.nrm), _f32(m.tgt)
+    h = C.c_void_p(ref.ref_model_create_subset(_p(pos), _p(nrm), _p(tgt), m.n, _p(sub), sub.size, 20.0, 0.17453292, 0.2, 1.0))
+    f10, tv, i5 = np.zeros(10, np.float32), np.zeros(16, np.float32), np.zeros(5, np.int32)
+    ref.ref_model_info(h, _p(f10), _p(tv), _p(i5))
+    om = po.OModel(m, subset=sub)
+    assert np.float32(om.diameter) == f10[1] and np.float32(om.diameter) < np.float32(om_full.diameter)
+    assert np.array_equal(om.extents, i5[:3]) and om.n_subset == int(i5[4]) and 0 < om.n_subset < om_full.n_subset
+    assert np.array_equal(om.to_voxel16.view(np.uint32), tv.view(np.uint32))
+    assert np.array_equal(om.feat_min.view(np.uint32), f10[2:6].view(np.uint32))
+    assert np.array_equal(om.feat_max.view(np.uint32), f10[6:10].view(np.uint32))
+    ref.ref_model_voxels.restype = C.c_uint64
+    grid = np.zeros(int(np.prod(om.extents.astype(np.int64))), np.uint32)
+    assert ref.ref_model_voxels(h, _p(grid)) == 0
+    assert np.array_equal(grid, om.voxel)
+    ref.ref_model_destroy(h)
+    hm = capi.HostModel(None, m.pos, m.nrm, m.tgt, curv_ok=m.tangent_mask, subset=sub, resolution=om.resolution)
+    assert np.float32(hm.diameter) == np.float32(om.diameter) and np.array_equal(hm.extents, om.extents)
+    assert np.array_equal(hm.to_voxel16.view(np.uint32), om.to_voxel16.view(np.uint32))
+    assert np.array_equal(hm.voxel, om.voxel) and hm.n_subset == om.n_subset
+    keys, offsets, pairs = om.table(200)
+    assert np.array_equal(hm.keys, keys) and np.array_equal(hm.offsets, offsets) and np.array_equal(hm.pairs, pairs)
+    hm.close()
+
+
 def test_reference_query_order_and_limit(refcfg):
     """Hash-hit order of the reference's own unordered_multimap + std::hash + query_limit loop."""
     name, m, s, om, osc, rec, rm, rs = refcfg

@@ -138,14 +138,11 @@ def test_gpu_knn_curvature_mask(ctx, name, morton):
     mn, mx, cov = gs.curvature(q, 30)
     omn, omx, ocov = po.curvature(s.pos, s.nrm, q, 30)
     assert np.array_equal(cov.view(np.uint32), ocov.view(np.uint32))
-    assert np.allclose(mx, omx, rtol=1e-5, atol=1e-9) and np.allclose(mn, omn, rtol=1e-4, atol=1e-7 * float(omx.max()))
+    # eigenvalues bit for bit: pcl::eigen33's cos / sin come from the shared tm_sincosf.h on both sides
+    assert np.array_equal(mx.view(np.uint32), omx.view(np.uint32)) and np.array_equal(mn.view(np.uint32), omn.view(np.uint32))
     mask, cnt = gs.compute_tangent_mask(30, 0.2, apply=False)
     omask, cand, c_mn, c_mx = po.tangent_mask(s)
-    ratio = np.full(s.n, 1.0)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        ratio[cand] = c_mn / c_mx
-    firm = ~(np.abs(ratio - 0.2) < 1e-4)
-    assert np.array_equal(mask[firm], omask[firm]) and cnt == int(mask.sum())
+    assert np.array_equal(mask, omask) and cnt == int(mask.sum())  # the whole mask, boundary points included
     if name == "crease":
         assert cnt > 100
     gs.close()

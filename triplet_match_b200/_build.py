@@ -46,7 +46,8 @@ def _headers() -> list[str]:
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hs.append(os.path.join(REPO, "include", "tm_b200.h"))
     hs.append(os.path.join(REPO, "include", "tm_b200_host.h"))
-    hs.append(os.path.join(REPO, "include", "triplet_match", "tm_atan2f.h"))
+    for h in ("tm_atan2f.h", "tm_sincosf.h", "tm_voxel_centre.h"):
+        hs.append(os.path.join(REPO, "include", "triplet_match", h))
     return hs
 
 

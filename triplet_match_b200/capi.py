@@ -67,7 +67,7 @@ EXPORTS = [
     "tm_nccl_unique_id", "tm_comm_create", "tm_comm_destroy", "tm_query_allreduce_best", "tm_queries_allreduce_best", "tm_icp_sharded",
 ]
 HOST_EXPORTS = [
-    "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_destroy",
+    "tm_host_last_error", "tm_host_resolution", "tm_hostmodel_build", "tm_hostmodel_build_subset", "tm_hostmodel_destroy",
     "tm_hostmodel_desc", "tm_hostmodel_counts", "tm_hostmodel_subset", "tm_hostmodel_entry_keys",
     "tm_hostmodel_entry_pairs", "tm_model_create", "tm_hostmodel_save", "tm_hostmodel_load",
 ]
@@ -239,16 +239,20 @@ class HostModel:
     """model::init on the host (+ GPU grid fill when ctx is given): tm_hostmodel_build."""
 
     def __init__(self, ctx, pos, nrm, tgt, curv_ok=None, distance_step_count=20.0,
-                 angle_step=0.17453292, min_df=0.2, max_df=1.0, resolution=-1.0, cap=200):
+                 angle_step=0.17453292, min_df=0.2, max_df=1.0, resolution=-1.0, cap=200, subset=None):
         self.lib = load()
         v, self._keep = _view(pos, nrm, tgt)
         self._view = v
         co = None if curv_ok is None else np.ascontiguousarray(curv_ok, dtype=np.uint8)
+        ins = None
+        if subset is not None:  # model::init(subset, params)
+            ins = np.zeros(int(v.n), dtype=np.uint8)
+            ins[np.asarray(subset, dtype=np.int64)] = 1
         self.h = C.c_void_p()
-        rc = self.lib.tm_hostmodel_build(ctx.h if ctx is not None else None, C.byref(v), _p(co),
-                                         C.c_float(distance_step_count), C.c_float(angle_step),
-                                         C.c_float(min_df), C.c_float(max_df), C.c_float(resolution),
-                                         C.c_uint32(cap), C.byref(self.h))
+        rc = self.lib.tm_hostmodel_build_subset(ctx.h if ctx is not None else None, C.byref(v), _p(ins), _p(co),
+                                                C.c_float(distance_step_count), C.c_float(angle_step),
+                                                C.c_float(min_df), C.c_float(max_df), C.c_float(resolution),
+                                                C.c_uint32(cap), C.byref(self.h))
         if rc != TM_OK:
             raise TmError(rc, self.lib.tm_host_last_error().decode("utf-8", "replace"))
         d = ModelDesc()

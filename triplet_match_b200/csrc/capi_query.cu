@@ -392,10 +392,13 @@ int tm_query_run(tm_query* q) {
             CU(cudaEventRecord(q->ev_s1, c->stream));
         }
     }
-    launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(), &out->n_local,
-                  out->shard, &out->best, c->sm_count * 2);
+    // a hypothesis the early drop abandoned cannot win on its partial count (scene.hpp:330: it returned fewer
+    // correspondences than the acceptance bound)
+    launch_argmax(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
+                  q->p.early_out ? q->dropped.as<uint8_t>() : nullptr, &out->n_local, out->shard, &out->best,
+                  c->sm_count * 2);
     // (a12) ICP of the local top-k
-    if (q->p.icp_top_k && q->p.max_icp_iterations) {
+    if (q->p.icp_top_k) {  // max_icp_iterations == 0: the top k unrefined, counted at the ICP threshold (scene.hpp:371)
         // a hypothesis the early drop gave up on never becomes a candidate (scene.hpp:330: a dropped
         // project_ returns fewer correspondences than the acceptance bound), whatever its partial count
         launch_select_topk(c->stream, q->counts.as<uint32_t>(), q->hyp_valid.as<uint8_t>(),
@@ -526,7 +529,7 @@ int tm_query_icp_results(tm_query* q, uint32_t* hyp_ids, float* T16s, uint32_t* 
                          double* scores, uint32_t* iters) {
     REQUIRE(q && q->ran, "null/unrun query");
     const uint32_t k = q->p.icp_top_k;
-    REQUIRE(k && q->p.max_icp_iterations, "query has no ICP stage");
+    REQUIRE(k, "query has no ICP stage");
     tm_ctx* c = q->s->ctx;
     TRY(bind(c));
     std::vector<long long> sums((size_t)k * ICP_NSUM);

@@ -210,8 +210,22 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
                        float distance_step_count, float angle_step, float min_diameter_factor,
                        float max_diameter_factor, float resolution, uint32_t cap,
                        tm_hostmodel** out) {
+    return tm_hostmodel_build_subset(ctx, c, nullptr, curv_ok, distance_step_count, angle_step, min_diameter_factor,
+                                     max_diameter_factor, resolution, cap, out);
+}
+
+int tm_hostmodel_build_subset(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* in_subset, const uint8_t* curv_ok,
+                              float distance_step_count, float angle_step, float min_diameter_factor,
+                              float max_diameter_factor, float resolution, uint32_t cap, tm_hostmodel** out) {
     if (!c || !out || !c->pos || !c->nrm || !c->tgt || c->n == 0) {
         g_host_err = "tm_hostmodel_build: bad cloud";
+        return TM_ERR_INVALID;
+    }
+    // the pair keys are packed k0 | k1 << 24 | k2 << 44 (host multimap order and the device table): distinct keys
+    // must stay distinct
+    if (!(distance_step_count >= 1.f) || distance_step_count > 16777216.f || !(angle_step > 0.f) ||
+        3.14159274f / angle_step >= 1048576.f) {
+        g_host_err = "tm_hostmodel_build: distance_step_count must be in [1, 2^24] and pi / angle_step below 2^20";
         return TM_ERR_INVALID;
     }
     auto P = [&](uint32_t i) { const float* p = c->pos + (size_t)i * c->stride; return v3{p[0], p[1], p[2]}; };
@@ -221,7 +235,8 @@ int tm_hostmodel_build(tm_ctx* ctx, const tm_cloud_view* c, const uint8_t* curv_
     m->distance_step_count = distance_step_count;
     m->angle_step = angle_step;
     std::vector<uint32_t> all;
-    for (uint32_t i = 0; i < c->n; ++i) {  // model.hpp:24-30
+    for (uint32_t i = 0; i < c->n; ++i) {  // model.hpp:17-30: subset_ (all points when empty), finite ones
+        if (in_subset && !in_subset[i]) continue;
         v3 p = P(i), n = N(i), t = T(i);
         bool fin = std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z) &&
                    std::isfinite(n.x) && std::isfinite(n.y) && std::isfinite(n.z) &&

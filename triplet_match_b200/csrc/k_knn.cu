@@ -13,6 +13,7 @@
 //                     normals into the tangent plane, running-mean centroid, covariance in the
 //                     reference's accumulation order) + pcl::eigen33's closed-form eigenvalues.
 #include "tm_kernels.cuh"
+#include "../../include/triplet_match/tm_sincosf.h"
 
 namespace tmk {
 
@@ -159,8 +160,9 @@ __device__ inline void eigen33_values(const float cov[3][3], float evals[3]) {
         if (q > 0.f) q = 0.f;
         const float rho = sqrtf(-a_over_3);
         const float theta = atan2f_full(sqrtf(-q), half_b) * s_inv3;
-        const float cos_theta = cosf(theta);
-        const float sin_theta = sinf(theta);
+        // theta in [0, pi/3]: the shared binary64-Taylor routine, same bits as the oracle (tm_sincosf.h)
+        const float cos_theta = tm_math::cosf_small(theta);
+        const float sin_theta = tm_math::sinf_small(theta);
         r[0] = c2_over_3 + 2.f * rho * cos_theta;
         r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
         r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);

@@ -95,7 +95,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 //          with REDUX and flushed with one coalesced RED per 32 hypotheses.
 // The per-inlier score term needs the scene point's ref vector (tangent or normal),
 // staged once per item in a per-warp shared-memory slab, and the model point's ref
-// vector, which sits in the second half of the same 32-byte grid cell.
+// vector, which comes from the compact per-model-point array mref (its index rides in the fused cell's .w).
 template <int P, bool FUSED, bool WITH_SCORE, bool CULL, bool OCC>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     score_full_kernel(ScoreArgs a) {
@@ -592,14 +592,15 @@ void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused) {
 // key = (inliers << 32) | (0xFFFFFFFF - global hypothesis id); ties -> lowest id.
 __global__ void __launch_bounds__(256)
     argmax_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
-                  const uint32_t* __restrict__ n_local, const unsigned long long* __restrict__ h_begin,
-                  unsigned long long* __restrict__ best) {
+                  const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local,
+                  const unsigned long long* __restrict__ h_begin, unsigned long long* __restrict__ best) {
     __shared__ unsigned long long wbest[8];
     const uint32_t n = *n_local;
     const unsigned long long hb = *h_begin;
     unsigned long long k = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (valid && !valid[i]) continue;
+        if (excluded && excluded[i]) continue;  // dropped by the early-drop test
         uint32_t c = counts[i];
         if (!c) continue;
         unsigned long long key =
@@ -618,11 +619,11 @@ __global__ void __launch_bounds__(256)
         if (k) atomicMax(best, k);
     }
 }
-void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                    const uint32_t* n_local, const unsigned long long* h_begin,
                    unsigned long long* best, int grid) {
     ++g_launch_count;
-    argmax_kernel<<<grid, 256, 0, st>>>(counts, valid, n_local, h_begin, best);
+    argmax_kernel<<<grid, 256, 0, st>>>(counts, valid, excluded, n_local, h_begin, best);
 }
 
 }  // namespace tmk

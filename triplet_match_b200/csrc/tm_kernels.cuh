@@ -152,7 +152,7 @@ void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
 void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
                               const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
                               float4* tile_lo, float4* tile_hi);
-void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid,
+void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                    const uint32_t* n_local, const unsigned long long* h_begin,
                    unsigned long long* best, int grid);
 
