@@ -398,8 +398,11 @@ int main(int argc, char** argv) {
     tr::scene<point_t> s(sc);
     s.set_curvature_test(curv);
     if (const char* e = std::getenv("TM_DROPIN_EARLY_DROP")) s.set_early_drop(std::atoi(e) != 0);  // A/B: default off
+    if (const char* e = std::getenv("TM_DROPIN_BATCH")) s.set_max_batch_hypotheses(std::strtoull(e, nullptr, 10));
+    uint32_t icp_iters = 5;
+    if (const char* e = std::getenv("TM_DROPIN_ICP_ITERS")) icp_iters = (uint32_t)std::atoi(e);
     auto t3 = now();
-    auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, 5);
+    auto matches = s.find_all_parallel(m, 1.0f, 0.5f, 0.9f, sp, icp_iters);
     auto t4 = now();
     std::printf("timing: load %.0f ms, model::init (incl. CUDA context) %.0f ms, find_all_parallel %.0f ms\n", ms(t0, t1),
                 ms(t1, t2), ms(t3, t4));

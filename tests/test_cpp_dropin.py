@@ -43,8 +43,10 @@ def _noisy_normals(cloud, seed, sigma=0.05):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("curv,shuffled", [(False, False), (True, False), (False, True)])
-def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
+@pytest.mark.parametrize("curv,shuffled,knobs", [(False, False, {}), (True, False, {}), (False, True, {}),
+                                                 (False, False, {"TM_DROPIN_BATCH": "4000"}),   # rounds split into several queries
+                                                 (False, False, {"TM_DROPIN_ICP_ITERS": "0"})])  # icp_ returns the match unchanged
+def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled, knobs):
     """curv=True: raw clouds with estimated (noisy) normals, tangent masks from the GPU 30-NN
     curvature criterion on both model and scene, as the reference does with PCL."""
     from triplet_match_b200 import synth
@@ -60,10 +62,10 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
     mp, sp, op = str(tmp_path / "m.bin"), str(tmp_path / "s.bin"), str(tmp_path / "o.txt")
     _write(m, mp)
     _write(s, sp)
-    extra = ["curv" if curv else "nocurv"] + ([str(tmp_path / "model.tmb")] if not curv and not shuffled else [])
+    extra = ["curv" if curv else "nocurv"] + ([str(tmp_path / "model.tmb")] if not curv and not shuffled and not knobs else [])
     dump = str(tmp_path / "rounds.txt")
     r = subprocess.run([exe, "find", mp, sp, op] + extra, capture_output=True, text=True,
-                       env=dict(os.environ, TM_DROPIN_DUMP=dump))
+                       env=dict(os.environ, TM_DROPIN_DUMP=dump, **knobs))
     assert r.returncode == 0, r.stderr + r.stdout
     if not curv:
         _check_rounds_against_oracle(dump, s if not shuffled else s, om)
@@ -78,7 +80,8 @@ def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled):
         placed = mpts @ T[:3, :3].T + T[:3, 3]
         errs = [np.abs(placed - (mpts @ P[:3, :3].T + P[:3, 3])).max() for P in s.poses]
         k = int(np.argmin(errs))
-        assert errs[k] < 3 * res, (errs, r.stdout)  # every reported instance is a real one
+        tol = (8 if knobs.get("TM_DROPIN_ICP_ITERS") == "0" else 3) * res  # unrefined poses are coarser
+        assert errs[k] < tol, (errs, r.stdout)  # every reported instance is a real one
         assert int(v[0]) >= 0.5 * m.n
         found.add(k)
         # correspondences are reported in the caller's index space: the matched scene points lie on the instance

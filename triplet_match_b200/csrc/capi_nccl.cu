@@ -106,6 +106,10 @@ int tm_queries_allreduce_best(tm_query** qs, uint32_t n, tm_comm* cm) {
         CU(cudaMemcpyAsync(recs + 72 * (size_t)i, &out->best_score, 72, cudaMemcpyDeviceToDevice, c->stream));
     }
     CU(cudaGetLastError());
+    // A broadcast from a rank that is only known on the device, written as a byte-wise SUM: the global key is
+    // unique, so exactly one rank (the owner of the winning hypothesis) exports a record and every other rank's
+    // 72 bytes are zero (memsets above) — each byte position therefore has at most one non-zero addend and the
+    // uint8 sum reproduces the owner's bytes exactly, without wrap-around.  Not a sum of floats.
     NC(g_nccl.AllReduce(recs, recs, (size_t)n * 72, ncclUint8_, ncclSum_, cm->comm, c->stream));
     for (uint32_t i = 0; i < n; ++i)
         CU(cudaMemcpyAsync(&qs[i]->out.as<QueryOut>()->best_score, recs + 72 * (size_t)i, 72,
@@ -143,7 +147,8 @@ int tm_query_allreduce_best(tm_query* q, tm_comm* cm) {
     CU(cudaMemsetAsync(&out->best_score, 0, 8, c->stream));
     TRY(finalize_best(q));
     CU(cudaGetLastError());
-    // best_score (8 B) and best_T16 (64 B) are adjacent in QueryOut
+    // best_score (8 B) and best_T16 (64 B) are adjacent in QueryOut.  Byte-wise sum = broadcast from the one rank
+    // that owns the (unique) winning key: all other ranks contribute zero bytes (see tm_queries_allreduce_best).
     NC(g_nccl.AllReduce(&out->best_score, &out->best_score, 72, ncclUint8_, ncclSum_, cm->comm,
                         c->stream));
     return TM_OK;
