@@ -139,3 +139,83 @@ def test_point_range_properties():
         for world in (1, 2, 3, 8):
             r = [capi.point_range(n, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+# ---- test-balanced shards (tm_query_set_balance) and pose-sharded ICP (tm_icp_pose_sharded) ------------
+def _balance_worker(rank, world, port, q):
+    """What the device path does with a communicator: every rank measures the subset sizes of the outer samples of its
+    count-based share only, one MAX all-reduce completes the table, every rank derives the same bounds."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, s, om, osc, rec = common.config("freeform_small")
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    n_outer = rec.outer.size
+    nh = np.bincount(rec.pair_outer[hp], minlength=n_outer).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(nh)])
+    hb, he = capi.shard_range(T.shape[0], rank, world)
+    sizes = np.zeros(n_outer, dtype=np.int64)
+    for o in range(n_outer):  # outer samples with hypotheses inside this rank's count-based shard
+        if nh[o] and starts[o] < he and starts[o + 1] > hb:
+            sizes[o] = osc.ball_subset(int(rec.outer[o]), om.diameter).size
+    t = torch.from_numpy(sizes.copy())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    bounds = capi.balanced_bounds(nh, t.numpy(), world)
+    # pose-sharded refinement: each rank's slice of 7 poses, gathered in rank order
+    pb, pe = capi.pose_range(7, rank, world)
+    mine = [(k, k * k) for k in range(pb, pe)]
+    allp = [None] * world
+    dist.all_gather_object(allp, mine)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (bounds, int(np.count_nonzero(sizes))))
+    if rank == 0:
+        q.put((gathered, t.numpy().copy(), nh, [x for part in allp for x in part]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_balanced_bounds_and_pose_gather():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_balance_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, sizes, nh, poses = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m, s, om, osc, rec = common.config("freeform_small")
+    full = np.array([osc.ball_subset(int(o), om.diameter).size if nh[k] else 0 for k, o in enumerate(rec.outer)])
+    assert np.array_equal(sizes, full)                       # the MAX all-reduce completed the table
+    assert gathered[0][0] == gathered[1][0]                  # every rank derives the same bounds
+    assert all(g[1] < np.count_nonzero(full) for g in gathered)  # ... after sizing only its own share
+    b = gathered[0][0]
+    H = int(nh.sum())
+    assert b[0] == 0 and b[-1] == H and all(x <= y for x, y in zip(b, b[1:]))
+    tests_of = np.repeat(full, nh)                           # cost of every hypothesis of the global list
+    per_rank = [int(tests_of[b[r]:b[r + 1]].sum()) for r in range(world)]
+    assert sum(per_rank) == int(tests_of.sum()) and max(per_rank) <= 1.01 * sum(per_rank) / world + int(full.max())
+    assert poses == [(k, k * k) for k in range(7)]           # slices concatenate in rank order
+
+
+def test_balanced_bounds_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for trial in range(20):
+            n = int(rng.integers(1, 40))
+            nh = rng.integers(0, 500, n)
+            sz = rng.integers(0, 3000, n)
+            b = capi.balanced_bounds(nh, sz, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == int(nh.sum())
+            assert all(x <= y for x, y in zip(b, b[1:]))
+            cost = np.repeat(sz, nh)
+            if cost.sum():
+                per = [int(cost[b[r]:b[r + 1]].sum()) for r in range(world)]
+                assert max(per) <= cost.sum() / world + sz.max() + 1
+    assert capi.balanced_bounds([4, 4], [10, 30], 2) == [0, 5, 8]  # 160 tests, half = 80 = 4 * 10 + 1.33 * 30 -> 4 + 1
+    for n in (0, 1, 7, 64):
+        for world in (1, 2, 3, 8):
+            r = [capi.pose_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b_[0] for a, b_ in zip(r, r[1:]))

@@ -706,6 +706,34 @@ def shard_range(n_hyp: int, rank: int, world: int, hyp_limit: int = 0):
     return hb, min(hb + per, H)
 
 
+def balanced_bounds(hyp_per_outer, sizes, world: int):
+    """Host mirror of balance_bounds_kernel (tm_query_set_balance): cuts the global hypothesis list — outer sample o
+    owns hyp_per_outer[o] consecutive hypotheses, each costing sizes[o] point tests — into `world` contiguous ranges
+    of (nearly) equal tests.  Returns world + 1 hypothesis indices."""
+    nh = np.asarray(hyp_per_outer, dtype=np.uint64)
+    sz = np.asarray(sizes, dtype=np.uint64)
+    hb = np.concatenate([[0], np.cumsum(nh)]).astype(np.uint64)
+    cum = np.concatenate([[0], np.cumsum(nh * sz)]).astype(np.uint64)
+    H, total = int(hb[-1]), int(cum[-1])
+    out = [0]
+    for r in range(1, world):
+        if total == 0:
+            out.append(min(H, (H + world - 1) // world * r))
+            continue
+        target = total * r // world
+        a = int(np.searchsorted(cum, np.uint64(target), side="right")) - 1  # last o with cum[o] <= target
+        a = min(a, nh.size - 1)
+        s = int(sz[a])
+        out.append(min(int(hb[a + 1]), int(hb[a]) + (target - int(cum[a])) // s) if s else int(hb[a]))
+    out.append(H)
+    return out
+
+
+def pose_range(n_poses: int, rank: int, world: int):
+    """Poses refined by `rank` when an ICP batch is sharded over the poses (tm_icp_pose_sharded)."""
+    return (n_poses * rank) // world, (n_poses * (rank + 1)) // world
+
+
 def point_range(n_points: int, rank: int, world: int):
     """Scene points of `rank` when an ICP pass is sharded over the scene (tm_icp_sharded)."""
     return (n_points * rank) // world, (n_points * (rank + 1)) // world
