@@ -524,7 +524,8 @@ def main():
     # ---- strong scaling: ONE 2^20-hypothesis C2 query split N ways ----------------------------------
     if world > 1:
         try:
-            sq, squeries, _ = run_query_config(ctx, D, comm, gs, [gm], [rec], HYP_PER_GPU // world, args.steps, args.warmup,
+            rec1 = wl.c2_record(scene, hm.diameter, 1)  # the 1-GPU headline's own list
+            sq, squeries, _ = run_query_config(ctx, D, comm, gs, [gm], [rec1], HYP_PER_GPU // world, args.steps, args.warmup,
                                                world, rank)
             line["strong"] = {"value": sq["value"], "unit": UNIT, "ms_per_step": sq["ms_per_step"],
                               "hypotheses_per_step": sq["hypotheses_per_step"], "per_rank": sq["per_rank"],

@@ -499,6 +499,10 @@ def test_full_size_properties(ctx):
         assert np.array_equal(np.concatenate(parts), d["counts"])
         assert sum(tests) == sum(tests_cnt) == int(q.result().n_tests)
         assert max(tests) <= 1.02 * (sum(tests) / world)
+        # the device's cut points are the host mirror's (capi.balanced_bounds)
+        nh = np.bincount(rec.pair_outer[d["hyp_pair"]], minlength=rec.outer.size)
+        sizes = np.diff(off.astype(np.int64))
+        assert np.concatenate([[0], np.cumsum([p.size for p in parts])]).tolist() == capi.balanced_bounds(nh, sizes, world)
     q2 = capi.Query(gs, gm)
     q2.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # sized for (0, 1)
     q2.set_shard(1, 2)                                    # then re-sharded

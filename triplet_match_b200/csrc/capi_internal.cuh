@@ -254,7 +254,7 @@ struct tm_query {
     bool by_tests = false;       // tm_query_set_balance: equal hypothesis-point tests instead of equal counts
     bool balanced = false;       // bounds[] holds the by-tests split of the current list
     tm_comm* comm = nullptr;     // completes the per-outer subset sizes of the by-tests split (one all-reduce)
-    DevBuf bounds, bal_cum;
+    DevBuf bounds, bal_cum, scan_scratch;
     bool pairs_set = false, need_size = false;
     uint32_t sized_rank = 0, sized_world = 1;
     std::vector<uint32_t> opo_host;  // pairs per outer sample (prefix), kept for re-sizing

@@ -17,7 +17,8 @@ static int enqueue_front_end(tm_query* q, unsigned long long* n_valid) {
                                q->valid.as<uint8_t>(), q->hit_begin.as<uint32_t>(), q->hit_count.as<uint32_t>(), n_valid);
     if (q->n_pairs == 0) CU(cudaMemsetAsync(q->hyp_off.p, 0, 8, c->stream));
     else
-        launch_exclusive_scan_u64(c->stream, q->hit_count.as<uint32_t>(), q->hyp_off.as<unsigned long long>(), q->n_pairs);
+        launch_exclusive_scan_u64_chained(c->stream, q->hit_count.as<uint32_t>(), q->hyp_off.as<unsigned long long>(),
+                                          q->n_pairs, q->scan_scratch.as<unsigned long long>(), c->sm_count);
     return TM_OK;
 }
 
@@ -47,6 +48,7 @@ static int size_for_shard(tm_query* q) {
     TRY(q->g_hyp.ensure((n_outer + 1) * 4ull));
     TRY(q->out.ensure(sizeof(QueryOut))); TRY(q->ctrl.ensure(64));
     TRY(q->bounds.ensure(((size_t)q->world + 1) * 8)); TRY(q->bal_cum.ensure(((size_t)n_outer + 1) * 8));
+    TRY(q->scan_scratch.ensure(scan_scratch_bytes(n_pairs)));
     QueryOut* out = q->out.as<QueryOut>();
     q->balanced = false;
     std::vector<uint32_t> gh(n_outer + 1, 0), sizes(n_outer + 1, 0);
@@ -153,7 +155,7 @@ void tm_query_destroy(tm_query* q) {
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum})
+          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum, &q->scan_scratch})
         b->release();
     q->icp.release();
     delete q;

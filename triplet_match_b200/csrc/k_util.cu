@@ -5,6 +5,8 @@
 //   ball subsets    radius subset of find_in_subset (include/impl/scene.hpp:273)
 //   voxel_fill      exact 1-NN grid fill (include/impl/model.hpp:81-94)
 //   traits_project  per-point closed forms (cylinder/plane/plane2/identity _traits::project)
+#include <algorithm>
+
 #include "tm_kernels.cuh"
 #include "../../include/triplet_match/tm_voxel_centre.h"
 
@@ -113,6 +115,89 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         __syncthreads();
     }
     if (threadIdx.x == 0) out[n] = (TOut)carry_s;
+}
+// The same scan over many CTAs for long inputs (the hit counts of an 8-GPU recorded list: 2.6e5 pairs, 64 rounds
+// of the single-CTA loop above).  Chained scan: a CTA takes the next tile by ticket (so tiles start in order and a
+// waiting CTA's predecessor is always running or done), scans its 4096 items, waits for the predecessor's inclusive
+// total, publishes its own.  scratch: [0] ticket, [1] unused, then per tile {ready flag, inclusive total}.
+__global__ void __launch_bounds__(SCAN_THREADS)
+    chained_scan_u64_kernel(const uint32_t* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n,
+                            unsigned long long* __restrict__ scratch) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    __shared__ uint32_t tile_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = (uint32_t)((n + (uint64_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((uint64_t)SCAN_THREADS * SCAN_ITEMS));
+    volatile unsigned long long* flag = scratch + 2;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) tile_s = (uint32_t)atomicAdd(&scratch[0], 1ull);
+        __syncthreads();
+        const uint32_t tile = tile_s;
+        if (tile >= n_tiles) break;
+        const uint64_t i0 = (uint64_t)tile * SCAN_THREADS * SCAN_ITEMS + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        unsigned long long v[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+            tsum += v[k];
+        }
+        unsigned long long incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sums[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - w;  // exclusive
+            if (lane == 31) {          // wi = the tile's total: chain it
+                unsigned long long prev = 0ull;
+                if (tile) {
+                    while (flag[2 * (tile - 1)] == 0ull) {}
+                    __threadfence();
+                    prev = flag[2 * (tile - 1) + 1];
+                }
+                carry_s = prev;
+                flag[2 * tile + 1] = prev + wi;
+                __threadfence();
+                flag[2 * tile] = 1ull;
+                if (tile == n_tiles - 1) out[n] = prev + wi;
+            }
+        }
+        __syncthreads();
+        unsigned long long excl = carry_s + warp_sums[warp] + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = excl;
+            excl += v[k];
+        }
+    }
+}
+size_t scan_scratch_bytes(uint64_t n) {
+    const uint64_t tiles = (n + (uint64_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((uint64_t)SCAN_THREADS * SCAN_ITEMS);
+    return (size_t)(2 + 2 * tiles) * 8;
+}
+// scratch == nullptr or a short input: the single-CTA kernel
+void launch_exclusive_scan_u64_chained(cudaStream_t st, const uint32_t* in, unsigned long long* out, uint64_t n,
+                                       unsigned long long* scratch, int max_ctas) {
+    if (!scratch || n <= (uint64_t)SCAN_THREADS * SCAN_ITEMS * 2) {
+        launch_exclusive_scan_u64(st, in, out, n);
+        return;
+    }
+    ++g_launch_count;
+    cudaMemsetAsync(scratch, 0, scan_scratch_bytes(n), st);
+    const uint64_t tiles = (n + (uint64_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((uint64_t)SCAN_THREADS * SCAN_ITEMS);
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)std::max(1, max_ctas));
+    chained_scan_u64_kernel<<<grid, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
 }
 void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n) {
     ++g_launch_count;

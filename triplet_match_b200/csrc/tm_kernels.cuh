@@ -89,6 +89,9 @@ void launch_set_mask(cudaStream_t st, float4* pos, uint32_t n, const uint8_t* ma
 void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n);
 void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned long long* out,
                                uint64_t n);
+size_t scan_scratch_bytes(uint64_t n);
+void launch_exclusive_scan_u64_chained(cudaStream_t st, const uint32_t* in, unsigned long long* out, uint64_t n,
+                                       unsigned long long* scratch, int max_ctas);
 void launch_seg_bbox(cudaStream_t st, const float4* pos, uint32_t n, float4* lo, float4* hi);
 void launch_ball_count(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
                        const uint32_t* active_ranges, float r2, uint32_t n_seg, uint32_t* counts);
