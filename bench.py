@@ -455,15 +455,20 @@ def main():
 
     log(f"headline done: {head['ms_per_step']:.2f} ms/step")
     # ---- e2e: host buffers in, host results out, through the C-ABI ----------
+    # inputs (the recorded list) and outputs (result record + per-hypothesis counts) live in pinned host memory
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    p_outer, p_pair_outer, p_pair_j = pinned(rec.outer.astype(np.uint32)), pinned(rec.pair_outer.astype(np.uint32)), pinned(rec.pair_j.astype(np.uint32))
+    p_counts = torch.empty(int(q.params.max_hypotheses), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     e2e_ms = []
     for it in range(2 + args.steps):
         D.barrier()
         t0 = time.perf_counter()
-        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)  # H2D: recorded list; front end + sizing of this rank's shard
+        q.set_pairs(p_outer, p_pair_outer, p_pair_j)         # H2D: recorded list; front end + sizing of this rank's shard
         q.run()
         if comm is not None:
             comm.allreduce_best(q)
-        q.download_counts()                                  # D2H: result + per-hypothesis counts
+        q.download_counts(out=p_counts)                      # D2H: result + per-hypothesis counts
         dt = (time.perf_counter() - t0) * 1e3
         if it >= 2:
             e2e_ms.append(dt)

@@ -636,11 +636,16 @@ class Query:
         return dict(counts=counts, scores=scores, T=T, valid=valid, hyp_pair=hyp_pair,
                     dropped=dropped, result=r)
 
-    def download_counts(self):
-        """result + per-hypothesis inlier counts only (the e2e read-back)."""
+    def download_counts(self, out=None):
+        """result + per-hypothesis inlier counts only (the e2e read-back).  out: a caller-owned uint32 buffer (e.g.
+        pinned host memory) of at least n_scored entries; a view of its first n_scored entries is returned."""
         r = self.result()
         n = int(r.n_scored)
-        counts = np.zeros(n, dtype=np.uint32)
+        if out is None:
+            counts = np.zeros(n, dtype=np.uint32)
+        else:
+            assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= n
+            counts = out[:n]
         if n:
             _chk(self.lib.tm_query_download(self.h, C.c_uint64(n), _p(counts), None, None, None,
                                             None, None))

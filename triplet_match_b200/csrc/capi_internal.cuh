@@ -211,14 +211,17 @@ int icp_run(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t ma
 
 // ------------------------------------------------------------ resident query
 struct QueryOut {  // one contiguous device block, read back in one copy
+    // written by the front end (pair features, probe, prefix, shard): kept when tm_query_run follows
+    // tm_query_set_pairs directly
     unsigned long long shard[3];  // h_begin, h_end, H
-    unsigned long long best;
-    unsigned long long n_tests;
     unsigned long long n_valid;
-    double best_score;
-    float best_T16[16];
     uint32_t n_local;
     uint32_t err;
+    // reset by every run
+    unsigned long long best;
+    unsigned long long n_tests;
+    double best_score;
+    float best_T16[16];  // directly behind best_score: the two travel as one 72-byte record
     uint32_t work_counter;
     uint32_t pad;
     unsigned long long best_acc[2];  // lazy score of the selected pose: fixed-point sum, inlier count
@@ -256,6 +259,9 @@ struct tm_query {
     tm_comm* comm = nullptr;     // completes the per-outer subset sizes of the by-tests split (one all-reduce)
     DevBuf bounds, bal_cum, scan_scratch;
     bool pairs_set = false, need_size = false;
+    bool front_ready = false;    // the front end's outputs for the current list and shard are on the device (set by
+                                 // the sizing pass of tm_query_set_pairs, consumed by the next tm_query_run)
+    bool balls_ready = false;    // ... and so are the radius-search counts of the shard's outer samples
     uint32_t sized_rank = 0, sized_world = 1;
     std::vector<uint32_t> opo_host;  // pairs per outer sample (prefix), kept for re-sizing
 };

@@ -1,6 +1,8 @@
 // capi_query.cu — the resident query (tm_query_*): the whole recorded-list search enqueued on one stream with
 // no host round trip: features + probe -> scan -> shard -> subsets -> hypotheses -> work list -> scoring ->
 // argmax (-> top-k -> ICP) -> best-pose export.
+#include <cstddef>
+
 #include "capi_internal.cuh"
 
 
@@ -55,12 +57,13 @@ static int size_for_shard(tm_query* q) {
     if (n_outer) {
         CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
         TRY(enqueue_front_end(q, &out->n_valid));
-        // count-based shard and the outer samples it touches
+        // count-based shard and the outer samples it touches (by-tests: unclipped, every outer sample must be sized
+        // by the rank whose count-based share holds it)
+        const bool by_tests = q->by_tests && q->world > 1;
         launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit, q->rank, q->world,
-                           ~0ull, nullptr, out->shard, &out->n_local, &out->err);
+                           by_tests ? ~0ull : q->cap_hyp, nullptr, out->shard, &out->n_local, &out->err);
         launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(), q->outer_pair_off.as<uint32_t>(), n_outer,
                                 out->shard, q->g_hyp.as<uint32_t>());
-        const bool by_tests = q->by_tests && q->world > 1;
         const uint32_t* active = (by_tests && !q->comm) ? nullptr : q->g_hyp.as<uint32_t>();
         TRY(ball_subsets_dev(c, q->s->dev, q->outer.as<uint32_t>(), n_outer, active, q->m->dev.diameter, q->ball_counts,
                              q->ball_seg_off, q->sub_off, nullptr, nullptr));
@@ -69,8 +72,9 @@ static int size_for_shard(tm_query* q) {
             launch_balance_bounds(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit,
                                   q->outer_pair_off.as<uint32_t>(), q->ball_seg_off.as<uint32_t>(), n_outer, q->world,
                                   q->bal_cum.as<unsigned long long>(), q->bounds.as<unsigned long long>());
+            CU(cudaMemsetAsync(&out->err, 0, 4, c->stream));
             launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), n_pairs, q->p.hyp_limit, q->rank, q->world,
-                               ~0ull, q->bounds.as<unsigned long long>(), out->shard, &out->n_local, &out->err);
+                               q->cap_hyp, q->bounds.as<unsigned long long>(), out->shard, &out->n_local, &out->err);
             launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(), q->outer_pair_off.as<uint32_t>(),
                                     n_outer, out->shard, q->g_hyp.as<uint32_t>());
             q->balanced = true;
@@ -116,6 +120,9 @@ static int size_for_shard(tm_query* q) {
     q->sized_rank = q->rank;
     q->sized_world = q->world;
     q->need_size = false;
+    // what the sizing pass left on the device is exactly what the next run would recompute
+    q->front_ready = n_outer != 0;
+    q->balls_ready = n_outer != 0 && !q->balanced;  // by-tests: the counts belong to the count-based share
     return TM_OK;
 }
 
@@ -278,30 +285,40 @@ int tm_query_run(tm_query* q) {
     const CloudDev& sc = q->s->dev;
     if (q->need_size) TRY(size_for_shard(q));  // rank / world / balance changed after tm_query_set_pairs
     QueryOut* out = q->out.as<QueryOut>();
-    CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
+    // a run that directly follows tm_query_set_pairs finds the front end's outputs (hit counts, prefix, shard,
+    // per-outer ranges) and, for count-based shards, the radius-search counts already on the device
+    const bool reuse_front = q->front_ready, reuse_balls = q->front_ready && q->balls_ready;
+    q->front_ready = q->balls_ready = false;
+    const size_t run_part = offsetof(QueryOut, best);
+    if (reuse_front) CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(out) + run_part, 0, sizeof(QueryOut) - run_part, c->stream));
+    else CU(cudaMemsetAsync(out, 0, sizeof(QueryOut), c->stream));
     CU(cudaMemsetAsync(q->counts.p, 0, q->cap_hyp * 4, c->stream));
     CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
     // (a1-a5) pair filter, feature, key, probe
     CU(cudaEventRecord(q->ev_f0, c->stream));
-    TRY(enqueue_front_end(q, &out->n_valid));
-    launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
-                       q->rank, q->world, q->cap_hyp, q->balanced ? q->bounds.as<unsigned long long>() : nullptr,
-                       out->shard, &out->n_local, &out->err);
-    launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
-                            q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
-                            q->g_hyp.as<uint32_t>());
+    if (!reuse_front) {
+        TRY(enqueue_front_end(q, &out->n_valid));
+        launch_shard_range(c->stream, q->hyp_off.as<unsigned long long>(), q->n_pairs, q->p.hyp_limit,
+                           q->rank, q->world, q->cap_hyp, q->balanced ? q->bounds.as<unsigned long long>() : nullptr,
+                           out->shard, &out->n_local, &out->err);
+        launch_group_hyp_ranges(c->stream, q->hyp_off.as<unsigned long long>(),
+                                q->outer_pair_off.as<uint32_t>(), q->n_outer, out->shard,
+                                q->g_hyp.as<uint32_t>());
+    }
     CU(cudaEventRecord(q->ev_f1, c->stream));
     // (a8) radius subsets, only of the outer samples that own hypotheses of this rank's shard
     // (g_hyp); the others get empty rows, so N ranks do not repeat each other's searches
     if (q->n_outer) {
         const float r2 = m->dev.diameter * m->dev.diameter;
         const uint32_t n_seg = (sc.n + BALL_SEG - 1) / BALL_SEG;
-        launch_ball_count(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
-                          q->ball_counts.as<uint32_t>());
-        launch_ball_seg_scan(c->stream, q->ball_counts.as<uint32_t>(), q->n_outer, n_seg,
-                             q->ball_seg_off.as<uint32_t>());
-        launch_exclusive_scan_u64(c->stream, q->ball_seg_off.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
-                                  q->n_outer);
+        if (!reuse_balls) {
+            launch_ball_count(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
+                              q->ball_counts.as<uint32_t>());
+            launch_ball_seg_scan(c->stream, q->ball_counts.as<uint32_t>(), q->n_outer, n_seg,
+                                 q->ball_seg_off.as<uint32_t>());
+            launch_exclusive_scan_u64(c->stream, q->ball_seg_off.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
+                                      q->n_outer);
+        }
         launch_ball_fill(c->stream, sc, q->outer.as<uint32_t>(), q->n_outer, q->g_hyp.as<uint32_t>(), r2, n_seg,
                          q->ball_counts.as<uint32_t>(), q->sub_off.as<unsigned long long>(),
                          q->sub_idx.as<int32_t>());
