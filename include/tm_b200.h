@@ -219,6 +219,10 @@ int tm_uvicp_correlation(tm_ctx* ctx, const float* scene4, uint32_t n_scene, con
                          const float centroid_scene[4], const float centroid_model[4], float* records16,
                          double cov9[9]);
 
+/* self-test hook: exclusive prefix sum (n + 1 x u64) of n x u32 with the chained multi-CTA scan that computes the
+ * hypothesis offsets of long recorded lists */
+int tm_ctx_scan_u64(tm_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out);
+
 /* ---- resident query: the whole recorded-list search in one call --------- */
 typedef struct tm_query_params {
     float min_diameter_factor; /* sample_parameters (include/common:72-82) */

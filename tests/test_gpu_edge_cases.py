@@ -220,3 +220,18 @@ def test_random_irregular_clouds(ctx, seed):
         assert np.array_equal(cg, co) and np.array_equal(dg, do) and np.allclose(sg, so, rtol=1e-9, atol=1e-9)
     assert co.max() > 50
     gs.close(); gm.close(); hm.close()
+
+
+@pytest.mark.gpu
+def test_chained_scan_matches_cumsum(ctx):
+    """The multi-CTA chained scan behind the hypothesis offsets of long recorded lists: every length around the tile
+    (4 096) and switch-over (8 192) boundaries, ragged tails, zeros, and sums beyond 2^32."""
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 4095, 4096, 4097, 8191, 8192, 8193, 12288, 12289, 100_003, 262_144, 1_000_001):
+        v = rng.integers(0, 201, size=n, dtype=np.uint32)
+        if n > 10:
+            v[rng.integers(0, n, n // 7)] = 0
+        exp = np.concatenate([[0], np.cumsum(v.astype(np.uint64))]).astype(np.uint64)
+        assert np.array_equal(ctx.scan_u64(v), exp), n
+    big = np.full(70_000, 0xFFFFFFF0, dtype=np.uint32)  # total far beyond 32 bits
+    assert np.array_equal(ctx.scan_u64(big), np.concatenate([[0], np.cumsum(big.astype(np.uint64))]).astype(np.uint64))

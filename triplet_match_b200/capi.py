@@ -57,7 +57,7 @@ class QueryResult(C.Structure):
 EXPORTS = [
     "tm_last_error", "tm_version", "tm_ctx_create", "tm_ctx_destroy", "tm_ctx_sync",
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
-    "tm_ctx_kernel_launches", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
+    "tm_ctx_kernel_launches", "tm_ctx_scan_u64", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
     "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
@@ -169,6 +169,13 @@ class Context:
 
     def flush_l2(self):
         _chk(self.lib.tm_ctx_flush_l2(self.h))
+
+    def scan_u64(self, values):
+        """tm_ctx_scan_u64: exclusive prefix sum (n + 1 entries) on the device."""
+        v = np.ascontiguousarray(values, dtype=np.uint32)
+        out = np.zeros(v.size + 1, dtype=np.uint64)
+        _chk(self.lib.tm_ctx_scan_u64(self.h, _p(v), C.c_uint64(v.size), _p(out)))
+        return out
 
     def measure_l2_gather(self, working_set_bytes: int = 32 << 20) -> float:
         g = C.c_double()

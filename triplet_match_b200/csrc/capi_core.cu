@@ -920,6 +920,22 @@ int tm_traits_project(tm_ctx* c, int kind, const float g2l[16], float radius, fl
     return TM_OK;
 }
 
+// self-test hook: exclusive prefix sum of `in` (n x u32) with the chained multi-CTA scan the resident query uses for
+// long pair lists; out: n + 1 x u64
+int tm_ctx_scan_u64(tm_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out) {
+    REQUIRE(c && out && (n == 0 || in), "tm_ctx_scan_u64: null argument");
+    TRY(bind(c));
+    DevBuf &din = c->scratch[0], &dout = c->scratch[1], &scr = c->scratch[2];
+    TRY(din.ensure(std::max<uint64_t>(n, 1) * 4)); TRY(dout.ensure((n + 1) * 8)); TRY(scr.ensure(scan_scratch_bytes(n)));
+    if (n) CU(cudaMemcpyAsync(din.p, in, n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_exclusive_scan_u64_chained(c->stream, din.as<uint32_t>(), dout.as<unsigned long long>(), n,
+                                      scr.as<unsigned long long>(), c->sm_count);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
 int tm_ctx_measure_l2_gather(tm_ctx* c, uint64_t working_set_bytes, double* gb_per_s) {
     REQUIRE(c && gb_per_s, "tm_ctx_measure_l2_gather: null argument");
     REQUIRE(working_set_bytes >= (1u << 20), "tm_ctx_measure_l2_gather: working set too small");
