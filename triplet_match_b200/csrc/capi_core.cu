@@ -704,6 +704,8 @@ static int score_full_dev(tm_ctx* c, const CloudDev& scene, const tm_model* m, c
     a.counts = d_counts;
     a.scores = d_scores;
     a.sq_thres = sq_thres;
+    a.thres = thres;
+    a.cell_reach = cell_reach_of(a.model);
     a.stats = nullptr;
     if (!with_score && knobs().scorer >= 8) {
         int& b = c->count_bps[m->fused ? 1 : 0];

@@ -170,6 +170,12 @@ struct tm_scene {
     CloudDev dev;
 };
 
+// 1.5 cell diagonals in model units, rounded up: how far a position can be from the centre of the cell voxel_query
+// maps it to (truncation toward zero makes cell 0 two cells wide)
+inline float cell_reach_of(const ModelDev& d) {
+    const double diag = std::sqrt(1.0 / ((double)d.sx * d.sx) + 1.0 / ((double)d.sy * d.sy) + 1.0 / ((double)d.sz * d.sz));
+    return (float)(1.5 * diag * 1.0001);
+}
 int bind(tm_ctx* c);
 // ModelDev for kernels that test against `thres`: the resident description plus, when it pays, the
 // block-occupancy mask of that threshold (built on first use, cached per model).  TM_OCC=0 disables.

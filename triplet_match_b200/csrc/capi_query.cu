@@ -354,6 +354,8 @@ int tm_query_run(tm_query* q) {
             a.counts = q->counts.as<uint32_t>();
             a.scores = q->scores.as<unsigned long long>();
             a.sq_thres = sqt;
+            a.thres = thres;
+            a.cell_reach = cell_reach_of(a.model);
             a.stats = nullptr;
             if (knobs().score_stats) {
                 TRY(q->stats.ensure(64));

@@ -159,6 +159,43 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                 TM_AXIS(r2, m.sz, m.tz, m.ezf)
 #undef TM_AXIS
                 survive = !out;
+                if (OCC && survive) {
+                    // Sphere cull for grids that are mostly empty space around a surface (the instantiations that also
+                    // use the occupancy mask).  The nearest-neighbour grid doubles as a distance field: with x_c = T c
+                    // (c = centre of the tile's box), z the centre of x_c's cell and q* that cell's nearest model point,
+                    // every model point m has |x_c - m| >= |z - q*| - |x_c - z| >= |x_c - q*| - 2 |x_c - z|, and every
+                    // tile point p has |T p - x_c| <= rho.  So if |x_c - q*| - 2 Dmax - rho > thres no point of the tile
+                    // is within the threshold of ANY model point: the pair has no inlier and is skipped.  rho comes from
+                    // the interval arithmetic above (no rigidity assumed): the transformed tile lies in the box cc +- ee.
+                    // NaN anywhere makes the comparison false (no cull).
+                    const float xc = r0.x * cx + r0.y * cy + r0.z * cz + r0.w, yc = r1.x * cx + r1.y * cy + r1.z * cz + r1.w,
+                                zc = r2.x * cx + r2.y * cy + r2.z * cz + r2.w;
+                    const float ex_ = fabsf(r0.x) * hx + fabsf(r0.y) * hy + fabsf(r0.z) * hz,
+                                ey_ = fabsf(r1.x) * hx + fabsf(r1.y) * hy + fabsf(r1.z) * hz,
+                                ez_ = fabsf(r2.x) * hx + fabsf(r2.y) * hy + fabsf(r2.z) * hz;
+                    const float vx = m.sx * xc + m.tx, vy = m.sy * yc + m.ty, vz = m.sz * zc + m.tz;
+                    if ((vx > -1.f) & (vx < m.exf) & (vy > -1.f) & (vy < m.eyf) & (vz > -1.f) & (vz < m.ezf)) {
+                        const uint32_t lc = (uint32_t)(((int)vz * m.ey + (int)vy) * m.ex + (int)vx);
+                        const float4 qn = FUSED ? __ldg(&m.vcell[lc]) : __ldg(&m.cloud.pos[__ldg(&m.voxel[lc])]);
+                        const float dx = xc - qn.x, dy = yc - qn.y, dz = zc - qn.z;
+                        const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                        float rho = sqrtf(ex_ * ex_ + ey_ * ey_ + ez_ * ez_);
+                        {   // a (numerically) orthonormal R maps the tile's circumscribed sphere onto a sphere of the same
+                            // radius: |R v| <= sqrt(1 + 3 delta) |v| with delta = max |R^T R - I| (Gershgorin) — tighter
+                            // than the box of the rotated box; transforms that are not rigid keep the box bound
+                            const float g00 = r0.x * r0.x + r1.x * r1.x + r2.x * r2.x, g11 = r0.y * r0.y + r1.y * r1.y + r2.y * r2.y,
+                                        g22 = r0.z * r0.z + r1.z * r1.z + r2.z * r2.z, g01 = r0.x * r0.y + r1.x * r1.y + r2.x * r2.y,
+                                        g02 = r0.x * r0.z + r1.x * r1.z + r2.x * r2.z, g12 = r0.y * r0.z + r1.y * r1.z + r2.y * r2.z;
+                            const float delta = fmaxf(fmaxf(fmaxf(fabsf(g00 - 1.f), fabsf(g11 - 1.f)), fabsf(g22 - 1.f)),
+                                                      fmaxf(fmaxf(fabsf(g01), fabsf(g02)), fabsf(g12)));
+                            if (delta < 0.01f) rho = fminf(rho, sqrtf(1.f + 3.f * delta) * sqrtf(hx * hx + hy * hy + hz * hz));
+                        }
+                        const float mag = fabsf(xc) + fabsf(yc) + fabsf(zc) + fabsf(qn.x) + fabsf(qn.y) + fabsf(qn.z);
+                        // slack: 2 Dmax (cell 0 is two cells wide: 1.5 cell diagonals from its centre), rounding of
+                        // everything above (1e-5 relative of the magnitudes involved), 0.1 % of the threshold
+                        if (dist - 2.f * a.cell_reach - rho * 1.0001f - 1e-5f * mag > a.thres * 1.001f) survive = false;
+                    }
+                }
             }
             uint32_t mask = __ballot_sync(0xffffffffu, survive);  // also orders the smem stores
             if (STATS && lane == 0) {
