@@ -3,7 +3,7 @@ import os, subprocess, sys, time, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import bench
+from triplet_match_b200 import workloads as wl
 import __graft_entry__ as ge
 ge.build()
 if os.environ.get("C3"):
@@ -11,7 +11,7 @@ if os.environ.get("C3"):
     model = synth.freeform_model(seed=3, n_points=50000, radius=0.01 * np.sqrt(50000 / (4 * np.pi)), n_bumps=12, n_curves=8)
     scene = synth.make_scene(seed=3, model=model, n_points=10_000_000, n_copies=8, extent=10.0 * np.sqrt(10.0), flat_copies=False)
 else:
-    model, scene = bench.build_workload(1)
+    model, scene = wl.c2_clouds()
 if os.environ.get("SHUFFLE"):
     from triplet_match_b200 import synth
     scene = scene.take(synth.shuffle_perm(9, 1, scene.n))
