@@ -235,3 +235,54 @@ def test_chained_scan_matches_cumsum(ctx):
         assert np.array_equal(ctx.scan_u64(v), exp), n
     big = np.full(70_000, 0xFFFFFFF0, dtype=np.uint32)  # total far beyond 32 bits
     assert np.array_equal(ctx.scan_u64(big), np.concatenate([[0], np.cumsum(big.astype(np.uint64))]).astype(np.uint64))
+
+
+@pytest.mark.gpu
+def test_sharding_edge_cases(ctx):
+    """Shards of equal counts and of equal tests at the edges: more ranks than outer samples or hypotheses, a hyp_limit
+    inside the list, an empty list, capacity clipping — the shards always tile the (clipped) global list in rank order."""
+    from triplet_match_b200 import capi
+    m, s, om, osc, rec = common.config("plane_small")
+    gm = common.upload_model(ctx, m, om)
+    gs = common.upload_scene(ctx, s)
+    q0 = capi.Query(gs, gm)
+    q0.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q0.run()
+    full = q0.download_counts()[0]
+    H = full.size
+    assert H > 50
+    for by_tests in (False, True):
+        for world, limit in ((2, 0), (5, 0), (16, 0), (64, 0), (3, H // 3 + 1), (4, 7), (2, 1)):
+            parts, keys = [], []
+            for rank in range(world):
+                q = capi.Query(gs, gm, hyp_limit=limit)
+                q.set_shard(rank, world)
+                q.set_balance(by_tests)
+                q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+                q.run()
+                c, r = q.download_counts()
+                parts.append(c)
+                keys.append(int(r.best_key))
+                assert int(r.n_hypotheses) == (min(H, limit) if limit else H)
+                q.close()
+            n = min(H, limit) if limit else H
+            assert np.array_equal(np.concatenate(parts), full[:n]), (by_tests, world, limit)
+            exp = max((capi.pack_key(int(c), i) for i, c in enumerate(full[:n]) if c), default=0)
+            assert max(keys) == exp
+    # empty list, any sharding
+    e = np.zeros(0, np.uint32)
+    q = capi.Query(gs, gm)
+    q.set_shard(1, 3)
+    q.set_balance(True)
+    q.set_pairs(e, e, e)
+    q.run()
+    assert q.result().n_hypotheses == 0 and q.download_counts()[0].size == 0
+    q.close()
+    # capacity smaller than the shard: reported, never silently truncated
+    q = capi.Query(gs, gm, max_hypotheses=H // 2)
+    q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    q.run()
+    with pytest.raises(capi.TmError):
+        q.result()
+    q.close()
+    q0.close(); gm.close(); gs.close()
