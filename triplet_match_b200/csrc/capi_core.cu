@@ -443,8 +443,8 @@ static int scene_upload_impl(tm_ctx* c, const tm_cloud_view* cloud, const uint8_
             if (!std::isfinite(blo[k])) blo[k] = 0.f;
         }
         const uint32_t nb = radix_blocks(n);
-        DevBuf ka, va, kb, vb, hist, offs, p2, n2, t2;
-        auto release = [&] { for (DevBuf* b : {&ka, &va, &kb, &vb, &hist, &offs, &p2, &n2, &t2}) b->release(); };
+        DevBuf ka, va, kb, vb, hist, offs, p2, n2, t2, scr;
+        auto release = [&] { for (DevBuf* b : {&ka, &va, &kb, &vb, &hist, &offs, &p2, &n2, &t2, &scr}) b->release(); };
         rc = ka.ensure((size_t)n * 4);
         if (!rc) rc = va.ensure((size_t)n * 4);
         if (!rc) rc = kb.ensure((size_t)n * 4);
@@ -454,10 +454,11 @@ static int scene_upload_impl(tm_ctx* c, const tm_cloud_view* cloud, const uint8_
         if (!rc) rc = p2.ensure((size_t)n * 16);
         if (!rc) rc = n2.ensure((size_t)n * 16);
         if (!rc) rc = t2.ensure((size_t)n * 16);
+        if (!rc) rc = scr.ensure(scan_scratch_bytes((uint64_t)256 * nb));
         if (rc) { release(); return bail(rc); }
         launch_morton_codes(c->stream, s->dev.pos, n, blo, inv, ka.as<uint32_t>(), va.as<uint32_t>());
         launch_radix_sort_pairs(c->stream, ka.as<uint32_t>(), va.as<uint32_t>(), kb.as<uint32_t>(), vb.as<uint32_t>(), n,
-                                hist.as<uint32_t>(), offs.as<uint32_t>());
+                                hist.as<uint32_t>(), offs.as<uint32_t>(), scr.as<unsigned long long>(), c->sm_count);
         launch_gather_cloud(c->stream, s->dev.pos, s->dev.nrm, s->dev.tgt, va.as<uint32_t>(), n, p2.as<float4>(),
                             n2.as<float4>(), t2.as<float4>());
         e = cudaGetLastError();
@@ -1083,8 +1084,11 @@ int tm_scene_tangent_mask(tm_scene* s, uint32_t k, float ratio, uint8_t* mask_ou
     DevBuf &fl = c->scratch[0], &off = c->scratch[1], &cand = c->scratch[2], &di = c->scratch[3],
            &dmn = c->scratch[4], &dmx = c->scratch[5], &dmask = c->scratch[6];
     TRY(fl.ensure((size_t)n * 4)); TRY(off.ensure(((size_t)n + 1) * 4)); TRY(dmask.ensure(n));
+    DevBuf& scr = c->scratch[7];
+    TRY(scr.ensure(scan_scratch_bytes(n)));
     launch_tangent_candidates(c->stream, s->dev.tgt, n, fl.as<uint32_t>());
-    launch_exclusive_scan_u32(c->stream, fl.as<uint32_t>(), off.as<uint32_t>(), n);
+    launch_exclusive_scan_u32_chained(c->stream, fl.as<uint32_t>(), off.as<uint32_t>(), n, scr.as<unsigned long long>(),
+                                      c->sm_count);
     uint32_t n_cand = 0;
     CU(cudaMemcpyAsync(&n_cand, off.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -115,7 +115,8 @@ void launch_morton_codes(cudaStream_t st, const float4* pos, uint32_t n, const f
 uint32_t radix_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 // keys/vals in `a`, scratch in `b`; after 4 passes the result is back in `a`.  hist: 256 * blocks + 1 u32 (x2).
 void launch_radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
-                             uint32_t n, uint32_t* hist, uint32_t* offsets) {
+                             uint32_t n, uint32_t* hist, uint32_t* offsets, unsigned long long* scan_scratch,
+                             int max_ctas) {
     if (!n) return;
     const uint32_t nb = radix_blocks(n);
     uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
@@ -123,7 +124,7 @@ void launch_radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* vals_a
         const int shift = 8 * pass;
         g_launch_count += 2;
         radix_hist_kernel<<<nb, 256, 0, st>>>(ki, n, shift, nb, hist);
-        launch_exclusive_scan_u32(st, hist, offsets, (uint64_t)256 * nb);
+        launch_exclusive_scan_u32_chained(st, hist, offsets, (uint64_t)256 * nb, scan_scratch, max_ctas);
         radix_scatter_kernel<<<nb, 256, 0, st>>>(ki, vi, n, shift, nb, offsets, ko, vo);
         uint32_t* t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;

@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 // of the single-CTA loop above).  Chained scan: a CTA takes the next tile by ticket (so tiles start in order and a
 // waiting CTA's predecessor is always running or done), scans its 4096 items, waits for the predecessor's inclusive
 // total, publishes its own.  scratch: [0] ticket, [1] unused, then per tile {ready flag, inclusive total}.
+template <typename TOut>
 __global__ void __launch_bounds__(SCAN_THREADS)
-    chained_scan_u64_kernel(const uint32_t* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n,
-                            unsigned long long* __restrict__ scratch) {
+    chained_scan_kernel(const uint32_t* __restrict__ in, TOut* __restrict__ out, uint64_t n,
+                        unsigned long long* __restrict__ scratch) {
     __shared__ unsigned long long warp_sums[32];
     __shared__ unsigned long long carry_s;
     __shared__ uint32_t tile_s;
@@ -170,14 +171,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
                 flag[2 * tile + 1] = prev + wi;
                 __threadfence();
                 flag[2 * tile] = 1ull;
-                if (tile == n_tiles - 1) out[n] = prev + wi;
+                if (tile == n_tiles - 1) out[n] = (TOut)(prev + wi);
             }
         }
         __syncthreads();
         unsigned long long excl = carry_s + warp_sums[warp] + (incl - tsum);
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k) {
-            if (i0 + k < n) out[i0 + k] = excl;
+            if (i0 + k < n) out[i0 + k] = (TOut)excl;
             excl += v[k];
         }
     }
@@ -197,7 +198,19 @@ void launch_exclusive_scan_u64_chained(cudaStream_t st, const uint32_t* in, unsi
     cudaMemsetAsync(scratch, 0, scan_scratch_bytes(n), st);
     const uint64_t tiles = (n + (uint64_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((uint64_t)SCAN_THREADS * SCAN_ITEMS);
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)std::max(1, max_ctas));
-    chained_scan_u64_kernel<<<grid, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+    chained_scan_kernel<unsigned long long><<<grid, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+}
+void launch_exclusive_scan_u32_chained(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n,
+                                       unsigned long long* scratch, int max_ctas) {
+    if (!scratch || n <= (uint64_t)SCAN_THREADS * SCAN_ITEMS * 2) {
+        launch_exclusive_scan_u32(st, in, out, n);
+        return;
+    }
+    ++g_launch_count;
+    cudaMemsetAsync(scratch, 0, scan_scratch_bytes(n), st);
+    const uint64_t tiles = (n + (uint64_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((uint64_t)SCAN_THREADS * SCAN_ITEMS);
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)std::max(1, max_ctas));
+    chained_scan_kernel<uint32_t><<<grid, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
 }
 void launch_exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n) {
     ++g_launch_count;

@@ -94,6 +94,8 @@ void launch_exclusive_scan_u64(cudaStream_t st, const uint32_t* in, unsigned lon
 size_t scan_scratch_bytes(uint64_t n);
 void launch_exclusive_scan_u64_chained(cudaStream_t st, const uint32_t* in, unsigned long long* out, uint64_t n,
                                        unsigned long long* scratch, int max_ctas);
+void launch_exclusive_scan_u32_chained(cudaStream_t st, const uint32_t* in, uint32_t* out, uint64_t n,
+                                       unsigned long long* scratch, int max_ctas);
 void launch_seg_bbox(cudaStream_t st, const float4* pos, uint32_t n, float4* lo, float4* hi);
 void launch_ball_count(cudaStream_t st, const CloudDev& scene, const uint32_t* centres, uint32_t n_centres,
                        const uint32_t* active_ranges, float r2, uint32_t n_seg, uint32_t* counts);
@@ -193,7 +195,8 @@ void launch_morton_codes(cudaStream_t st, const float4* pos, uint32_t n, const f
                          uint32_t* codes, uint32_t* idx);
 uint32_t radix_blocks(uint32_t n);
 void launch_radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
-                             uint32_t n, uint32_t* hist, uint32_t* offsets);
+                             uint32_t n, uint32_t* hist, uint32_t* offsets, unsigned long long* scan_scratch = nullptr,
+                             int max_ctas = 1);
 void launch_gather_cloud(cudaStream_t st, const float4* pos, const float4* nrm, const float4* tgt, const uint32_t* perm,
                          uint32_t n, float4* opos, float4* onrm, float4* otgt);
 
