@@ -373,19 +373,6 @@ void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const 
 }
 
 // ------------------------------------------------------------------ early drop
-// The reference's bound (scene.hpp:493-500) restated with defined integer
-// arithmetic (the original casts negative doubles to uint32_t): see DESIGN.md.
-__device__ __forceinline__ uint32_t early_drop_upper(uint32_t tried, uint32_t nsub, uint32_t corrs) {
-    double N = -2.0 - (double)tried;
-    double x = -2.0 - (double)nsub;
-    double n = -1.0 - (double)corrs;
-    double tmp = sqrt((x * n * (N - x) * (N - n)) / (N - 1.0));
-    double v = (x * n + tmp) / N;
-    uint32_t a = (uint32_t)(unsigned long long)(long long)v;
-    double b = -1.0 - (double)a;
-    return (uint32_t)(unsigned long long)(long long)b;
-}
-
 // One warp per hypothesis, subset walked in order 32 elements at a time.
 // g_of_hyp: subset row of each hypothesis (null => row 0); sub_idx null => identity.
 // bounding box of every 32 consecutive positions of every subset row (mask_ ignored: a

@@ -172,4 +172,18 @@ __device__ __forceinline__ unsigned long long score_fixed(float term) {
     return __float2ull_rz(term * 68719476736.0f);
 }
 
+// The reference's bound (scene.hpp:493-500) restated with defined integer
+// arithmetic (the original casts negative doubles to uint32_t): see DESIGN.md.
+__device__ __forceinline__ uint32_t early_drop_upper(uint32_t tried, uint32_t nsub, uint32_t corrs) {
+    double N = -2.0 - (double)tried;
+    double x = -2.0 - (double)nsub;
+    double n = -1.0 - (double)corrs;
+    double tmp = sqrt((x * n * (N - x) * (N - n)) / (N - 1.0));
+    double v = (x * n + tmp) / N;
+    uint32_t a = (uint32_t)(unsigned long long)(long long)v;
+    double b = -1.0 - (double)a;
+    return (uint32_t)(unsigned long long)(long long)b;
+}
+
+
 }  // namespace tmk
