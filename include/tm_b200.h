@@ -277,6 +277,10 @@ int tm_query_result_get(tm_query* q, tm_query_result* out); /* synchronises, sma
 /* device time of the scoring kernel of the last tm_query_run (CUDA events on the context
  * stream around that one launch) — the roofline numerator's denominator */
 int tm_query_score_kernel_ms(tm_query* q, float* ms);
+/* early_out = 2 runs the drop test checkpoint range by checkpoint range with the tiled scorer; a hypothesis one of
+ * whose ranges reaches no grid cell is walked on its own afterwards.  *n = how many of the last run's were
+ * (0 when the run did not use the level scheme).  Synchronises. */
+int tm_query_early_walked(tm_query* q, uint32_t* n);
 void* tm_query_best_key_device(tm_query* q); /* resident u64 for the NCCL max-reduce */
 int tm_query_set_global_best(tm_query* q, uint64_t key); /* after the all-reduce */
 /* full per-hypothesis arrays of this shard (parity tests); any pointer may be NULL */

@@ -286,3 +286,46 @@ def test_sharding_edge_cases(ctx):
         q.result()
     q.close()
     q0.close(); gm.close(); gs.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("keep", [400, 2500])
+def test_early_drop_levels_on_tiny_and_sparse_subsets(ctx, keep):
+    """tm_query_run(early_out = 2), level scheme (k_early2.cu), where its regular case does not hold: subsets of a
+    handful of points (checkpoint ranges that are empty — several checkpoints share an element) and hypotheses whose
+    ranges reach no grid cell are walked one by one; the outcome still equals the oracle's walk, hypothesis by
+    hypothesis.  A scene with non-finite points rides along."""
+    from triplet_match_b200 import capi
+    m, s0, om, osc0, rec0 = common.config("cylinder_small")
+    rng = np.random.default_rng(keep)
+    pick = np.sort(rng.choice(s0.n, keep, replace=False))
+    s = s0.take(pick)
+    s.pos[::97] = np.nan  # never reaching, never inliers
+    s.pos[5::131, 1] = np.inf
+    osc = po.OScene(s)
+    rec = synth.record_pairs(3, s, om.diameter, 12, 16)
+    gm = common.upload_model(ctx, m, om)
+    gs = common.upload_scene(ctx, s)
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    subs = [osc.ball_subset(int(o), om.diameter) for o in rec.outer]
+    off = np.zeros(len(subs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([x.size for x in subs])
+    walk = np.concatenate([x[capi.walk_order(x.size)] for x in subs]).astype(np.int32)
+    hyp_sub = rec.pair_outer[hp]
+    walked = []
+    for accept in (0.02, 0.5):
+        co, so, do = osc.score_batch(om, T, hyp_sub, off, walk, early_out=True, accept_prob=accept, nthreads=4)
+        q = capi.Query(gs, gm, early_out=2, accept_prob=accept)
+        q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+        q.run()
+        d = q.download()
+        assert d["counts"].size == co.size
+        assert np.array_equal(d["counts"], co), (keep, accept, np.flatnonzero(d["counts"] != co)[:8])
+        assert np.array_equal(d["dropped"], do)
+        assert np.allclose(d["scores"], so, rtol=1e-9, atol=1e-9)
+        walked.append(q.early_walked())
+        q.close()
+    sizes = np.diff(off.astype(np.int64))
+    if keep == 400:
+        assert sizes.min() < 20 and max(walked) > 0  # the irregular path is exercised
+    gs.close(); gm.close()

@@ -136,11 +136,57 @@ def test_early_drop_over_the_evenly_sampling_walk(setup):
     q.run()
     d = q.download()
     assert np.array_equal(d["counts"], co) and np.array_equal(d["dropped"], do)
+    assert np.allclose(d["scores"], so, rtol=1e-9, atol=1e-9)  # on request, through the walker
     ids, *_ = q.icp_results()
     keep = np.flatnonzero((do == 0) & (co > 0))
     want = keep[np.argsort(-co[keep].astype(np.int64), kind="stable")][:4]
     assert np.array_equal(ids[: want.size], want.astype(np.uint32)) and np.all(ids[want.size:] == 0xFFFFFFFF)
+    if keep.size:  # the winner is never a dropped hypothesis; its score is the full sum
+        r = d["result"]
+        best = keep[np.argmax(co[keep])]
+        assert r.best_hypothesis == best and r.best_inliers == co[best] and abs(r.best_score - so[best]) < 1e-9
     q.close()
+
+
+@pytest.mark.parametrize("accept_prob", [0.05, 0.3, 0.9])
+def test_early_drop_level_by_level(setup, accept_prob):
+    """tm_query_run(early_out = 2) evaluates the drop test checkpoint range by checkpoint range with the tiled scorer
+    (k_early2.cu).  Counts and drop flags equal the oracle's walk of the permuted subsets for acceptance bounds that
+    make hypotheses fail at early, middle and late checkpoints, with and without a scene mask."""
+    from triplet_match_b200 import capi
+    name, m, s, om, osc, rec, gm, gs = setup
+    T, hp, *_ = osc.hypotheses(om, rec.pair_i, rec.pair_j)
+    off, idx = _subsets(osc, om, rec)
+    hyp_sub = rec.pair_outer[hp]
+    walk = idx.copy()
+    for g in range(off.size - 1):
+        b, e = int(off[g]), int(off[g + 1])
+        walk[b:e] = idx[b:e][capi.walk_order(e - b)]
+    rng = np.random.default_rng(5)
+    for mask in (None, (rng.random(s.n) < 0.4).astype(np.uint8)):
+        if mask is not None:
+            gs.set_mask(mask)
+            osc.set_mask(mask)
+        try:
+            co, so, do = osc.score_batch(om, T, hyp_sub, off, walk, early_out=True, accept_prob=accept_prob, nthreads=4)
+            q = capi.Query(gs, gm, early_out=2, accept_prob=accept_prob)
+            q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+            q.run()
+            cg, r = q.download_counts()
+            d = q.download()
+            assert np.array_equal(cg, co), (name, accept_prob, mask is not None)
+            assert np.array_equal(d["dropped"], do)
+            assert np.allclose(d["scores"], so, rtol=1e-9, atol=1e-9)
+            assert q.early_walked() <= cg.size
+            # a second run on the same query (buffers reused, accumulators reset) gives the same answer
+            q.run()
+            c2, r2 = q.download_counts()
+            assert np.array_equal(c2, co) and r2.n_tests == r.n_tests and r2.best_key == r.best_key
+            q.close()
+        finally:
+            if mask is not None:
+                gs.set_mask(None)
+                osc.set_mask(np.zeros(s.n, np.uint8))
 
 
 def test_scoring_with_mask_and_all_scene(setup):

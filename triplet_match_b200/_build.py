@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
 ] + os.environ.get("TM_NVCC_EXTRA", "").split()
-SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_score2.cu", "k_icp.cu", "k_uvicp.cu", "k_knn.cu", "k_sort.cu", "k_model.cu", "k_query.cu", "capi_core.cu", "capi_icp.cu", "capi_query.cu", "capi_nccl.cu"]
+SOURCES = ["k_util.cu", "k_pairs.cu", "k_score.cu", "k_score2.cu", "k_early2.cu", "k_icp.cu", "k_uvicp.cu", "k_knn.cu", "k_sort.cu", "k_model.cu", "k_query.cu", "capi_core.cu", "capi_icp.cu", "capi_query.cu", "capi_nccl.cu"]
 HOST_SOURCES = ["host_model.cpp"]
 CXX = os.environ.get("CXX", "g++")
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",

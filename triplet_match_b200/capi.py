@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_scan_u64", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -611,6 +611,12 @@ class Query:
         ms = C.c_float()
         _chk(self.lib.tm_query_frontend_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def early_walked(self) -> int:
+        """early_out = 2: hypotheses of the last run that were walked one by one (tm_query_early_walked)."""
+        n = C.c_uint32()
+        _chk(self.lib.tm_query_early_walked(self.h, C.byref(n)))
+        return int(n.value)
 
     def result(self) -> QueryResult:
         r = QueryResult()

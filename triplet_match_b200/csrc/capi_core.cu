@@ -20,6 +20,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("TM_SCORE_GRID")) v.score_grid = std::max(1, atoi(e));
         v.score_stats = getenv("TM_SCORE_STATS") != nullptr;
         if (const char* e = getenv("TM_SCORER")) v.scorer = atoi(e);
+        if (const char* e = getenv("TM_EARLY_LEVELS")) v.early_levels = atoi(e) != 0;
         return v;
     }();
     return k;

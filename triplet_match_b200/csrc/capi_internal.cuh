@@ -49,6 +49,8 @@ struct Knobs {
     bool score_stats = false;      // TM_SCORE_STATS=1: cull / inlier statistics of the scoring kernel on stderr
     int scorer = 8;                // TM_SCORER=7: the fused count+score kernel everywhere (A/B against the count-only
                                    // packed-FP32 kernel + lazy score, which is the default where scores are not asked for)
+    bool early_levels = true;      // TM_EARLY_LEVELS=0: early_out = 2 of tm_query_run through the one-warp-per-hypothesis
+                                   // walker instead of the level-by-level tiled scorer (k_early2.cu); same results
 };
 const Knobs& knobs();
 
@@ -143,6 +145,7 @@ struct tm_ctx {
     size_t pinned_gather_cap = 0;
     int score_bps[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the scoring kernel [fused][with_score]
     int count_bps[2] = {0, 0};               // the same for the count-only kernel [fused]
+    int level_bps[2] = {0, 0};               // ... and for the per-level scorer of the early drop [fused]
     IcpBufs icp;                             // refinement state of tm_icp*, grow-only (no allocation per call)
     DevBuf icp_d16, icp_pack;                // poses in / out (column-major), packed records of the pose-sharded gather
     IcpGraph icp_graph;
@@ -250,6 +253,10 @@ struct tm_query {
     DevBuf n_items_g, item_off, items, ctrl;
     DevBuf out;  // QueryOut
     DevBuf topk_ids, topk_keys, icp_T16, stats, tile_lo, tile_hi;
+    // early_out = 2, level by level (k_early2.cu)
+    DevBuf lvl_idx, lvl_pos, el_n_items, el_item_off, el_items, el_alive, el_corrs, el_cnt, el_minkey, el_irregular, el_ctrl;
+    uint32_t el_items_cap = 0;
+    bool levels = false;        // last run used the level scheme (scores[] on demand through the walker)
     uint32_t max_sub = 0;
     IcpBufs icp;
     QueryOut host_out;

@@ -87,7 +87,7 @@ static int size_for_shard(tm_query* q) {
         CU(cudaMemsetAsync(q->sub_off.p, 0, 8, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
-    uint64_t total = 0, items = 0;
+    uint64_t total = 0, items = 0, el_items = 0;
     q->max_sub = 0;
     for (uint32_t o = 0; o < n_outer; ++o) {
         const uint64_t nh = gh[o + 1] - gh[o];
@@ -96,6 +96,7 @@ static int size_for_shard(tm_query* q) {
         total += np;
         q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
         items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
+        el_items += ((np + SCORE_TILE - 1) / SCORE_TILE + EL_LEVELS) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
     }
     (void)opo;
     q->sub_total = total;
@@ -110,6 +111,17 @@ static int size_for_shard(tm_query* q) {
         TRY(q->tile_lo.ensure(n_tiles * 16)); TRY(q->tile_hi.ensure(n_tiles * 16));
     } else if (q->p.early_out == 2) {
         TRY(q->sub_idx_walk.ensure(std::max<uint64_t>(total, 1) * 4));
+        if (knobs().early_levels) {
+            REQUIRE(el_items < (1ull << 31), "too many work items");
+            q->el_items_cap = (uint32_t)std::max<uint64_t>(el_items, 1);
+            const size_t lg = (size_t)EL_LEVELS * std::max(n_outer, 1u);
+            TRY(q->lvl_idx.ensure(std::max<uint64_t>(total, 1) * 4)); TRY(q->lvl_pos.ensure(std::max<uint64_t>(total, 1) * 4));
+            TRY(q->el_n_items.ensure(lg * 4)); TRY(q->el_item_off.ensure((lg + 1) * 4));
+            TRY(q->el_items.ensure((size_t)q->el_items_cap * sizeof(WorkItem)));
+            TRY(q->el_alive.ensure(cap)); TRY(q->el_corrs.ensure(cap * 4)); TRY(q->el_cnt.ensure(cap * 4));
+            TRY(q->el_minkey.ensure(cap * 4)); TRY(q->el_irregular.ensure(cap * 4));
+            TRY(q->el_ctrl.ensure((EL_LEVELS + 1) * 4));
+        }
     }
     if (q->p.icp_top_k) {
         TRY(q->icp.ensure(q->p.icp_top_k));
@@ -162,7 +174,9 @@ void tm_query_destroy(tm_query* q) {
           &q->ball_seg_off, &q->sub_off, &q->sub_idx, &q->sub_idx_walk, &q->valid, &q->hit_begin, &q->hit_count,
           &q->hyp_off, &q->g_hyp, &q->g_of_hyp, &q->T, &q->hyp_valid, &q->hyp_pair, &q->counts,
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
-          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum, &q->scan_scratch})
+          &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum, &q->scan_scratch,
+          &q->lvl_idx, &q->lvl_pos, &q->el_n_items, &q->el_item_off, &q->el_items, &q->el_alive, &q->el_corrs, &q->el_cnt,
+          &q->el_minkey, &q->el_irregular, &q->el_ctrl})
         b->release();
     q->icp.release();
     delete q;
@@ -246,12 +260,24 @@ int finalize_best(tm_query* q) {
 
 // scores[] of every hypothesis on request (tm_query_download): re-run the scoring pass with the fused
 // count+score kernel over the resident work list.  Counts go to a scratch array and must come out the same.
+static int enqueue_walker(tm_query* q, const ModelDev& md, uint32_t* counts, unsigned long long* scores, uint8_t* dropped,
+                          unsigned long long* n_tests, const uint32_t* hyp_list, const uint32_t* n_list);
 static int ensure_scores(tm_query* q) {
     if (q->scores_valid || !q->lazy || !q->n_outer) return TM_OK;
     tm_ctx* c = q->s->ctx;
     QueryOut* out = q->out.as<QueryOut>();
     DevBuf& cnt2 = c->scratch[5];
-    TRY(cnt2.ensure(q->cap_hyp * 4));
+    TRY(cnt2.ensure(q->cap_hyp * 5));
+    if (q->levels) {  // partial scores of dropped hypotheses depend on the walk: the walker produces them
+        ModelDev md;
+        TRY(model_dev_for(c, q->m, q->run_thres, &md));
+        CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
+        TRY(enqueue_walker(q, md, cnt2.as<uint32_t>(), q->scores.as<unsigned long long>(),
+                           cnt2.as<uint8_t>() + q->cap_hyp * 4, nullptr, nullptr, nullptr));
+        CU(cudaGetLastError());
+        q->scores_valid = true;
+        return TM_OK;
+    }
     CU(cudaMemsetAsync(cnt2.p, 0, q->cap_hyp * 4, c->stream));
     CU(cudaMemsetAsync(q->scores.p, 0, q->cap_hyp * 8, c->stream));
     CU(cudaMemsetAsync(&out->work_counter, 0, 4, c->stream));
@@ -272,6 +298,108 @@ static int ensure_scores(tm_query* q) {
     launch_score_full(c->stream, a, c->sm_count * b, q->m->fused, true);
     CU(cudaGetLastError());
     q->scores_valid = true;
+    return TM_OK;
+}
+
+// project_(early_out = true) with one warp per hypothesis (score_early_drop_kernel): in subset order with tile boxes
+// (early_out = 1) or over the evenly sampling walk (early_out = 2; rows permuted by walk_order_rows_kernel).
+// hyp_list / n_list: walk only the listed hypotheses.
+static int enqueue_walker(tm_query* q, const ModelDev& md, uint32_t* counts, unsigned long long* scores, uint8_t* dropped,
+                          unsigned long long* n_tests, const uint32_t* hyp_list, const uint32_t* n_list) {
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    EarlyArgs a;
+    a.sub_idx = q->sub_idx.as<int32_t>();
+    if (q->p.early_out == 2) {  // evenly sampling walk order (see tm_score)
+        launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(), q->n_outer,
+                               q->max_sub, q->sub_idx_walk.as<int32_t>());
+        a.sub_idx = q->sub_idx_walk.as<int32_t>();
+    } else {
+        a.tile_lo = q->tile_lo.as<float4>();
+        a.tile_hi = q->tile_hi.as<float4>();
+    }
+    a.scene = q->s->dev;
+    a.model = md;
+    a.sub_off = q->sub_off.as<unsigned long long>();
+    a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
+    a.T = q->T.as<float4>();
+    a.n_hyp = (uint32_t)q->cap_hyp;  // grid bound; the kernel clips to n_local (or to the list's length)
+    a.n_hyp_dev = n_list ? n_list : &out->n_local;
+    a.hyp_list = hyp_list;
+    a.n_tests = n_tests;
+    a.sq_thres = q->run_sqt;
+    a.accept_prob = q->p.accept_prob;
+    a.early_out = 1;
+    a.counts = counts;
+    a.scores = scores;
+    a.dropped = dropped;
+    a.tested = nullptr;
+    launch_score_early_drop(c->stream, a, q->m->fused);
+    return TM_OK;
+}
+
+// early_out = 2 level by level (k_early2.cu): regroup the subset rows by checkpoint range, then per range one tiled
+// scoring launch over the hypotheses still alive and one checkpoint launch; the few hypotheses with a range that
+// reaches nothing are walked one by one at the end.  Counts and drop flags equal the walker's.
+static int enqueue_levels(tm_query* q, float thres, float sqt) {
+    tm_ctx* c = q->s->ctx;
+    QueryOut* out = q->out.as<QueryOut>();
+    const tm_model* m = q->m;
+    const uint32_t G = q->n_outer;
+    launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), G, q->g_of_hyp.as<uint32_t>());
+    launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(), G,
+                       q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
+    launch_el_work_count(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G,
+                         q->el_n_items.as<uint32_t>());
+    launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(),
+                              (uint64_t)EL_LEVELS * G);
+    launch_el_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G,
+                        q->el_item_off.as<uint32_t>(), q->el_items.as<WorkItem>());
+    launch_el_init(c->stream, &out->n_local, (uint32_t)q->cap_hyp, q->el_alive.as<uint8_t>(), q->el_corrs.as<uint32_t>(),
+                   q->el_cnt.as<uint32_t>(), q->el_minkey.as<uint32_t>(), q->dropped.as<uint8_t>(), q->counts.as<uint32_t>());
+    CU(cudaMemsetAsync(q->el_ctrl.p, 0, (EL_LEVELS + 1) * 4, c->stream));
+    LevelArgs a;
+    a.scene = q->s->dev;
+    TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
+    a.lvl_idx = q->lvl_idx.as<int32_t>();
+    a.lvl_pos = q->lvl_pos.as<uint32_t>();
+    a.items = q->el_items.as<WorkItem>();
+    a.item_off = q->el_item_off.as<uint32_t>();
+    a.n_groups = G;
+    a.T = q->T.as<float4>();
+    a.alive = q->el_alive.as<uint8_t>();
+    a.lvl_cnt = q->el_cnt.as<uint32_t>();
+    a.minkey = q->el_minkey.as<uint32_t>();
+    a.sq_thres = sqt;
+    EvalArgs e;
+    e.n_local = &out->n_local;
+    e.g_of_hyp = q->g_of_hyp.as<uint32_t>();
+    e.sub_off = q->sub_off.as<unsigned long long>();
+    e.alive = q->el_alive.as<uint8_t>();
+    e.corrs = q->el_corrs.as<uint32_t>();
+    e.lvl_cnt = a.lvl_cnt;
+    e.minkey = a.minkey;
+    e.counts = q->counts.as<uint32_t>();
+    e.dropped = q->dropped.as<uint8_t>();
+    e.irregular = q->el_irregular.as<uint32_t>();
+    e.n_irregular = q->el_ctrl.as<uint32_t>() + EL_LEVELS;
+    e.n_tests = &out->n_tests;
+    e.accept_bound = q->p.accept_prob * (float)m->dev.cloud.n;  // scene.hpp:500
+    int& b = c->level_bps[m->fused ? 1 : 0];
+    if (!b) b = score_level_max_blocks_per_sm(m->fused);
+    const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
+    CU(cudaEventRecord(q->ev_s0, c->stream));
+    for (int L = 0; L < EL_LEVELS; ++L) {
+        a.level = e.level = L;
+        a.work_counter = q->el_ctrl.as<uint32_t>() + L;
+        launch_score_level(c->stream, a, grid, m->fused);
+        launch_el_eval(c->stream, e, (uint32_t)q->cap_hyp);
+    }
+    TRY(enqueue_walker(q, a.model, q->counts.as<uint32_t>(), nullptr, q->dropped.as<uint8_t>(), &out->n_tests,
+                       q->el_irregular.as<uint32_t>(), e.n_irregular));
+    CU(cudaEventRecord(q->ev_s1, c->stream));
+    q->lazy = true;
+    q->levels = true;
     return TM_OK;
 }
 
@@ -332,6 +460,7 @@ int tm_query_run(tm_query* q) {
     const float thres = q->p.dist_thres * m->dev.resolution;
     const float sqt = sq_threshold(thres);
     q->lazy = false;
+    q->levels = false;
     q->run_thres = thres;
     q->run_sqt = sqt;
     if (q->n_outer) {
@@ -378,38 +507,19 @@ int tm_query_run(tm_query* q) {
                 launch_score_full(c->stream, a, grid, m->fused, true);
                 CU(cudaEventRecord(q->ev_s1, c->stream));
             }
+        } else if (q->p.early_out == 2 && knobs().early_levels) {
+            TRY(enqueue_levels(q, thres, sqt));
         } else {
             launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), q->n_outer,
                                 q->g_of_hyp.as<uint32_t>());
-            EarlyArgs a;
-            a.sub_idx = q->sub_idx.as<int32_t>();
-            if (q->p.early_out == 2) {  // evenly sampling walk order (see tm_score)
-                launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
-                                       q->n_outer, q->max_sub, q->sub_idx_walk.as<int32_t>());
-                a.sub_idx = q->sub_idx_walk.as<int32_t>();
-            } else {
+            ModelDev md;
+            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &md));
+            if (q->p.early_out == 1)
                 launch_subset_tile_boxes(c->stream, sc, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(),
                                          q->n_outer, q->max_sub, q->tile_lo.as<float4>(), q->tile_hi.as<float4>());
-                a.tile_lo = q->tile_lo.as<float4>();
-                a.tile_hi = q->tile_hi.as<float4>();
-            }
-            a.scene = sc;
-            TRY(model_dev_for(c, const_cast<tm_model*>(m), thres, &a.model));
-            a.sub_off = q->sub_off.as<unsigned long long>();
-            a.g_of_hyp = q->g_of_hyp.as<uint32_t>();
-            a.T = q->T.as<float4>();
-            a.n_hyp = (uint32_t)q->cap_hyp;  // grid bound; the kernel clips to n_local
-            a.n_hyp_dev = &out->n_local;
-            a.n_tests = &out->n_tests;
-            a.sq_thres = sqt;
-            a.accept_prob = q->p.accept_prob;
-            a.early_out = 1;
-            a.counts = q->counts.as<uint32_t>();
-            a.scores = q->scores.as<unsigned long long>();
-            a.dropped = q->dropped.as<uint8_t>();
-            a.tested = nullptr;
             CU(cudaEventRecord(q->ev_s0, c->stream));
-            launch_score_early_drop(c->stream, a, m->fused);
+            TRY(enqueue_walker(q, md, q->counts.as<uint32_t>(), q->scores.as<unsigned long long>(),
+                               q->dropped.as<uint8_t>(), &out->n_tests, nullptr, nullptr));
             CU(cudaEventRecord(q->ev_s1, c->stream));
         }
     }
@@ -484,6 +594,15 @@ int tm_query_frontend_ms(tm_query* q, float* ms) {
     TRY(bind(q->s->ctx));
     CU(cudaEventSynchronize(q->ev_f1));
     CU(cudaEventElapsedTime(ms, q->ev_f0, q->ev_f1));
+    return TM_OK;
+}
+int tm_query_early_walked(tm_query* q, uint32_t* n) {
+    REQUIRE(q && n && q->ran, "tm_query_early_walked: null/unrun query");
+    TRY(bind(q->s->ctx));
+    *n = 0;
+    if (!q->levels) return TM_OK;
+    CU(cudaMemcpyAsync(n, q->el_ctrl.as<uint32_t>() + EL_LEVELS, 4, cudaMemcpyDeviceToHost, q->s->ctx->stream));
+    CU(cudaStreamSynchronize(q->s->ctx->stream));
     return TM_OK;
 }
 void* tm_query_best_key_device(tm_query* q) {

@@ -1,0 +1,418 @@
+// k_early2.cu — project_(early_out = true) (include/impl/scene.hpp:411-510, checkpoints :422-426, 492-506) over the
+// evenly sampling walk of each subset (early_out = 2), evaluated LEVEL BY LEVEL with the tiled, box-culled scorer
+// instead of one warp walking one hypothesis (score_early_drop_kernel).
+//
+// The reference walks a subset in order and, at the first *reaching* element (unmasked, voxel_query succeeded) at or
+// after 5 %, 10 %, ..., 90 % of it, extrapolates the final count from the inliers so far and drops the hypothesis when
+// the bound falls below the acceptance threshold — 18 checkpoints, at most one per element.  The 18 thresholds cut the
+// walk positions into 19 ranges ("levels"); in walk order p -> (p * s) mod n a level is every ~20th point of the ball,
+// so the points of one level, kept in the subset's own (spatial) order, tile like the whole subset does.  Per level:
+//
+//   score_level_kernel   the count-only scorer of k_score2.cu over the level's tiles x the group's hypotheses; dead
+//                        hypotheses (dropped at an earlier checkpoint) are skipped in the cull phase.  Besides the
+//                        level's inlier count it reduces, per hypothesis, the smallest walk position of a reaching
+//                        element together with that element's inlier bit (atomicMin of pos << 1 | !inlier).
+//   el_eval_kernel       checkpoint L fires at the first reaching position of level L (the previous checkpoint fired in
+//                        level L - 1, so "one checkpoint per element" is automatic): corrs = inliers of the levels
+//                        before + that element's inlier bit, tried = position + 1, same bound, same comparison.  A
+//                        hypothesis that fails is dropped with exactly the walker's partial count.
+//
+// A level without a reaching element (or an empty level: subsets of a few points) breaks the one-level-one-checkpoint
+// correspondence; such hypotheses are flagged and re-walked exactly by score_early_drop_kernel (they touch the grid
+// almost nowhere, so they are few and cheap).  Counts, drop flags and drop points equal the walker's bit for bit
+// (tests/test_gpu_parity.py); the un-normalised partial scores are produced by the walker on request.
+#include <algorithm>
+
+#include "tm_kernels.cuh"
+#include "tm_x2.cuh"
+
+namespace tmk {
+
+// first walk position of level L for a subset of n elements: b[0] = 0, b[L] = t_L - 1 (0 when t_L <= 1) with
+// t_L = uint32(0.05f * L * n) the reference's tests[L-1] (scene.hpp:422-426), b[19] = n.  A checkpoint with threshold t
+// fires at the first reaching element whose 1-based position is >= t.
+__host__ __device__ inline uint32_t level_begin(uint32_t n, int L) {
+    if (L <= 0) return 0u;
+    if (L >= EL_LEVELS) return n;
+    const uint32_t t = (uint32_t)(0.05f * (float)L * (float)n);
+    const uint32_t b = t > 1u ? t - 1u : 0u;
+    return b < n ? b : n;
+}
+
+// modular inverse of s modulo n (gcd(s, n) == 1, n >= 1)
+__device__ inline uint32_t mod_inverse(uint32_t s, uint32_t n) {
+    if (n <= 1u) return 0u;
+    long long t = 0, nt = 1, r = (long long)n, nr = (long long)(s % n);
+    while (nr) {
+        const long long qq = r / nr;
+        long long tmp = t - qq * nt; t = nt; nt = tmp;
+        tmp = r - qq * nr; r = nr; nr = tmp;
+    }
+    if (t < 0) t += (long long)n;
+    return (uint32_t)t;
+}
+
+// Rows of the subset CSR regrouped by level: within a group the elements of level L occupy
+// [sub_off[g] + level_begin(n, L), sub_off[g] + level_begin(n, L + 1)), in ascending element (= spatial) order.
+// lvl_idx = scene index, lvl_pos = walk position.  One CTA per group; stable partition by level through
+// __match_any_sync ranks.
+__global__ void __launch_bounds__(256)
+    walk_levels_kernel(const int32_t* __restrict__ sub_idx, const unsigned long long* __restrict__ sub_off,
+                       int32_t* __restrict__ lvl_idx, uint32_t* __restrict__ lvl_pos) {
+    __shared__ uint32_t bnd[EL_LEVELS + 1];
+    __shared__ uint32_t run[EL_LEVELS];
+    __shared__ uint32_t wcnt[8][EL_LEVELS];
+    __shared__ uint32_t sinv_s;
+    const uint32_t g = blockIdx.x;
+    const unsigned long long sb = sub_off[g];
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
+    if (!n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x <= EL_LEVELS) bnd[threadIdx.x] = level_begin(n, (int)threadIdx.x);
+    if (threadIdx.x < EL_LEVELS) run[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) sinv_s = mod_inverse(walk_stride(n), n);
+    __syncthreads();
+    const uint32_t sinv = sinv_s;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        for (int t = threadIdx.x; t < 8 * EL_LEVELS; t += blockDim.x) (&wcnt[0][0])[t] = 0u;
+        __syncthreads();
+        const uint32_t e = base + threadIdx.x;
+        const bool live = e < n;
+        uint32_t p = 0u;
+        int L = EL_LEVELS;  // dead lanes form their own match group
+        if (live) {
+            p = (uint32_t)(((unsigned long long)e * sinv) % n);  // (p * s) mod n == e
+            L = 0;
+#pragma unroll
+            for (int k = 1; k < EL_LEVELS; ++k) L += (p >= bnd[k]) ? 1 : 0;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, L);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (live && rank == 0u) wcnt[warp][L] = __popc(peers);
+        __syncthreads();
+        if (live) {
+            uint32_t off = run[L];
+            for (int w = 0; w < warp; ++w) off += wcnt[w][L];
+            const unsigned long long dst = sb + bnd[L] + off + rank;
+            lvl_idx[dst] = sub_idx ? sub_idx[sb + e] : (int32_t)(sb + e);
+            lvl_pos[dst] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < EL_LEVELS) {
+            uint32_t t = 0u;
+            for (int w = 0; w < 8; ++w) t += wcnt[w][threadIdx.x];
+            run[threadIdx.x] += t;
+        }
+        __syncthreads();
+    }
+}
+void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
+                        int32_t* lvl_idx, uint32_t* lvl_pos) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    walk_levels_kernel<<<n_groups, 256, 0, st>>>(sub_idx, sub_off, lvl_idx, lvl_pos);
+}
+
+// ---- work list: (level, group) major, so that a level's items are one contiguous range -------------------------------
+__global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
+                                     uint32_t n_groups, uint32_t* __restrict__ n_items) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * EL_LEVELS) return;
+    const uint32_t L = t / n_groups, g = t % n_groups;
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
+    const uint32_t np = level_begin(n, (int)L + 1) - level_begin(n, (int)L);
+    const uint32_t nh = g_hyp[g + 1] - g_hyp[g];
+    n_items[t] = ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK);
+}
+__global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
+                                    uint32_t n_groups, const uint32_t* __restrict__ item_off, WorkItem* __restrict__ items) {
+    const uint32_t t = blockIdx.x;
+    if (t >= n_groups * EL_LEVELS) return;
+    const uint32_t L = t / n_groups, g = t % n_groups;
+    const unsigned long long sb = sub_off[g];
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
+    const uint32_t b0 = level_begin(n, (int)L), np = level_begin(n, (int)L + 1) - b0;
+    const uint32_t hb = g_hyp[g], nh = g_hyp[g + 1] - hb;
+    const uint32_t tiles = (np + SCORE_TILE - 1) / SCORE_TILE, chunks = (nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK;
+    const uint32_t base = item_off[t];
+    for (uint32_t k = threadIdx.x; k < tiles * chunks; k += blockDim.x) {
+        const uint32_t tile = k % tiles, chunk = k / tiles;
+        WorkItem w;
+        w.sub_begin = sb + b0 + (unsigned long long)tile * SCORE_TILE;
+        w.npts = min((uint32_t)SCORE_TILE, np - tile * SCORE_TILE);
+        w.hyp_begin = hb + chunk * SCORE_HCHUNK;
+        w.hyp_end = min(hb + nh, w.hyp_begin + SCORE_HCHUNK);
+        w.pad = 0;
+        items[base + k] = w;
+    }
+}
+void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
+                          uint32_t* n_items) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    const uint32_t n = n_groups * EL_LEVELS;
+    el_work_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(sub_off, g_hyp, n_groups, n_items);
+}
+void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
+                         const uint32_t* item_off, WorkItem* items) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    el_work_fill_kernel<<<n_groups * EL_LEVELS, 128, 0, st>>>(sub_off, g_hyp, n_groups, item_off, items);
+}
+
+// ---- one level: counts + first reaching position per live hypothesis ------------------------------------------------
+template <bool FUSED, bool OCC>
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
+    score_level_kernel(LevelArgs a, p2 k_nz, p2 k_one) {
+    static_assert(SCORE_P == 4, "two point pairs per lane");
+    __shared__ float4 s_rows[(SCORE_THREADS / 32) * 32 * 3];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float4* my_rows = s_rows + warp * 32 * 3;
+    const uint32_t item_begin = a.item_off[a.level * a.n_groups], item_end = a.item_off[(a.level + 1) * a.n_groups];
+    const ModelDev& m = a.model;
+    X2 e;
+    e.nz = k_nz; e.one = k_one; e.mone = 0ull;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = item_begin + atomicAdd(a.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= item_end) break;
+        const WorkItem w = a.items[item];
+        float px[4], py[4], pz[4];
+        uint32_t wpos[4];     // walk position of point k (only meaningful where live)
+        uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
+        const float nanv = __int_as_float(0x7fc00000);
+        float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t q = k * 32 + lane;
+            px[k] = py[k] = pz[k] = nanv;  // masked / padding points: NaN, never reaching, never inliers
+            wpos[k] = 0x7fffffffu;
+            if (q < w.npts) {
+                const uint32_t idx = (uint32_t)a.lvl_idx[w.sub_begin + q];
+                const float4 v = a.scene.pos[idx];
+                const uint32_t fl = __float_as_uint(v.w);
+                if (!(fl & FLAG_MASKED)) {  // mask_ (scene.hpp:434): skipped before anything is counted
+                    px[k] = v.x; py[k] = v.y; pz[k] = v.z;
+                    wpos[k] = a.lvl_pos[w.sub_begin + q];
+                    if (fl & FLAG_TANGENT) tflags |= 1u << k;
+                    mnx = fminf(mnx, v.x); mxx = fmaxf(mxx, v.x);
+                    mny = fminf(mny, v.y); mxy = fmaxf(mxy, v.y);
+                    mnz = fminf(mnz, v.z); mxz = fmaxf(mxz, v.z);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+            mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+        }
+        if (!(mnx <= mxx)) continue;  // no live (finite, unmasked) point in this tile
+        const float cx = 0.5f * (mnx + mxx), hx = 0.5f * (mxx - mnx);
+        const float cy = 0.5f * (mny + mxy), hy = 0.5f * (mxy - mny);
+        const float cz = 0.5f * (mnz + mxz), hz = 0.5f * (mxz - mnz);
+        const p2 pxA = e.add(pack2(px[0], px[1]), e.nz), pyA = e.add(pack2(py[0], py[1]), e.nz),
+                 pzA = e.add(pack2(pz[0], pz[1]), e.nz);
+        const p2 pxB = e.add(pack2(px[2], px[3]), e.nz), pyB = e.add(pack2(py[2], py[3]), e.nz),
+                 pzB = e.add(pack2(pz[2], pz[3]), e.nz);
+        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {
+            const uint32_t h = h0 + lane;
+            bool survive = false;
+            __syncwarp();  // readers of the previous batch's rows are done
+            if (h < w.hyp_end && a.alive[h]) {  // hypotheses dropped at an earlier checkpoint are not walked any further
+                const float4 r0 = __ldg(&a.T[3 * (size_t)h]), r1 = __ldg(&a.T[3 * (size_t)h + 1]),
+                             r2 = __ldg(&a.T[3 * (size_t)h + 2]);
+                my_rows[lane] = r0;
+                my_rows[32 + lane] = r1;
+                my_rows[64 + lane] = r2;
+                const float acx = fabsf(cx) + hx, acy = fabsf(cy) + hy, acz = fabsf(cz) + hz;
+                bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                  \
+    {                                                                                           \
+        float cc = r.x * cx + r.y * cy + r.z * cz + r.w;                                        \
+        float ee = fabsf(r.x) * hx + fabsf(r.y) * hy + fabsf(r.z) * hz;                         \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
+        ee += 1e-5f * mag + 1e-30f;                                                             \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
+        float lo = S * (cc - ee) + TV - sl, hi = S * (cc + ee) + TV + sl;                       \
+        out = out || (lo >= EXF) || (hi <= -1.0f);                                              \
+    }
+                TM_AXIS(r0, m.sx, m.tx, m.exf)
+                TM_AXIS(r1, m.sy, m.ty, m.eyf)
+                TM_AXIS(r2, m.sz, m.tz, m.ezf)
+#undef TM_AXIS
+                survive = !out;  // a culled tile holds no reaching element: it changes neither count nor checkpoint
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, survive);  // also orders the smem stores
+            uint32_t mycnt = 0, mymin = 0xffffffffu;
+            while (mask) {
+                const int hh = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const float4 r0 = my_rows[hh], r1 = my_rows[32 + hh], r2 = my_rows[64 + hh];
+                const p2 xA = e.row_apply(r0, pxA, pyA, pzA), xB = e.row_apply(r0, pxB, pyB, pzB);
+                const p2 yA = e.row_apply(r1, pxA, pyA, pzA), yB = e.row_apply(r1, pxB, pyB, pzB);
+                const p2 zA = e.row_apply(r2, pxA, pyA, pzA), zB = e.row_apply(r2, pxB, pyB, pzB);
+                const p2 vxA = e.add(e.mul(m.sx, xA), m.tx), vxB = e.add(e.mul(m.sx, xB), m.tx);
+                const p2 vyA = e.add(e.mul(m.sy, yA), m.ty), vyB = e.add(e.mul(m.sy, yB), m.ty);
+                const p2 vzA = e.add(e.mul(m.sz, zA), m.tz), vzB = e.add(e.mul(m.sz, zB), m.tz);
+                const float x[4] = {lo2(xA), hi2(xA), lo2(xB), hi2(xB)}, y[4] = {lo2(yA), hi2(yA), lo2(yB), hi2(yB)},
+                            z[4] = {lo2(zA), hi2(zA), lo2(zB), hi2(zB)};
+                const float vx[4] = {lo2(vxA), hi2(vxA), lo2(vxB), hi2(vxB)},
+                            vy[4] = {lo2(vyA), hi2(vyA), lo2(vyB), hi2(vyB)},
+                            vz[4] = {lo2(vzA), hi2(vzA), lo2(vzB), hi2(vzB)};
+                uint32_t lin[4];
+                bool reach[4], look[4];
+                bool any_reach = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // voxel_query succeeded (model.hpp:186-189) in the float domain: int(v) in [0, e) <=> -1 < v < e for
+                    // every finite v; NaN (masked / padding points) and +-inf are out, as with the walker
+                    const bool ok = (vx[k] > -1.f) & (vx[k] < m.exf) & (vy[k] > -1.f) & (vy[k] < m.eyf) & (vz[k] > -1.f) &
+                                    (vz[k] < m.ezf);
+                    const int i = (int)vx[k], j = (int)vy[k], kk = (int)vz[k];
+                    bool lk = ok;
+                    if (OCC) {  // the occupancy mask only saves the gather; the element reaches either way
+                        const uint32_t b = ok ? (uint32_t)(((kk >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx +
+                                                           (i >> OCC_SHIFT))
+                                              : 0u;
+                        lk = ok & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
+                    }
+                    lin[k] = (uint32_t)((kk * m.ey + j) * m.ex + i);
+                    reach[k] = ok;
+                    look[k] = lk;
+                    any_reach |= ok;
+                }
+                if (!__any_sync(0xffffffffu, any_reach)) continue;  // nothing reaches the grid
+                float4 mp[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (look[k]) {
+                        if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
+                        else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+                    }
+                }
+                const p2 dxA = pack2(x[0] - mp[0].x, x[1] - mp[1].x), dxB = pack2(x[2] - mp[2].x, x[3] - mp[3].x);
+                const p2 dyA = pack2(y[0] - mp[0].y, y[1] - mp[1].y), dyB = pack2(y[2] - mp[2].y, y[3] - mp[3].y);
+                const p2 dzA = pack2(z[0] - mp[0].z, z[1] - mp[1].z), dzB = pack2(z[2] - mp[2].z, z[3] - mp[3].z);
+                const p2 sqA = e.sqnorm(dxA, dyA, dzA), sqB = e.sqnorm(dxB, dyB, dzB);
+                const float sq[4] = {lo2(sqA), hi2(sqA), lo2(sqB), hi2(sqB)};
+                uint32_t c = 0, mn = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t pfl = (tflags >> k) & 1u;
+                    const bool inl = look[k] && (sq[k] <= a.sq_thres) &&
+                                     (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
+                    c += inl ? 1u : 0u;
+                    if (reach[k]) mn = min(mn, (wpos[k] << 1) | (inl ? 0u : 1u));
+                }
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+                const uint32_t wmn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == hh) {
+                    mycnt = tot;
+                    mymin = wmn;
+                }
+            }
+            if (mycnt) atomicAdd(&a.lvl_cnt[h], mycnt);
+            if (mymin != 0xffffffffu) atomicMin(&a.minkey[h], mymin);
+        }
+    }
+}
+void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused) {
+    ++g_launch_count;
+    const p2 nz = host_pair(-0.0f), one = host_pair(1.0f);
+    if (fused) {
+        if (a.model.occ) score_level_kernel<true, true><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+        else score_level_kernel<true, false><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+    } else {
+        if (a.model.occ) score_level_kernel<false, true><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+        else score_level_kernel<false, false><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+    }
+}
+int score_level_max_blocks_per_sm(bool fused) {
+    int nb = 0, nb2 = 0;
+    if (fused) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<true, false>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<true, true>, SCORE_THREADS, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<false, false>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<false, true>, SCORE_THREADS, 0);
+    }
+    nb = nb < nb2 ? nb : nb2;
+    return nb > 0 ? nb : 1;
+}
+
+// ---- checkpoint L after level L (L = 0: nothing to test; L = 18 also closes the walk) ------------------------------
+__global__ void __launch_bounds__(256)
+    el_eval_kernel(EvalArgs a) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= *a.n_local) return;
+    if (!a.alive[h]) return;
+    const uint32_t g = a.g_of_hyp[h];
+    const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - a.sub_off[g]);
+    const uint32_t cnt = a.lvl_cnt[h], mk = a.minkey[h];
+    a.lvl_cnt[h] = 0u;
+    a.minkey[h] = 0xffffffffu;
+    const int L = a.level;
+    bool done = false;
+    if (L >= 1) {
+        if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
+            // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint may
+            // also claim — walked exactly afterwards
+            a.irregular[atomicAdd(a.n_irregular, 1u)] = h;
+            a.alive[h] = 0;
+            return;
+        }
+        const uint32_t inl = (mk & 1u) ? 0u : 1u, tried = (mk >> 1) + 1u;
+        const uint32_t c_here = a.corrs[h] + inl;
+        const uint32_t upper = early_drop_upper(tried, nsub, c_here);
+        if ((float)upper < a.accept_bound) {  // scene.hpp:500-503
+            a.counts[h] = c_here;
+            a.dropped[h] = 1;
+            a.alive[h] = 0;
+            if (a.n_tests) atomicAdd(a.n_tests, (unsigned long long)tried);
+            return;
+        }
+    }
+    const uint32_t total = a.corrs[h] + cnt;
+    a.corrs[h] = total;
+    if (L == EL_LEVELS - 1) done = true;
+    if (done) {
+        a.counts[h] = total;
+        a.dropped[h] = 0;
+        a.alive[h] = 0;
+        if (a.n_tests) atomicAdd(a.n_tests, (unsigned long long)nsub);
+    }
+}
+void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound) {
+    if (!n_hyp_bound) return;
+    ++g_launch_count;
+    el_eval_kernel<<<(n_hyp_bound + 255) / 256, 256, 0, st>>>(a);
+}
+
+// alive[h] = 1 for h < n_local, per-hypothesis accumulators reset
+__global__ void el_init_kernel(const uint32_t* __restrict__ n_local, uint32_t cap, uint8_t* __restrict__ alive,
+                               uint32_t* __restrict__ corrs, uint32_t* __restrict__ lvl_cnt, uint32_t* __restrict__ minkey,
+                               uint8_t* __restrict__ dropped, uint32_t* __restrict__ counts) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= cap) return;
+    alive[h] = h < *n_local ? 1 : 0;
+    corrs[h] = 0u;
+    lvl_cnt[h] = 0u;
+    minkey[h] = 0xffffffffu;
+    dropped[h] = 0;
+    counts[h] = 0u;
+}
+void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* corrs,
+                    uint32_t* lvl_cnt, uint32_t* minkey, uint8_t* dropped, uint32_t* counts) {
+    if (!cap) return;
+    ++g_launch_count;
+    el_init_kernel<<<(cap + 255) / 256, 256, 0, st>>>(n_local, cap, alive, corrs, lvl_cnt, minkey, dropped, counts);
+}
+
+}  // namespace tmk

@@ -447,8 +447,9 @@ template <bool FUSED>
 __global__ void __launch_bounds__(256)
     score_early_drop_kernel(EarlyArgs a) {
     const int lane = threadIdx.x & 31;
-    const uint32_t h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (h >= (a.n_hyp_dev ? *a.n_hyp_dev : a.n_hyp)) return;
+    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (a.n_hyp_dev ? *a.n_hyp_dev : a.n_hyp)) return;
+    const uint32_t h = a.hyp_list ? a.hyp_list[wid] : wid;
     const uint32_t g = a.g_of_hyp ? a.g_of_hyp[h] : 0u;
     const unsigned long long sb = a.sub_off[g];
     const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - sb);

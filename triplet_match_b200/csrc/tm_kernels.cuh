@@ -72,6 +72,42 @@ struct EarlyArgs {
     // tile t of group g is entry sub_off[g]/32 + g + t
     const float4* tile_lo = nullptr;
     const float4* tile_hi = nullptr;
+    const uint32_t* hyp_list = nullptr;  // optional: warp w walks hypothesis hyp_list[w] (n_hyp_dev entries)
+};
+
+// k_early2.cu: the early drop over the evenly sampling walk, level by level
+constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoints (scene.hpp:422-426)
+struct LevelArgs {
+    CloudDev scene;
+    ModelDev model;
+    const int32_t* lvl_idx;    // subset rows regrouped by level (walk_levels_kernel): scene index ...
+    const uint32_t* lvl_pos;   // ... and walk position of every element
+    const WorkItem* items;     // (level, group)-major work list
+    const uint32_t* item_off;  // [EL_LEVELS * n_groups + 1]
+    uint32_t n_groups;
+    int level;
+    uint32_t* work_counter;    // this level's
+    const float4* T;
+    const uint8_t* alive;
+    uint32_t* lvl_cnt;         // inliers of this level per hypothesis
+    uint32_t* minkey;          // min over reaching elements of (walk position << 1) | !inlier
+    float sq_thres;
+};
+struct EvalArgs {
+    const uint32_t* n_local;
+    const uint32_t* g_of_hyp;
+    const unsigned long long* sub_off;
+    uint8_t* alive;
+    uint32_t* corrs;           // inliers of the levels before the current one
+    uint32_t* lvl_cnt;
+    uint32_t* minkey;
+    uint32_t* counts;
+    uint8_t* dropped;
+    uint32_t* irregular;       // hypotheses to be walked one by one (a level without a reaching element)
+    uint32_t* n_irregular;
+    unsigned long long* n_tests;
+    float accept_bound;
+    int level;
 };
 
 struct IcpState {
@@ -159,6 +195,18 @@ void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
 void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
                               const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
                               float4* tile_lo, float4* tile_hi);
+// k_early2.cu
+void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
+                        int32_t* lvl_idx, uint32_t* lvl_pos);
+void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
+                          uint32_t* n_items);
+void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
+                         const uint32_t* item_off, WorkItem* items);
+void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused);
+int score_level_max_blocks_per_sm(bool fused);
+void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound);
+void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* corrs,
+                    uint32_t* lvl_cnt, uint32_t* minkey, uint8_t* dropped, uint32_t* counts);
 void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                    const uint32_t* n_local, const unsigned long long* h_begin,
                    unsigned long long* best, int grid);
