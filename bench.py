@@ -608,12 +608,16 @@ def early_drop_legs(ctx, capi, gs, gm, rec, r_full, QP, hyp):
         d = qe.download()
         alive = d["dropped"] == 0
         out[key] = {"value": re_.n_scored / (float(np.mean(ms)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)),
-                    "tests_per_step": int(re_.n_tests), "survivors": int(alive.sum()),
+                    "scoring_ms": float(qe.score_kernel_ms()), "tests_per_step": int(re_.n_tests), "survivors": int(alive.sum()),
                     "best_pose_survives": bool(alive.any() and int(d["counts"][alive].max()) == int(r_full.best_inliers))}
+        if mode == 2:
+            out[key]["kernel"] = "score_level_kernel x 19 checkpoint ranges (k_early2.cu)"
+            out[key]["walked_one_by_one"] = qe.early_walked()
         qe.close()
     out["note"] = ("project_(early_out=true) semantics, bit-exact with the reference incl. drop points: in the subset's own order "
-                   "(early_out=1) and over the evenly sampling walk p -> (p*s) mod n (early_out=2); not the headline, which scores "
-                   "every hypothesis over its whole subset")
+                   "(early_out=1, one warp walks one hypothesis) and over the evenly sampling walk p -> (p*s) mod n (early_out=2, "
+                   "evaluated per checkpoint range with the tiled, box-culled scorer); not the headline, which scores every "
+                   "hypothesis over its whole subset")
     return out
 
 

@@ -96,7 +96,7 @@ static int size_for_shard(tm_query* q) {
         total += np;
         q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
         items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
-        el_items += ((np + SCORE_TILE - 1) / SCORE_TILE + EL_LEVELS) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
+        el_items += ((np + SCORE_TILE - 1) / SCORE_TILE + EL_LEVELS) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK + 1);
     }
     (void)opo;
     q->sub_total = total;
@@ -371,6 +371,11 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     a.lvl_cnt = q->el_cnt.as<uint32_t>();
     a.minkey = q->el_minkey.as<uint32_t>();
     a.sq_thres = sqt;
+    if (knobs().score_stats) {
+        TRY(q->stats.ensure(64));
+        CU(cudaMemsetAsync(q->stats.p, 0, 64, c->stream));
+        a.stats = q->stats.as<unsigned long long>();
+    }
     EvalArgs e;
     e.n_local = &out->n_local;
     e.g_of_hyp = q->g_of_hyp.as<uint32_t>();
@@ -560,6 +565,12 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
     if (q->stats.p && knobs().score_stats) {
         unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CU(cudaMemcpy(st, q->stats.p, 64, cudaMemcpyDeviceToHost));
+        if (q->levels)
+            fprintf(stderr, "[tm stats] level scheme: (tile,hyp) pairs %llu  of live hypotheses %llu (%.1f%%)  survive cull %llu "
+                    "(%.1f%% of live; 64-point halves evaluated %llu = %.1f%%)  with a reaching element %llu\n", st[0], st[1],
+                    st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[1] ? 100.0 * st[2] / st[1] : 0.0, st[4],
+                    st[1] ? 50.0 * st[4] / st[1] : 0.0, st[3]);
+        else
         fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)"
                 "  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
                 st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4],

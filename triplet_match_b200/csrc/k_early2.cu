@@ -122,7 +122,7 @@ __global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
     const uint32_t np = level_begin(n, (int)L + 1) - level_begin(n, (int)L);
     const uint32_t nh = g_hyp[g + 1] - g_hyp[g];
-    n_items[t] = ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK);
+    n_items[t] = ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK);
 }
 __global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
                                     uint32_t n_groups, const uint32_t* __restrict__ item_off, WorkItem* __restrict__ items) {
@@ -133,15 +133,15 @@ __global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_o
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
     const uint32_t b0 = level_begin(n, (int)L), np = level_begin(n, (int)L + 1) - b0;
     const uint32_t hb = g_hyp[g], nh = g_hyp[g + 1] - hb;
-    const uint32_t tiles = (np + SCORE_TILE - 1) / SCORE_TILE, chunks = (nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK;
+    const uint32_t tiles = (np + SCORE_TILE - 1) / SCORE_TILE, chunks = (nh + EL_HCHUNK - 1) / EL_HCHUNK;
     const uint32_t base = item_off[t];
     for (uint32_t k = threadIdx.x; k < tiles * chunks; k += blockDim.x) {
         const uint32_t tile = k % tiles, chunk = k / tiles;
         WorkItem w;
         w.sub_begin = sb + b0 + (unsigned long long)tile * SCORE_TILE;
         w.npts = min((uint32_t)SCORE_TILE, np - tile * SCORE_TILE);
-        w.hyp_begin = hb + chunk * SCORE_HCHUNK;
-        w.hyp_end = min(hb + nh, w.hyp_begin + SCORE_HCHUNK);
+        w.hyp_begin = hb + chunk * EL_HCHUNK;
+        w.hyp_end = min(hb + nh, w.hyp_begin + EL_HCHUNK);
         w.pad = 0;
         items[base + k] = w;
     }
@@ -161,6 +161,129 @@ void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, con
 }
 
 // ---- one level: counts + first reaching position per live hypothesis ------------------------------------------------
+// Exact test of one hypothesis against the tile's point pairs A (points 0..63) and / or B (64..127): inliers c and the
+// smallest (walk position << 1 | !inlier) of a reaching element.  A pair the cull excluded is not evaluated (it holds no
+// reaching element, so it contributes neither).  Returns false when nothing reaches the grid.
+template <bool FUSED, bool OCC, bool DO_A, bool DO_B>
+__device__ __forceinline__ bool level_eval(const ModelDev& m, const X2& e, float sq_thres, float4 r0, float4 r1, float4 r2,
+                                           p2 pxA, p2 pyA, p2 pzA, p2 pxB, p2 pyB, p2 pzB, const uint32_t (&wpos)[4],
+                                           uint32_t tflags, uint32_t& c, uint32_t& mn) {
+    float x[4], y[4], z[4], vx[4], vy[4], vz[4];
+    if (DO_A) {
+        const p2 xA = e.row_apply(r0, pxA, pyA, pzA), yA = e.row_apply(r1, pxA, pyA, pzA), zA = e.row_apply(r2, pxA, pyA, pzA);
+        const p2 vxA = e.add(e.mul(m.sx, xA), m.tx), vyA = e.add(e.mul(m.sy, yA), m.ty), vzA = e.add(e.mul(m.sz, zA), m.tz);
+        x[0] = lo2(xA); x[1] = hi2(xA); y[0] = lo2(yA); y[1] = hi2(yA); z[0] = lo2(zA); z[1] = hi2(zA);
+        vx[0] = lo2(vxA); vx[1] = hi2(vxA); vy[0] = lo2(vyA); vy[1] = hi2(vyA); vz[0] = lo2(vzA); vz[1] = hi2(vzA);
+    }
+    if (DO_B) {
+        const p2 xB = e.row_apply(r0, pxB, pyB, pzB), yB = e.row_apply(r1, pxB, pyB, pzB), zB = e.row_apply(r2, pxB, pyB, pzB);
+        const p2 vxB = e.add(e.mul(m.sx, xB), m.tx), vyB = e.add(e.mul(m.sy, yB), m.ty), vzB = e.add(e.mul(m.sz, zB), m.tz);
+        x[2] = lo2(xB); x[3] = hi2(xB); y[2] = lo2(yB); y[3] = hi2(yB); z[2] = lo2(zB); z[3] = hi2(zB);
+        vx[2] = lo2(vxB); vx[3] = hi2(vxB); vy[2] = lo2(vyB); vy[3] = hi2(vyB); vz[2] = lo2(vzB); vz[3] = hi2(vzB);
+    }
+    uint32_t lin[4];
+    bool reach[4], look[4];
+    bool any_reach = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        reach[k] = look[k] = false;
+        lin[k] = 0u;
+        if (k < 2 ? DO_A : DO_B) {
+            // voxel_query succeeded (model.hpp:186-189) in the float domain: int(v) in [0, e) <=> -1 < v < e for every
+            // finite v; NaN (masked / padding points) and +-inf are out, as with the walker
+            const bool ok = (vx[k] > -1.f) & (vx[k] < m.exf) & (vy[k] > -1.f) & (vy[k] < m.eyf) & (vz[k] > -1.f) &
+                            (vz[k] < m.ezf);
+            const int i = (int)vx[k], j = (int)vy[k], kk = (int)vz[k];
+            bool lk = ok;
+            if (OCC) {  // the occupancy mask only saves the gather; the element reaches either way
+                const uint32_t b = ok ? (uint32_t)(((kk >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx + (i >> OCC_SHIFT))
+                                      : 0u;
+                lk = ok & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
+            }
+            lin[k] = (uint32_t)((kk * m.ey + j) * m.ex + i);
+            reach[k] = ok;
+            look[k] = lk;
+            any_reach |= ok;
+        }
+    }
+    if (!__any_sync(0xffffffffu, any_reach)) return false;  // nothing reaches the grid
+    float4 mp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((k < 2 ? DO_A : DO_B) && look[k]) {
+            if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
+            else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
+        }
+    }
+    float sq[4];
+    if (DO_A) {
+        const p2 sqA = e.sqnorm(pack2(x[0] - mp[0].x, x[1] - mp[1].x), pack2(y[0] - mp[0].y, y[1] - mp[1].y),
+                                pack2(z[0] - mp[0].z, z[1] - mp[1].z));
+        sq[0] = lo2(sqA); sq[1] = hi2(sqA);
+    }
+    if (DO_B) {
+        const p2 sqB = e.sqnorm(pack2(x[2] - mp[2].x, x[3] - mp[3].x), pack2(y[2] - mp[2].y, y[3] - mp[3].y),
+                                pack2(z[2] - mp[2].z, z[3] - mp[3].z));
+        sq[2] = lo2(sqB); sq[3] = hi2(sqB);
+    }
+    c = 0;
+    mn = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < 2 ? DO_A : DO_B) {
+            const uint32_t pfl = (tflags >> k) & 1u;
+            const bool inl = look[k] && (sq[k] <= sq_thres) && (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
+            c += inl ? 1u : 0u;
+            if (reach[k]) mn = min(mn, (wpos[k] << 1) | (inl ? 0u : 1u));
+        }
+    }
+    return true;
+}
+
+// bounding box of one point pair's 64 tile points -> centre / half extents; valid = the pair holds a live point
+struct HalfBox {
+    float cx, cy, cz, hx, hy, hz;
+    bool valid;
+};
+__device__ __forceinline__ HalfBox half_box(float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
+    }
+    HalfBox b;
+    b.valid = mnx <= mxx;
+    b.cx = 0.5f * (mnx + mxx); b.hx = 0.5f * (mxx - mnx);
+    b.cy = 0.5f * (mny + mxy); b.hy = 0.5f * (mxy - mny);
+    b.cz = 0.5f * (mnz + mxz); b.hz = 0.5f * (mxz - mnz);
+    return b;
+}
+// interval test of k_score2.cu's cull: true when the transformed box provably misses the grid (NaN never culls)
+__device__ __forceinline__ bool box_misses_grid(const ModelDev& m, const HalfBox& b, float4 r0, float4 r1, float4 r2) {
+    const float acx = fabsf(b.cx) + b.hx, acy = fabsf(b.cy) + b.hy, acz = fabsf(b.cz) + b.hz;
+    bool out = false;
+#define TM_AXIS(r, S, TV, EXF)                                                                        \
+    {                                                                                                 \
+        float cc = r.x * b.cx + r.y * b.cy + r.z * b.cz + r.w;                                        \
+        float ee = fabsf(r.x) * b.hx + fabsf(r.y) * b.hy + fabsf(r.z) * b.hz;                         \
+        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);              \
+        ee += 1e-5f * mag + 1e-30f;                                                                   \
+        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                            \
+        float lo = S * (cc - ee) + TV - sl, hi = S * (cc + ee) + TV + sl;                             \
+        out = out || (lo >= EXF) || (hi <= -1.0f);                                                    \
+    }
+    TM_AXIS(r0, m.sx, m.tx, m.exf)
+    TM_AXIS(r1, m.sy, m.ty, m.eyf)
+    TM_AXIS(r2, m.sz, m.tz, m.ezf)
+#undef TM_AXIS
+    return out;
+}
+
 template <bool FUSED, bool OCC>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     score_level_kernel(LevelArgs a, p2 k_nz, p2 k_one) {
@@ -179,11 +302,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= item_end) break;
         const WorkItem w = a.items[item];
+        // points k = 0..3 of this lane: pairs A = (0, 1) = tile points 0..63, B = (2, 3) = 64..127.  A level's tile spans
+        // ~20x the subset range a full tile does, so each pair gets its own box and is culled on its own.
         float px[4], py[4], pz[4];
-        uint32_t wpos[4];     // walk position of point k (only meaningful where live)
+        uint32_t wpos[4];     // walk position of point k (only meaningful where the point is live)
         uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
         const float nanv = __int_as_float(0x7fc00000);
-        float mnx = 3.0e38f, mny = 3.0e38f, mnz = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f, mxz = -3.0e38f;
+        float mn[2][3] = {{3.0e38f, 3.0e38f, 3.0e38f}, {3.0e38f, 3.0e38f, 3.0e38f}};
+        float mx[2][3] = {{-3.0e38f, -3.0e38f, -3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t q = k * 32 + lane;
@@ -197,122 +323,67 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     px[k] = v.x; py[k] = v.y; pz[k] = v.z;
                     wpos[k] = a.lvl_pos[w.sub_begin + q];
                     if (fl & FLAG_TANGENT) tflags |= 1u << k;
-                    mnx = fminf(mnx, v.x); mxx = fmaxf(mxx, v.x);
-                    mny = fminf(mny, v.y); mxy = fmaxf(mxy, v.y);
-                    mnz = fminf(mnz, v.z); mxz = fmaxf(mxz, v.z);
+                    mn[k >> 1][0] = fminf(mn[k >> 1][0], v.x); mx[k >> 1][0] = fmaxf(mx[k >> 1][0], v.x);
+                    mn[k >> 1][1] = fminf(mn[k >> 1][1], v.y); mx[k >> 1][1] = fmaxf(mx[k >> 1][1], v.y);
+                    mn[k >> 1][2] = fminf(mn[k >> 1][2], v.z); mx[k >> 1][2] = fmaxf(mx[k >> 1][2], v.z);
                 }
             }
         }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
-            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
-            mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, d));
-            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
-            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
-            mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, d));
-        }
-        if (!(mnx <= mxx)) continue;  // no live (finite, unmasked) point in this tile
-        const float cx = 0.5f * (mnx + mxx), hx = 0.5f * (mxx - mnx);
-        const float cy = 0.5f * (mny + mxy), hy = 0.5f * (mxy - mny);
-        const float cz = 0.5f * (mnz + mxz), hz = 0.5f * (mxz - mnz);
+        const HalfBox bA = half_box(mn[0][0], mn[0][1], mn[0][2], mx[0][0], mx[0][1], mx[0][2]);
+        const HalfBox bB = half_box(mn[1][0], mn[1][1], mn[1][2], mx[1][0], mx[1][1], mx[1][2]);
+        if (!bA.valid && !bB.valid) continue;  // no live (finite, unmasked) point in this tile
         const p2 pxA = e.add(pack2(px[0], px[1]), e.nz), pyA = e.add(pack2(py[0], py[1]), e.nz),
                  pzA = e.add(pack2(pz[0], pz[1]), e.nz);
         const p2 pxB = e.add(pack2(px[2], px[3]), e.nz), pyB = e.add(pack2(py[2], py[3]), e.nz),
                  pzB = e.add(pack2(pz[2], pz[3]), e.nz);
         for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {
             const uint32_t h = h0 + lane;
-            bool survive = false;
+            bool sA = false, sB = false;
             __syncwarp();  // readers of the previous batch's rows are done
-            if (h < w.hyp_end && a.alive[h]) {  // hypotheses dropped at an earlier checkpoint are not walked any further
+            const bool live = h < w.hyp_end && a.alive[h];  // dropped at an earlier checkpoint: not walked any further
+            if (live) {
                 const float4 r0 = __ldg(&a.T[3 * (size_t)h]), r1 = __ldg(&a.T[3 * (size_t)h + 1]),
                              r2 = __ldg(&a.T[3 * (size_t)h + 2]);
                 my_rows[lane] = r0;
                 my_rows[32 + lane] = r1;
                 my_rows[64 + lane] = r2;
-                const float acx = fabsf(cx) + hx, acy = fabsf(cy) + hy, acz = fabsf(cz) + hz;
-                bool out = false;
-#define TM_AXIS(r, S, TV, EXF)                                                                  \
-    {                                                                                           \
-        float cc = r.x * cx + r.y * cy + r.z * cz + r.w;                                        \
-        float ee = fabsf(r.x) * hx + fabsf(r.y) * hy + fabsf(r.z) * hz;                         \
-        float mag = fabsf(r.x) * acx + fabsf(r.y) * acy + fabsf(r.z) * acz + fabsf(r.w);        \
-        ee += 1e-5f * mag + 1e-30f;                                                             \
-        float sl = 1e-5f * (S * mag + fabsf(TV)) + 1e-30f;                                      \
-        float lo = S * (cc - ee) + TV - sl, hi = S * (cc + ee) + TV + sl;                       \
-        out = out || (lo >= EXF) || (hi <= -1.0f);                                              \
-    }
-                TM_AXIS(r0, m.sx, m.tx, m.exf)
-                TM_AXIS(r1, m.sy, m.ty, m.eyf)
-                TM_AXIS(r2, m.sz, m.tz, m.ezf)
-#undef TM_AXIS
-                survive = !out;  // a culled tile holds no reaching element: it changes neither count nor checkpoint
+                // a culled pair holds no reaching element: it changes neither count nor checkpoint
+                sA = bA.valid && !box_misses_grid(m, bA, r0, r1, r2);
+                sB = bB.valid && !box_misses_grid(m, bB, r0, r1, r2);
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, survive);  // also orders the smem stores
+            const uint32_t maskA = __ballot_sync(0xffffffffu, sA);  // also orders the smem stores
+            const uint32_t maskB = __ballot_sync(0xffffffffu, sB);
+            uint32_t mask = maskA | maskB;
+            if (a.stats) {
+                const uint32_t al = __ballot_sync(0xffffffffu, live);
+                if (lane == 0) {
+                    atomicAdd(&a.stats[0], (unsigned long long)min(32u, w.hyp_end - h0));
+                    atomicAdd(&a.stats[1], (unsigned long long)__popc(al));
+                    atomicAdd(&a.stats[2], (unsigned long long)__popc(mask));
+                    atomicAdd(&a.stats[4], (unsigned long long)(__popc(maskA) + __popc(maskB)));
+                }
+            }
             uint32_t mycnt = 0, mymin = 0xffffffffu;
             while (mask) {
                 const int hh = __ffs(mask) - 1;
                 mask &= mask - 1u;
                 const float4 r0 = my_rows[hh], r1 = my_rows[32 + hh], r2 = my_rows[64 + hh];
-                const p2 xA = e.row_apply(r0, pxA, pyA, pzA), xB = e.row_apply(r0, pxB, pyB, pzB);
-                const p2 yA = e.row_apply(r1, pxA, pyA, pzA), yB = e.row_apply(r1, pxB, pyB, pzB);
-                const p2 zA = e.row_apply(r2, pxA, pyA, pzA), zB = e.row_apply(r2, pxB, pyB, pzB);
-                const p2 vxA = e.add(e.mul(m.sx, xA), m.tx), vxB = e.add(e.mul(m.sx, xB), m.tx);
-                const p2 vyA = e.add(e.mul(m.sy, yA), m.ty), vyB = e.add(e.mul(m.sy, yB), m.ty);
-                const p2 vzA = e.add(e.mul(m.sz, zA), m.tz), vzB = e.add(e.mul(m.sz, zB), m.tz);
-                const float x[4] = {lo2(xA), hi2(xA), lo2(xB), hi2(xB)}, y[4] = {lo2(yA), hi2(yA), lo2(yB), hi2(yB)},
-                            z[4] = {lo2(zA), hi2(zA), lo2(zB), hi2(zB)};
-                const float vx[4] = {lo2(vxA), hi2(vxA), lo2(vxB), hi2(vxB)},
-                            vy[4] = {lo2(vyA), hi2(vyA), lo2(vyB), hi2(vyB)},
-                            vz[4] = {lo2(vzA), hi2(vzA), lo2(vzB), hi2(vzB)};
-                uint32_t lin[4];
-                bool reach[4], look[4];
-                bool any_reach = false;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // voxel_query succeeded (model.hpp:186-189) in the float domain: int(v) in [0, e) <=> -1 < v < e for
-                    // every finite v; NaN (masked / padding points) and +-inf are out, as with the walker
-                    const bool ok = (vx[k] > -1.f) & (vx[k] < m.exf) & (vy[k] > -1.f) & (vy[k] < m.eyf) & (vz[k] > -1.f) &
-                                    (vz[k] < m.ezf);
-                    const int i = (int)vx[k], j = (int)vy[k], kk = (int)vz[k];
-                    bool lk = ok;
-                    if (OCC) {  // the occupancy mask only saves the gather; the element reaches either way
-                        const uint32_t b = ok ? (uint32_t)(((kk >> OCC_SHIFT) * m.oby + (j >> OCC_SHIFT)) * m.obx +
-                                                           (i >> OCC_SHIFT))
-                                              : 0u;
-                        lk = ok & (((__ldg(&m.occ[b >> 5]) >> (b & 31u)) & 1u) != 0u);
-                    }
-                    lin[k] = (uint32_t)((kk * m.ey + j) * m.ex + i);
-                    reach[k] = ok;
-                    look[k] = lk;
-                    any_reach |= ok;
-                }
-                if (!__any_sync(0xffffffffu, any_reach)) continue;  // nothing reaches the grid
-                float4 mp[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    mp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (look[k]) {
-                        if (FUSED) mp[k] = __ldg(&m.vcell[lin[k]]);
-                        else mp[k] = __ldg(&m.cloud.pos[__ldg(&m.voxel[lin[k]])]);
-                    }
-                }
-                const p2 dxA = pack2(x[0] - mp[0].x, x[1] - mp[1].x), dxB = pack2(x[2] - mp[2].x, x[3] - mp[3].x);
-                const p2 dyA = pack2(y[0] - mp[0].y, y[1] - mp[1].y), dyB = pack2(y[2] - mp[2].y, y[3] - mp[3].y);
-                const p2 dzA = pack2(z[0] - mp[0].z, z[1] - mp[1].z), dzB = pack2(z[2] - mp[2].z, z[3] - mp[3].z);
-                const p2 sqA = e.sqnorm(dxA, dyA, dzA), sqB = e.sqnorm(dxB, dyB, dzB);
-                const float sq[4] = {lo2(sqA), hi2(sqA), lo2(sqB), hi2(sqB)};
-                uint32_t c = 0, mn = 0xffffffffu;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t pfl = (tflags >> k) & 1u;
-                    const bool inl = look[k] && (sq[k] <= a.sq_thres) &&
-                                     (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
-                    c += inl ? 1u : 0u;
-                    if (reach[k]) mn = min(mn, (wpos[k] << 1) | (inl ? 0u : 1u));
-                }
+                const bool doA = (maskA >> hh) & 1u, doB = (maskB >> hh) & 1u;  // warp-uniform
+                uint32_t c, mnk;
+                bool any;
+                if (doA && doB)
+                    any = level_eval<FUSED, OCC, true, true>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
+                                                             tflags, c, mnk);
+                else if (doA)
+                    any = level_eval<FUSED, OCC, true, false>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
+                                                              tflags, c, mnk);
+                else
+                    any = level_eval<FUSED, OCC, false, true>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
+                                                              tflags, c, mnk);
+                if (!any) continue;
+                if (a.stats && lane == 0) atomicAdd(&a.stats[3], 1ull);
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
-                const uint32_t wmn = __reduce_min_sync(0xffffffffu, mn);
+                const uint32_t wmn = __reduce_min_sync(0xffffffffu, mnk);
                 if (lane == hh) {
                     mycnt = tot;
                     mymin = wmn;

@@ -77,6 +77,11 @@ struct EarlyArgs {
 
 // k_early2.cu: the early drop over the evenly sampling walk, level by level
 constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoints (scene.hpp:422-426)
+#ifndef TM_EL_HCHUNK
+#define TM_EL_HCHUNK 256
+#endif
+constexpr int EL_HCHUNK = TM_EL_HCHUNK;  // hypotheses per work item: a level holds 1/20 of a subset's tiles, so the
+                                         // items are made shorter than the full scorer's to keep the tail small
 struct LevelArgs {
     CloudDev scene;
     ModelDev model;
@@ -92,6 +97,9 @@ struct LevelArgs {
     uint32_t* lvl_cnt;         // inliers of this level per hypothesis
     uint32_t* minkey;          // min over reaching elements of (walk position << 1) | !inlier
     float sq_thres;
+    unsigned long long* stats = nullptr;  // optional debug counters: [0] (tile, hyp) pairs, [1] of live hypotheses,
+                                          // [2] surviving the cull, [3] with a reaching element, [4] 64-point
+                                          // halves evaluated
 };
 struct EvalArgs {
     const uint32_t* n_local;
