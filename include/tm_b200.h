@@ -232,7 +232,8 @@ typedef struct tm_query_params {
     float dist_thres;
     float accept_prob;         /* model_match_factor */
     int32_t early_out;         /* 0 = finish_find semantics, 1 = reference early-drop in subset order,
-                                  2 = early-drop over the evenly sampling walk (see tm_score) */
+                                  2 = early-drop over the evenly sampling walk (see tm_score), evaluated
+                                  checkpoint range by checkpoint range with the tiled scorer */
     uint32_t icp_top_k;        /* 0 = no ICP stage */
     uint32_t max_icp_iterations;
     uint64_t max_hypotheses;   /* capacity; 0 = n_pairs * query_limit */
