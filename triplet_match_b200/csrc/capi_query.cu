@@ -571,10 +571,10 @@ int tm_query_result_get(tm_query* q, tm_query_result* r) {
                     st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[1] ? 100.0 * st[2] / st[1] : 0.0, st[4],
                     st[1] ? 50.0 * st[4] / st[1] : 0.0, st[3]);
         else
-        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%)  with inliers %llu (%.1f%%)"
-                "  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
-                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[2], st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4],
-                st[5]);
+        fprintf(stderr, "[tm stats] (warp-tile,hyp) pairs %llu  survive cull %llu (%.1f%%; 64-point halves evaluated %.1f%%)  "
+                "with inliers %llu (%.1f%%)  all-inlier tiles %llu  >=90%% %llu  inliers %llu\n",
+                st[0], st[1], st[0] ? 100.0 * st[1] / st[0] : 0.0, st[0] ? 50.0 * st[6] / st[0] : 0.0, st[2],
+                st[0] ? 100.0 * st[2] / st[0] : 0.0, st[3], st[4], st[5]);
     }
     if (o.err) return fail(TM_ERR_CAPACITY, "query: hypothesis capacity exceeded (max_hypotheses)");
     memset(r, 0, sizeof(*r));

@@ -48,7 +48,8 @@ struct ScoreArgs {
     float thres = 0.f;       // the distance threshold itself (sqrtf(sq_thres) rounded up) and
     float cell_reach = 0.f;  // 1.5 cell diagonals in model units: the sphere cull of score_count_x2_kernel
     unsigned long long* stats;  // optional debug counters: [0] (warp,hyp) pairs, [1] survivors,
-                                // [2] warp-tiles with an inlier
+                                // [2] warp-tiles with an inlier, [3] all-inlier tiles, [4] >= 90 %, [5] inliers,
+                                // [6] 64-point halves evaluated
 };
 
 struct EarlyArgs {
