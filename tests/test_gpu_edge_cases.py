@@ -269,6 +269,23 @@ def test_sharding_edge_cases(ctx):
             assert np.array_equal(np.concatenate(parts), full[:n]), (by_tests, world, limit)
             exp = max((capi.pack_key(int(c), i) for i, c in enumerate(full[:n]) if c), default=0)
             assert max(keys) == exp
+    # the level-by-level early drop on shards: outer samples outside a rank's range have empty rows and no work items
+    qe = capi.Query(gs, gm, early_out=2, max_hypotheses=H + 64)
+    qe.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+    qe.run()
+    de = qe.download()
+    qe.close()
+    for world in (2, 5):
+        cs, ds = [], []
+        for r in range(world):
+            q = capi.Query(gs, gm, early_out=2, max_hypotheses=H + 64)
+            q.set_shard(r, world)
+            q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
+            q.run()
+            d = q.download()
+            cs.append(d["counts"]); ds.append(d["dropped"])
+            q.close()
+        assert np.array_equal(np.concatenate(cs), de["counts"]) and np.array_equal(np.concatenate(ds), de["dropped"])
     # empty list, any sharding
     e = np.zeros(0, np.uint32)
     q = capi.Query(gs, gm)
