@@ -152,6 +152,11 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
 /* stride of the evenly sampling walk: the integer nearest n / golden ratio that is coprime with n
  * (1 for n <= 2), so that p -> (p * s) mod n is a permutation whose prefixes spread over [0, n) */
 uint32_t tm_walk_stride(uint32_t n);
+/* early_out = 2 on the resident query: the 18 checkpoint thresholds tests[i] = uint32(0.05f * (i + 1) * n)
+ * (scene.hpp:422-426) cut the walk positions [0, n) into 19 ranges; range `level` starts at position
+ * tm_early_level_begin(n, level): 0 for level <= 0, max(tests[level - 1] - 1, 0) for 1..18, n for level >= 19.
+ * Checkpoint i + 1 fires at the first reaching element at or after the start of range i + 1. */
+uint32_t tm_early_level_begin(uint32_t n, int level);
 /* correspondences of one transform over the whole scene (finish_find's
  * scene_corrs / model_corrs, ascending scene index).  Buffers sized scene n. */
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,

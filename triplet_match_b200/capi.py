@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_scan_u64", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked", "tm_early_level_begin",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -707,6 +707,13 @@ def walk_stride(n: int) -> int:
     lib = load()
     lib.tm_walk_stride.restype = C.c_uint32
     return int(lib.tm_walk_stride(C.c_uint32(n)))
+
+
+def early_level_begin(n: int, level: int) -> int:
+    """tm_early_level_begin: first walk position of checkpoint range `level` of an n-element subset."""
+    lib = load()
+    lib.tm_early_level_begin.restype = C.c_uint32
+    return int(lib.tm_early_level_begin(C.c_uint32(n), C.c_int(level)))
 
 
 def walk_order(n: int) -> np.ndarray:

@@ -860,6 +860,7 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
 }
 
 uint32_t tm_walk_stride(uint32_t n) { return walk_stride(n); }
+uint32_t tm_early_level_begin(uint32_t n, int level) { return level_begin(n, level); }
 
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
                        uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,

@@ -28,17 +28,6 @@
 
 namespace tmk {
 
-// first walk position of level L for a subset of n elements: b[0] = 0, b[L] = t_L - 1 (0 when t_L <= 1) with
-// t_L = uint32(0.05f * L * n) the reference's tests[L-1] (scene.hpp:422-426), b[19] = n.  A checkpoint with threshold t
-// fires at the first reaching element whose 1-based position is >= t.
-__host__ __device__ inline uint32_t level_begin(uint32_t n, int L) {
-    if (L <= 0) return 0u;
-    if (L >= EL_LEVELS) return n;
-    const uint32_t t = (uint32_t)(0.05f * (float)L * (float)n);
-    const uint32_t b = t > 1u ? t - 1u : 0u;
-    return b < n ? b : n;
-}
-
 // modular inverse of s modulo n (gcd(s, n) == 1, n >= 1)
 __device__ inline uint32_t mod_inverse(uint32_t s, uint32_t n) {
     if (n <= 1u) return 0u;

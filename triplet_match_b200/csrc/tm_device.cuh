@@ -81,6 +81,17 @@ __host__ __device__ inline uint32_t walk_stride(uint32_t n) {
     }
 }
 
+// first walk position of level L for a subset of n elements: b[0] = 0, b[L] = t_L - 1 (0 when t_L <= 1) with
+// t_L = uint32(0.05f * L * n) the reference's tests[L-1] (scene.hpp:422-426), b[19] = n (19 ranges: tmk::EL_LEVELS).  A checkpoint with threshold t
+// fires at the first reaching element whose 1-based position is >= t.
+__host__ __device__ inline uint32_t level_begin(uint32_t n, int L) {
+    if (L <= 0) return 0u;
+    if (L >= 19) return n;
+    const uint32_t t = (uint32_t)(0.05f * (float)L * (float)n);
+    const uint32_t b = t > 1u ? t - 1u : 0u;
+    return b < n ? b : n;
+}
+
 // hypothesis transform: rows 0..2 of the 4x4 (row 3 is 0,0,0,1)
 struct Rows {
     float4 r0, r1, r2;

@@ -77,7 +77,8 @@ struct EarlyArgs {
 };
 
 // k_early2.cu: the early drop over the evenly sampling walk, level by level
-constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoints (scene.hpp:422-426)
+constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoints (scene.hpp:422-426); level_begin()
+                               // in tm_device.cuh is written for this value
 #ifndef TM_EL_HCHUNK
 #define TM_EL_HCHUNK 256
 #endif
