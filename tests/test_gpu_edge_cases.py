@@ -219,6 +219,24 @@ def test_random_irregular_clouds(ctx, seed):
         co, so, do = osc.score_batch(om, T16, early_out=eo, nthreads=4)
         assert np.array_equal(cg, co) and np.array_equal(dg, do) and np.allclose(sg, so, rtol=1e-9, atol=1e-9)
     assert co.max() > 50
+    # the resident query's early drop over the evenly sampling walk (level-by-level evaluation, k_early2.cu) on the
+    # same clouds: recorded list from the random pairs, the oracle walks the permuted balls of the query's own hypotheses
+    order = np.argsort(pi, kind="stable")
+    outer, pair_outer = np.unique(pi[order], return_inverse=True)
+    subs = [osc.ball_subset(int(o), om.diameter) for o in outer]
+    offs = np.zeros(len(subs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([x.size for x in subs])
+    walk = np.concatenate([x[capi.walk_order(x.size)] for x in subs]).astype(np.int32)
+    for accept in (0.1 * seed, 0.6):
+        q = capi.Query(gs, gm, early_out=2, accept_prob=accept)
+        q.set_pairs(outer.astype(np.uint32), pair_outer.astype(np.uint32), pj[order])
+        q.run()
+        d = q.download()
+        cw, sw, dw = osc.score_batch(om, d["T"], pair_outer.astype(np.uint32)[d["hyp_pair"]], offs, walk, early_out=True,
+                                     accept_prob=accept, nthreads=4)
+        assert np.array_equal(d["counts"], cw) and np.array_equal(d["dropped"], dw), (seed, accept)
+        assert np.allclose(d["scores"], sw, rtol=1e-9, atol=1e-9)
+        q.close()
     gs.close(); gm.close(); hm.close()
 
 
