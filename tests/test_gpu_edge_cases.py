@@ -3,6 +3,8 @@ every decision boundary of the path — voxel cell edges and the (-1, 0) truncat
 voxel_query (model.hpp:182-189), points exactly at the distance threshold, non-finite points and
 transforms, duplicate points, zero tangents, and a table with thousands of keys (open-addressing
 collisions)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -362,5 +364,7 @@ def test_early_drop_levels_on_tiny_and_sparse_subsets(ctx, keep):
         q.close()
     sizes = np.diff(off.astype(np.int64))
     if keep == 400:
-        assert sizes.min() < 20 and max(walked) > 0  # the irregular path is exercised
+        assert sizes.min() < 20
+        if os.environ.get("TM_EARLY_LEVELS", "1") != "0":  # (the knob routes everything through the walker)
+            assert max(walked) > 0  # the irregular path is exercised
     gs.close(); gm.close()
