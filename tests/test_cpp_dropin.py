@@ -45,7 +45,9 @@ def _noisy_normals(cloud, seed, sigma=0.05):
 @pytest.mark.gpu
 @pytest.mark.parametrize("curv,shuffled,knobs", [(False, False, {}), (True, False, {}), (False, True, {}),
                                                  (False, False, {"TM_DROPIN_BATCH": "4000"}),   # rounds split into several queries
-                                                 (False, False, {"TM_DROPIN_ICP_ITERS": "0"})])  # icp_ returns the match unchanged
+                                                 (False, False, {"TM_DROPIN_ICP_ITERS": "0"}),  # icp_ returns the match unchanged
+                                                 (False, False, {"TM_DROPIN_EARLY_DROP": "1"}),  # project_(early_out = true) over the even walk
+                                                 (False, False, {"TM_DROPIN_EARLY_DROP": "1", "TM_DROPIN_BATCH": "4000"})])
 def test_cpp_find_all_parallel(exe, tmp_path, curv, shuffled, knobs):
     """curv=True: raw clouds with estimated (noisy) normals, tangent masks from the GPU 30-NN
     curvature criterion on both model and scene, as the reference does with PCL."""
