@@ -162,6 +162,13 @@ uint32_t tm_early_level_begin(uint32_t n, int level);
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
                        uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,
                        double* score);
+/* The same for n_T transforms in one pass (the candidate lists of a find_parallel round, scene.hpp:162-190):
+ * the correspondences of transform t are scene_corrs / model_corrs [offsets[t], offsets[t + 1]), ascending scene
+ * index each; offsets has n_T + 1 entries, scores (optional) n_T.  scene_corrs == model_corrs == NULL sizes only
+ * (offsets and scores are still filled); otherwise capacity >= offsets[n_T] entries or TM_ERR_CAPACITY. */
+int tm_correspondences_batch(tm_scene* s, tm_model* m, const float* T16s, uint32_t n_T, float dist_thres,
+                             uint64_t* offsets, uint32_t* scene_corrs, uint32_t* model_corrs, uint64_t capacity,
+                             double* scores);
 /* icp_ (include/impl/scene.hpp:369-404; replaces opencl/icp.cl icp_projection +
  * icp_correlation + the absent host reduction) for n start transforms. */
 int tm_icp(tm_scene* s, tm_model* m, const float* T16s, uint32_t n, uint32_t max_iterations,

@@ -220,6 +220,27 @@ def test_correspondences_and_icp(setup):
         pr = osc.project(om, np.arange(s.n, dtype=np.int32), T[h])
         assert np.array_equal(sc, pr["scene_corrs"]) and np.array_equal(mc, pr["model_corrs"])
         assert abs(score - pr["score"]) < 1e-9
+    # the batch call (candidate lists of a find_parallel round in one pass) == the single calls == the oracle, incl. a
+    # transform without correspondences and a non-finite one
+    far = np.eye(4, dtype=np.float32); far[:3, 3] = 1e3
+    nanT = np.eye(4, dtype=np.float32); nanT[0, 0] = np.nan
+    Tb = np.concatenate([T[top[:3]], far.T.reshape(1, 16), T[top[3:5]], nanT.T.reshape(1, 16)])
+    off, bsc, bmc, bscore = gs.correspondences_batch(gm, Tb, 2.0)
+    assert off[0] == 0 and off[4] == off[3] and off[-1] == off[-2] == bsc.size
+    for t in range(Tb.shape[0]):
+        sc, mc, score = gs.correspondences(gm, Tb[t], 2.0)
+        assert np.array_equal(bsc[int(off[t]):int(off[t + 1])], sc) and np.array_equal(bmc[int(off[t]):int(off[t + 1])], mc)
+        assert bscore[t] == score
+    pr = osc.project(om, np.arange(s.n, dtype=np.int32), Tb[1], dist_thres=2.0)
+    assert np.array_equal(bsc[int(off[1]):int(off[2])], pr["scene_corrs"])
+    import ctypes as C
+    from triplet_match_b200 import capi
+    o2 = np.zeros(Tb.shape[0] + 1, np.uint64)
+    small = np.zeros(4, np.uint32)
+    rc = gs.lib.tm_correspondences_batch(gs.h, gm.h, Tb.ctypes.data_as(C.c_void_p), C.c_uint32(Tb.shape[0]), C.c_float(2.0),
+                                         o2.ctypes.data_as(C.c_void_p), small.ctypes.data_as(C.c_void_p),
+                                         small.ctypes.data_as(C.c_void_p), C.c_uint64(4), None)
+    assert rc != 0 and np.array_equal(o2, off)  # too small a buffer is reported, nothing is written past it
     for iters in (0, 1, 5):
         To, cnt, scr, it = gs.icp(gm, T[top], iters, 1.0)
         for r, h in enumerate(top):

@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_scan_u64", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked", "tm_early_level_begin",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_correspondences_batch", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked", "tm_early_level_begin",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -503,6 +503,23 @@ class Scene:
         _chk(self.lib.tm_correspondences(self.h, model.h, _p(T), C.c_float(dist_thres), _p(sc),
                                          _p(mc), C.byref(n), C.byref(score)))
         return sc[:n.value].copy(), mc[:n.value].copy(), float(score.value)
+
+    def correspondences_batch(self, model: Model, T16s, dist_thres: float):
+        """tm_correspondences_batch: (offsets, scene_corrs, model_corrs, scores) of n transforms, sized then filled."""
+        T = _f32(T16s, (-1, 16))
+        n = T.shape[0]
+        off = np.zeros(n + 1, dtype=np.uint64)
+        scores = np.zeros(n, dtype=np.float64)
+        _chk(self.lib.tm_correspondences_batch(self.h, model.h, _p(T), C.c_uint32(n), C.c_float(dist_thres), _p(off),
+                                               None, None, C.c_uint64(0), _p(scores)))
+        tot = int(off[-1])
+        sc = np.zeros(max(tot, 1), dtype=np.uint32)
+        mc = np.zeros(max(tot, 1), dtype=np.uint32)
+        off2 = np.zeros(n + 1, dtype=np.uint64)
+        _chk(self.lib.tm_correspondences_batch(self.h, model.h, _p(T), C.c_uint32(n), C.c_float(dist_thres), _p(off2),
+                                               _p(sc), _p(mc), C.c_uint64(tot), _p(scores)))
+        assert np.array_equal(off, off2)
+        return off, sc[:tot], mc[:tot], scores
 
     def icp(self, model: Model, T16s, max_iterations: int, dist_thres: float):
         T = _f32(T16s, (-1, 16))

@@ -862,44 +862,72 @@ int tm_score(tm_scene* s, tm_model* m, const float* T16s, uint64_t n_hyp, const 
 uint32_t tm_walk_stride(uint32_t n) { return walk_stride(n); }
 uint32_t tm_early_level_begin(uint32_t n, int level) { return level_begin(n, level); }
 
+int tm_correspondences_batch(tm_scene* s, tm_model* m, const float* T16s, uint32_t n_T, float dist_thres,
+                             uint64_t* offsets, uint32_t* scene_corrs, uint32_t* model_corrs, uint64_t capacity,
+                             double* scores) {
+    REQUIRE(s && m && offsets && (n_T == 0 || T16s), "tm_correspondences_batch: null argument");
+    REQUIRE((scene_corrs == nullptr) == (model_corrs == nullptr), "tm_correspondences_batch: pass both lists or neither");
+    tm_ctx* c = s->ctx;
+    TRY(bind(c));
+    for (uint32_t t = 0; t <= n_T; ++t) offsets[t] = 0;
+    if (scores) for (uint32_t t = 0; t < n_T; ++t) scores[t] = 0.0;
+    if (!s->dev.n || !n_T) return TM_OK;
+    REQUIRE((uint64_t)n_T * s->dev.n < (1ull << 32), "tm_correspondences_batch: too many transforms for one call");
+    const uint32_t n_seg = (s->dev.n + CORR_SEG - 1) / CORR_SEG;
+    const size_t slots = (size_t)n_T * n_seg;
+    DevBuf &cnt = c->scratch[0], &off = c->scratch[1], &sc = c->scratch[2], &mc = c->scratch[3], &acc = c->scratch[4],
+           &rows = c->scratch[5];
+    TRY(cnt.ensure(slots * 4)); TRY(off.ensure((slots + 1) * 4)); TRY(acc.ensure(n_T * 8ull)); TRY(rows.ensure(n_T * 48ull));
+    std::vector<float4> hrows(3 * (size_t)n_T);
+    for (uint32_t t = 0; t < n_T; ++t) {
+        const float* T16 = T16s + 16 * (size_t)t;
+        hrows[3 * t] = make_float4(T16[0], T16[4], T16[8], T16[12]);
+        hrows[3 * t + 1] = make_float4(T16[1], T16[5], T16[9], T16[13]);
+        hrows[3 * t + 2] = make_float4(T16[2], T16[6], T16[10], T16[14]);
+    }
+    const float sqt = sq_threshold(dist_thres * m->dev.resolution);
+    CU(cudaMemcpyAsync(rows.p, hrows.data(), n_T * 48ull, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(acc.p, 0, n_T * 8ull, c->stream));
+    launch_corr_count(c->stream, s->dev, m->dev, rows.as<float4>(), n_T, sqt, n_seg, cnt.as<uint32_t>(),
+                      acc.as<unsigned long long>(), m->fused);
+    launch_exclusive_scan_u32(c->stream, cnt.as<uint32_t>(), off.as<uint32_t>(), slots);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> hoff(slots + 1);
+    std::vector<unsigned long long> fx(n_T);
+    CU(cudaMemcpyAsync(hoff.data(), off.p, (slots + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(fx.data(), acc.p, n_T * 8ull, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t t = 0; t <= n_T; ++t) offsets[t] = hoff[(size_t)t * n_seg];
+    if (scores) for (uint32_t t = 0; t < n_T; ++t) scores[t] = (double)fx[t] / SCORE_SCALE / (double)m->dev.cloud.n;
+    const uint64_t total = offsets[n_T];
+    if (!scene_corrs || !total) return TM_OK;
+    if (capacity < total) return fail(TM_ERR_CAPACITY, "tm_correspondences_batch: capacity too small (size with NULL lists first)");
+    TRY(sc.ensure(total * 4)); TRY(mc.ensure(total * 4));
+    launch_corr_fill(c->stream, s->dev, m->dev, rows.as<float4>(), n_T, sqt, n_seg, off.as<uint32_t>(), sc.as<uint32_t>(),
+                     mc.as<uint32_t>(), m->fused);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(scene_corrs, sc.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(model_corrs, mc.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
 int tm_correspondences(tm_scene* s, tm_model* m, const float* T16, float dist_thres,
                        uint32_t* scene_corrs, uint32_t* model_corrs, uint32_t* n_corr,
                        double* score) {
     REQUIRE(s && m && T16 && n_corr, "tm_correspondences: null argument");
-    tm_ctx* c = s->ctx;
-    TRY(bind(c));
     *n_corr = 0;
-    if (score) *score = 0.0;
-    if (!s->dev.n) return TM_OK;
-    Rows R;
-    R.r0 = make_float4(T16[0], T16[4], T16[8], T16[12]);
-    R.r1 = make_float4(T16[1], T16[5], T16[9], T16[13]);
-    R.r2 = make_float4(T16[2], T16[6], T16[10], T16[14]);
-    const uint32_t n_seg = (s->dev.n + CORR_SEG - 1) / CORR_SEG;
-    DevBuf &cnt = c->scratch[0], &off = c->scratch[1], &sc = c->scratch[2], &mc = c->scratch[3],
-           &acc = c->scratch[4];
-    TRY(cnt.ensure(n_seg * 4)); TRY(off.ensure((n_seg + 1) * 4)); TRY(acc.ensure(8));
-    TRY(sc.ensure((size_t)s->dev.n * 4)); TRY(mc.ensure((size_t)s->dev.n * 4));
-    const float sqt = sq_threshold(dist_thres * m->dev.resolution);
-    CU(cudaMemsetAsync(acc.p, 0, 8, c->stream));
-    launch_corr_count(c->stream, s->dev, m->dev, R, sqt, n_seg, cnt.as<uint32_t>(),
-                      acc.as<unsigned long long>(), m->fused);
-    launch_exclusive_scan_u32(c->stream, cnt.as<uint32_t>(), off.as<uint32_t>(), n_seg);
-    launch_corr_fill(c->stream, s->dev, m->dev, R, sqt, n_seg, off.as<uint32_t>(),
-                     sc.as<uint32_t>(), mc.as<uint32_t>(), m->fused);
-    CU(cudaGetLastError());
-    uint32_t total = 0;
-    unsigned long long fx = 0;
-    CU(cudaMemcpyAsync(&total, off.as<uint32_t>() + n_seg, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&fx, acc.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (total && scene_corrs)
-        CU(cudaMemcpyAsync(scene_corrs, sc.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (total && model_corrs)
-        CU(cudaMemcpyAsync(model_corrs, mc.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    *n_corr = total;
-    if (score) *score = (double)fx / SCORE_SCALE / (double)m->dev.cloud.n;
+    uint64_t offsets[2] = {0, 0};
+    // lists are optional here; the batch call wants both or neither
+    const bool lists = scene_corrs && model_corrs;
+    if (!lists && (scene_corrs || model_corrs)) {
+        std::vector<uint32_t> other(s->dev.n ? s->dev.n : 1);
+        TRY(tm_correspondences_batch(s, m, T16, 1, dist_thres, offsets, scene_corrs ? scene_corrs : other.data(),
+                                     model_corrs ? model_corrs : other.data(), s->dev.n, score));
+    } else {
+        TRY(tm_correspondences_batch(s, m, T16, 1, dist_thres, offsets, scene_corrs, model_corrs, s->dev.n, score));
+    }
+    *n_corr = (uint32_t)offsets[1];
     return TM_OK;
 }
 

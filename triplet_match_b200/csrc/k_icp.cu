@@ -371,15 +371,19 @@ void launch_icp_step(cudaStream_t stream, const IcpState& st, uint32_t n_hyp, in
 // order, like the ball subsets): count -> scan -> fill.
 template <bool FILL, bool FUSED>
 __global__ void __launch_bounds__(256)
-    corr_kernel(CloudDev scene, ModelDev model, Rows T, float sq_thres, uint32_t n_seg,
+    corr_kernel(CloudDev scene, ModelDev model, const float4* __restrict__ Trows, float sq_thres, uint32_t n_seg,
                 uint32_t* __restrict__ counts, const uint32_t* __restrict__ seg_off,
                 uint32_t* __restrict__ scene_corrs, uint32_t* __restrict__ model_corrs,
                 unsigned long long* __restrict__ score) {
     const int lane = threadIdx.x & 31;
     const uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (seg >= n_seg) return;
+    const uint32_t t = blockIdx.y;  // transform of the batch; counts / seg_off are [transform][segment]
+    Rows T;
+    T.r0 = Trows[3 * t]; T.r1 = Trows[3 * t + 1]; T.r2 = Trows[3 * t + 2];
+    const size_t slot = (size_t)t * n_seg + seg;
     uint32_t base = seg * CORR_SEG, cnt = 0;
-    uint32_t off = FILL ? seg_off[seg] : 0u;
+    uint32_t off = FILL ? seg_off[slot] : 0u;
     unsigned long long sc = 0;
     for (uint32_t k = 0; k < CORR_SEG / 32; ++k) {
         uint32_t i = base + k * 32 + lane;
@@ -409,39 +413,36 @@ __global__ void __launch_bounds__(256)
         cnt += __popc(b);
     }
     if (!FILL) {
-        if (lane == 0) counts[seg] = cnt;
+        if (lane == 0) counts[slot] = cnt;
 #pragma unroll
         for (int d = 16; d; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
-        if (lane == 0 && sc) atomicAdd(score, sc);
+        if (lane == 0 && sc) atomicAdd(&score[t], sc);
     }
 }
-void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
-                       float sq_thres, uint32_t n_seg, uint32_t* counts,
-                       unsigned long long* score, bool fused) {
-    if (!n_seg) return;
+void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const float4* Trows, uint32_t n_T,
+                       float sq_thres, uint32_t n_seg, uint32_t* counts, unsigned long long* score, bool fused) {
+    if (!n_seg || !n_T) return;
     ++g_launch_count;
+    const dim3 grid((n_seg + 7) / 8, n_T);
     if (fused)
-        corr_kernel<false, true><<<(n_seg + 7) / 8, 256, 0, st>>>(scene, model, T, sq_thres, n_seg,
-                                                                  counts, nullptr, nullptr, nullptr,
-                                                                  score);
+        corr_kernel<false, true><<<grid, 256, 0, st>>>(scene, model, Trows, sq_thres, n_seg, counts, nullptr, nullptr,
+                                                       nullptr, score);
     else
-        corr_kernel<false, false><<<(n_seg + 7) / 8, 256, 0, st>>>(scene, model, T, sq_thres, n_seg,
-                                                                   counts, nullptr, nullptr,
-                                                                   nullptr, score);
+        corr_kernel<false, false><<<grid, 256, 0, st>>>(scene, model, Trows, sq_thres, n_seg, counts, nullptr, nullptr,
+                                                        nullptr, score);
 }
-void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
-                      float sq_thres, uint32_t n_seg, const uint32_t* seg_off,
-                      uint32_t* scene_corrs, uint32_t* model_corrs, bool fused) {
-    if (!n_seg) return;
+void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const float4* Trows, uint32_t n_T,
+                      float sq_thres, uint32_t n_seg, const uint32_t* seg_off, uint32_t* scene_corrs,
+                      uint32_t* model_corrs, bool fused) {
+    if (!n_seg || !n_T) return;
     ++g_launch_count;
+    const dim3 grid((n_seg + 7) / 8, n_T);
     if (fused)
-        corr_kernel<true, true><<<(n_seg + 7) / 8, 256, 0, st>>>(scene, model, T, sq_thres, n_seg,
-                                                                 nullptr, seg_off, scene_corrs,
-                                                                 model_corrs, nullptr);
+        corr_kernel<true, true><<<grid, 256, 0, st>>>(scene, model, Trows, sq_thres, n_seg, nullptr, seg_off, scene_corrs,
+                                                      model_corrs, nullptr);
     else
-        corr_kernel<true, false><<<(n_seg + 7) / 8, 256, 0, st>>>(scene, model, T, sq_thres, n_seg,
-                                                                  nullptr, seg_off, scene_corrs,
-                                                                  model_corrs, nullptr);
+        corr_kernel<true, false><<<grid, 256, 0, st>>>(scene, model, Trows, sq_thres, n_seg, nullptr, seg_off, scene_corrs,
+                                                       model_corrs, nullptr);
 }
 
 }  // namespace tmk

@@ -230,12 +230,11 @@ void launch_icp_accumulate(cudaStream_t st, const CloudDev& scene, const ModelDe
 size_t icp_pairs_bytes(uint32_t pt_begin, uint32_t pt_end, uint32_t n_hyp);
 void launch_icp_step(cudaStream_t stream, const IcpState& st, uint32_t n_hyp, int first,
                      uint32_t max_iterations, double inv_scale, float cx, float cy, float cz);
-void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
-                       float sq_thres, uint32_t n_seg, uint32_t* counts,
-                       unsigned long long* score, bool fused);
-void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const Rows& T,
-                      float sq_thres, uint32_t n_seg, const uint32_t* seg_off,
-                      uint32_t* scene_corrs, uint32_t* model_corrs, bool fused);
+void launch_corr_count(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const float4* Trows, uint32_t n_T,
+                       float sq_thres, uint32_t n_seg, uint32_t* counts, unsigned long long* score, bool fused);
+void launch_corr_fill(cudaStream_t st, const CloudDev& scene, const ModelDev& model, const float4* Trows, uint32_t n_T,
+                      float sq_thres, uint32_t n_seg, const uint32_t* seg_off, uint32_t* scene_corrs,
+                      uint32_t* model_corrs, bool fused);
 
 // k_uvicp.cu (the opencl/icp.cl path, a15)
 void launch_uvicp_projection(cudaStream_t st, int projector, const float4* pnts, int n, const float4* image,
