@@ -411,42 +411,59 @@ int score_level_max_blocks_per_sm(bool fused) {
 __global__ void __launch_bounds__(256)
     el_eval_kernel(EvalArgs a) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= *a.n_local) return;
-    if (!a.alive[h]) return;
-    const uint32_t g = a.g_of_hyp[h];
-    const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - a.sub_off[g]);
-    const uint32_t cnt = a.lvl_cnt[h], mk = a.minkey[h];
-    a.lvl_cnt[h] = 0u;
-    a.minkey[h] = 0xffffffffu;
-    const int L = a.level;
-    bool done = false;
-    if (L >= 1) {
-        if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
-            // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint may
-            // also claim — walked exactly afterwards
-            a.irregular[atomicAdd(a.n_irregular, 1u)] = h;
-            a.alive[h] = 0;
-            return;
+    unsigned long long tested = 0;  // walk positions this hypothesis' walk ends with (summed per warp: one atomic)
+    bool irregular = false;         // to be walked on its own (appended per warp: one atomic)
+    if (h < *a.n_local && a.alive[h]) {
+        const uint32_t g = a.g_of_hyp[h];
+        const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - a.sub_off[g]);
+        const uint32_t cnt = a.lvl_cnt[h], mk = a.minkey[h];
+        a.lvl_cnt[h] = 0u;
+        a.minkey[h] = 0xffffffffu;
+        const int L = a.level;
+        bool open = true;  // still walking after this checkpoint
+        if (L >= 1) {
+            if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
+                // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint may
+                // also claim — walked exactly afterwards
+                irregular = true;
+                a.alive[h] = 0;
+                open = false;
+            } else {
+                const uint32_t inl = (mk & 1u) ? 0u : 1u, tried = (mk >> 1) + 1u;
+                const uint32_t c_here = a.corrs[h] + inl;
+                const uint32_t upper = early_drop_upper(tried, nsub, c_here);
+                if ((float)upper < a.accept_bound) {  // scene.hpp:500-503
+                    a.counts[h] = c_here;
+                    a.dropped[h] = 1;
+                    a.alive[h] = 0;
+                    tested = tried;
+                    open = false;
+                }
+            }
         }
-        const uint32_t inl = (mk & 1u) ? 0u : 1u, tried = (mk >> 1) + 1u;
-        const uint32_t c_here = a.corrs[h] + inl;
-        const uint32_t upper = early_drop_upper(tried, nsub, c_here);
-        if ((float)upper < a.accept_bound) {  // scene.hpp:500-503
-            a.counts[h] = c_here;
-            a.dropped[h] = 1;
-            a.alive[h] = 0;
-            if (a.n_tests) atomicAdd(a.n_tests, (unsigned long long)tried);
-            return;
+        if (open) {
+            const uint32_t total = a.corrs[h] + cnt;
+            a.corrs[h] = total;
+            if (L == EL_LEVELS - 1) {  // passed every checkpoint: the walk ends with the subset
+                a.counts[h] = total;
+                a.dropped[h] = 0;
+                a.alive[h] = 0;
+                tested = nsub;
+            }
         }
     }
-    const uint32_t total = a.corrs[h] + cnt;
-    a.corrs[h] = total;
-    if (L == EL_LEVELS - 1) done = true;
-    if (done) {
-        a.counts[h] = total;
-        a.dropped[h] = 0;
-        a.alive[h] = 0;
-        if (a.n_tests) atomicAdd(a.n_tests, (unsigned long long)nsub);
+    const uint32_t irr = __ballot_sync(0xffffffffu, irregular);
+    if (irr) {
+        const int lane = threadIdx.x & 31, leader = __ffs(irr) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(a.n_irregular, (uint32_t)__popc(irr));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (irregular) a.irregular[base + __popc(irr & ((1u << lane) - 1u))] = h;
+    }
+    if (a.n_tests) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) tested += __shfl_xor_sync(0xffffffffu, tested, d);
+        if ((threadIdx.x & 31) == 0 && tested) atomicAdd(a.n_tests, tested);
     }
 }
 void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound) {
