@@ -21,6 +21,7 @@ const Knobs& knobs() {
         v.score_stats = getenv("TM_SCORE_STATS") != nullptr;
         if (const char* e = getenv("TM_SCORER")) v.scorer = atoi(e);
         if (const char* e = getenv("TM_EARLY_LEVELS")) v.early_levels = atoi(e) != 0;
+        if (const char* e = getenv("TM_EARLY_MERGE")) v.early_merge = atoi(e) != 0;
         return v;
     }();
     return k;

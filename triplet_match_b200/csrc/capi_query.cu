@@ -96,7 +96,7 @@ static int size_for_shard(tm_query* q) {
         total += np;
         q->max_sub = (uint32_t)std::max<uint64_t>(q->max_sub, np);
         items += ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + SCORE_HCHUNK - 1) / SCORE_HCHUNK + 1);
-        el_items += ((np + SCORE_TILE - 1) / SCORE_TILE + EL_LEVELS) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK + 1);
+        el_items += el_items_bound(np, nh);
     }
     (void)opo;
     q->sub_total = total;
@@ -114,12 +114,12 @@ static int size_for_shard(tm_query* q) {
         if (knobs().early_levels) {
             REQUIRE(el_items < (1ull << 31), "too many work items");
             q->el_items_cap = (uint32_t)std::max<uint64_t>(el_items, 1);
-            const size_t lg = (size_t)EL_LEVELS * std::max(n_outer, 1u);
+            const size_t lg = (size_t)EL_LEVELS * std::max(n_outer, 1u);  // (at most EL_LEVELS stages)
             TRY(q->lvl_idx.ensure(std::max<uint64_t>(total, 1) * 4)); TRY(q->lvl_pos.ensure(std::max<uint64_t>(total, 1) * 4));
             TRY(q->el_n_items.ensure(lg * 4)); TRY(q->el_item_off.ensure((lg + 1) * 4));
             TRY(q->el_items.ensure((size_t)q->el_items_cap * sizeof(WorkItem)));
-            TRY(q->el_alive.ensure(cap)); TRY(q->el_corrs.ensure(cap * 4)); TRY(q->el_cnt.ensure(cap * 4));
-            TRY(q->el_minkey.ensure(cap * 4)); TRY(q->el_irregular.ensure(cap * 4));
+            TRY(q->el_alive.ensure(cap)); TRY(q->el_corrs.ensure(cap * 4)); TRY(q->el_cnt.ensure(cap * 4 * EL_MAX_MERGE));
+            TRY(q->el_minkey.ensure(cap * 4 * EL_MAX_MERGE)); TRY(q->el_irregular.ensure(cap * 4));
             TRY(q->el_ctrl.ensure((EL_LEVELS + 1) * 4));
         }
     }
@@ -338,22 +338,41 @@ static int enqueue_walker(tm_query* q, const ModelDev& md, uint32_t* counts, uns
     return TM_OK;
 }
 
-// early_out = 2 level by level (k_early2.cu): regroup the subset rows by checkpoint range, then per range one tiled
-// scoring launch over the hypotheses still alive and one checkpoint launch; the few hypotheses with a range that
-// reaches nothing are walked one by one at the end.  Counts and drop flags equal the walker's.
+// The stages of the level-by-level early drop: levels 0 and 1 together (checkpoint 1 is where most hypotheses that are
+// going to be dropped are dropped, so nothing later shares a launch with it), then four levels per launch, the last
+// level (10 % of the walk) on its own.  TM_EARLY_MERGE=0: one level per launch.
+static LevelPlan level_plan() {
+    LevelPlan p;
+    memset(&p, 0, sizeof(p));
+    if (!knobs().early_merge) {
+        p.n_stages = EL_LEVELS;
+        for (int L = 0; L < EL_LEVELS; ++L) { p.L0[L] = L; p.M[L] = 1; }
+        return p;
+    }
+    auto add = [&](int L0, int M) { p.L0[p.n_stages] = L0; p.M[p.n_stages] = M; ++p.n_stages; };
+    add(0, 2);
+    for (int L = 2; L + 4 <= EL_LEVELS - 1; L += 4) add(L, 4);
+    add(EL_LEVELS - 1, 1);
+    return p;
+}
+
+// early_out = 2 level by level (k_early2.cu): regroup the subset rows by checkpoint range, then per stage (one or a few
+// ranges) one tiled scoring launch over the hypotheses still alive and one checkpoint launch; the few hypotheses with a
+// range that reaches nothing are walked one by one at the end.  Counts and drop flags equal the walker's.
 static int enqueue_levels(tm_query* q, float thres, float sqt) {
     tm_ctx* c = q->s->ctx;
     QueryOut* out = q->out.as<QueryOut>();
     const tm_model* m = q->m;
     const uint32_t G = q->n_outer;
+    const LevelPlan plan = level_plan();
     launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), G, q->g_of_hyp.as<uint32_t>());
     launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(), G,
                        q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
-    launch_el_work_count(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G,
+    launch_el_work_count(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G, plan,
                          q->el_n_items.as<uint32_t>());
     launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(),
-                              (uint64_t)EL_LEVELS * G);
-    launch_el_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G,
+                              (uint64_t)plan.n_stages * G);
+    launch_el_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G, plan,
                         q->el_item_off.as<uint32_t>(), q->el_items.as<WorkItem>());
     launch_el_init(c->stream, &out->n_local, (uint32_t)q->cap_hyp, q->el_alive.as<uint8_t>(), q->el_corrs.as<uint32_t>(),
                    q->el_cnt.as<uint32_t>(), q->el_minkey.as<uint32_t>(), q->dropped.as<uint8_t>(), q->counts.as<uint32_t>());
@@ -368,6 +387,7 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     a.n_groups = G;
     a.T = q->T.as<float4>();
     a.alive = q->el_alive.as<uint8_t>();
+    a.cap = (uint32_t)q->cap_hyp;
     a.lvl_cnt = q->el_cnt.as<uint32_t>();
     a.minkey = q->el_minkey.as<uint32_t>();
     a.sq_thres = sqt;
@@ -382,6 +402,7 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     e.sub_off = q->sub_off.as<unsigned long long>();
     e.alive = q->el_alive.as<uint8_t>();
     e.corrs = q->el_corrs.as<uint32_t>();
+    e.cap = a.cap;
     e.lvl_cnt = a.lvl_cnt;
     e.minkey = a.minkey;
     e.counts = q->counts.as<uint32_t>();
@@ -394,10 +415,12 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     if (!b) b = score_level_max_blocks_per_sm(m->fused);
     const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
     CU(cudaEventRecord(q->ev_s0, c->stream));
-    for (int L = 0; L < EL_LEVELS; ++L) {
-        a.level = e.level = L;
-        a.work_counter = q->el_ctrl.as<uint32_t>() + L;
-        launch_score_level(c->stream, a, grid, m->fused);
+    for (int st = 0; st < plan.n_stages; ++st) {
+        a.stage = st;
+        a.L0 = e.L0 = plan.L0[st];
+        e.M = plan.M[st];
+        a.work_counter = q->el_ctrl.as<uint32_t>() + st;
+        launch_score_level(c->stream, a, grid, m->fused, plan.M[st]);
         launch_el_eval(c->stream, e, (uint32_t)q->cap_hyp);
     }
     TRY(enqueue_walker(q, a.model, q->counts.as<uint32_t>(), nullptr, q->dropped.as<uint8_t>(), &out->n_tests,

@@ -102,61 +102,85 @@ void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned 
     walk_levels_kernel<<<n_groups, 256, 0, st>>>(sub_idx, sub_off, lvl_idx, lvl_pos);
 }
 
-// ---- work list: (level, group) major, so that a level's items are one contiguous range -------------------------------
-__global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
-                                     uint32_t n_groups, uint32_t* __restrict__ n_items) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups * EL_LEVELS) return;
-    const uint32_t L = t / n_groups, g = t % n_groups;
-    const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
-    const uint32_t np = level_begin(n, (int)L + 1) - level_begin(n, (int)L);
-    const uint32_t nh = g_hyp[g + 1] - g_hyp[g];
-    n_items[t] = ((np + SCORE_TILE - 1) / SCORE_TILE) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK);
+// ---- stages and their work lists -------------------------------------------------------------------------------------
+// A stage scores M consecutive levels in one launch.  Its tiles take 32-point chunks from each of the M levels over
+// the same stretch of the subset: point group k (the lane's k-th point, k = 0..3) of tile j holds chunk
+// j * (4 / M) + k / M of level L0 + k % M.  A level is an even 1/20 sample of the subset, so the chunks of one tile
+// cover about the same elements and a tile of a 4-level stage is half as wide as four chunks of one level — which is
+// what decides how many (tile, hypothesis) pairs the box cull has to let through.  Each level keeps its own
+// accumulators, so the checkpoints are applied exactly as if the levels had been scored one after the other; what a
+// stage gives up is the work on the later levels of hypotheses that one of its own checkpoints drops.
+__host__ __device__ inline uint32_t stage_tiles(uint32_t n, int L0, int M) {
+    const uint32_t per = (uint32_t)(4 / M) * 32u;  // points of one level per tile
+    uint32_t tiles = 0;
+    for (int r = 0; r < M; ++r) {
+        const uint32_t cnt = level_begin(n, L0 + r + 1) - level_begin(n, L0 + r);
+        const uint32_t t = (cnt + per - 1) / per;
+        tiles = t > tiles ? t : tiles;
+    }
+    return tiles;
 }
+// (stage, group)-major item ranges, so that a stage's items are contiguous
+__global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
+                                     uint32_t n_groups, LevelPlan plan, uint32_t* __restrict__ n_items) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * (uint32_t)plan.n_stages) return;
+    const uint32_t st = t / n_groups, g = t % n_groups;
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
+    const uint32_t nh = g_hyp[g + 1] - g_hyp[g];
+    n_items[t] = stage_tiles(n, plan.L0[st], plan.M[st]) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK);
+}
+// item: sub_begin = first row of the subset, npts = its size, pad = tile index within the stage
 __global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
-                                    uint32_t n_groups, const uint32_t* __restrict__ item_off, WorkItem* __restrict__ items) {
+                                    uint32_t n_groups, LevelPlan plan, const uint32_t* __restrict__ item_off,
+                                    WorkItem* __restrict__ items) {
     const uint32_t t = blockIdx.x;
-    if (t >= n_groups * EL_LEVELS) return;
-    const uint32_t L = t / n_groups, g = t % n_groups;
+    if (t >= n_groups * (uint32_t)plan.n_stages) return;
+    const uint32_t st = t / n_groups, g = t % n_groups;
     const unsigned long long sb = sub_off[g];
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
-    const uint32_t b0 = level_begin(n, (int)L), np = level_begin(n, (int)L + 1) - b0;
     const uint32_t hb = g_hyp[g], nh = g_hyp[g + 1] - hb;
-    const uint32_t tiles = (np + SCORE_TILE - 1) / SCORE_TILE, chunks = (nh + EL_HCHUNK - 1) / EL_HCHUNK;
+    const uint32_t tiles = stage_tiles(n, plan.L0[st], plan.M[st]), chunks = (nh + EL_HCHUNK - 1) / EL_HCHUNK;
     const uint32_t base = item_off[t];
     for (uint32_t k = threadIdx.x; k < tiles * chunks; k += blockDim.x) {
         const uint32_t tile = k % tiles, chunk = k / tiles;
         WorkItem w;
-        w.sub_begin = sb + b0 + (unsigned long long)tile * SCORE_TILE;
-        w.npts = min((uint32_t)SCORE_TILE, np - tile * SCORE_TILE);
+        w.sub_begin = sb;
+        w.npts = n;
         w.hyp_begin = hb + chunk * EL_HCHUNK;
         w.hyp_end = min(hb + nh, w.hyp_begin + EL_HCHUNK);
-        w.pad = 0;
+        w.pad = tile;
         items[base + k] = w;
     }
 }
 void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                          uint32_t* n_items) {
+                          const LevelPlan& plan, uint32_t* n_items) {
     if (!n_groups) return;
     ++g_launch_count;
-    const uint32_t n = n_groups * EL_LEVELS;
-    el_work_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(sub_off, g_hyp, n_groups, n_items);
+    const uint32_t n = n_groups * (uint32_t)plan.n_stages;
+    el_work_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(sub_off, g_hyp, n_groups, plan, n_items);
 }
 void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                         const uint32_t* item_off, WorkItem* items) {
+                         const LevelPlan& plan, const uint32_t* item_off, WorkItem* items) {
     if (!n_groups) return;
     ++g_launch_count;
-    el_work_fill_kernel<<<n_groups * EL_LEVELS, 128, 0, st>>>(sub_off, g_hyp, n_groups, item_off, items);
+    el_work_fill_kernel<<<n_groups * (uint32_t)plan.n_stages, 128, 0, st>>>(sub_off, g_hyp, n_groups, plan, item_off, items);
+}
+uint64_t el_items_bound(uint64_t n_points, uint64_t n_hyp) {
+    // sum over the stages of (tiles x hypothesis chunks): tiles of a stage <= its points / 128 + 1 + the unevenness of
+    // its levels (a few points), at most EL_LEVELS stages
+    return (n_points / SCORE_TILE + 2 * EL_LEVELS + 2) * ((n_hyp + EL_HCHUNK - 1) / EL_HCHUNK + 1);
 }
 
 // ---- one level: counts + first reaching position per live hypothesis ------------------------------------------------
-// Exact test of one hypothesis against the tile's point pairs A (points 0..63) and / or B (64..127): inliers c and the
-// smallest (walk position << 1 | !inlier) of a reaching element.  A pair the cull excluded is not evaluated (it holds no
-// reaching element, so it contributes neither).  Returns false when nothing reaches the grid.
+// Exact test of one hypothesis against the tile's point pairs A (point groups 0, 1) and / or B (2, 3): per point group k
+// of this lane the inlier bit (cbits) and, for a reaching element, key = walk position << 1 | !inlier.  A pair the cull
+// excluded is not evaluated (it holds no reaching element, so it contributes neither).  Returns false when nothing
+// reaches the grid.
 template <bool FUSED, bool OCC, bool DO_A, bool DO_B>
 __device__ __forceinline__ bool level_eval(const ModelDev& m, const X2& e, float sq_thres, float4 r0, float4 r1, float4 r2,
                                            p2 pxA, p2 pyA, p2 pzA, p2 pxB, p2 pyB, p2 pzB, const uint32_t (&wpos)[4],
-                                           uint32_t tflags, uint32_t& c, uint32_t& mn) {
+                                           uint32_t tflags, uint32_t& cbits, uint32_t (&key)[4]) {
     float x[4], y[4], z[4], vx[4], vy[4], vz[4];
     if (DO_A) {
         const p2 xA = e.row_apply(r0, pxA, pyA, pzA), yA = e.row_apply(r1, pxA, pyA, pzA), zA = e.row_apply(r2, pxA, pyA, pzA);
@@ -216,15 +240,15 @@ __device__ __forceinline__ bool level_eval(const ModelDev& m, const X2& e, float
                                 pack2(z[2] - mp[2].z, z[3] - mp[3].z));
         sq[2] = lo2(sqB); sq[3] = hi2(sqB);
     }
-    c = 0;
-    mn = 0xffffffffu;
+    cbits = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        key[k] = 0xffffffffu;
         if (k < 2 ? DO_A : DO_B) {
             const uint32_t pfl = (tflags >> k) & 1u;
             const bool inl = look[k] && (sq[k] <= sq_thres) && (((pfl ^ __float_as_uint(mp[k].w)) & FLAG_TANGENT) == 0u);
-            c += inl ? 1u : 0u;
-            if (reach[k]) mn = min(mn, (wpos[k] << 1) | (inl ? 0u : 1u));
+            cbits |= inl ? (1u << k) : 0u;
+            if (reach[k]) key[k] = (wpos[k] << 1) | (inl ? 0u : 1u);
         }
     }
     return true;
@@ -273,15 +297,15 @@ __device__ __forceinline__ bool box_misses_grid(const ModelDev& m, const HalfBox
     return out;
 }
 
-template <bool FUSED, bool OCC>
+template <bool FUSED, bool OCC, int M>
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     score_level_kernel(LevelArgs a, p2 k_nz, p2 k_one) {
-    static_assert(SCORE_P == 4, "two point pairs per lane");
+    static_assert(SCORE_P == 4 && (M == 1 || M == 2 || M == 4), "two point pairs per lane, 4 / M chunks per level");
     __shared__ float4 s_rows[(SCORE_THREADS / 32) * 32 * 3];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float4* my_rows = s_rows + warp * 32 * 3;
-    const uint32_t item_begin = a.item_off[a.level * a.n_groups], item_end = a.item_off[(a.level + 1) * a.n_groups];
+    const uint32_t item_begin = a.item_off[a.stage * a.n_groups], item_end = a.item_off[(a.stage + 1) * a.n_groups];
     const ModelDev& m = a.model;
     X2 e;
     e.nz = k_nz; e.one = k_one; e.mone = 0ull;
@@ -291,8 +315,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= item_end) break;
         const WorkItem w = a.items[item];
-        // points k = 0..3 of this lane: pairs A = (0, 1) = tile points 0..63, B = (2, 3) = 64..127.  A level's tile spans
-        // ~20x the subset range a full tile does, so each pair gets its own box and is culled on its own.
+        // point group k of this lane: chunk w.pad * (4 / M) + k / M of level L0 + k % M (see stage_tiles); pairs
+        // A = groups (0, 1), B = (2, 3).  For M < 4 the two pairs cover different stretches of the subset, so each gets
+        // its own box and is culled on its own.
         float px[4], py[4], pz[4];
         uint32_t wpos[4];     // walk position of point k (only meaningful where the point is live)
         uint32_t tflags = 0;  // bit k: tangent_mask_ of point k
@@ -301,16 +326,19 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
         float mx[2][3] = {{-3.0e38f, -3.0e38f, -3.0e38f}, {-3.0e38f, -3.0e38f, -3.0e38f}};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t q = k * 32 + lane;
             px[k] = py[k] = pz[k] = nanv;  // masked / padding points: NaN, never reaching, never inliers
             wpos[k] = 0x7fffffffu;
-            if (q < w.npts) {
-                const uint32_t idx = (uint32_t)a.lvl_idx[w.sub_begin + q];
+            const int lvl = a.L0 + (k % M);
+            const uint32_t b0 = level_begin(w.npts, lvl), cnt = level_begin(w.npts, lvl + 1) - b0;
+            const uint32_t q = (w.pad * (4 / M) + (uint32_t)(k / M)) * 32u + lane;  // position within the level
+            if (q < cnt) {
+                const unsigned long long row = w.sub_begin + b0 + q;
+                const uint32_t idx = (uint32_t)a.lvl_idx[row];
                 const float4 v = a.scene.pos[idx];
                 const uint32_t fl = __float_as_uint(v.w);
                 if (!(fl & FLAG_MASKED)) {  // mask_ (scene.hpp:434): skipped before anything is counted
                     px[k] = v.x; py[k] = v.y; pz[k] = v.z;
-                    wpos[k] = a.lvl_pos[w.sub_begin + q];
+                    wpos[k] = a.lvl_pos[row];
                     if (fl & FLAG_TANGENT) tflags |= 1u << k;
                     mn[k >> 1][0] = fminf(mn[k >> 1][0], v.x); mx[k >> 1][0] = fmaxf(mx[k >> 1][0], v.x);
                     mn[k >> 1][1] = fminf(mn[k >> 1][1], v.y); mx[k >> 1][1] = fmaxf(mx[k >> 1][1], v.y);
@@ -352,62 +380,84 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                     atomicAdd(&a.stats[4], (unsigned long long)(__popc(maskA) + __popc(maskB)));
                 }
             }
-            uint32_t mycnt = 0, mymin = 0xffffffffu;
+            uint32_t mycnt = 0;  // level r of the stage: bits 8r .. 8r+7 (at most 128 points of a level per tile)
+            uint32_t mymin[M];
+#pragma unroll
+            for (int r = 0; r < M; ++r) mymin[r] = 0xffffffffu;
             while (mask) {
                 const int hh = __ffs(mask) - 1;
                 mask &= mask - 1u;
                 const float4 r0 = my_rows[hh], r1 = my_rows[32 + hh], r2 = my_rows[64 + hh];
                 const bool doA = (maskA >> hh) & 1u, doB = (maskB >> hh) & 1u;  // warp-uniform
-                uint32_t c, mnk;
+                uint32_t cbits, key[4];
                 bool any;
                 if (doA && doB)
                     any = level_eval<FUSED, OCC, true, true>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
-                                                             tflags, c, mnk);
+                                                             tflags, cbits, key);
                 else if (doA)
                     any = level_eval<FUSED, OCC, true, false>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
-                                                              tflags, c, mnk);
+                                                              tflags, cbits, key);
                 else
                     any = level_eval<FUSED, OCC, false, true>(m, e, a.sq_thres, r0, r1, r2, pxA, pyA, pzA, pxB, pyB, pzB, wpos,
-                                                              tflags, c, mnk);
+                                                              tflags, cbits, key);
                 if (!any) continue;
                 if (a.stats && lane == 0) atomicAdd(&a.stats[3], 1ull);
-                const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
-                const uint32_t wmn = __reduce_min_sync(0xffffffffu, mnk);
-                if (lane == hh) {
-                    mycnt = tot;
-                    mymin = wmn;
+#pragma unroll
+                for (int r = 0; r < M; ++r) {  // the point groups k with k % M == r belong to level L0 + r
+                    uint32_t c = 0, mnk = 0xffffffffu;
+#pragma unroll
+                    for (int k = r; k < 4; k += M) {
+                        c += (cbits >> k) & 1u;
+                        mnk = min(mnk, key[k]);
+                    }
+                    const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+                    const uint32_t wmn = __reduce_min_sync(0xffffffffu, mnk);
+                    if (lane == hh) {
+                        mycnt |= tot << (8 * r);
+                        mymin[r] = wmn;
+                    }
                 }
             }
-            if (mycnt) atomicAdd(&a.lvl_cnt[h], mycnt);
-            if (mymin != 0xffffffffu) atomicMin(&a.minkey[h], mymin);
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                const uint32_t c = (mycnt >> (8 * r)) & 0xffu;
+                if (c) atomicAdd(&a.lvl_cnt[(size_t)r * a.cap + h], c);
+                if (mymin[r] != 0xffffffffu) atomicMin(&a.minkey[(size_t)r * a.cap + h], mymin[r]);
+            }
         }
     }
 }
-void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused) {
-    ++g_launch_count;
+template <bool FUSED, bool OCC>
+static void launch_level_m(cudaStream_t st, const LevelArgs& a, int grid, int M) {
     const p2 nz = host_pair(-0.0f), one = host_pair(1.0f);
+    if (M == 4) score_level_kernel<FUSED, OCC, 4><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+    else if (M == 2) score_level_kernel<FUSED, OCC, 2><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+    else score_level_kernel<FUSED, OCC, 1><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+}
+void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused, int M) {
+    ++g_launch_count;
     if (fused) {
-        if (a.model.occ) score_level_kernel<true, true><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
-        else score_level_kernel<true, false><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+        if (a.model.occ) launch_level_m<true, true>(st, a, grid, M);
+        else launch_level_m<true, false>(st, a, grid, M);
     } else {
-        if (a.model.occ) score_level_kernel<false, true><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
-        else score_level_kernel<false, false><<<grid, SCORE_THREADS, 0, st>>>(a, nz, one);
+        if (a.model.occ) launch_level_m<false, true>(st, a, grid, M);
+        else launch_level_m<false, false>(st, a, grid, M);
     }
 }
 int score_level_max_blocks_per_sm(bool fused) {
     int nb = 0, nb2 = 0;
     if (fused) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<true, false>, SCORE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<true, true>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<true, false, 4>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<true, true, 4>, SCORE_THREADS, 0);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<false, false>, SCORE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<false, true>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_level_kernel<false, false, 4>, SCORE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, score_level_kernel<false, true, 4>, SCORE_THREADS, 0);
     }
     nb = nb < nb2 ? nb : nb2;
     return nb > 0 ? nb : 1;
 }
 
-// ---- checkpoint L after level L (L = 0: nothing to test; L = 18 also closes the walk) ------------------------------
+// ---- the checkpoints of a stage's levels, in order (level 0 has none; level 18 also closes the walk) ---------------
 __global__ void __launch_bounds__(256)
     el_eval_kernel(EvalArgs a) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,41 +466,44 @@ __global__ void __launch_bounds__(256)
     if (h < *a.n_local && a.alive[h]) {
         const uint32_t g = a.g_of_hyp[h];
         const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - a.sub_off[g]);
-        const uint32_t cnt = a.lvl_cnt[h], mk = a.minkey[h];
-        a.lvl_cnt[h] = 0u;
-        a.minkey[h] = 0xffffffffu;
-        const int L = a.level;
-        bool open = true;  // still walking after this checkpoint
-        if (L >= 1) {
-            if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
-                // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint may
-                // also claim — walked exactly afterwards
-                irregular = true;
-                a.alive[h] = 0;
-                open = false;
-            } else {
+        uint32_t corrs = a.corrs[h];
+        bool open = true;  // still walking
+        for (int r = 0; r < a.M; ++r) {
+            const size_t slot = (size_t)r * a.cap + h;
+            const uint32_t cnt = a.lvl_cnt[slot], mk = a.minkey[slot];
+            a.lvl_cnt[slot] = 0u;
+            a.minkey[slot] = 0xffffffffu;
+            if (!open) continue;  // (the accumulators of the later levels are still reset)
+            const int L = a.L0 + r;
+            if (L >= 1) {
+                if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
+                    // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint
+                    // may also claim — walked exactly afterwards
+                    irregular = true;
+                    open = false;
+                    continue;
+                }
                 const uint32_t inl = (mk & 1u) ? 0u : 1u, tried = (mk >> 1) + 1u;
-                const uint32_t c_here = a.corrs[h] + inl;
+                const uint32_t c_here = corrs + inl;
                 const uint32_t upper = early_drop_upper(tried, nsub, c_here);
                 if ((float)upper < a.accept_bound) {  // scene.hpp:500-503
                     a.counts[h] = c_here;
                     a.dropped[h] = 1;
-                    a.alive[h] = 0;
                     tested = tried;
                     open = false;
+                    continue;
                 }
             }
-        }
-        if (open) {
-            const uint32_t total = a.corrs[h] + cnt;
-            a.corrs[h] = total;
+            corrs += cnt;
             if (L == EL_LEVELS - 1) {  // passed every checkpoint: the walk ends with the subset
-                a.counts[h] = total;
+                a.counts[h] = corrs;
                 a.dropped[h] = 0;
-                a.alive[h] = 0;
                 tested = nsub;
+                open = false;
             }
         }
+        if (open) a.corrs[h] = corrs;
+        else a.alive[h] = 0;
     }
     const uint32_t irr = __ballot_sync(0xffffffffu, irregular);
     if (irr) {
@@ -472,7 +525,7 @@ void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound) {
     el_eval_kernel<<<(n_hyp_bound + 255) / 256, 256, 0, st>>>(a);
 }
 
-// alive[h] = 1 for h < n_local, per-hypothesis accumulators reset
+// alive[h] = 1 for h < n_local, per-hypothesis accumulators reset (lvl_cnt / minkey: EL_MAX_MERGE levels x cap)
 __global__ void el_init_kernel(const uint32_t* __restrict__ n_local, uint32_t cap, uint8_t* __restrict__ alive,
                                uint32_t* __restrict__ corrs, uint32_t* __restrict__ lvl_cnt, uint32_t* __restrict__ minkey,
                                uint8_t* __restrict__ dropped, uint32_t* __restrict__ counts) {
@@ -480,8 +533,11 @@ __global__ void el_init_kernel(const uint32_t* __restrict__ n_local, uint32_t ca
     if (h >= cap) return;
     alive[h] = h < *n_local ? 1 : 0;
     corrs[h] = 0u;
-    lvl_cnt[h] = 0u;
-    minkey[h] = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < EL_MAX_MERGE; ++r) {
+        lvl_cnt[(size_t)r * cap + h] = 0u;
+        minkey[(size_t)r * cap + h] = 0xffffffffu;
+    }
     dropped[h] = 0;
     counts[h] = 0u;
 }

@@ -84,20 +84,28 @@ constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoint
 #endif
 constexpr int EL_HCHUNK = TM_EL_HCHUNK;  // hypotheses per work item: a level holds 1/20 of a subset's tiles, so the
                                          // items are made shorter than the full scorer's to keep the tail small
+constexpr int EL_MAX_MERGE = 4;  // levels scored by one launch ("stage")
+struct LevelPlan {               // the stages of a run: stage s scores levels L0[s] .. L0[s] + M[s] - 1, M in {1, 2, 4}
+    int n_stages;
+    int L0[EL_LEVELS];
+    int M[EL_LEVELS];
+};
 struct LevelArgs {
     CloudDev scene;
     ModelDev model;
     const int32_t* lvl_idx;    // subset rows regrouped by level (walk_levels_kernel): scene index ...
     const uint32_t* lvl_pos;   // ... and walk position of every element
-    const WorkItem* items;     // (level, group)-major work list
-    const uint32_t* item_off;  // [EL_LEVELS * n_groups + 1]
+    const WorkItem* items;     // (stage, group)-major work list
+    const uint32_t* item_off;  // [n_stages * n_groups + 1]
     uint32_t n_groups;
-    int level;
-    uint32_t* work_counter;    // this level's
+    int stage;
+    int L0;                    // first level of the stage
+    uint32_t* work_counter;    // this stage's
     const float4* T;
     const uint8_t* alive;
-    uint32_t* lvl_cnt;         // inliers of this level per hypothesis
-    uint32_t* minkey;          // min over reaching elements of (walk position << 1) | !inlier
+    uint32_t cap;              // hypothesis capacity = stride of the per-level accumulators
+    uint32_t* lvl_cnt;         // [EL_MAX_MERGE][cap] inliers per level of the stage and hypothesis
+    uint32_t* minkey;          // [EL_MAX_MERGE][cap] min over reaching elements of (walk position << 1) | !inlier
     float sq_thres;
     unsigned long long* stats = nullptr;  // optional debug counters: [0] (tile, hyp) pairs, [1] of live hypotheses,
                                           // [2] surviving the cull, [3] with a reaching element, [4] 64-point
@@ -108,7 +116,8 @@ struct EvalArgs {
     const uint32_t* g_of_hyp;
     const unsigned long long* sub_off;
     uint8_t* alive;
-    uint32_t* corrs;           // inliers of the levels before the current one
+    uint32_t* corrs;           // inliers of the levels before the current stage
+    uint32_t cap;
     uint32_t* lvl_cnt;
     uint32_t* minkey;
     uint32_t* counts;
@@ -117,7 +126,7 @@ struct EvalArgs {
     uint32_t* n_irregular;
     unsigned long long* n_tests;
     float accept_bound;
-    int level;
+    int L0, M;
 };
 
 struct IcpState {
@@ -209,10 +218,11 @@ void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int3
 void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
                         int32_t* lvl_idx, uint32_t* lvl_pos);
 void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                          uint32_t* n_items);
+                          const LevelPlan& plan, uint32_t* n_items);
 void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                         const uint32_t* item_off, WorkItem* items);
-void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused);
+                         const LevelPlan& plan, const uint32_t* item_off, WorkItem* items);
+uint64_t el_items_bound(uint64_t n_points, uint64_t n_hyp);
+void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused, int M);
 int score_level_max_blocks_per_sm(bool fused);
 void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound);
 void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* corrs,
