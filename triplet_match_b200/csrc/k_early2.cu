@@ -17,6 +17,10 @@
 //                        before + that element's inlier bit, tried = position + 1, same bound, same comparison.  A
 //                        hypothesis that fails is dropped with exactly the walker's partial count.
 //
+// One launch ("stage") scores up to four consecutive levels, each tile holding 32-point chunks of all of them over the
+// same stretch of the subset (narrower tiles, fewer of them pass the box cull) with per-level accumulators; el_eval_kernel
+// then applies the stage's checkpoints in order.
+//
 // A level without a reaching element (or an empty level: subsets of a few points) breaks the one-level-one-checkpoint
 // correspondence; such hypotheses are flagged and re-walked exactly by score_early_drop_kernel (they touch the grid
 // almost nowhere, so they are few and cheap).  Counts, drop flags and drop points equal the walker's bit for bit
