@@ -611,7 +611,7 @@ def early_drop_legs(ctx, capi, gs, gm, rec, r_full, QP, hyp):
                     "scoring_ms": float(qe.score_kernel_ms()), "tests_per_step": int(re_.n_tests), "survivors": int(alive.sum()),
                     "best_pose_survives": bool(alive.any() and int(d["counts"][alive].max()) == int(r_full.best_inliers))}
         if mode == 2:
-            out[key]["kernel"] = "score_level_kernel x 19 checkpoint ranges (k_early2.cu)"
+            out[key]["kernel"] = "score_level_kernel: 19 checkpoint ranges in 6 launches + el_eval_kernel (k_early2.cu)"
             out[key]["walked_one_by_one"] = qe.early_walked()
         qe.close()
     out["note"] = ("project_(early_out=true) semantics, bit-exact with the reference incl. drop points: in the subset's own order "
