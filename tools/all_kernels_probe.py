@@ -1,5 +1,6 @@
 """One pass over every kernel of the path on the C2 workload (for an ncu --metrics capture):
-model::init, scene upload + tangent-mask pre-processing, full query, early-drop query, ICP."""
+model::init, scene upload + tangent-mask pre-processing, full query, early-drop queries (subset order; even walk, staged), ICP,
+correspondence lists."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +15,7 @@ gm = hm.upload(ctx)
 gs = capi.Scene(ctx, scene.pos, scene.nrm, scene.tgt, scene.tangent_mask)
 gs.compute_tangent_mask(30, 0.2, apply=False)
 rec = bench_wl.c2_record(scene, hm.diameter, 1)
-for eo in (False, True):
+for eo in (0, 1, 2):
     q = capi.Query(gs, gm, **bench_wl.QP, early_out=eo, hyp_limit=1 << 20, max_hypotheses=1 << 20, icp_top_k=64, max_icp_iterations=5)
     q.set_pairs(rec.outer, rec.pair_outer, rec.pair_j)
     q.run()
@@ -22,4 +23,4 @@ for eo in (False, True):
     print("early_out", eo, "scored", r.n_scored, "tests", r.n_tests, "best", r.best_inliers, flush=True)
     q.close()
 d = np.eye(4, dtype=np.float32).T.reshape(1, 16)
-gs.correspondences(gm, d[0], 1.0)
+gs.correspondences_batch(gm, np.repeat(d, 4, axis=0), 1.0)
