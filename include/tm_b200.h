@@ -234,6 +234,10 @@ int tm_uvicp_correlation(tm_ctx* ctx, const float* scene4, uint32_t n_scene, con
 /* self-test hook: exclusive prefix sum (n + 1 x u64) of n x u32 with the chained multi-CTA scan that computes the
  * hypothesis offsets of long recorded lists */
 int tm_ctx_scan_u64(tm_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out);
+/* self-test hook: the top-k selection of the resident query's ICP stage on caller-supplied counts (count descending,
+ * index ascending; zero counts and entries with excluded[i] != 0 are never selected; excluded may be NULL).
+ * ids: k entries, 0xFFFFFFFF where fewer than k qualify. */
+int tm_ctx_select_topk(tm_ctx* ctx, const uint32_t* counts, const uint8_t* excluded, uint32_t n, uint32_t k, uint32_t* ids);
 
 /* ---- resident query: the whole recorded-list search in one call --------- */
 typedef struct tm_query_params {

@@ -368,3 +368,38 @@ def test_early_drop_levels_on_tiny_and_sparse_subsets(ctx, keep):
         if os.environ.get("TM_EARLY_LEVELS", "1") != "0":  # (the knob routes everything through the walker)
             assert max(walked) > 0  # the irregular path is exercised
     gs.close(); gm.close()
+
+
+@pytest.mark.gpu
+def test_topk_selection_paths(ctx):
+    """The top-k of the ICP stage (count descending, index ascending): threshold + compaction + ranking where few keys
+    compete, the slice kernels where the short list overflows (many equal counts); both equal a stable host sort.
+    Zero counts and excluded entries never appear; fewer than k candidates leave 0xFFFFFFFF."""
+    rng = np.random.default_rng(3)
+
+    def expect(counts, k, excluded=None):
+        ok = counts > 0
+        if excluded is not None:
+            ok &= excluded == 0
+        idx = np.flatnonzero(ok)
+        order = idx[np.argsort(-counts[idx].astype(np.int64), kind="stable")][:k]
+        out = np.full(k, 0xFFFFFFFF, np.uint32)
+        out[: order.size] = order
+        return out
+
+    cases = []
+    cases.append((rng.integers(0, 50000, 1 << 20).astype(np.uint32), 64, None))          # the usual case: short list
+    cases.append((np.full(300000, 7, np.uint32), 64, None))                                # all equal: the list overflows
+    c = rng.integers(0, 3, 200000).astype(np.uint32)
+    cases.append((c, 100, (rng.random(c.size) < 0.5).astype(np.uint8)))                    # few distinct values, exclusions
+    cases.append((np.zeros(5000, np.uint32), 16, None))                                    # nothing qualifies
+    c = np.zeros(70000, np.uint32); c[[5, 69999, 4096, 4095]] = [9, 9, 3, 12]
+    cases.append((c, 8, None))                                                             # fewer than k candidates
+    cases.append((rng.integers(1, 1000, 37).astype(np.uint32), 64, None))                  # n < k
+    c = rng.integers(0, 1 << 31, 4096 * 70 + 13).astype(np.uint32)
+    cases.append((c, 64, None))                                                            # more slices than k, huge counts
+    c = np.arange(1, 4096 * 80 + 1, dtype=np.uint32)[::-1].copy()
+    cases.append((c, 4096, None))                                                          # k = 4096, descending
+    for counts, k, ex in cases:
+        got = ctx.select_topk(counts, k, ex)
+        assert np.array_equal(got, expect(counts, k, ex)), (counts.size, k)

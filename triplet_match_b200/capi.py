@@ -59,7 +59,7 @@ EXPORTS = [
     "tm_ctx_stream", "tm_ctx_sm_count", "tm_timer_start", "tm_timer_stop", "tm_ctx_flush_l2",
     "tm_ctx_kernel_launches", "tm_ctx_scan_u64", "tm_ctx_measure_l2_gather", "tm_model_upload", "tm_model_destroy", "tm_voxel_fill",
     "tm_scene_upload", "tm_scene_upload_sorted", "tm_scene_set_mask", "tm_scene_destroy", "tm_features", "tm_probe",
-    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_correspondences_batch", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked", "tm_early_level_begin",
+    "tm_hypotheses", "tm_ball_subsets", "tm_score", "tm_walk_stride", "tm_correspondences", "tm_correspondences_batch", "tm_ctx_select_topk", "tm_icp", "tm_icp_pose_sharded", "tm_query_set_balance", "tm_query_frontend_ms", "tm_query_early_walked", "tm_early_level_begin",
     "tm_traits_project", "tm_scene_knn", "tm_scene_curvature", "tm_scene_tangent_mask", "tm_uvicp_projection", "tm_uvicp_correlation", "tm_query_create", "tm_query_destroy", "tm_query_set_pairs",
     "tm_query_set_shard", "tm_query_run", "tm_query_result_get", "tm_query_best_key_device",
     "tm_query_score_kernel_ms",
@@ -169,6 +169,14 @@ class Context:
 
     def flush_l2(self):
         _chk(self.lib.tm_ctx_flush_l2(self.h))
+
+    def select_topk(self, counts, k: int, excluded=None) -> np.ndarray:
+        """tm_ctx_select_topk (self-test hook): ids of the k largest counts (ties: lower index first)."""
+        cnt = np.ascontiguousarray(counts, dtype=np.uint32)
+        ex = None if excluded is None else np.ascontiguousarray(excluded, dtype=np.uint8)
+        ids = np.zeros(k, dtype=np.uint32)
+        _chk(self.lib.tm_ctx_select_topk(self.h, _p(cnt), _p(ex), C.c_uint32(cnt.size), C.c_uint32(k), _p(ids)))
+        return ids
 
     def scan_u64(self, values):
         """tm_ctx_scan_u64: exclusive prefix sum (n + 1 entries) on the device."""

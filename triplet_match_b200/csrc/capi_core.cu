@@ -970,6 +970,27 @@ int tm_ctx_scan_u64(tm_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out) {
     return TM_OK;
 }
 
+// self-test hook: the top-k selection of the resident query's ICP stage (by count descending, index ascending; zero
+// counts and excluded entries never selected) on caller-supplied counts; ids: k x u32, 0xFFFFFFFF where fewer than k
+// qualify
+int tm_ctx_select_topk(tm_ctx* c, const uint32_t* counts, const uint8_t* excluded, uint32_t n, uint32_t k, uint32_t* ids) {
+    REQUIRE(c && ids && (n == 0 || counts) && k > 0 && k <= 4096, "tm_ctx_select_topk: bad argument");
+    TRY(bind(c));
+    DevBuf &dc = c->scratch[0], &dx = c->scratch[1], &dn = c->scratch[2], &did = c->scratch[3], &scr = c->scratch[4];
+    const uint64_t cap = std::max<uint32_t>(n, 1);
+    TRY(dc.ensure(cap * 4)); TRY(dx.ensure(cap)); TRY(dn.ensure(4)); TRY(did.ensure(k * 4ull));
+    TRY(scr.ensure(topk_scratch_bytes(cap, k)));
+    if (n) CU(cudaMemcpyAsync(dc.p, counts, n * 4ull, cudaMemcpyHostToDevice, c->stream));
+    if (n && excluded) CU(cudaMemcpyAsync(dx.p, excluded, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dn.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
+    launch_select_topk(c->stream, dc.as<uint32_t>(), nullptr, excluded ? dx.as<uint8_t>() : nullptr, dn.as<uint32_t>(), cap, k,
+                       did.as<uint32_t>(), scr.as<unsigned long long>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ids, did.p, k * 4ull, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
 int tm_ctx_measure_l2_gather(tm_ctx* c, uint64_t working_set_bytes, double* gb_per_s) {
     REQUIRE(c && gb_per_s, "tm_ctx_measure_l2_gather: null argument");
     REQUIRE(working_set_bytes >= (1u << 20), "tm_ctx_measure_l2_gather: working set too small");

@@ -4,6 +4,8 @@
 // one stream-ordered sequence with no host round trip.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "tm_kernels.cuh"
 
 namespace tmk {
@@ -168,10 +170,9 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = wbest[w] > r ? wbest[w] : r;
     return r;
 }
-__global__ void __launch_bounds__(1024)
-    topk_slice_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
-                      const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local, uint32_t k,
-                      unsigned long long* __restrict__ cand) {
+__device__ __forceinline__ void topk_slice_body(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
+                                                const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local,
+                                                uint32_t k, unsigned long long* __restrict__ cand) {
     __shared__ unsigned long long keys[TOPK_SLICE];
     __shared__ unsigned long long wbest[32];
     const uint32_t n = *n_local;
@@ -200,9 +201,8 @@ __global__ void __launch_bounds__(1024)
         }
     }
 }
-__global__ void __launch_bounds__(1024)
-    topk_final_kernel(const unsigned long long* __restrict__ cand, uint32_t n_cand, uint32_t k,
-                      uint32_t* __restrict__ topk_ids) {
+__device__ __forceinline__ void topk_final_body(const unsigned long long* __restrict__ cand, uint32_t n_cand, uint32_t k,
+                                                uint32_t* __restrict__ topk_ids) {
     __shared__ unsigned long long wbest[32];
     unsigned long long last = ~0ull;
     for (uint32_t r = 0; r < k; ++r) {
@@ -222,18 +222,133 @@ __global__ void __launch_bounds__(1024)
         }
     }
 }
-// capacity = upper bound of *n_local (sizes the grid); scratch_keys: ceil(capacity / TOPK_SLICE) * k u64
+// ---- fast path: threshold + compaction -----------------------------------------------------------------------------
+// The k-th largest of the slice maxima is a lower bound T0 of the k-th largest key overall (those maxima are k keys
+// >= T0), so the top k are among the keys >= T0 — usually a few hundred of the 2^20.  They are compacted into a short
+// list and ranked there.  When the list would overflow (many equal counts) a flag routes the selection through the
+// slice kernels above instead; both paths select the same k keys.
+constexpr uint32_t TOPK_LIST = 4096;  // 32 KB of static shared memory in the rank kernel
+__device__ __forceinline__ unsigned long long topk_key(const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
+                                                       uint32_t i, uint32_t n) {
+    if (i < n && (!valid || valid[i]) && (!excluded || !excluded[i]) && counts[i])
+        return ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+    return 0ull;
+}
+__global__ void __launch_bounds__(1024)
+    topk_slice_max_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
+                          const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local,
+                          unsigned long long* __restrict__ slice_max) {
+    __shared__ unsigned long long wbest[32];
+    const uint32_t n = *n_local, base = blockIdx.x * TOPK_SLICE;
+    unsigned long long best = 0;
+    for (uint32_t t = threadIdx.x; t < TOPK_SLICE; t += blockDim.x) {
+        const unsigned long long key = topk_key(counts, valid, excluded, base + t, n);
+        best = key > best ? key : best;
+    }
+    best = block_max_u64(best, wbest);
+    if (threadIdx.x == 0) slice_max[blockIdx.x] = best;
+}
+// ctrl[0] = T0 (0 when fewer than k slices hold a key), ctrl[1] = list length, ctrl[2] = overflow flag
+__global__ void __launch_bounds__(1024)
+    topk_threshold_kernel(const unsigned long long* __restrict__ slice_max, uint32_t n_slices, uint32_t k,
+                          unsigned long long* __restrict__ ctrl) {
+    if (threadIdx.x == 0) { ctrl[0] = 0ull; ctrl[1] = 0ull; ctrl[2] = 0ull; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_slices; i += blockDim.x) {
+        const unsigned long long v = slice_max[i];
+        if (!v) continue;
+        uint32_t rank = 0;  // keys are unique: exactly one maximum has rank k - 1
+        for (uint32_t j = 0; j < n_slices; ++j) rank += slice_max[j] > v ? 1u : 0u;
+        if (rank == k - 1u) ctrl[0] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+    topk_compact_kernel(const uint32_t* __restrict__ counts, const uint8_t* __restrict__ valid,
+                        const uint8_t* __restrict__ excluded, const uint32_t* __restrict__ n_local,
+                        unsigned long long* __restrict__ ctrl, unsigned long long* __restrict__ list) {
+    const uint32_t n = *n_local;
+    const unsigned long long T0 = ctrl[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = topk_key(counts, valid, excluded, i, n);
+        if (key && key >= T0) {
+            const unsigned long long at = atomicAdd(&ctrl[1], 1ull);
+            if (at < TOPK_LIST) list[at] = key;
+            else ctrl[2] = 1ull;
+        }
+    }
+}
+// rank the compacted keys; rank r < k goes to topk_ids[r]
+__global__ void __launch_bounds__(1024)
+    topk_rank_kernel(const unsigned long long* __restrict__ ctrl, const unsigned long long* __restrict__ list, uint32_t k,
+                     uint32_t* __restrict__ topk_ids) {
+    if (ctrl[2]) return;  // overflow: the slice kernels produce the result
+    __shared__ unsigned long long keys[TOPK_LIST];
+    const uint32_t m = (uint32_t)ctrl[1];
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) keys[i] = list[i];
+    for (uint32_t r = threadIdx.x; r < k; r += blockDim.x) topk_ids[r] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned long long v = keys[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < m; ++j) rank += keys[j] > v ? 1u : 0u;
+        if (rank < k) topk_ids[rank] = 0xFFFFFFFFu - (uint32_t)(v & 0xFFFFFFFFull);
+    }
+}
+// the slice path, only when the list overflowed (uniform early exit otherwise)
+__global__ void __launch_bounds__(1024)
+    topk_slice_guarded_kernel(const unsigned long long* __restrict__ ctrl, const uint32_t* __restrict__ counts,
+                              const uint8_t* __restrict__ valid, const uint8_t* __restrict__ excluded,
+                              const uint32_t* __restrict__ n_local, uint32_t k, unsigned long long* __restrict__ cand,
+                              int force);
+__global__ void __launch_bounds__(1024)
+    topk_final_guarded_kernel(const unsigned long long* __restrict__ ctrl, const unsigned long long* __restrict__ cand,
+                              uint32_t n_cand, uint32_t k, uint32_t* __restrict__ topk_ids, int force);
+static bool topk_force_slices() {  // TM_TOPK_SLICES=1: development knob, read once — always select through the slice kernels
+    static const bool v = [] {
+        const char* e = getenv("TM_TOPK_SLICES");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
+
+// capacity = upper bound of *n_local (sizes the grid); scratch_keys: topk_scratch_bytes(capacity, k)
+// layout: [slices * k] slice candidates | [slices] slice maxima | [TOPK_LIST] list | [4] ctrl
 size_t topk_scratch_bytes(uint64_t capacity, uint32_t k) {
-    return (size_t)((capacity + TOPK_SLICE - 1) / TOPK_SLICE) * k * 8 + 8;
+    const size_t slices = (size_t)((capacity + TOPK_SLICE - 1) / TOPK_SLICE);
+    return (slices * k + slices + TOPK_LIST + 4) * 8 + 8;
 }
 void launch_select_topk(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                         const uint32_t* n_local, uint64_t capacity, uint32_t k, uint32_t* topk_ids,
                         unsigned long long* scratch_keys) {
     if (!k) return;
     const uint32_t slices = (uint32_t)std::max<uint64_t>(1, (capacity + TOPK_SLICE - 1) / TOPK_SLICE);
-    g_launch_count += 2;
-    topk_slice_kernel<<<slices, 1024, 0, st>>>(counts, valid, excluded, n_local, k, scratch_keys);
-    topk_final_kernel<<<1, 1024, 0, st>>>(scratch_keys, slices * k, k, topk_ids);
+    unsigned long long* cand = scratch_keys;
+    unsigned long long* slice_max = cand + (size_t)slices * k;
+    unsigned long long* list = slice_max + slices;
+    unsigned long long* ctrl = list + TOPK_LIST;
+    g_launch_count += 6;
+    topk_slice_max_kernel<<<slices, 1024, 0, st>>>(counts, valid, excluded, n_local, slice_max);
+    topk_threshold_kernel<<<1, 1024, 0, st>>>(slice_max, slices, k, ctrl);
+    topk_compact_kernel<<<std::min<uint32_t>(slices * 4u, 1184u), 256, 0, st>>>(counts, valid, excluded, n_local, ctrl, list);
+    topk_rank_kernel<<<1, 1024, 0, st>>>(ctrl, list, k, topk_ids);
+    const int force = topk_force_slices() ? 1 : 0;
+    topk_slice_guarded_kernel<<<slices, 1024, 0, st>>>(ctrl, counts, valid, excluded, n_local, k, cand, force);
+    topk_final_guarded_kernel<<<1, 1024, 0, st>>>(ctrl, cand, slices * k, k, topk_ids, force);
+}
+
+__global__ void __launch_bounds__(1024)
+    topk_slice_guarded_kernel(const unsigned long long* __restrict__ ctrl, const uint32_t* __restrict__ counts,
+                              const uint8_t* __restrict__ valid, const uint8_t* __restrict__ excluded,
+                              const uint32_t* __restrict__ n_local, uint32_t k, unsigned long long* __restrict__ cand,
+                              int force) {
+    if (!ctrl[2] && !force) return;
+    topk_slice_body(counts, valid, excluded, n_local, k, cand);
+}
+__global__ void __launch_bounds__(1024)
+    topk_final_guarded_kernel(const unsigned long long* __restrict__ ctrl, const unsigned long long* __restrict__ cand,
+                              uint32_t n_cand, uint32_t k, uint32_t* __restrict__ topk_ids, int force) {
+    if (!ctrl[2] && !force) return;
+    topk_final_body(cand, n_cand, k, topk_ids);
 }
 
 __global__ void gather_rows_kernel(const float4* __restrict__ T, const uint32_t* __restrict__ ids,
