@@ -634,6 +634,11 @@ def bench_c3_c5(ctx, D, comm, capi, wl, steps, warmup, world, rank):
     c3["scaling"] = "weak"
     c3["workload"] = (f"free-form {model.n}-point model vs {scene.n}-point scene, 2^20 hypotheses per GPU, grid "
                       f"{hm.extents.tolist()}")
+    if world == 1:  # the reference's operating mode on this workload, beside full scoring (as for C2)
+        try:
+            c3["early_drop_modes"] = early_drop_legs(ctx, capi, gs, gm, rec, queries[0].result(), wl.QP, wl.HYP_PER_GPU)
+        except Exception as e:  # noqa: BLE001 - a failing side leg must not take the line with it
+            c3["early_drop_modes"] = {"error": repr(e)}
     for q in queries:
         q.close()
     # C5
