@@ -114,9 +114,10 @@ static int size_for_shard(tm_query* q) {
         if (knobs().early_levels) {
             REQUIRE(el_items < (1ull << 31), "too many work items");
             q->el_items_cap = (uint32_t)std::max<uint64_t>(el_items, 1);
-            const size_t lg = (size_t)EL_LEVELS * std::max(n_outer, 1u);  // (at most EL_LEVELS stages)
+            const size_t lg = std::max(n_outer, 1u);
             TRY(q->lvl_idx.ensure(std::max<uint64_t>(total, 1) * 4)); TRY(q->lvl_pos.ensure(std::max<uint64_t>(total, 1) * 4));
             TRY(q->el_n_items.ensure(lg * 4)); TRY(q->el_item_off.ensure((lg + 1) * 4));
+            TRY(q->el_list.ensure(cap * 8)); TRY(q->el_goff.ensure((lg + 1) * 8));
             TRY(q->el_items.ensure((size_t)q->el_items_cap * sizeof(WorkItem)));
             TRY(q->el_alive.ensure(cap)); TRY(q->el_corrs.ensure(cap * 4)); TRY(q->el_cnt.ensure(cap * 4 * EL_MAX_MERGE));
             TRY(q->el_minkey.ensure(cap * 4 * EL_MAX_MERGE)); TRY(q->el_irregular.ensure(cap * 4));
@@ -176,7 +177,7 @@ void tm_query_destroy(tm_query* q) {
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
           &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum, &q->scan_scratch,
           &q->lvl_idx, &q->lvl_pos, &q->el_n_items, &q->el_item_off, &q->el_items, &q->el_alive, &q->el_corrs, &q->el_cnt,
-          &q->el_minkey, &q->el_irregular, &q->el_ctrl})
+          &q->el_minkey, &q->el_irregular, &q->el_ctrl, &q->el_list, &q->el_goff})
         b->release();
     q->icp.release();
     delete q;
@@ -364,18 +365,18 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     QueryOut* out = q->out.as<QueryOut>();
     const tm_model* m = q->m;
     const uint32_t G = q->n_outer;
+    const uint32_t cap = (uint32_t)q->cap_hyp;
     const LevelPlan plan = level_plan();
+    const unsigned long long* sub_off = q->sub_off.as<unsigned long long>();
     launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), G, q->g_of_hyp.as<uint32_t>());
-    launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), q->sub_off.as<unsigned long long>(), G,
-                       q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
-    launch_el_work_count(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G, plan,
-                         q->el_n_items.as<uint32_t>());
-    launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(),
-                              (uint64_t)plan.n_stages * G);
-    launch_el_work_fill(c->stream, q->sub_off.as<unsigned long long>(), q->g_hyp.as<uint32_t>(), G, plan,
-                        q->el_item_off.as<uint32_t>(), q->el_items.as<WorkItem>());
-    launch_el_init(c->stream, &out->n_local, (uint32_t)q->cap_hyp, q->el_alive.as<uint8_t>(), q->el_corrs.as<uint32_t>(),
+    launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), sub_off, G, q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
+    // the list of hypotheses still alive (two buffers, swapped after every stage) and its per-subset ranges: at first
+    // every hypothesis of the shard, ranges = g_hyp
+    uint32_t* hl[2] = {q->el_list.as<uint32_t>(), q->el_list.as<uint32_t>() + cap};
+    uint32_t* goff[2] = {q->el_goff.as<uint32_t>(), q->el_goff.as<uint32_t>() + (G + 1)};
+    launch_el_init(c->stream, &out->n_local, cap, q->el_alive.as<uint8_t>(), hl[0], q->el_corrs.as<uint32_t>(),
                    q->el_cnt.as<uint32_t>(), q->el_minkey.as<uint32_t>(), q->dropped.as<uint8_t>(), q->counts.as<uint32_t>());
+    CU(cudaMemcpyAsync(goff[0], q->g_hyp.p, (G + 1) * 4ull, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemsetAsync(q->el_ctrl.p, 0, (EL_LEVELS + 1) * 4, c->stream));
     LevelArgs a;
     a.scene = q->s->dev;
@@ -383,11 +384,9 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     a.lvl_idx = q->lvl_idx.as<int32_t>();
     a.lvl_pos = q->lvl_pos.as<uint32_t>();
     a.items = q->el_items.as<WorkItem>();
-    a.item_off = q->el_item_off.as<uint32_t>();
-    a.n_groups = G;
+    a.n_items = q->el_item_off.as<uint32_t>() + G;
     a.T = q->T.as<float4>();
-    a.alive = q->el_alive.as<uint8_t>();
-    a.cap = (uint32_t)q->cap_hyp;
+    a.cap = cap;
     a.lvl_cnt = q->el_cnt.as<uint32_t>();
     a.minkey = q->el_minkey.as<uint32_t>();
     a.sq_thres = sqt;
@@ -397,12 +396,11 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
         a.stats = q->stats.as<unsigned long long>();
     }
     EvalArgs e;
-    e.n_local = &out->n_local;
     e.g_of_hyp = q->g_of_hyp.as<uint32_t>();
-    e.sub_off = q->sub_off.as<unsigned long long>();
+    e.sub_off = sub_off;
     e.alive = q->el_alive.as<uint8_t>();
     e.corrs = q->el_corrs.as<uint32_t>();
-    e.cap = a.cap;
+    e.cap = cap;
     e.lvl_cnt = a.lvl_cnt;
     e.minkey = a.minkey;
     e.counts = q->counts.as<uint32_t>();
@@ -415,13 +413,26 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     if (!b) b = score_level_max_blocks_per_sm(m->fused);
     const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
     CU(cudaEventRecord(q->ev_s0, c->stream));
+    int cur = 0;
     for (int st = 0; st < plan.n_stages; ++st) {
-        a.stage = st;
-        a.L0 = e.L0 = plan.L0[st];
-        e.M = plan.M[st];
+        const int L0 = plan.L0[st], M = plan.M[st];
+        // this stage's work list over the hypotheses still alive
+        launch_el_work_count(c->stream, sub_off, goff[cur], G, L0, M, q->el_n_items.as<uint32_t>());
+        launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(), G);
+        launch_el_work_fill(c->stream, sub_off, goff[cur], G, L0, M, q->el_item_off.as<uint32_t>(), q->el_items.as<WorkItem>());
+        a.hl = e.hl = hl[cur];
+        a.L0 = e.L0 = L0;
+        e.M = M;
+        e.n_alive = goff[cur] + G;
         a.work_counter = q->el_ctrl.as<uint32_t>() + st;
-        launch_score_level(c->stream, a, grid, m->fused, plan.M[st]);
-        launch_el_eval(c->stream, e, (uint32_t)q->cap_hyp);
+        launch_score_level(c->stream, a, grid, m->fused, M);
+        launch_el_eval(c->stream, e, cap);
+        if (st + 1 < plan.n_stages) {  // drop the dead from the list
+            launch_el_alive_count(c->stream, hl[cur], goff[cur], G, e.alive, q->el_n_items.as<uint32_t>());
+            launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), goff[cur ^ 1], G);
+            launch_el_alive_fill(c->stream, hl[cur], goff[cur], G, e.alive, goff[cur ^ 1], hl[cur ^ 1]);
+            cur ^= 1;
+        }
     }
     TRY(enqueue_walker(q, a.model, q->counts.as<uint32_t>(), nullptr, q->dropped.as<uint8_t>(), &out->n_tests,
                        q->el_irregular.as<uint32_t>(), e.n_irregular));

@@ -124,28 +124,29 @@ __host__ __device__ inline uint32_t stage_tiles(uint32_t n, int L0, int M) {
     }
     return tiles;
 }
-// (stage, group)-major item ranges, so that a stage's items are contiguous
-__global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
-                                     uint32_t n_groups, LevelPlan plan, uint32_t* __restrict__ n_items) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups * (uint32_t)plan.n_stages) return;
-    const uint32_t st = t / n_groups, g = t % n_groups;
+// Work items of one stage: (tile, 256-hypothesis chunk) over the hypotheses still alive.  The alive hypotheses are kept
+// as a compacted list hl[] grouped by subset (ranges goff[g] .. goff[g + 1]); an item's hypothesis range is a range
+// of list positions.
+__global__ void el_work_count_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ goff,
+                                     uint32_t n_groups, int L0, int M, uint32_t* __restrict__ n_items) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
-    const uint32_t nh = g_hyp[g + 1] - g_hyp[g];
-    n_items[t] = stage_tiles(n, plan.L0[st], plan.M[st]) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK);
+    const uint32_t nh = goff[g + 1] - goff[g];
+    n_items[g] = nh ? stage_tiles(n, L0, M) * ((nh + EL_HCHUNK - 1) / EL_HCHUNK) : 0u;
 }
 // item: sub_begin = first row of the subset, npts = its size, pad = tile index within the stage
-__global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ g_hyp,
-                                    uint32_t n_groups, LevelPlan plan, const uint32_t* __restrict__ item_off,
+__global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_off, const uint32_t* __restrict__ goff,
+                                    uint32_t n_groups, int L0, int M, const uint32_t* __restrict__ item_off,
                                     WorkItem* __restrict__ items) {
-    const uint32_t t = blockIdx.x;
-    if (t >= n_groups * (uint32_t)plan.n_stages) return;
-    const uint32_t st = t / n_groups, g = t % n_groups;
+    const uint32_t g = blockIdx.x;
+    if (g >= n_groups) return;
     const unsigned long long sb = sub_off[g];
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
-    const uint32_t hb = g_hyp[g], nh = g_hyp[g + 1] - hb;
-    const uint32_t tiles = stage_tiles(n, plan.L0[st], plan.M[st]), chunks = (nh + EL_HCHUNK - 1) / EL_HCHUNK;
-    const uint32_t base = item_off[t];
+    const uint32_t hb = goff[g], nh = goff[g + 1] - hb;
+    if (!nh) return;
+    const uint32_t tiles = stage_tiles(n, L0, M), chunks = (nh + EL_HCHUNK - 1) / EL_HCHUNK;
+    const uint32_t base = item_off[g];
     for (uint32_t k = threadIdx.x; k < tiles * chunks; k += blockDim.x) {
         const uint32_t tile = k % tiles, chunk = k / tiles;
         WorkItem w;
@@ -157,23 +158,65 @@ __global__ void el_work_fill_kernel(const unsigned long long* __restrict__ sub_o
         items[base + k] = w;
     }
 }
-void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                          const LevelPlan& plan, uint32_t* n_items) {
+void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
+                          int L0, int M, uint32_t* n_items) {
     if (!n_groups) return;
     ++g_launch_count;
-    const uint32_t n = n_groups * (uint32_t)plan.n_stages;
-    el_work_count_kernel<<<(n + 127) / 128, 128, 0, st>>>(sub_off, g_hyp, n_groups, plan, n_items);
+    el_work_count_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(sub_off, goff, n_groups, L0, M, n_items);
 }
-void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                         const LevelPlan& plan, const uint32_t* item_off, WorkItem* items) {
+void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
+                         int L0, int M, const uint32_t* item_off, WorkItem* items) {
     if (!n_groups) return;
     ++g_launch_count;
-    el_work_fill_kernel<<<n_groups * (uint32_t)plan.n_stages, 128, 0, st>>>(sub_off, g_hyp, n_groups, plan, item_off, items);
+    el_work_fill_kernel<<<n_groups, 128, 0, st>>>(sub_off, goff, n_groups, L0, M, item_off, items);
+}
+// The alive list after a stage's checkpoints: per subset group, the hypotheses still alive, order kept.  One warp per
+// group: count, then (after a scan of the counts over the groups) an ordered ballot compaction.
+__global__ void __launch_bounds__(256)
+    el_alive_count_kernel(const uint32_t* __restrict__ hl, const uint32_t* __restrict__ goff, uint32_t n_groups,
+                          const uint8_t* __restrict__ alive, uint32_t* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    uint32_t c = 0;
+    for (uint32_t p = goff[g] + lane; p < goff[g + 1]; p += 32) c += alive[hl[p]] ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) cnt[g] = c;
+}
+__global__ void __launch_bounds__(256)
+    el_alive_fill_kernel(const uint32_t* __restrict__ hl, const uint32_t* __restrict__ goff, uint32_t n_groups,
+                         const uint8_t* __restrict__ alive, const uint32_t* __restrict__ goff_new,
+                         uint32_t* __restrict__ hl_new) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    uint32_t out = goff_new[g];
+    const uint32_t b = goff[g], e = goff[g + 1];
+    for (uint32_t p0 = b; p0 < e; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        const uint32_t h = p < e ? hl[p] : 0u;
+        const bool keep = p < e && alive[h];
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) hl_new[out + __popc(m & ((1u << lane) - 1u))] = h;
+        out += __popc(m);
+    }
+}
+void launch_el_alive_count(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
+                           uint32_t* cnt) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    el_alive_count_kernel<<<(n_groups + 7) / 8, 256, 0, st>>>(hl, goff, n_groups, alive, cnt);
+}
+void launch_el_alive_fill(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
+                          const uint32_t* goff_new, uint32_t* hl_new) {
+    if (!n_groups) return;
+    ++g_launch_count;
+    el_alive_fill_kernel<<<(n_groups + 7) / 8, 256, 0, st>>>(hl, goff, n_groups, alive, goff_new, hl_new);
 }
 uint64_t el_items_bound(uint64_t n_points, uint64_t n_hyp) {
-    // sum over the stages of (tiles x hypothesis chunks): tiles of a stage <= its points / 128 + 1 + the unevenness of
-    // its levels (a few points), at most EL_LEVELS stages
-    return (n_points / SCORE_TILE + 2 * EL_LEVELS + 2) * ((n_hyp + EL_HCHUNK - 1) / EL_HCHUNK + 1);
+    // (tiles x hypothesis chunks) of the largest stage: a stage holds at most 4 of the 19 levels plus the double-sized
+    // last one, i.e. well under half of the subset's 128-point tiles; bounded by all of them
+    return (n_points / SCORE_TILE + 4) * ((n_hyp + EL_HCHUNK - 1) / EL_HCHUNK + 1);
 }
 
 // ---- one level: counts + first reaching position per live hypothesis ------------------------------------------------
@@ -309,13 +352,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float4* my_rows = s_rows + warp * 32 * 3;
-    const uint32_t item_begin = a.item_off[a.stage * a.n_groups], item_end = a.item_off[(a.stage + 1) * a.n_groups];
+    const uint32_t item_end = *a.n_items;
     const ModelDev& m = a.model;
     X2 e;
     e.nz = k_nz; e.one = k_one; e.mone = 0ull;
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = item_begin + atomicAdd(a.work_counter, 1u);
+        if (lane == 0) item = atomicAdd(a.work_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= item_end) break;
         const WorkItem w = a.items[item];
@@ -357,11 +400,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_MIN_BLOCKS)
                  pzA = e.add(pack2(pz[0], pz[1]), e.nz);
         const p2 pxB = e.add(pack2(px[2], px[3]), e.nz), pyB = e.add(pack2(py[2], py[3]), e.nz),
                  pzB = e.add(pack2(pz[2], pz[3]), e.nz);
-        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {
-            const uint32_t h = h0 + lane;
+        for (uint32_t h0 = w.hyp_begin; h0 < w.hyp_end; h0 += 32) {  // positions in the list of hypotheses still alive
+            const bool live = h0 + lane < w.hyp_end;
+            const uint32_t h = live ? a.hl[h0 + lane] : 0u;
             bool sA = false, sB = false;
             __syncwarp();  // readers of the previous batch's rows are done
-            const bool live = h < w.hyp_end && a.alive[h];  // dropped at an earlier checkpoint: not walked any further
             if (live) {
                 const float4 r0 = __ldg(&a.T[3 * (size_t)h]), r1 = __ldg(&a.T[3 * (size_t)h + 1]),
                              r2 = __ldg(&a.T[3 * (size_t)h + 2]);
@@ -464,10 +507,11 @@ int score_level_max_blocks_per_sm(bool fused) {
 // ---- the checkpoints of a stage's levels, in order (level 0 has none; level 18 also closes the walk) ---------------
 __global__ void __launch_bounds__(256)
     el_eval_kernel(EvalArgs a) {
-    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;  // position in the list of hypotheses still alive
     unsigned long long tested = 0;  // walk positions this hypothesis' walk ends with (summed per warp: one atomic)
     bool irregular = false;         // to be walked on its own (appended per warp: one atomic)
-    if (h < *a.n_local && a.alive[h]) {
+    const uint32_t h = pos < *a.n_alive ? a.hl[pos] : 0u;
+    if (pos < *a.n_alive) {
         const uint32_t g = a.g_of_hyp[h];
         const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - a.sub_off[g]);
         uint32_t corrs = a.corrs[h];
@@ -529,13 +573,15 @@ void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound) {
     el_eval_kernel<<<(n_hyp_bound + 255) / 256, 256, 0, st>>>(a);
 }
 
-// alive[h] = 1 for h < n_local, per-hypothesis accumulators reset (lvl_cnt / minkey: EL_MAX_MERGE levels x cap)
+// alive[h] = 1 for h < n_local, the list of alive hypotheses = all of them, per-hypothesis accumulators reset
+// (lvl_cnt / minkey: EL_MAX_MERGE levels x cap)
 __global__ void el_init_kernel(const uint32_t* __restrict__ n_local, uint32_t cap, uint8_t* __restrict__ alive,
-                               uint32_t* __restrict__ corrs, uint32_t* __restrict__ lvl_cnt, uint32_t* __restrict__ minkey,
-                               uint8_t* __restrict__ dropped, uint32_t* __restrict__ counts) {
+                               uint32_t* __restrict__ hl, uint32_t* __restrict__ corrs, uint32_t* __restrict__ lvl_cnt,
+                               uint32_t* __restrict__ minkey, uint8_t* __restrict__ dropped, uint32_t* __restrict__ counts) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= cap) return;
     alive[h] = h < *n_local ? 1 : 0;
+    hl[h] = h;
     corrs[h] = 0u;
 #pragma unroll
     for (int r = 0; r < EL_MAX_MERGE; ++r) {
@@ -545,11 +591,11 @@ __global__ void el_init_kernel(const uint32_t* __restrict__ n_local, uint32_t ca
     dropped[h] = 0;
     counts[h] = 0u;
 }
-void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* corrs,
+void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* hl, uint32_t* corrs,
                     uint32_t* lvl_cnt, uint32_t* minkey, uint8_t* dropped, uint32_t* counts) {
     if (!cap) return;
     ++g_launch_count;
-    el_init_kernel<<<(cap + 255) / 256, 256, 0, st>>>(n_local, cap, alive, corrs, lvl_cnt, minkey, dropped, counts);
+    el_init_kernel<<<(cap + 255) / 256, 256, 0, st>>>(n_local, cap, alive, hl, corrs, lvl_cnt, minkey, dropped, counts);
 }
 
 }  // namespace tmk

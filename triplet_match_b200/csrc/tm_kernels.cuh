@@ -95,14 +95,12 @@ struct LevelArgs {
     ModelDev model;
     const int32_t* lvl_idx;    // subset rows regrouped by level (walk_levels_kernel): scene index ...
     const uint32_t* lvl_pos;   // ... and walk position of every element
-    const WorkItem* items;     // (stage, group)-major work list
-    const uint32_t* item_off;  // [n_stages * n_groups + 1]
-    uint32_t n_groups;
-    int stage;
+    const WorkItem* items;     // this stage's work list; hypothesis ranges are positions in hl[]
+    const uint32_t* n_items;   // (device) how many
+    const uint32_t* hl;        // hypotheses still alive, grouped by subset, order kept
     int L0;                    // first level of the stage
     uint32_t* work_counter;    // this stage's
     const float4* T;
-    const uint8_t* alive;
     uint32_t cap;              // hypothesis capacity = stride of the per-level accumulators
     uint32_t* lvl_cnt;         // [EL_MAX_MERGE][cap] inliers per level of the stage and hypothesis
     uint32_t* minkey;          // [EL_MAX_MERGE][cap] min over reaching elements of (walk position << 1) | !inlier
@@ -112,7 +110,8 @@ struct LevelArgs {
                                           // halves evaluated
 };
 struct EvalArgs {
-    const uint32_t* n_local;
+    const uint32_t* hl;        // hypotheses still alive before this stage's checkpoints ...
+    const uint32_t* n_alive;   // (device) ... and how many
     const uint32_t* g_of_hyp;
     const unsigned long long* sub_off;
     uint8_t* alive;
@@ -217,15 +216,19 @@ void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int3
 // k_early2.cu
 void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
                         int32_t* lvl_idx, uint32_t* lvl_pos);
-void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                          const LevelPlan& plan, uint32_t* n_items);
-void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* g_hyp, uint32_t n_groups,
-                         const LevelPlan& plan, const uint32_t* item_off, WorkItem* items);
+void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
+                          int L0, int M, uint32_t* n_items);
+void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
+                         int L0, int M, const uint32_t* item_off, WorkItem* items);
+void launch_el_alive_count(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
+                           uint32_t* cnt);
+void launch_el_alive_fill(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
+                          const uint32_t* goff_new, uint32_t* hl_new);
 uint64_t el_items_bound(uint64_t n_points, uint64_t n_hyp);
 void launch_score_level(cudaStream_t st, const LevelArgs& a, int grid, bool fused, int M);
 int score_level_max_blocks_per_sm(bool fused);
 void launch_el_eval(cudaStream_t st, const EvalArgs& a, uint32_t n_hyp_bound);
-void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* corrs,
+void launch_el_init(cudaStream_t st, const uint32_t* n_local, uint32_t cap, uint8_t* alive, uint32_t* hl, uint32_t* corrs,
                     uint32_t* lvl_cnt, uint32_t* minkey, uint8_t* dropped, uint32_t* counts);
 void launch_argmax(cudaStream_t st, const uint32_t* counts, const uint8_t* valid, const uint8_t* excluded,
                    const uint32_t* n_local, const unsigned long long* h_begin,
