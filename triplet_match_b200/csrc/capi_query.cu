@@ -339,22 +339,28 @@ static int enqueue_walker(tm_query* q, const ModelDev& md, uint32_t* counts, uns
     return TM_OK;
 }
 
-// The stages of the level-by-level early drop: levels 0 and 1 together (checkpoint 1 is where most hypotheses that are
-// going to be dropped are dropped, so nothing later shares a launch with it), then four levels per launch, the last
-// level (10 % of the walk) on its own.  TM_EARLY_MERGE=0: one level per launch.
-static LevelPlan level_plan() {
-    LevelPlan p;
-    memset(&p, 0, sizeof(p));
+// The steps of the level-by-level early drop.  A scoring stage scores M consecutive levels and applies their
+// checkpoints; a probe step applies one level's checkpoint from its first reaching element alone (found by walking the
+// level in walk order, level_probe_kernel), so that the level is scored afterwards, for the survivors only.
+// Default: level 0 is scored for everybody, checkpoint 1 — where most hypotheses that are going to be dropped are
+// dropped — is probed, level 1 follows for the survivors, then four levels per stage and the (double-length) last level.  TM_EARLY_MERGE=0: one level per stage, no probe.
+struct LevelStep {
+    int probe;       // 1: probe the checkpoint of level L0
+    int L0, M;       // scoring stage: levels L0 .. L0 + M - 1
+    int skip_first;  // scoring stage whose first level's checkpoint was probed before
+};
+static std::vector<LevelStep> level_steps() {
+    std::vector<LevelStep> v;
     if (!knobs().early_merge) {
-        p.n_stages = EL_LEVELS;
-        for (int L = 0; L < EL_LEVELS; ++L) { p.L0[L] = L; p.M[L] = 1; }
-        return p;
+        for (int L = 0; L < EL_LEVELS; ++L) v.push_back({0, L, 1, 0});
+        return v;
     }
-    auto add = [&](int L0, int M) { p.L0[p.n_stages] = L0; p.M[p.n_stages] = M; ++p.n_stages; };
-    add(0, 2);
-    for (int L = 2; L + 4 <= EL_LEVELS - 1; L += 4) add(L, 4);
-    add(EL_LEVELS - 1, 1);
-    return p;
+    v.push_back({0, 0, 1, 0});
+    v.push_back({1, 1, 1, 0});
+    v.push_back({0, 1, 1, 1});  // level 1 itself, for the survivors of its checkpoint
+    for (int L = 2; L + 4 <= EL_LEVELS - 1; L += 4) v.push_back({0, L, 4, 0});
+    v.push_back({0, EL_LEVELS - 1, 1, 0});  // the last level is twice as long as the others: its chunks fill tiles of their own
+    return v;
 }
 
 // early_out = 2 level by level (k_early2.cu): regroup the subset rows by checkpoint range, then per stage (one or a few
@@ -366,7 +372,7 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     const tm_model* m = q->m;
     const uint32_t G = q->n_outer;
     const uint32_t cap = (uint32_t)q->cap_hyp;
-    const LevelPlan plan = level_plan();
+    const std::vector<LevelStep> steps = level_steps();
     const unsigned long long* sub_off = q->sub_off.as<unsigned long long>();
     launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), G, q->g_of_hyp.as<uint32_t>());
     launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), sub_off, G, q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
@@ -413,21 +419,43 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     if (!b) b = score_level_max_blocks_per_sm(m->fused);
     const int grid = knobs().score_grid ? knobs().score_grid : c->sm_count * b;
     CU(cudaEventRecord(q->ev_s0, c->stream));
-    int cur = 0;
-    for (int st = 0; st < plan.n_stages; ++st) {
-        const int L0 = plan.L0[st], M = plan.M[st];
-        // this stage's work list over the hypotheses still alive
-        launch_el_work_count(c->stream, sub_off, goff[cur], G, L0, M, q->el_n_items.as<uint32_t>());
-        launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(), G);
-        launch_el_work_fill(c->stream, sub_off, goff[cur], G, L0, M, q->el_item_off.as<uint32_t>(), q->el_items.as<WorkItem>());
-        a.hl = e.hl = hl[cur];
-        a.L0 = e.L0 = L0;
-        e.M = M;
-        e.n_alive = goff[cur] + G;
-        a.work_counter = q->el_ctrl.as<uint32_t>() + st;
-        launch_score_level(c->stream, a, grid, m->fused, M);
+    ProbeArgs pr;
+    pr.scene = a.scene;
+    pr.model = a.model;
+    pr.sub_idx_walk = q->sub_idx_walk.as<int32_t>();
+    pr.sub_off = sub_off;
+    pr.g_of_hyp = e.g_of_hyp;
+    pr.T = a.T;
+    pr.sq_thres = sqt;
+    pr.minkey = a.minkey;  // slot 0
+    bool walk_rows = false;
+    int cur = 0, n_score = 0;
+    for (size_t st = 0; st < steps.size(); ++st) {
+        const LevelStep& s = steps[st];
+        a.hl = e.hl = pr.hl = hl[cur];
+        e.n_alive = pr.n_alive = goff[cur] + G;
+        a.L0 = e.L0 = s.L0;
+        e.M = s.M;
+        e.probe = s.probe;
+        e.skip_first = s.skip_first;
+        if (s.probe) {
+            if (!walk_rows) {  // the subset rows in walk order (also what the walker of the irregular hypotheses reads)
+                launch_walk_order_rows(c->stream, q->sub_idx.as<int32_t>(), sub_off, G, q->max_sub, q->sub_idx_walk.as<int32_t>());
+                walk_rows = true;
+            }
+            pr.level = s.L0;
+            launch_level_probe(c->stream, pr, cap, m->fused);
+        } else {
+            // this stage's work list over the hypotheses still alive
+            launch_el_work_count(c->stream, sub_off, goff[cur], G, s.L0, s.M, q->el_n_items.as<uint32_t>());
+            launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), q->el_item_off.as<uint32_t>(), G);
+            launch_el_work_fill(c->stream, sub_off, goff[cur], G, s.L0, s.M, q->el_item_off.as<uint32_t>(),
+                                q->el_items.as<WorkItem>());
+            a.work_counter = q->el_ctrl.as<uint32_t>() + n_score++;
+            launch_score_level(c->stream, a, grid, m->fused, s.M);
+        }
         launch_el_eval(c->stream, e, cap);
-        if (st + 1 < plan.n_stages) {  // drop the dead from the list
+        if (st + 1 < steps.size() && !(st + 1 < steps.size() && steps[st + 1].probe)) {  // drop the dead from the list
             launch_el_alive_count(c->stream, hl[cur], goff[cur], G, e.alive, q->el_n_items.as<uint32_t>());
             launch_exclusive_scan_u32(c->stream, q->el_n_items.as<uint32_t>(), goff[cur ^ 1], G);
             launch_el_alive_fill(c->stream, hl[cur], goff[cur], G, e.alive, goff[cur ^ 1], hl[cur ^ 1]);

@@ -170,48 +170,64 @@ void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, con
     ++g_launch_count;
     el_work_fill_kernel<<<n_groups, 128, 0, st>>>(sub_off, goff, n_groups, L0, M, item_off, items);
 }
-// The alive list after a stage's checkpoints: per subset group, the hypotheses still alive, order kept.  One warp per
-// group: count, then (after a scan of the counts over the groups) an ordered ballot compaction.
+// The alive list after a stage's checkpoints: per subset group, the hypotheses still alive, order kept.  One CTA per
+// group: count, then (after a scan of the counts over the groups) an ordered compaction (warp ballots + a prefix over
+// the CTA's warps).
 __global__ void __launch_bounds__(256)
     el_alive_count_kernel(const uint32_t* __restrict__ hl, const uint32_t* __restrict__ goff, uint32_t n_groups,
                           const uint8_t* __restrict__ alive, uint32_t* __restrict__ cnt) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= n_groups) return;
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x;
     uint32_t c = 0;
-    for (uint32_t p = goff[g] + lane; p < goff[g + 1]; p += 32) c += alive[hl[p]] ? 1u : 0u;
+    for (uint32_t p = goff[g] + threadIdx.x; p < goff[g + 1]; p += blockDim.x) c += alive[hl[p]] ? 1u : 0u;
     c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) cnt[g] = c;
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        cnt[g] = t;
+    }
 }
 __global__ void __launch_bounds__(256)
     el_alive_fill_kernel(const uint32_t* __restrict__ hl, const uint32_t* __restrict__ goff, uint32_t n_groups,
                          const uint8_t* __restrict__ alive, const uint32_t* __restrict__ goff_new,
                          uint32_t* __restrict__ hl_new) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= n_groups) return;
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x;
     uint32_t out = goff_new[g];
     const uint32_t b = goff[g], e = goff[g + 1];
-    for (uint32_t p0 = b; p0 < e; p0 += 32) {
-        const uint32_t p = p0 + lane;
+    for (uint32_t p0 = b; p0 < e; p0 += blockDim.x) {  // uniform trip count across the CTA
+        const uint32_t p = p0 + threadIdx.x;
         const uint32_t h = p < e ? hl[p] : 0u;
         const bool keep = p < e && alive[h];
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) hl_new[out + __popc(m & ((1u << lane) - 1u))] = h;
-        out += __popc(m);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += w < warp ? wsum[w] : 0u;
+            total += wsum[w];
+        }
+        if (keep) hl_new[out + before + __popc(m & ((1u << lane) - 1u))] = h;
+        out += total;
+        __syncthreads();  // wsum is rewritten by the next round
     }
 }
 void launch_el_alive_count(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
                            uint32_t* cnt) {
     if (!n_groups) return;
     ++g_launch_count;
-    el_alive_count_kernel<<<(n_groups + 7) / 8, 256, 0, st>>>(hl, goff, n_groups, alive, cnt);
+    el_alive_count_kernel<<<n_groups, 256, 0, st>>>(hl, goff, n_groups, alive, cnt);
 }
 void launch_el_alive_fill(cudaStream_t st, const uint32_t* hl, const uint32_t* goff, uint32_t n_groups, const uint8_t* alive,
                           const uint32_t* goff_new, uint32_t* hl_new) {
     if (!n_groups) return;
     ++g_launch_count;
-    el_alive_fill_kernel<<<(n_groups + 7) / 8, 256, 0, st>>>(hl, goff, n_groups, alive, goff_new, hl_new);
+    el_alive_fill_kernel<<<n_groups, 256, 0, st>>>(hl, goff, n_groups, alive, goff_new, hl_new);
 }
 uint64_t el_items_bound(uint64_t n_points, uint64_t n_hyp) {
     // (tiles x hypothesis chunks) of the largest stage: a stage holds at most 4 of the 19 levels plus the double-sized
@@ -523,7 +539,7 @@ __global__ void __launch_bounds__(256)
             a.minkey[slot] = 0xffffffffu;
             if (!open) continue;  // (the accumulators of the later levels are still reset)
             const int L = a.L0 + r;
-            if (L >= 1) {
+            if (L >= 1 && !(a.skip_first && r == 0)) {
                 if (level_begin(nsub, L) == level_begin(nsub, L + 1) || mk == 0xffffffffu) {
                     // the level holds no reaching element: its checkpoint fires later, on an element another checkpoint
                     // may also claim — walked exactly afterwards
@@ -542,6 +558,7 @@ __global__ void __launch_bounds__(256)
                     continue;
                 }
             }
+            if (a.probe) continue;  // the level itself is scored by the next stage
             corrs += cnt;
             if (L == EL_LEVELS - 1) {  // passed every checkpoint: the walk ends with the subset
                 a.counts[h] = corrs;

@@ -576,6 +576,54 @@ void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused) {
     else score_early_drop_kernel<false><<<grid, 256, 0, st>>>(a);
 }
 
+// First reaching element of one checkpoint range ("level", k_early2.cu) per hypothesis, found by walking the range in
+// walk order: key = (position << 1) | !inlier into minkey[h], untouched (0xFFFFFFFF) when the range reaches nothing.
+// One warp per listed hypothesis; on real data the first 32 positions hold a reaching element.  This is what a
+// checkpoint needs of its own range, so a range can be scored after its checkpoint, for the survivors only.
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+    level_probe_kernel(ProbeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= *a.n_alive) return;
+    const uint32_t h = a.hl[wid];
+    const uint32_t g = a.g_of_hyp[h];
+    const unsigned long long sb = a.sub_off[g];
+    const uint32_t nsub = (uint32_t)(a.sub_off[g + 1] - sb);
+    const uint32_t b0 = level_begin(nsub, a.level), b1 = level_begin(nsub, a.level + 1);
+    const float4 r0 = a.T[3 * (size_t)h], r1 = a.T[3 * (size_t)h + 1], r2 = a.T[3 * (size_t)h + 2];
+    for (uint32_t p0 = b0; p0 < b1; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        bool reach = false, inl = false;
+        if (p < b1) {
+            const uint32_t idx = (uint32_t)a.sub_idx_walk[sb + p];
+            const float4 v = a.scene.pos[idx];
+            const uint32_t fl = __float_as_uint(v.w);
+            if (!(fl & FLAG_MASKED)) {
+                float x, y, z;
+                uint32_t lin = 0xffffffffu;
+                inl = a.model.occ ? point_test<FUSED, true>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z, lin)
+                                  : point_test<FUSED, false>(a.model, r0, r1, r2, v.x, v.y, v.z, fl, a.sq_thres, x, y, z, lin);
+                reach = lin != 0xffffffffu;
+            }
+        }
+        const uint32_t rm = __ballot_sync(0xffffffffu, reach);
+        if (rm) {
+            const int l = __ffs(rm) - 1;
+            const uint32_t im = __ballot_sync(0xffffffffu, inl);
+            if (lane == 0) a.minkey[h] = ((p0 + (uint32_t)l) << 1) | (((im >> l) & 1u) ? 0u : 1u);
+            return;
+        }
+    }
+}
+void launch_level_probe(cudaStream_t st, const ProbeArgs& a, uint32_t n_bound, bool fused) {
+    if (!n_bound) return;
+    ++g_launch_count;
+    const unsigned grid = (n_bound + 7) / 8;
+    if (fused) level_probe_kernel<true><<<grid, 256, 0, st>>>(a);
+    else level_probe_kernel<false><<<grid, 256, 0, st>>>(a);
+}
+
 // ---------------------------------------------------------------------- argmax
 // key = (inliers << 32) | (0xFFFFFFFF - global hypothesis id); ties -> lowest id.
 __global__ void __launch_bounds__(256)

@@ -85,11 +85,6 @@ constexpr int EL_LEVELS = 19;  // walk-position ranges between the 18 checkpoint
 constexpr int EL_HCHUNK = TM_EL_HCHUNK;  // hypotheses per work item: a level holds 1/20 of a subset's tiles, so the
                                          // items are made shorter than the full scorer's to keep the tail small
 constexpr int EL_MAX_MERGE = 4;  // levels scored by one launch ("stage")
-struct LevelPlan {               // the stages of a run: stage s scores levels L0[s] .. L0[s] + M[s] - 1, M in {1, 2, 4}
-    int n_stages;
-    int L0[EL_LEVELS];
-    int M[EL_LEVELS];
-};
 struct LevelArgs {
     CloudDev scene;
     ModelDev model;
@@ -109,6 +104,19 @@ struct LevelArgs {
                                           // [2] surviving the cull, [3] with a reaching element, [4] 64-point
                                           // halves evaluated
 };
+struct ProbeArgs {  // level_probe_kernel (k_score.cu)
+    CloudDev scene;
+    ModelDev model;
+    const int32_t* sub_idx_walk;  // subset rows in walk order (walk_order_rows_kernel)
+    const unsigned long long* sub_off;
+    const uint32_t* g_of_hyp;
+    const float4* T;
+    const uint32_t* hl;           // hypotheses still alive ...
+    const uint32_t* n_alive;      // (device) ... and how many
+    int level;
+    float sq_thres;
+    uint32_t* minkey;             // [cap]: slot 0 of the per-level accumulators
+};
 struct EvalArgs {
     const uint32_t* hl;        // hypotheses still alive before this stage's checkpoints ...
     const uint32_t* n_alive;   // (device) ... and how many
@@ -126,6 +134,8 @@ struct EvalArgs {
     unsigned long long* n_tests;
     float accept_bound;
     int L0, M;
+    int probe = 0;       // the checkpoint of level L0 from a probed key only: the level is scored later, nothing is added
+    int skip_first = 0;  // level L0's checkpoint was already applied from a probe: only its count is added
 };
 
 struct IcpState {
@@ -210,6 +220,7 @@ void launch_work_fill(cudaStream_t st, const unsigned long long* sub_off, const 
 void launch_walk_order_rows(cudaStream_t st, const int32_t* in, const unsigned long long* sub_off, uint32_t n_groups,
                             uint32_t max_sub, int32_t* out);
 void launch_score_early_drop(cudaStream_t st, const EarlyArgs& a, bool fused);
+void launch_level_probe(cudaStream_t st, const ProbeArgs& a, uint32_t n_bound, bool fused);
 void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int32_t* sub_idx,
                               const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
                               float4* tile_lo, float4* tile_hi);
