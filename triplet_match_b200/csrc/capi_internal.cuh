@@ -256,7 +256,7 @@ struct tm_query {
     DevBuf topk_ids, topk_keys, icp_T16, stats, tile_lo, tile_hi;
     // early_out = 2, level by level (k_early2.cu)
     DevBuf lvl_idx, lvl_pos, el_n_items, el_item_off, el_items, el_alive, el_corrs, el_cnt, el_minkey, el_irregular, el_ctrl,
-        el_list, el_goff;
+        el_list, el_goff, el_hist;
     uint32_t el_items_cap = 0;
     bool levels = false;        // last run used the level scheme (scores[] on demand through the walker)
     uint32_t max_sub = 0;

@@ -118,6 +118,7 @@ static int size_for_shard(tm_query* q) {
             TRY(q->lvl_idx.ensure(std::max<uint64_t>(total, 1) * 4)); TRY(q->lvl_pos.ensure(std::max<uint64_t>(total, 1) * 4));
             TRY(q->el_n_items.ensure(lg * 4)); TRY(q->el_item_off.ensure((lg + 1) * 4));
             TRY(q->el_list.ensure(cap * 8)); TRY(q->el_goff.ensure((lg + 1) * 8));
+            TRY(q->el_hist.ensure(walk_levels_hist_bytes(n_outer, q->max_sub)));
             TRY(q->el_items.ensure((size_t)q->el_items_cap * sizeof(WorkItem)));
             TRY(q->el_alive.ensure(cap)); TRY(q->el_corrs.ensure(cap * 4)); TRY(q->el_cnt.ensure(cap * 4 * EL_MAX_MERGE));
             TRY(q->el_minkey.ensure(cap * 4 * EL_MAX_MERGE)); TRY(q->el_irregular.ensure(cap * 4));
@@ -177,7 +178,7 @@ void tm_query_destroy(tm_query* q) {
           &q->scores, &q->dropped, &q->n_items_g, &q->item_off, &q->items, &q->ctrl, &q->out,
           &q->topk_ids, &q->topk_keys, &q->icp_T16, &q->stats, &q->tile_lo, &q->tile_hi, &q->bounds, &q->bal_cum, &q->scan_scratch,
           &q->lvl_idx, &q->lvl_pos, &q->el_n_items, &q->el_item_off, &q->el_items, &q->el_alive, &q->el_corrs, &q->el_cnt,
-          &q->el_minkey, &q->el_irregular, &q->el_ctrl, &q->el_list, &q->el_goff})
+          &q->el_minkey, &q->el_irregular, &q->el_ctrl, &q->el_list, &q->el_goff, &q->el_hist})
         b->release();
     q->icp.release();
     delete q;
@@ -375,7 +376,8 @@ static int enqueue_levels(tm_query* q, float thres, float sqt) {
     const std::vector<LevelStep> steps = level_steps();
     const unsigned long long* sub_off = q->sub_off.as<unsigned long long>();
     launch_group_of_hyp(c->stream, q->g_hyp.as<uint32_t>(), G, q->g_of_hyp.as<uint32_t>());
-    launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), sub_off, G, q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
+    launch_walk_levels(c->stream, q->sub_idx.as<int32_t>(), sub_off, G, q->max_sub, q->el_hist.as<uint32_t>(),
+                       q->lvl_idx.as<int32_t>(), q->lvl_pos.as<uint32_t>());
     // the list of hypotheses still alive (two buffers, swapped after every stage) and its per-subset ranges: at first
     // every hypothesis of the shard, ranges = g_hyp
     uint32_t* hl[2] = {q->el_list.as<uint32_t>(), q->el_list.as<uint32_t>() + cap};

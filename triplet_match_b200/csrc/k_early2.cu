@@ -47,37 +47,76 @@ __device__ inline uint32_t mod_inverse(uint32_t s, uint32_t n) {
 
 // Rows of the subset CSR regrouped by level: within a group the elements of level L occupy
 // [sub_off[g] + level_begin(n, L), sub_off[g] + level_begin(n, L + 1)), in ascending element (= spatial) order.
-// lvl_idx = scene index, lvl_pos = walk position.  One CTA per group; stable partition by level through
-// __match_any_sync ranks.
+// lvl_idx = scene index, lvl_pos = walk position.  A group is cut into chunks of WL_CHUNK elements, one CTA each:
+// walk_levels_hist_kernel counts the chunk's elements per level, walk_levels_kernel places them — a stable partition
+// by level through __match_any_sync ranks, starting at the level's base plus what the chunks before it hold.
+constexpr uint32_t WL_CHUNK = 2048;
+__device__ __forceinline__ int level_of(uint32_t p, const uint32_t* bnd) {
+    int L = 0;
+#pragma unroll
+    for (int k = 1; k < EL_LEVELS; ++k) L += (p >= bnd[k]) ? 1 : 0;
+    return L;
+}
+__global__ void __launch_bounds__(256)
+    walk_levels_hist_kernel(const unsigned long long* __restrict__ sub_off, uint32_t max_chunks, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t bnd[EL_LEVELS + 1];
+    __shared__ uint32_t cnt[EL_LEVELS];
+    __shared__ uint32_t sinv_s;
+    const uint32_t g = blockIdx.y, chunk = blockIdx.x;
+    const uint32_t n = (uint32_t)(sub_off[g + 1] - sub_off[g]);
+    const uint32_t e0 = chunk * WL_CHUNK;
+    if (e0 >= n) return;
+    if (threadIdx.x <= EL_LEVELS) bnd[threadIdx.x] = level_begin(n, (int)threadIdx.x);
+    if (threadIdx.x < EL_LEVELS) cnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) sinv_s = mod_inverse(walk_stride(n), n);
+    __syncthreads();
+    const uint32_t sinv = sinv_s;
+    const int lane = threadIdx.x & 31;
+    const uint32_t e1 = min(n, e0 + WL_CHUNK);
+    for (uint32_t base = e0; base < e1; base += blockDim.x) {  // uniform trip count: every lane reaches the match
+        const uint32_t e = base + threadIdx.x;
+        int L = EL_LEVELS;  // dead lanes form their own match group
+        if (e < e1) L = level_of((uint32_t)(((unsigned long long)e * sinv) % n), bnd);
+        const uint32_t peers = __match_any_sync(0xffffffffu, L);
+        if (L < EL_LEVELS && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&cnt[L], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < EL_LEVELS) hist[((size_t)g * max_chunks + chunk) * EL_LEVELS + threadIdx.x] = cnt[threadIdx.x];
+}
 __global__ void __launch_bounds__(256)
     walk_levels_kernel(const int32_t* __restrict__ sub_idx, const unsigned long long* __restrict__ sub_off,
-                       int32_t* __restrict__ lvl_idx, uint32_t* __restrict__ lvl_pos) {
+                       uint32_t max_chunks, const uint32_t* __restrict__ hist, int32_t* __restrict__ lvl_idx,
+                       uint32_t* __restrict__ lvl_pos) {
     __shared__ uint32_t bnd[EL_LEVELS + 1];
     __shared__ uint32_t run[EL_LEVELS];
     __shared__ uint32_t wcnt[8][EL_LEVELS];
     __shared__ uint32_t sinv_s;
-    const uint32_t g = blockIdx.x;
+    const uint32_t g = blockIdx.y, chunk = blockIdx.x;
     const unsigned long long sb = sub_off[g];
     const uint32_t n = (uint32_t)(sub_off[g + 1] - sb);
-    if (!n) return;
+    const uint32_t e0 = chunk * WL_CHUNK;
+    if (e0 >= n) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x <= EL_LEVELS) bnd[threadIdx.x] = level_begin(n, (int)threadIdx.x);
-    if (threadIdx.x < EL_LEVELS) run[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) sinv_s = mod_inverse(walk_stride(n), n);
+    if (threadIdx.x < EL_LEVELS) {  // what the chunks before this one put into the level
+        uint32_t t = 0;
+        for (uint32_t c = 0; c < chunk; ++c) t += hist[((size_t)g * max_chunks + c) * EL_LEVELS + threadIdx.x];
+        run[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 32) sinv_s = mod_inverse(walk_stride(n), n);
     __syncthreads();
     const uint32_t sinv = sinv_s;
-    for (uint32_t base = 0; base < n; base += blockDim.x) {
+    const uint32_t e1 = min(n, e0 + WL_CHUNK);
+    for (uint32_t base = e0; base < e1; base += blockDim.x) {
         for (int t = threadIdx.x; t < 8 * EL_LEVELS; t += blockDim.x) (&wcnt[0][0])[t] = 0u;
         __syncthreads();
         const uint32_t e = base + threadIdx.x;
-        const bool live = e < n;
+        const bool live = e < e1;
         uint32_t p = 0u;
         int L = EL_LEVELS;  // dead lanes form their own match group
         if (live) {
             p = (uint32_t)(((unsigned long long)e * sinv) % n);  // (p * s) mod n == e
-            L = 0;
-#pragma unroll
-            for (int k = 1; k < EL_LEVELS; ++k) L += (p >= bnd[k]) ? 1 : 0;
+            L = level_of(p, bnd);
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, L);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -99,11 +138,17 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
     }
 }
+size_t walk_levels_hist_bytes(uint32_t n_groups, uint32_t max_sub) {
+    const size_t chunks = (max_sub + WL_CHUNK - 1) / WL_CHUNK;
+    return std::max<size_t>(1, (size_t)n_groups * chunks * EL_LEVELS) * 4;
+}
 void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
-                        int32_t* lvl_idx, uint32_t* lvl_pos) {
-    if (!n_groups) return;
-    ++g_launch_count;
-    walk_levels_kernel<<<n_groups, 256, 0, st>>>(sub_idx, sub_off, lvl_idx, lvl_pos);
+                        uint32_t max_sub, uint32_t* hist, int32_t* lvl_idx, uint32_t* lvl_pos) {
+    if (!n_groups || !max_sub) return;
+    const uint32_t chunks = (max_sub + WL_CHUNK - 1) / WL_CHUNK;
+    g_launch_count += 2;
+    walk_levels_hist_kernel<<<dim3(chunks, n_groups), 256, 0, st>>>(sub_off, chunks, hist);
+    walk_levels_kernel<<<dim3(chunks, n_groups), 256, 0, st>>>(sub_idx, sub_off, chunks, hist, lvl_idx, lvl_pos);
 }
 
 // ---- stages and their work lists -------------------------------------------------------------------------------------

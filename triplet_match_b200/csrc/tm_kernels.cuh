@@ -225,8 +225,9 @@ void launch_subset_tile_boxes(cudaStream_t st, const CloudDev& scene, const int3
                               const unsigned long long* sub_off, uint32_t n_groups, uint32_t max_sub,
                               float4* tile_lo, float4* tile_hi);
 // k_early2.cu
+size_t walk_levels_hist_bytes(uint32_t n_groups, uint32_t max_sub);
 void launch_walk_levels(cudaStream_t st, const int32_t* sub_idx, const unsigned long long* sub_off, uint32_t n_groups,
-                        int32_t* lvl_idx, uint32_t* lvl_pos);
+                        uint32_t max_sub, uint32_t* hist, int32_t* lvl_idx, uint32_t* lvl_pos);
 void launch_el_work_count(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
                           int L0, int M, uint32_t* n_items);
 void launch_el_work_fill(cudaStream_t st, const unsigned long long* sub_off, const uint32_t* goff, uint32_t n_groups,
