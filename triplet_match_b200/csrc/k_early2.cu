@@ -19,7 +19,9 @@
 //
 // One launch ("stage") scores up to four consecutive levels, each tile holding 32-point chunks of all of them over the
 // same stretch of the subset (narrower tiles, fewer of them pass the box cull) with per-level accumulators; el_eval_kernel
-// then applies the stage's checkpoints in order.
+// then applies the stage's checkpoints in order, and the hypotheses still alive are compacted into a list the next
+// stage's work items run over.  Checkpoint 1 — where most of the dropping happens — is applied from a probe of level 1's
+// first reaching element (level_probe_kernel, k_score.cu), so that level 1 is only scored for its survivors.
 //
 // A level without a reaching element (or an empty level: subsets of a few points) breaks the one-level-one-checkpoint
 // correspondence; such hypotheses are flagged and re-walked exactly by score_early_drop_kernel (they touch the grid
