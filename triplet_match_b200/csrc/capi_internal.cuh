@@ -51,7 +51,8 @@ struct Knobs {
                                    // packed-FP32 kernel + lazy score, which is the default where scores are not asked for)
     bool early_levels = true;      // TM_EARLY_LEVELS=0: early_out = 2 of tm_query_run through the one-warp-per-hypothesis
                                    // walker instead of the level-by-level tiled scorer (k_early2.cu); same results
-    bool early_merge = true;       // TM_EARLY_MERGE=0: one checkpoint range per launch instead of up to four; same results
+    bool early_merge = true;       // TM_EARLY_MERGE=0: one checkpoint range per launch instead of up to four, no probe of
+                                   // checkpoint 1; same results
 };
 const Knobs& knobs();
 
